@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — ref-views/s of the RC-MVSNet depth-inference hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on the host cores
+
+One step = one CascadeMVSNet_eval forward of one reference view (BASELINE configs[1]: 5 views, 512x640,
+cascade D=192/64/8, synthetic DTU-shaped cameras, the reference's shipped weights as a numpy fixture).
+Multi-GPU = independent reference views per rank (weak scaling, no data-path collective).
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally:
+  roofline      — the fused plane-sweep + variance kernel of stage 1 (HBM-bound), algorithmic bytes / CUDA-event time
+  roofline_all  — the same for every hot kernel of the step
+  cpu_baseline  — the oracle port timed on this box's host cores on a bounded sample (N=1 only)
+  e2e           — same metric through the public API with pinned HOST buffers (H2D + D2H inside the timed region)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "rc-mvsnet_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GOLDEN_WEIGHTS = os.path.join(ROOT, "tests", "golden", "cas_model_000014.npz")
+V, H, W = 5, 512, 640
+NDEPTHS = (192, 64, 8)
+METRIC = "ref-views/sec (5-view, 512x640, D=192/64/8 cascade)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        hot = [c for c, pw in zip(sm, power) if pw > 0.5 * max(power)] if power else sm
+        return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes_costvolume(Vv, C, D, h, w, per_pixel):
+    """4·(V·C·h·w + D·h·w + C·D·h·w) — features once, hypotheses once, variance written once."""
+    hyp = D * h * w if per_pixel else D
+    return 4 * (Vv * C * h * w + hyp + C * D * h * w)
+
+
+def conv_flops(cin, cout, vox):
+    return 2 * 27 * cin * cout * vox
+
+
+def time_kernel(fn, iters, stream):
+    """CUDA-event time of `fn` alone on `stream` (ms per launch), after one warm-up call."""
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def kernel_rooflines(model, dev, inputs, pk):
+    """Per-kernel timings on the tensors of a real forward (stage shapes of the BASELINE config)."""
+    from rcmvs import ops
+    from models.modules import as_channels_last_views
+    imgs, proj, dv = inputs
+    stream = torch.cuda.current_stream()
+    res = {}
+    with torch.no_grad():
+        out = model.feature(imgs.reshape(V, 3, H, W))
+        feats = {k: as_channels_last_views(f).view(1, V, *f.shape[2:], f.shape[1]) for k, f in out.items()}
+        depth = None
+        interval = (float(dv[0, -1]) - float(dv[0, 0])) / dv.shape[1]
+        for s, D in enumerate(NDEPTHS):
+            key = "stage%d" % (s + 1)
+            scale = (4, 2, 1)[s]
+            h, w = H // scale, W // scale
+            C = feats[key].shape[-1]
+            hyp = (ops.depth_hypotheses_first(dv, D) if depth is None else
+                   ops.depth_hypotheses_next(depth, D, model.depth_interals_ratio[s] * interval, H, W, h, w))
+            rt = ops.relative_projections(proj[key])
+            ms = time_kernel(lambda: ops.costvolume_variance(feats[key], rt, hyp), 10, stream)
+            nbytes = algorithmic_bytes_costvolume(V, C, D, h, w, hyp.dim() == 4)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            res["costvolume_var_" + key] = {"bound": "hbm", "ms": round(ms, 4), "achieved": round(gbs, 1),
+                                            "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                            "frac": round(gbs / pk["hbm_gbs"], 4), "bytes": nbytes}
+            var = ops.costvolume_variance(feats[key], rt, hyp)
+            cr = model.cost_regularization[s]
+            P = cr.packed()
+            ms0 = time_kernel(lambda: ops.conv3d(var, *P["conv0"]), 5, stream)
+            fl = conv_flops(C, 8, D * h * w)
+            # conv0 is the dominant CostRegNet layer; tensor roofline = TF32 dense = half the measured bf16 peak
+            tf32_peak = pk["bf16_tflops"] / 2
+            res["conv0_" + key] = {"bound": "tensor", "ms": round(ms0, 4), "achieved": round(fl / (ms0 * 1e-3) / 1e12, 2),
+                                   "peak": tf32_peak, "unit": "TFLOP/s", "frac": round(fl / (ms0 * 1e-3) / 1e12 / tf32_peak, 4),
+                                   "hbm_gbs": round(4 * (C + 8) * D * h * w / (ms0 * 1e-3) / 1e9, 1), "flops": fl}
+            msr = time_kernel(lambda: cr.forward_cl(var), 3, stream)
+            res["costregnet_" + key] = {"ms": round(msr, 4)}
+            cost = cr.forward_cl(var)
+            mss = time_kernel(lambda: ops.softargmin_conf(cost, hyp), 10, stream)
+            res["softargmin_" + key] = {"ms": round(mss, 4)}
+            depth, _ = ops.softargmin_conf(cost, hyp)
+            del var, cost
+        msf = time_kernel(lambda: model.feature(imgs.reshape(V, 3, H, W)), 5, stream)
+        res["featurenet_library"] = {"ms": round(msf, 4)}
+    return res
+
+
+def make_inputs(seed):
+    from rcmvs import synth
+    return synth.mvs_inputs(V, H, W, kind="textured", seed=seed)
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's CPU algorithm (oracle port, all host threads) on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import ref_torch as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = dict(np.load(GOLDEN_WEIGHTS))
+    from rcmvs import synth
+    sh, sw = H // 2, W // 2                      # 1/4-area crop: every op of the path is linear in pixel count
+    frac = (sh * sw) / float(H * W)
+    imgs, proj, dv = synth.mvs_inputs(V, sh, sw, kind="textured", seed=0)
+    pr = {k: v[0] for k, v in proj.items()}
+
+    def step():
+        T.cascade_forward_eval(imgs[0], pr, dv[0], P, ndepths=NDEPTHS)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * frac / dt
+    sample = "%dx%d crop (%.3g of a ref-view per step), full D=%s, %d views; value = frac/step_time" % (
+        sh, sw, frac, "/".join(map(str, NDEPTHS)), V)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "ref-views/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CascadeMVSNet_eval forward, %d views %dx%d D=%s" % (V, H, W, "/".join(map(str, NDEPTHS)))},
+            "cpu_baseline": {"value": value, "unit": "ref-views/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "ref-views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="rcmvs", choices=["rcmvs", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="reference views per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rcmvs import _ffi, weights
+    rc = _ffi.lib().rcmvs_check_device()
+    assert rc == 0, _ffi.lib().rcmvs_last_error()
+    from models import CascadeMVSNet_eval
+    torch.backends.cudnn.benchmark = True          # as the reference's eval script (eval_rcmvsnet_dtu.py:24)
+    model = CascadeMVSNet_eval(ndepths=list(NDEPTHS))
+    weights.load_model(model, GOLDEN_WEIGHTS)
+    model.to(dev).eval()
+
+    B = args.batch
+    host = []
+    for b in range(B):
+        host.append(make_inputs(seed=rank * 131 + b))
+    imgs_h = torch.from_numpy(np.concatenate([h[0] for h in host])).pin_memory()
+    proj_h = {k: torch.from_numpy(np.concatenate([h[1][k] for h in host])).pin_memory() for k in host[0][1]}
+    dv_h = torch.from_numpy(np.concatenate([h[2] for h in host])).pin_memory()
+    imgs, proj, dv = imgs_h.to(dev), {k: v.to(dev) for k, v in proj_h.items()}, dv_h.to(dev)
+    depth_out_h = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    conf_out_h = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    h2d = imgs_h.numel() * 4 + sum(v.numel() for v in proj_h.values()) * 4 + dv_h.numel() * 4
+    d2h = 2 * B * H * W * 4
+
+    def step_resident():
+        with torch.no_grad():
+            return model(imgs, proj, dv)
+
+    def step_e2e():
+        with torch.no_grad():
+            i = imgs_h.to(dev, non_blocking=True)
+            p = {k: v.to(dev, non_blocking=True) for k, v in proj_h.items()}
+            d = dv_h.to(dev, non_blocking=True)
+            out = model(i, p, d)
+            depth_out_h.copy_(out["depth"], non_blocking=True)
+            conf_out_h.copy_(out["photometric_confidence"], non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        stream = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _ffi.launches
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _ffi.launches - n0
+
+    for _ in range(args.warmup):
+        step_resident()
+    for _ in range(args.warmup):
+        step_e2e()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches = timed(step_resident, args.steps)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    pk = peaks()
+    roof_all, cpu_baseline = None, None
+    if rank == 0 and not args.no_kernel_rooflines:
+        roof_all = kernel_rooflines(model, dev, (imgs[:1], {k: v[:1] for k, v in proj.items()}, dv[:1]), pk)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_torch as T
+        from rcmvs import synth
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        P = dict(np.load(GOLDEN_WEIGHTS))
+        sh, sw = H // 2, W // 2
+        frac = (sh * sw) / float(H * W)
+        ci, cp, cd = synth.mvs_inputs(V, sh, sw, kind="textured", seed=0)
+        cpj = {k: v[0] for k, v in cp.items()}
+        T.cascade_forward_eval(ci[0], cpj, cd[0], P, ndepths=NDEPTHS)            # warm-up
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            T.cascade_forward_eval(ci[0], cpj, cd[0], P, ndepths=NDEPTHS)
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": frac / dt, "unit": "ref-views/s", "cores": cores, "kind": "port",
+                        "sample": "%dx%d crop = %.3g ref-view per pass, full D=%s, %d views, %d passes of %.1f s"
+                                  % (sh, sw, frac, "/".join(map(str, NDEPTHS)), V, reps, dt)}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    s1 = (roof_all or {}).get("costvolume_var_stage1")
+    roofline = None
+    if s1:
+        roofline = {"kernel": "costvolume_var_kernel<32> (stage 1, D=192, 128x160, V=5)", "bound": "hbm",
+                    "achieved": s1["achieved"], "peak": s1["peak"], "unit": "GB/s", "frac": s1["frac"],
+                    "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": None}
+    line = {
+        "metric": METRIC, "value": value, "unit": "ref-views/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CascadeMVSNet_eval forward: %d views, %dx%d, D=%s (BASELINE configs[1]); "
+                               "reference pretrained weights (numpy fixture), synthetic DTU-shaped cameras"
+                               % (V, H, W, "/".join(map(str, NDEPTHS))),
+                   "batch_per_gpu": B, "parallelism": "view-sharded replicas x%d" % world,
+                   "cache": "per-step working set %.0f MB of volumes >> 126 MB L2 (no explicit flush needed)"
+                            % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6),
+                   "conv_precision": os.environ.get("RCMVS_CONV", "fp32")},
+        "e2e": {"value": e2e_value, "unit": "ref-views/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_all": roof_all,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

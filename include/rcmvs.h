@@ -1,0 +1,102 @@
+/* rcmvs.h — C ABI of librcmvs.so: the B200 (sm_100a) implementation of RC-MVSNet's per-view depth-inference
+ * hot path.  The reference (Boese0601/RC-MVSNet) has no FFI of its own — its boundary is the Python API of
+ * models/modules.py, models/casmvsnet.py, models/renderer.py, losses/homography.py.  Each entry
+ * point below replaces the body of one of those Python functions and cites it; the Python packages under
+ * rc-mvsnet_b200/{models,losses} keep the reference signatures and call these through ctypes (rcmvs/_ffi.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless noted; the caller (torch) owns all buffers incl. workspace;
+ *   - the library never allocates device memory, never synchronises, and only enqueues on `stream`;
+ *   - return 0 on success, a negative rcmvs_status otherwise; rcmvs_last_error() gives a thread-local message;
+ *   - "NHWC"/"NDHWC" = channels-last internal layout; "NCHW"/"NCDHW" = the reference's layout;
+ *   - B = batch, V = views (ref first), C = channels, D = depth planes, (h,w) = stage resolution.
+ */
+#ifndef RCMVS_H_
+#define RCMVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rcmvs_stream_t; /* cudaStream_t */
+
+enum rcmvs_status {
+  RCMVS_OK = 0,
+  RCMVS_ERR_BAD_ARG = -1,     /* null pointer, non-positive dim */
+  RCMVS_ERR_UNSUPPORTED = -2, /* shape/channel count outside what the kernels are instantiated for */
+  RCMVS_ERR_CUDA = -3,        /* launch failure; message holds cudaGetErrorString */
+  RCMVS_ERR_ARCH = -4         /* device is not sm_100 */
+};
+
+int rcmvs_version(void);
+const char* rcmvs_last_error(void);
+/* 0 if the current device can run the library (compute capability 10.x), RCMVS_ERR_ARCH otherwise. */
+int rcmvs_check_device(void);
+
+/* ---- layout ------------------------------------------------------------------------------------------------ */
+/* [N][C][S] -> [N][S][C] and back (S = H*W or D*H*W).  Used at the API boundary only. */
+int rcmvs_planar_to_cl(const float* src, float* dst, int N, int C, int64_t S, rcmvs_stream_t stream);
+int rcmvs_cl_to_planar(const float* src, float* dst, int N, int C, int64_t S, rcmvs_stream_t stream);
+
+/* ---- projections: models/casmvsnet.py:78-81 + models/modules.py:315-317 ------------------------------------- */
+/* proj [B][V][2][4][4] (extrinsic, intrinsic) -> rt [B][V-1][12]: row-major 3x4 [rot|trans] of
+ * (K_v·E_v) · inverse(K_0·E_0), computed on device in fp64 and rounded to fp32 once. */
+int rcmvs_relative_projections(const float* proj, float* rt, int B, int V, rcmvs_stream_t stream);
+/* Same for already-multiplied 4x4 projections as homo_warping receives them: src_proj, ref_proj [B][4][4]. */
+int rcmvs_relative_projection_pair(const float* src_proj, const float* ref_proj, float* rt, int B,
+                                   rcmvs_stream_t stream);
+
+/* ---- a5 depth hypotheses: models/modules.py:549-588, models/casmvsnet.py:191-217 ---------------------------- */
+/* Stage 1: depth_values [B][Dv] -> planes [B][D]: dmin + i*(dmax-dmin)/(D-1). */
+int rcmvs_depth_hypotheses_first(const float* depth_values, float* planes, int B, int Dv, int D,
+                                 rcmvs_stream_t stream);
+/* Stage >=2: prev_depth [B][hp][wp] -> hyp [B][D][h][w]: bilinear upsample to (H,W) (align_corners=False),
+ * cur -/+ D/2*interval, D planes, then bilinear resize to (h,w). */
+int rcmvs_depth_hypotheses_next(const float* prev_depth, float* hyp, int B, int hp, int wp, int H, int W, int h,
+                                int w, int D, double interval_pixel, rcmvs_stream_t stream);
+
+/* ---- a1 homo_warping: models/modules.py:304-339 ------------------------------------------------------------- */
+/* src_fea [B][C][h][w] (NCHW), rt [B][12], depth [B][D] (per_pixel=0) or [B][D][h][w] (per_pixel=1)
+ * -> out [B][C][D][h][w].  Bilinear, zero padding per tap, align_corners=True.  C % 4 == 0, or C == 3. */
+int rcmvs_homo_warp_fwd(const float* src_fea, const float* rt, const float* depth, int per_pixel, float* out,
+                        int B, int C, int D, int h, int w, rcmvs_stream_t stream);
+/* grad_out [B][C][D][h][w] -> grad_src [B][C][h][w] (must be zero-filled by the caller); the sample grid carries
+ * no gradient in the reference (modules.py:314 torch.no_grad). */
+int rcmvs_homo_warp_bwd(const float* grad_out, const float* rt, const float* depth, int per_pixel,
+                        float* grad_src, int B, int C, int D, int h, int w, rcmvs_stream_t stream);
+
+/* ---- a1+a2 fused plane sweep + variance: models/casmvsnet.py:65-100 / 254-288 -------------------------------- */
+/* feats [B][V][h][w][C] (channels-last, ref view first), rt [B][V-1][12], depth as above
+ * -> var [B][D][h][w][C] = Σ_v f_v²/V − (Σ_v f_v/V)²  (written once, channels-last so conv0 reads it directly).
+ * var_noref (optional, may be NULL): same sums over the V-1 warped sources only, still divided by V
+ * (training-mode DepthNet, casmvsnet.py:100).  C in {8,16,32}. */
+int rcmvs_costvolume_var_fwd(const float* feats, const float* rt, const float* depth, int per_pixel, float* var,
+                             float* var_noref, int B, int V, int C, int D, int h, int w, rcmvs_stream_t stream);
+
+/* ---- a3 CostRegNet building blocks: models/modules.py:118-210, 470-501 --------------------------------------- */
+/* Weight packing (once per checkpoint): w [Cout][Cin][3][3][3] (Conv3d) or [Cin][Cout][3][3][3]
+ * (ConvTranspose3d) times the folded BatchNorm scale[Cout] (NULL = 1) -> packed [27][Cin][Cout]. */
+int rcmvs_pack_conv3d_weight(const float* w, const float* scale, float* packed, int Cout, int Cin,
+                             int transposed, rcmvs_stream_t stream);
+/* y = act(conv3d(x, k=3, pad=1, stride) + bias) (+ skip);  x [B][D][H][W][Cin], y [B][Do][Ho][Wo][Cout].
+ * bias/skip may be NULL; relu in {0,1}; stride in {1,2}.  The skip is added AFTER the ReLU (modules.py:497-499). */
+int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip, float* y, int B,
+                     int D, int H, int W, int Cin, int Cout, int stride, int relu, rcmvs_stream_t stream);
+/* ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1): x [B][D][H][W][Cin] -> y [B][2D][2H][2W][Cout]. */
+int rcmvs_conv_transpose3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip,
+                               float* y, int B, int D, int H, int W, int Cin, int Cout, int relu,
+                               rcmvs_stream_t stream);
+
+/* ---- a4 softmax + soft-argmin + photometric confidence: models/casmvsnet.py:111-122, modules.py:519-525 ------ */
+/* cost [B][D][h][w]; depth planes [B][D] (per_pixel=0) or [B][D][h][w]; -> depth [B][h][w], conf [B][h][w],
+ * idx [B][h][w] int32 (optional, may be NULL: clamp(trunc(Σ p·i))), prob [B][D][h][w] (optional, may be NULL). */
+int rcmvs_softargmin_conf_fwd(const float* cost, const float* depth_planes, int per_pixel, float* depth,
+                              float* conf, int32_t* idx, float* prob, int B, int D, int h, int w,
+                              rcmvs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCMVS_H_ */

@@ -1,0 +1,400 @@
+// a3 CostRegNet building blocks, exact-fp32 CUDA-core path (reference models/modules.py:118-210: Conv3d/Deconv3d =
+// conv(k3,p1,bias=False) -> BatchNorm3d -> ReLU, then the skip add in CostRegNet.forward :497-499).
+//
+// Eval-mode BatchNorm is folded at pack time (scale into the weights, shift into `bias`), so one kernel does
+// conv + bias + ReLU + skip and each activation is written exactly once, channels-last [D][H][W][C].
+//
+// Mapping (direct convolution, register-blocked):
+//   CTA   = output tile 1(d) x TH(h) x 32(w), all Cout
+//   warp  = 32 consecutive w positions; thread = 4 output rows (h) x CO_T(<=8) output channels -> 32 accumulators
+//   smem  = input halo tile for CB=8 input channels at a time, stored [kd][row][c4][col] as float4 so that a warp's
+//           LDS.128 for one tap is 32 consecutive 16-byte words (conflict-free at stride 1), plus the 27xCBxCout
+//           weight slice (read as warp-uniform broadcasts).
+//   Per (kd,kw,c4) a thread loads 6 input float4 and 24 weight float4 for 384 FMAs.
+// This is the fp32 reference-precision path; the tcgen05 implicit-GEMM path lives in conv3d_umma.cu.
+#include "common.cuh"
+
+namespace rcmvs {
+
+constexpr int CB = 8;  // input channels staged per pass
+
+template <int COUT>
+struct ConvTile {
+  static constexpr int CO_T = COUT >= 8 ? 8 : COUT;
+  static constexpr int COG = COUT / CO_T;
+  static constexpr int NWH = (COG >= 4) ? 1 : (COG == 2 ? 2 : 4);
+  static constexpr int TH = 4 * NWH;
+  static constexpr int THREADS = 32 * NWH * COG;
+};
+
+template <int COUT, int STRIDE>
+struct ConvSmem {
+  using T = ConvTile<COUT>;
+  static constexpr int IH = (T::TH - 1) * STRIDE + 3;
+  static constexpr int IW = 31 * STRIDE + 3;
+  static constexpr int X_F4 = 3 * IH * 2 * IW;            // float4 count
+  static constexpr int W_F = 27 * CB * COUT;              // float count
+  static constexpr size_t BYTES = (size_t)X_F4 * 16 + (size_t)W_F * 4;
+};
+
+template <int COUT, int STRIDE>
+__global__ void __launch_bounds__(ConvTile<COUT>::THREADS)
+conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                     const float* __restrict__ skip, float* __restrict__ y, int D, int H, int W, int Cin, int Do,
+                     int Ho, int Wo, int relu) {
+  using T = ConvTile<COUT>;
+  using S = ConvSmem<COUT, STRIDE>;
+  constexpr int CO_T = T::CO_T, TH = T::TH, IH = S::IH, IW = S::IW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* xs = reinterpret_cast<float4*>(smem_raw);
+  float* ws = reinterpret_cast<float*>(smem_raw + (size_t)S::X_F4 * 16);
+
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int hg = wid % T::NWH;
+  const int cog = wid / T::NWH;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * TH;
+  const int b = blockIdx.z / Do, od = blockIdx.z % Do;
+  const int iz0 = od * STRIDE - 1, iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+  x += (int64_t)b * D * H * W * Cin;
+
+  float acc[4][CO_T];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) acc[j][c] = 0.f;
+
+  for (int cb0 = 0; cb0 < Cin; cb0 += CB) {
+    __syncthreads();
+    // ---- stage the input halo tile for channels [cb0, cb0+8): element e -> (kd, iy, ix, c4), c4 fastest ----
+    for (int e = threadIdx.x; e < S::X_F4; e += T::THREADS) {
+      const int c4 = e & 1;
+      int r = e >> 1;
+      const int ix = r % IW; r /= IW;
+      const int iy = r % IH;
+      const int kd = r / IH;
+      const int gz = iz0 + kd, gy = iy0 + iy, gx = ix0 + ix;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = ldg4(x + (((int64_t)gz * H + gy) * W + gx) * Cin + cb0 + c4 * 4);
+      xs[((kd * IH + iy) * 2 + c4) * IW + ix] = v;
+    }
+    // ---- stage the weight slice [27][CB][COUT] ----
+    for (int e = threadIdx.x; e < S::W_F; e += T::THREADS) {
+      const int co = e % COUT;
+      const int r = e / COUT;
+      const int ci = r % CB, tap = r / CB;
+      ws[e] = __ldg(wp + ((int64_t)tap * Cin + cb0 + ci) * COUT + co);
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+          constexpr int NR = 3 * STRIDE + 3;  // distinct input rows touched by 4 output rows
+          float4 xr[NR];
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+            xr[r] = xs[((kd * IH + hg * 4 * STRIDE + r) * 2 + c4) * IW + lane * STRIDE + kw];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const int tap = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+              float wv[CO_T];
+              const float* wrow = ws + ((tap * CB) + c4 * 4 + ci) * COUT + cog * CO_T;
+              if constexpr (CO_T == 8) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+                const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+                wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+                wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+              } else {
+#pragma unroll
+                for (int c = 0; c < CO_T; ++c) wv[c] = wrow[c];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 xv4 = xr[j * STRIDE + kh];
+                const float xv = ci == 0 ? xv4.x : (ci == 1 ? xv4.y : (ci == 2 ? xv4.z : xv4.w));
+#pragma unroll
+                for (int c = 0; c < CO_T; ++c) acc[j][c] = fmaf(xv, wv[c], acc[j][c]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: + bias, ReLU, + skip (after the ReLU), streaming store ----
+  const int ox = ox0 + lane;
+  if (ox >= Wo) return;
+  float bv[CO_T];
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) bv[c] = bias ? __ldg(bias + cog * CO_T + c) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int oy = oy0 + hg * 4 + j;
+    if (oy >= Ho) continue;
+    const int64_t o = ((((int64_t)b * Do + od) * Ho + oy) * Wo + ox) * COUT + cog * CO_T;
+    float v[CO_T];
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) {
+      v[c] = acc[j][c] + bv[c];
+      if (relu) v[c] = fmaxf(v[c], 0.f);
+    }
+    if constexpr (CO_T == 8) {
+      if (skip) {
+        const float4 s0 = ldg4(skip + o), s1 = ldg4(skip + o + 4);
+        v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+        v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+      }
+      st4(y + o, make_float4(v[0], v[1], v[2], v[3]));
+      st4(y + o + 4, make_float4(v[4], v[5], v[6], v[7]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) y[o + c] = v[c] + (skip ? __ldg(skip + o + c) : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1): out[z] += x[i]·w[k] with z = 2i + k - 1.
+// Per dimension: even output (a=0) <- (k=1, i); odd output (a=1) <- (k=2, i) and (k=0, i+1).
+// Thread = one input-space voxel -> its 2x2x2 output block x 8 output channels (64 accumulators).
+// CTA = input tile 1(d) x TH(h) x 32(w); smem = (2 x (TH+1) x 33) input voxels x 8 channels + 27x8xCout weights.
+// ------------------------------------------------------------------------------------------------------------------
+template <int COUT>
+struct TConvTile {
+  static constexpr int COG = COUT / 8;
+  static constexpr int NWH = (COG >= 4) ? 1 : (COG == 2 ? 2 : 4);
+  static constexpr int TH = NWH;  // one input row per warp-row
+  static constexpr int THREADS = 32 * NWH * COG;
+  static constexpr int IH = TH + 1, IW = 33;
+  static constexpr int X_F4 = 2 * IH * 2 * IW;
+  static constexpr int W_F = 27 * CB * COUT;
+  static constexpr size_t BYTES = (size_t)X_F4 * 16 + (size_t)W_F * 4;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(TConvTile<COUT>::THREADS)
+conv_transpose3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                               const float* __restrict__ bias, const float* __restrict__ skip, float* __restrict__ y,
+                               int D, int H, int W, int Cin, int relu) {
+  using T = TConvTile<COUT>;
+  constexpr int IH = T::IH, IW = T::IW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* xs = reinterpret_cast<float4*>(smem_raw);
+  float* ws = reinterpret_cast<float*>(smem_raw + (size_t)T::X_F4 * 16);
+
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int hg = wid % T::NWH;
+  const int cog = wid / T::NWH;
+  const int ix0 = blockIdx.x * 32, iy0 = blockIdx.y * T::TH;
+  const int b = blockIdx.z / D, iz = blockIdx.z % D;
+  x += (int64_t)b * D * H * W * Cin;
+
+  float acc[8][8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[o][c] = 0.f;
+
+  for (int cb0 = 0; cb0 < Cin; cb0 += CB) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < T::X_F4; e += T::THREADS) {
+      const int c4 = e & 1;
+      int r = e >> 1;
+      const int ix = r % IW; r /= IW;
+      const int iy = r % IH;
+      const int dz = r / IH;
+      const int gz = iz + dz, gy = iy0 + iy, gx = ix0 + ix;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gz < D && gy < H && gx < W) v = ldg4(x + (((int64_t)gz * H + gy) * W + gx) * Cin + cb0 + c4 * 4);
+      xs[((dz * IH + iy) * 2 + c4) * IW + ix] = v;
+    }
+    for (int e = threadIdx.x; e < T::W_F; e += T::THREADS) {
+      const int co = e % COUT;
+      const int r = e / COUT;
+      const int ci = r % CB, tap = r / CB;
+      ws[e] = __ldg(wp + ((int64_t)tap * Cin + cb0 + ci) * COUT + co);
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int c4 = 0; c4 < 2; ++c4) {
+      float4 xn[8];  // neighbourhood (dz,dy,dx) in {0,1}^3
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+        xn[n] = xs[(((n >> 2) * IH + hg + ((n >> 1) & 1)) * 2 + c4) * IW + lane + (n & 1)];
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {       // output parity (a,b,c) = (o>>2, (o>>1)&1, o&1)
+          const int a = o >> 2, bq = (o >> 1) & 1, cq = o & 1;
+#pragma unroll
+          for (int ta = 0; ta <= a; ++ta)   // a=0: one term (k=1,di=0); a=1: (k=2,di=0),(k=0,di=1)
+#pragma unroll
+            for (int tb = 0; tb <= bq; ++tb)
+#pragma unroll
+              for (int tc = 0; tc <= cq; ++tc) {
+                const int kd = a ? (ta ? 0 : 2) : 1, dz = a ? ta : 0;
+                const int kh = bq ? (tb ? 0 : 2) : 1, dy = bq ? tb : 0;
+                const int kw = cq ? (tc ? 0 : 2) : 1, dx = cq ? tc : 0;
+                const int tap = (kd * 3 + kh) * 3 + kw;
+                const float4 xv4 = xn[dz * 4 + dy * 2 + dx];
+                const float xv = ci == 0 ? xv4.x : (ci == 1 ? xv4.y : (ci == 2 ? xv4.z : xv4.w));
+                const float* wrow = ws + ((tap * CB) + c4 * 4 + ci) * COUT + cog * 8;
+                const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+                const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+                acc[o][0] = fmaf(xv, w0.x, acc[o][0]); acc[o][1] = fmaf(xv, w0.y, acc[o][1]);
+                acc[o][2] = fmaf(xv, w0.z, acc[o][2]); acc[o][3] = fmaf(xv, w0.w, acc[o][3]);
+                acc[o][4] = fmaf(xv, w1.x, acc[o][4]); acc[o][5] = fmaf(xv, w1.y, acc[o][5]);
+                acc[o][6] = fmaf(xv, w1.z, acc[o][6]); acc[o][7] = fmaf(xv, w1.w, acc[o][7]);
+              }
+        }
+      }
+    }
+  }
+
+  const int ix = ix0 + lane, iy = iy0 + hg;
+  if (ix >= W || iy >= H) return;
+  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+  float bv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bv[c] = bias ? __ldg(bias + cog * 8 + c) : 0.f;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const int oz = 2 * iz + (o >> 2), oy = 2 * iy + ((o >> 1) & 1), ox = 2 * ix + (o & 1);
+    const int64_t off = ((((int64_t)b * Do + oz) * Ho + oy) * Wo + ox) * COUT + cog * 8;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      v[c] = acc[o][c] + bv[c];
+      if (relu) v[c] = fmaxf(v[c], 0.f);
+    }
+    if (skip) {
+      const float4 s0 = ldg4(skip + off), s1 = ldg4(skip + off + 4);
+      v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+      v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+    }
+    st4(y + off, make_float4(v[0], v[1], v[2], v[3]));
+    st4(y + off + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight packing: torch OIDHW (conv) / IODHW (transposed conv) x BN scale -> [27][Cin][Cout]
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                   float* __restrict__ packed, int Cout, int Cin, int transposed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 27 * Cin * Cout) return;
+  const int co = i % Cout;
+  const int ci = (i / Cout) % Cin;
+  const int tap = i / (Cout * Cin);
+  const float v = transposed ? w[((int64_t)ci * Cout + co) * 27 + tap] : w[((int64_t)co * Cin + ci) * 27 + tap];
+  packed[i] = scale ? v * scale[co] : v;
+}
+
+template <int COUT, int STRIDE>
+static int launch_conv(const float* x, const float* wp, const float* bias, const float* skip, float* y, int B, int D,
+                       int H, int W, int Cin, int relu, cudaStream_t st) {
+  using T = ConvTile<COUT>;
+  using S = ConvSmem<COUT, STRIDE>;
+  const int Do = (D - 1) / STRIDE + 1, Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
+  auto kern = conv3d_direct_kernel<COUT, STRIDE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES);
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  RCMVS_REQUIRE((int64_t)B * Do <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv3d_fwd: grid too large");
+  dim3 grid(ceil_div(Wo, 32), ceil_div(Ho, T::TH), B * Do);
+  kern<<<grid, T::THREADS, S::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, Do, Ho, Wo, relu);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv3d_fwd");
+  return RCMVS_OK;
+}
+
+template <int COUT>
+static int launch_tconv(const float* x, const float* wp, const float* bias, const float* skip, float* y, int B, int D,
+                        int H, int W, int Cin, int relu, cudaStream_t st) {
+  using T = TConvTile<COUT>;
+  auto kern = conv_transpose3d_direct_kernel<COUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES);
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_transpose3d_fwd: cudaFuncSetAttribute: %s",
+                  cudaGetErrorString(e));
+    attr_set = true;
+  }
+  RCMVS_REQUIRE((int64_t)B * D <= 65535 && ceil_div(H, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv_transpose3d_fwd: grid too large");
+  dim3 grid(ceil_div(W, 32), ceil_div(H, T::TH), B * D);
+  kern<<<grid, T::THREADS, T::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, relu);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv_transpose3d_fwd");
+  return RCMVS_OK;
+}
+
+}  // namespace rcmvs
+
+extern "C" int rcmvs_pack_conv3d_weight(const float* w, const float* scale, float* packed, int Cout, int Cin,
+                                        int transposed, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(w && packed, RCMVS_ERR_BAD_ARG, "rcmvs_pack_conv3d_weight: null pointer");
+  RCMVS_REQUIRE(Cout > 0 && Cin > 0, RCMVS_ERR_BAD_ARG, "rcmvs_pack_conv3d_weight: bad dims");
+  const int n = 27 * Cin * Cout;
+  pack_weight_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(w, scale, packed, Cout, Cin, transposed);
+  RCMVS_CHECK_LAUNCH("rcmvs_pack_conv3d_weight");
+  return RCMVS_OK;
+}
+
+extern "C" int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip, float* y,
+                                int B, int D, int H, int W, int Cin, int Cout, int stride, int relu,
+                                rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(x && packed_w && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_fwd: null pointer");
+  RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_fwd: bad dims");
+  RCMVS_REQUIRE(Cin % 8 == 0 && Cin > 0, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_fwd: Cin=%d must be a multiple of 8", Cin);
+  RCMVS_REQUIRE(stride == 1 || stride == 2, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_fwd: stride must be 1 or 2");
+  cudaStream_t st = as_stream(stream);
+#define RCMVS_CONV_CASE(CO)                                                                       \
+  case CO:                                                                                        \
+    return stride == 1 ? launch_conv<CO, 1>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st) \
+                       : launch_conv<CO, 2>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st)
+  switch (Cout) {
+    RCMVS_CONV_CASE(1);
+    RCMVS_CONV_CASE(8);
+    RCMVS_CONV_CASE(16);
+    RCMVS_CONV_CASE(32);
+    RCMVS_CONV_CASE(64);
+    default: break;
+  }
+#undef RCMVS_CONV_CASE
+  set_error("rcmvs_conv3d_fwd: Cout=%d not in {1,8,16,32,64}", Cout);
+  return RCMVS_ERR_UNSUPPORTED;
+}
+
+extern "C" int rcmvs_conv_transpose3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip,
+                                          float* y, int B, int D, int H, int W, int Cin, int Cout, int relu,
+                                          rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(x && packed_w && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_fwd: null pointer");
+  RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_fwd: bad dims");
+  RCMVS_REQUIRE(Cin % 8 == 0 && Cin > 0, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_transpose3d_fwd: Cin=%d must be a multiple of 8", Cin);
+  cudaStream_t st = as_stream(stream);
+  switch (Cout) {
+    case 8: return launch_tconv<8>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st);
+    case 16: return launch_tconv<16>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st);
+    case 32: return launch_tconv<32>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st);
+    default: break;
+  }
+  set_error("rcmvs_conv_transpose3d_fwd: Cout=%d not in {8,16,32}", Cout);
+  return RCMVS_ERR_UNSUPPORTED;
+}

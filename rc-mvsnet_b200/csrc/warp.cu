@@ -1,0 +1,288 @@
+// a1 homo_warping (reference models/modules.py:304-339) and the fused plane sweep + variance reduction that replaces
+// DepthNet's inner loop (reference models/casmvsnet.py:65-100 / 254-288).
+//
+// Fused kernel data flow (per reference view, per stage):
+//   read   V·C·h·w   fp32 source/ref features, channels-last [V][h][w][C]  (<= 52 MB at DTU sizes: L2-resident)
+//   read   D·h·w     depth hypotheses (or D scalars at stage 1)
+//   write  C·D·h·w   variance volume, channels-last [D][h][w][C], exactly once, streaming stores
+// The reference materialises (V-1) warped volumes and streams the volume 3(V-1)+4 times; here Σf and Σf² live in
+// registers and nothing but the final variance touches HBM.
+//
+// Thread mapping: one thread = one reference pixel × one group of 4 channels (float4).  Consecutive lanes hold the
+// channel groups of one pixel, then the next pixel, so a warp's tap load is (32/CQ) contiguous C·4-byte runs and a
+// warp's store is one contiguous (32/CQ)·C·4 = 512-byte run.
+#include "common.cuh"
+
+namespace rcmvs {
+
+constexpr int kMaxSrc = 15;  // V-1 upper bound (rt staged in shared memory)
+
+struct Tap {
+  int off00, off01, off10, off11;  // element offsets of the 4 taps (pixel index, not yet × C), clamped in-bounds
+  float w00, w01, w10, w11;        // bilinear weights, zeroed for out-of-bounds taps
+  bool any;
+};
+
+// Pixel-space sample position -> taps.  grid_sample(bilinear, zeros, align_corners=True): tap (xi,yi) contributes
+// iff 0<=xi<w and 0<=yi<h; NaN/inf/huge coordinates contribute nothing.
+__device__ __forceinline__ Tap make_tap(float px, float py, int h, int w) {
+  Tap t;
+  const bool finite = (fabsf(px) < 1e8f) && (fabsf(py) < 1e8f);  // false for NaN
+  const float fx = floorf(px), fy = floorf(py);
+  const float ax = px - fx, ay = py - fy;  // exact
+  const int x0 = finite ? (int)fx : -4, y0 = finite ? (int)fy : -4;
+  const bool vx0 = (x0 >= 0) && (x0 < w), vx1 = (x0 + 1 >= 0) && (x0 + 1 < w);
+  const bool vy0 = (y0 >= 0) && (y0 < h), vy1 = (y0 + 1 >= 0) && (y0 + 1 < h);
+  const float bx = 1.f - ax, by = 1.f - ay;
+  t.w00 = (vx0 && vy0) ? bx * by : 0.f;
+  t.w01 = (vx1 && vy0) ? ax * by : 0.f;
+  t.w10 = (vx0 && vy1) ? bx * ay : 0.f;
+  t.w11 = (vx1 && vy1) ? ax * ay : 0.f;
+  t.any = (vx0 || vx1) && (vy0 || vy1);
+  const int cx0 = min(max(x0, 0), w - 1), cx1 = min(max(x0 + 1, 0), w - 1);
+  const int cy0 = min(max(y0, 0), h - 1), cy1 = min(max(y0 + 1, 0), h - 1);
+  t.off00 = cy0 * w + cx0;
+  t.off01 = cy0 * w + cx1;
+  t.off10 = cy1 * w + cx0;
+  t.off11 = cy1 * w + cx1;
+  return t;
+}
+
+__device__ __forceinline__ void project(const float* __restrict__ rt, float rx, float ry, float rz, float d,
+                                        float& px, float& py) {
+  // p = rot·(x,y,1)·depth + trans ; (px,py) = p.xy / p.z   (modules.py:325-329)
+  const float X = fmaf(rx, d, rt[3]);
+  const float Y = fmaf(ry, d, rt[7]);
+  const float Z = fmaf(rz, d, rt[11]);
+  px = __fdiv_rn(X, Z);
+  py = __fdiv_rn(Y, Z);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused plane sweep + variance
+// ------------------------------------------------------------------------------------------------------------------
+template <int C, bool PER_PIXEL, bool NOREF>
+__global__ void __launch_bounds__(256)
+costvolume_var_kernel(const float* __restrict__ feats, const float* __restrict__ rt_g,
+                      const float* __restrict__ depth,
+                      float* __restrict__ var, float* __restrict__ var_noref, int V, int D, int h, int w,
+                      int d_chunk, int chunks_per_batch) {
+  constexpr int CQ = C / 4;        // float4 groups per pixel
+  constexpr int PXB = 256 / CQ;    // pixels per block
+  const int q = threadIdx.x % CQ;
+  const int x = blockIdx.x * PXB + threadIdx.x / CQ;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / chunks_per_batch;
+  const int d_begin = (blockIdx.z % chunks_per_batch) * d_chunk;
+  const int d_end = min(D, d_begin + d_chunk);
+  __shared__ float rt_s[kMaxSrc * 12];
+  for (int i = threadIdx.x; i < (V - 1) * 12; i += 256) rt_s[i] = __ldg(rt_g + (int64_t)b * (V - 1) * 12 + i);
+  __syncthreads();
+  if (x >= w) return;
+
+  const int64_t hw = (int64_t)h * w;
+  feats += (int64_t)b * V * hw * C + q * 4;
+  var += (int64_t)b * D * hw * C + q * 4;
+  if (NOREF) var_noref += (int64_t)b * D * hw * C + q * 4;
+  depth += PER_PIXEL ? (int64_t)b * D * hw + (int64_t)y * w + x : (int64_t)b * D;
+
+  const float4 ref = ldg4(feats + ((int64_t)y * w + x) * C);
+  const float inv_v = 1.f / (float)V;
+  const float xf = (float)x, yf = (float)y;
+
+  for (int d = d_begin; d < d_end; ++d) {
+    const float dep = PER_PIXEL ? __ldg(depth + (int64_t)d * hw) : __ldg(depth + d);
+    float4 s = ref;
+    float4 s2 = make_float4(ref.x * ref.x, ref.y * ref.y, ref.z * ref.z, ref.w * ref.w);
+    float4 n = make_float4(0.f, 0.f, 0.f, 0.f), n2 = n;
+    for (int v = 0; v < V - 1; ++v) {
+      const float* m = rt_s + v * 12;
+      const float rx = fmaf(m[0], xf, fmaf(m[1], yf, m[2]));
+      const float ry = fmaf(m[4], xf, fmaf(m[5], yf, m[6]));
+      const float rz = fmaf(m[8], xf, fmaf(m[9], yf, m[10]));
+      float px, py;
+      project(m, rx, ry, rz, dep, px, py);
+      const Tap t = make_tap(px, py, h, w);
+      if (t.any) {
+        const float* src = feats + (int64_t)(v + 1) * hw * C;
+        const float4 a = ldg4(src + (int64_t)t.off00 * C);
+        const float4 bb = ldg4(src + (int64_t)t.off01 * C);
+        const float4 c = ldg4(src + (int64_t)t.off10 * C);
+        const float4 e = ldg4(src + (int64_t)t.off11 * C);
+        float4 f;
+        f.x = fmaf(e.x, t.w11, fmaf(c.x, t.w10, fmaf(bb.x, t.w01, a.x * t.w00)));
+        f.y = fmaf(e.y, t.w11, fmaf(c.y, t.w10, fmaf(bb.y, t.w01, a.y * t.w00)));
+        f.z = fmaf(e.z, t.w11, fmaf(c.z, t.w10, fmaf(bb.z, t.w01, a.z * t.w00)));
+        f.w = fmaf(e.w, t.w11, fmaf(c.w, t.w10, fmaf(bb.w, t.w01, a.w * t.w00)));
+        s.x += f.x; s.y += f.y; s.z += f.z; s.w += f.w;
+        s2.x = fmaf(f.x, f.x, s2.x); s2.y = fmaf(f.y, f.y, s2.y);
+        s2.z = fmaf(f.z, f.z, s2.z); s2.w = fmaf(f.w, f.w, s2.w);
+        if (NOREF) {
+          n.x += f.x; n.y += f.y; n.z += f.z; n.w += f.w;
+          n2.x = fmaf(f.x, f.x, n2.x); n2.y = fmaf(f.y, f.y, n2.y);
+          n2.z = fmaf(f.z, f.z, n2.z); n2.w = fmaf(f.w, f.w, n2.w);
+        }
+      }
+    }
+    // var = Σf²/V − (Σf/V)²   (casmvsnet.py:99)
+    float4 o;
+    float mx = s.x * inv_v, my = s.y * inv_v, mz = s.z * inv_v, mw = s.w * inv_v;
+    o.x = fmaf(-mx, mx, s2.x * inv_v);
+    o.y = fmaf(-my, my, s2.y * inv_v);
+    o.z = fmaf(-mz, mz, s2.z * inv_v);
+    o.w = fmaf(-mw, mw, s2.w * inv_v);
+    const int64_t oidx = (((int64_t)d * h + y) * w + x) * C;
+    st4_stream(var + oidx, o);
+    if (NOREF) {
+      mx = n.x * inv_v; my = n.y * inv_v; mz = n.z * inv_v; mw = n.w * inv_v;
+      o.x = fmaf(-mx, mx, n2.x * inv_v);
+      o.y = fmaf(-my, my, n2.y * inv_v);
+      o.z = fmaf(-mz, mz, n2.z * inv_v);
+      o.w = fmaf(-mw, mw, n2.w * inv_v);
+      st4_stream(var_noref + oidx, o);
+    }
+  }
+}
+
+template <int C>
+static int launch_costvolume(const float* feats, const float* rt, const float* depth, int per_pixel, float* var,
+                             float* var_noref, int B, int V, int D, int h, int w, cudaStream_t st) {
+  constexpr int PXB = 256 / (C / 4);
+  // enough CTAs for >= ~4 waves of 148 SMs x 8 resident CTAs, but >= 8 planes per CTA to amortise the setup
+  const int xy_blocks = ceil_div(w, PXB) * h * B;
+  int chunks = max(1, min(ceil_div(D, 8), ceil_div(148 * 8 * 4, xy_blocks)));
+  const int d_chunk = ceil_div(D, chunks);
+  chunks = ceil_div(D, d_chunk);
+  dim3 grid(ceil_div(w, PXB), h, B * chunks);
+#define RCMVS_CV_LAUNCH(PP, NR)                                                                              \
+  costvolume_var_kernel<C, PP, NR><<<grid, 256, 0, st>>>(feats, rt, depth, var, var_noref, V, D, h, w, d_chunk, \
+                                                         chunks)
+  if (per_pixel) {
+    if (var_noref) RCMVS_CV_LAUNCH(true, true); else RCMVS_CV_LAUNCH(true, false);
+  } else {
+    if (var_noref) RCMVS_CV_LAUNCH(false, true); else RCMVS_CV_LAUNCH(false, false);
+  }
+#undef RCMVS_CV_LAUNCH
+  RCMVS_CHECK_LAUNCH("rcmvs_costvolume_var_fwd");
+  return RCMVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Standalone homo_warping (API parity with the reference function): NCHW in, NCDHW out, any C.
+// One thread per (x, y, d); coordinates computed once and reused for all channels; stores are 128 B coalesced rows.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(128)
+homo_warp_fwd_kernel(const float* __restrict__ src, const float* __restrict__ rt_g, const float* __restrict__ depth,
+                     float* __restrict__ out, int C, int D, int h, int w) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / D, d = blockIdx.z % D;
+  if (x >= w) return;
+  const int64_t hw = (int64_t)h * w;
+  const float* m = rt_g + (int64_t)b * 12;
+  const float xf = (float)x, yf = (float)y;
+  const float rx = fmaf(__ldg(m + 0), xf, fmaf(__ldg(m + 1), yf, __ldg(m + 2)));
+  const float ry = fmaf(__ldg(m + 4), xf, fmaf(__ldg(m + 5), yf, __ldg(m + 6)));
+  const float rz = fmaf(__ldg(m + 8), xf, fmaf(__ldg(m + 9), yf, __ldg(m + 10)));
+  const float dep = PER_PIXEL ? __ldg(depth + ((int64_t)b * D + d) * hw + (int64_t)y * w + x)
+                              : __ldg(depth + (int64_t)b * D + d);
+  const float px = __fdiv_rn(fmaf(rx, dep, __ldg(m + 3)), fmaf(rz, dep, __ldg(m + 11)));
+  const float py = __fdiv_rn(fmaf(ry, dep, __ldg(m + 7)), fmaf(rz, dep, __ldg(m + 11)));
+  const Tap t = make_tap(px, py, h, w);
+  src += (int64_t)b * C * hw;
+  out += ((int64_t)b * C * D + d) * hw + (int64_t)y * w + x;
+  if (!t.any) {
+    for (int c = 0; c < C; ++c) __stcs(out + (int64_t)c * D * hw, 0.f);
+    return;
+  }
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float* p = src + (int64_t)c * hw;
+    const float v = fmaf(__ldg(p + t.off11), t.w11,
+                         fmaf(__ldg(p + t.off10), t.w10, fmaf(__ldg(p + t.off01), t.w01, __ldg(p + t.off00) * t.w00)));
+    __stcs(out + (int64_t)c * D * hw, v);
+  }
+}
+
+// Backward w.r.t. src_fea only (the grid is built under torch.no_grad in the reference, modules.py:314):
+// grad_src[c, tap] += w_tap * grad_out[c, d, y, x]  — bilinear scatter-add with red.global.add.f32.
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(128)
+homo_warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ rt_g, const float* __restrict__ depth,
+                     float* __restrict__ gsrc, int C, int D, int h, int w) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / D, d = blockIdx.z % D;
+  if (x >= w) return;
+  const int64_t hw = (int64_t)h * w;
+  const float* m = rt_g + (int64_t)b * 12;
+  const float xf = (float)x, yf = (float)y;
+  const float rx = fmaf(__ldg(m + 0), xf, fmaf(__ldg(m + 1), yf, __ldg(m + 2)));
+  const float ry = fmaf(__ldg(m + 4), xf, fmaf(__ldg(m + 5), yf, __ldg(m + 6)));
+  const float rz = fmaf(__ldg(m + 8), xf, fmaf(__ldg(m + 9), yf, __ldg(m + 10)));
+  const float dep = PER_PIXEL ? __ldg(depth + ((int64_t)b * D + d) * hw + (int64_t)y * w + x)
+                              : __ldg(depth + (int64_t)b * D + d);
+  const float px = __fdiv_rn(fmaf(rx, dep, __ldg(m + 3)), fmaf(rz, dep, __ldg(m + 11)));
+  const float py = __fdiv_rn(fmaf(ry, dep, __ldg(m + 7)), fmaf(rz, dep, __ldg(m + 11)));
+  const Tap t = make_tap(px, py, h, w);
+  if (!t.any) return;
+  gsrc += (int64_t)b * C * hw;
+  gout += ((int64_t)b * C * D + d) * hw + (int64_t)y * w + x;
+  for (int c = 0; c < C; ++c) {
+    const float g = __ldg(gout + (int64_t)c * D * hw);
+    float* p = gsrc + (int64_t)c * hw;
+    if (t.w00 != 0.f) atomicAdd(p + t.off00, g * t.w00);
+    if (t.w01 != 0.f) atomicAdd(p + t.off01, g * t.w01);
+    if (t.w10 != 0.f) atomicAdd(p + t.off10, g * t.w10);
+    if (t.w11 != 0.f) atomicAdd(p + t.off11, g * t.w11);
+  }
+}
+
+}  // namespace rcmvs
+
+extern "C" int rcmvs_costvolume_var_fwd(const float* feats, const float* rt, const float* depth, int per_pixel,
+                                        float* var, float* var_noref, int B, int V, int C, int D, int h, int w,
+                                        rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(feats && rt && depth && var, RCMVS_ERR_BAD_ARG, "rcmvs_costvolume_var_fwd: null pointer");
+  RCMVS_REQUIRE(B > 0 && V > 1 && D > 0 && h > 0 && w > 0, RCMVS_ERR_BAD_ARG,
+                "rcmvs_costvolume_var_fwd: bad dims B=%d V=%d D=%d h=%d w=%d", B, V, D, h, w);
+  RCMVS_REQUIRE(V - 1 <= kMaxSrc, RCMVS_ERR_UNSUPPORTED, "rcmvs_costvolume_var_fwd: at most %d source views", kMaxSrc);
+  RCMVS_REQUIRE(h <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_costvolume_var_fwd: h > 65535");
+  cudaStream_t st = as_stream(stream);
+  switch (C) {
+    case 8: return launch_costvolume<8>(feats, rt, depth, per_pixel, var, var_noref, B, V, D, h, w, st);
+    case 16: return launch_costvolume<16>(feats, rt, depth, per_pixel, var, var_noref, B, V, D, h, w, st);
+    case 32: return launch_costvolume<32>(feats, rt, depth, per_pixel, var, var_noref, B, V, D, h, w, st);
+    default: break;
+  }
+  set_error("rcmvs_costvolume_var_fwd: C=%d not in {8,16,32}", C);
+  return RCMVS_ERR_UNSUPPORTED;
+}
+
+extern "C" int rcmvs_homo_warp_fwd(const float* src_fea, const float* rt, const float* depth, int per_pixel,
+                                   float* out, int B, int C, int D, int h, int w, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(src_fea && rt && depth && out, RCMVS_ERR_BAD_ARG, "rcmvs_homo_warp_fwd: null pointer");
+  RCMVS_REQUIRE(B > 0 && C > 0 && D > 0 && h > 0 && w > 0, RCMVS_ERR_BAD_ARG, "rcmvs_homo_warp_fwd: bad dims");
+  RCMVS_REQUIRE(h <= 65535 && (int64_t)B * D <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_homo_warp_fwd: h or B*D > 65535");
+  dim3 grid(ceil_div(w, 128), h, B * D);
+  if (per_pixel) homo_warp_fwd_kernel<true><<<grid, 128, 0, as_stream(stream)>>>(src_fea, rt, depth, out, C, D, h, w);
+  else homo_warp_fwd_kernel<false><<<grid, 128, 0, as_stream(stream)>>>(src_fea, rt, depth, out, C, D, h, w);
+  RCMVS_CHECK_LAUNCH("rcmvs_homo_warp_fwd");
+  return RCMVS_OK;
+}
+
+extern "C" int rcmvs_homo_warp_bwd(const float* grad_out, const float* rt, const float* depth, int per_pixel,
+                                   float* grad_src, int B, int C, int D, int h, int w, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(grad_out && rt && depth && grad_src, RCMVS_ERR_BAD_ARG, "rcmvs_homo_warp_bwd: null pointer");
+  RCMVS_REQUIRE(B > 0 && C > 0 && D > 0 && h > 0 && w > 0, RCMVS_ERR_BAD_ARG, "rcmvs_homo_warp_bwd: bad dims");
+  RCMVS_REQUIRE(h <= 65535 && (int64_t)B * D <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_homo_warp_bwd: h or B*D > 65535");
+  dim3 grid(ceil_div(w, 128), h, B * D);
+  if (per_pixel) homo_warp_bwd_kernel<true><<<grid, 128, 0, as_stream(stream)>>>(grad_out, rt, depth, grad_src, C, D, h, w);
+  else homo_warp_bwd_kernel<false><<<grid, 128, 0, as_stream(stream)>>>(grad_out, rt, depth, grad_src, C, D, h, w);
+  RCMVS_CHECK_LAUNCH("rcmvs_homo_warp_bwd");
+  return RCMVS_OK;
+}

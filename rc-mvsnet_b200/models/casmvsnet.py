@@ -1,0 +1,227 @@
+"""Drop-in for the reference's models/casmvsnet.py (CascadeMVSNet / CascadeMVSNet_eval / DepthNet / DepthNet_eval).
+
+Same constructor arguments, forward() signatures, output dictionaries and state_dict keys as the reference
+(models/casmvsnet.py:45-124, 126-231, 234-311, 313-417); the per-stage work runs on librcmvs.so kernels:
+
+    hypotheses (a5) -> fused plane sweep + variance (a1+a2) -> CostRegNet (a3) -> softmax/soft-argmin/conf (a4)
+
+with channels-last volumes in between, no [B,D,H,W] full-resolution hypothesis tensor, no warped-volume
+temporaries, no torch.inverse and no host synchronisation anywhere in forward().
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from rcmvs import ops
+from .modules import CostRegNet, FeatureNet, as_channels_last_views, homo_warping
+
+Align_Corners_Range = False
+_STAGE_SCALE = {"stage1": 4, "stage2": 2, "stage3": 1}
+
+
+def _stack_views_cl(features):
+    """list of V tensors [B,C,h,w] -> [B,V,h,w,C] contiguous (one kernel per view only if not already NHWC)."""
+    return torch.stack([as_channels_last_views(f) for f in features], dim=1)
+
+
+def _sweep_regularise_regress(feats_cl, proj_matrices, depth_values, cost_regularization, want_noref=False):
+    """feats_cl [B,V,h,w,C]; proj_matrices [B,V,2,4,4]; depth_values [B,D] (uniform planes) or [B,D,h,w]."""
+    rt = ops.relative_projections(proj_matrices.float().contiguous())
+    depth_values = depth_values.float().contiguous()
+    res = ops.costvolume_variance(feats_cl, rt, depth_values, want_noref)
+    var, noref = res if want_noref else (res, None)
+    cost = cost_regularization.forward_cl(var)
+    depth, conf = ops.softargmin_conf(cost, depth_values)
+    return depth, conf, noref, rt
+
+
+class DepthNet_eval(nn.Module):
+    """reference models/casmvsnet.py:234-311."""
+
+    def forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization, imgs, pad=0,
+                prob_volume_init=None):
+        assert len(features) == proj_matrices.shape[1], "Different number of images and projection matrices"
+        assert depth_values.shape[1] == num_depth, "depth_values.shape[1]:{}  num_depth:{}".format(
+            depth_values.shape[1], num_depth)
+        if prob_volume_init is not None:
+            raise NotImplementedError("prob_volume_init is never passed by the reference callers")
+        with torch.no_grad():
+            depth, conf, _, _ = _sweep_regularise_regress(_stack_views_cl(features), proj_matrices, depth_values,
+                                                          cost_regularization)
+        return {"depth": depth, "photometric_confidence": conf}
+
+
+class DepthNet(nn.Module):
+    """reference models/casmvsnet.py:45-124 (training class: also returns volume_feature_no_ref =
+    cat[warped source RGB at stage resolution (3·(V-1) ch), variance over the sources only (C ch)])."""
+
+    def forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization, imgs, pad=0,
+                prob_volume_init=None):
+        assert len(features) == proj_matrices.shape[1], "Different number of images and projection matrices"
+        assert depth_values.shape[1] == num_depth, "depth_values.shape[1]:{}  num_depth:{}".format(
+            depth_values.shape[1], num_depth)
+        if prob_volume_init is not None:
+            raise NotImplementedError("prob_volume_init is never passed by the reference callers")
+        needs_grad = torch.is_grad_enabled() and any(f.requires_grad for f in features)
+        if needs_grad:
+            return self._forward_autograd(features, proj_matrices, depth_values, num_depth, cost_regularization, imgs)
+        B, V = imgs.shape[:2]
+        C, h, w = features[0].shape[1:]
+        with torch.no_grad():
+            depth, conf, noref, rt = _sweep_regularise_regress(_stack_views_cl(features), proj_matrices,
+                                                              depth_values, cost_regularization, want_noref=True)
+            small = F.interpolate(imgs.reshape(B * V, *imgs.shape[2:]).float(), (h, w), mode="bilinear",
+                                  align_corners=False).view(B, V, 3, h, w)
+            dv = depth_values.float().contiguous()
+            vol = torch.empty((B, 3 * (V - 1) + C, num_depth, h, w), device=imgs.device, dtype=torch.float32)
+            for i in range(V - 1):
+                vol[:, 3 * i:3 * i + 3] = ops.homo_warp_fwd(small[:, i + 1].contiguous(), rt[:, i].contiguous(), dv)
+            vol[:, 3 * (V - 1):] = ops.to_planar(noref)
+        return {"depth": depth, "photometric_confidence": conf, "volume_feature_no_ref": vol}
+
+    def _forward_autograd(self, features, proj_matrices, depth_values, num_depth, cost_regularization, imgs):
+        """Differentiable path for train_rcmvsnet.py: CUDA warp (with its scatter-add backward) + library ops for
+        the reductions and the 3-D CNN until the fused train-mode kernels land."""
+        B, V = imgs.shape[:2]
+        C, h, w = features[0].shape[1:]
+        projs = torch.unbind(proj_matrices, 1)
+
+        def kext(p):
+            q = p[:, 0].clone()
+            q[:, :3, :4] = torch.matmul(p[:, 1, :3, :3], p[:, 0, :3, :4])
+            return q
+        ref_proj = kext(projs[0])
+        small = F.interpolate(imgs.reshape(B * V, *imgs.shape[2:]), (h, w), mode="bilinear",
+                              align_corners=False).view(B, V, 3, h, w)
+        ref = features[0].unsqueeze(2)
+        vsum, vsq = ref.expand(-1, -1, num_depth, -1, -1), (ref ** 2).expand(-1, -1, num_depth, -1, -1)
+        nsum, nsq, rgb = 0, 0, []
+        for i in range(1, V):
+            sp = kext(projs[i])
+            rgb.append(homo_warping(small[:, i], sp, ref_proj, depth_values))
+            wv = homo_warping(features[i], sp, ref_proj, depth_values)
+            vsum, vsq = vsum + wv, vsq + wv ** 2
+            nsum, nsq = nsum + wv, nsq + wv ** 2
+        var = vsq / V - (vsum / V) ** 2
+        var_noref = nsq / V - (nsum / V) ** 2
+        prob = F.softmax(cost_regularization(var).squeeze(1), dim=1)
+        depth = torch.sum(prob * depth_values, 1)
+        with torch.no_grad():
+            _, conf = ops.softargmin_conf(torch.log(prob.detach().clamp_min(1e-38)).contiguous(),
+                                          depth_values.float().contiguous())
+        return {"depth": depth, "photometric_confidence": conf,
+                "volume_feature_no_ref": torch.cat(rgb + [var_noref], dim=1)}
+
+
+class _CascadeBase(nn.Module):
+    depthnet_cls = None
+
+    def __init__(self, refine=False, ndepths=[48, 32, 8], depth_interals_ratio=[4, 2, 1], share_cr=False,
+                 grad_method="detach", arch_mode="fpn", cr_base_chs=[8, 8, 8]):
+        super().__init__()
+        if refine:
+            raise NotImplementedError("refine=True is dead code in the reference (RefineNet uses F.cat)")
+        assert len(ndepths) == len(depth_interals_ratio)
+        self.refine, self.share_cr, self.ndepths = refine, share_cr, list(ndepths)
+        self.depth_interals_ratio, self.grad_method = list(depth_interals_ratio), grad_method
+        self.arch_mode, self.cr_base_chs, self.num_stage = arch_mode, list(cr_base_chs), len(ndepths)
+        self.stage_infos = {k: {"scale": float(v)} for k, v in _STAGE_SCALE.items()}
+        self.feature = FeatureNet(base_channels=8, stride=4, num_stage=self.num_stage, arch_mode=arch_mode)
+        if share_cr:
+            self.cost_regularization = CostRegNet(in_channels=self.feature.out_channels, base_channels=8)
+        else:
+            self.cost_regularization = nn.ModuleList(
+                [CostRegNet(in_channels=self.feature.out_channels[i], base_channels=self.cr_base_chs[i])
+                 for i in range(self.num_stage)])
+        self.DepthNet = self.depthnet_cls()
+
+    def _cr(self, i):
+        return self.cost_regularization if self.share_cr else self.cost_regularization[i]
+
+    def _features(self, imgs):
+        """FeatureNet on all views.  Eval: one batched call, channels-last outputs [B,V,h,w,C] per stage.
+        Train: one call per view like the reference (BatchNorm statistics are per call, casmvsnet.py:178-180)."""
+        B, V = imgs.shape[:2]
+        if self.training:
+            per_view = [self.feature(imgs[:, v]) for v in range(V)]
+            return per_view, None
+        out = self.feature(imgs.reshape(B * V, *imgs.shape[2:]))
+        stacked = {}
+        for k, f in out.items():
+            cl = as_channels_last_views(f)                     # [B*V,h,w,C]
+            stacked[k] = cl.view(B, V, *cl.shape[1:])
+        return None, stacked
+
+    def _run(self, imgs, proj_matrices, depth_values):
+        B, V, _, H, W = imgs.shape
+        imgs = imgs.float()
+        depth_values = depth_values.float().contiguous()
+        # (max-min)/192 of batch element 0, kept on the device (the reference pulls it to the host, :172-174)
+        interval = (depth_values[0, -1].double() - depth_values[0, 0].double()) / depth_values.size(1)
+        per_view, stacked = self._features(imgs)
+        fused = stacked is not None and (not torch.is_grad_enabled() or self.depthnet_cls is DepthNet_eval)
+        if not fused and stacked is not None:
+            per_view = [{k: stacked[k][:, v].permute(0, 3, 1, 2) for k in stacked} for v in range(V)]
+        interval_host = None
+        outputs, depth = {}, None
+        for s in range(self.num_stage):
+            key = "stage%d" % (s + 1)
+            scale = _STAGE_SCALE[key]
+            h, w, D = H // scale, W // scale, self.ndepths[s]
+            if depth is None:
+                planes = ops.depth_hypotheses_first(depth_values, D)               # [B,D]: uniform per plane
+                hyp = planes
+            else:
+                if interval_host is None:
+                    interval_host = float(interval)     # one scalar read-back per forward (after stage 1 is queued)
+                cur = depth.detach() if self.grad_method == "detach" else depth
+                hyp = ops.depth_hypotheses_next(cur.contiguous(), D, self.depth_interals_ratio[s] * interval_host,
+                                                H, W, h, w)
+            if fused:
+                with torch.no_grad():
+                    want_noref = self.depthnet_cls is DepthNet and s == 0
+                    d, c, noref, rt = _sweep_regularise_regress(stacked[key], proj_matrices[key], hyp, self._cr(s),
+                                                                want_noref)
+                    st = {"depth": d, "photometric_confidence": c}
+                    if want_noref:    # only stage 1's is consumed by the caller (reference casmvsnet.py:231)
+                        st["volume_feature_no_ref"] = self._volume_feature(imgs, rt, hyp, noref, h, w)
+            else:
+                hyp4 = hyp if hyp.dim() == 4 else hyp.view(B, D, 1, 1).expand(-1, -1, h, w).contiguous()
+                st = self.DepthNet([f[key] for f in per_view], proj_matrices[key], depth_values=hyp4, num_depth=D,
+                                   cost_regularization=self._cr(s), imgs=imgs)
+            depth = st["depth"]
+            outputs[key] = st
+            outputs.update(st)
+        return outputs
+
+    @staticmethod
+    def _volume_feature(imgs, rt, hyp, noref, h, w):
+        """cat[warped source RGB (3·(V-1)), var_no_ref (C)] as [B,3(V-1)+C,D,h,w] (casmvsnet.py:59-60,83,100-102)."""
+        B, V = imgs.shape[:2]
+        D = hyp.shape[1]
+        small = F.interpolate(imgs.reshape(B * V, *imgs.shape[2:]), (h, w), mode="bilinear",
+                              align_corners=False).view(B, V, 3, h, w)
+        C = noref.shape[-1]
+        vol = torch.empty((B, 3 * (V - 1) + C, D, h, w), device=imgs.device, dtype=torch.float32)
+        for i in range(V - 1):
+            vol[:, 3 * i:3 * i + 3] = ops.homo_warp_fwd(small[:, i + 1].contiguous(), rt[:, i].contiguous(), hyp)
+        vol[:, 3 * (V - 1):] = ops.to_planar(noref)
+        return vol
+
+
+class CascadeMVSNet_eval(_CascadeBase):
+    """reference models/casmvsnet.py:313-417: forward(imgs [B,V,3,H,W], proj_matrices {stageK: [B,V,2,4,4]},
+    depth_values [B,Dv]) -> outputs dict."""
+    depthnet_cls = DepthNet_eval
+
+    def forward(self, imgs, proj_matrices, depth_values):
+        return self._run(imgs, proj_matrices, depth_values)
+
+
+class CascadeMVSNet(_CascadeBase):
+    """reference models/casmvsnet.py:126-231: returns (outputs, outputs['stage1']['volume_feature_no_ref'])."""
+    depthnet_cls = DepthNet
+
+    def forward(self, imgs, proj_matrices, depth_values):
+        outputs = self._run(imgs, proj_matrices, depth_values)
+        return outputs, outputs["stage1"]["volume_feature_no_ref"]

@@ -1,0 +1,279 @@
+"""Drop-in for the reference's models/modules.py on the depth-inference hot path.
+
+Same public names, constructor arguments, state_dict keys and call signatures as the reference
+(models/modules.py: homo_warping :304, CostRegNet :470, FeatureNet :363, depth_regression :519,
+get_depth_range_samples :569, get_cur_depth_range_samples :549), but the bodies enqueue the sm_100a kernels of
+librcmvs.so through rcmvs.ops.  CUDA tensors only — there is no CPU fallback.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from rcmvs import ops
+
+__all__ = ["homo_warping", "CostRegNet", "FeatureNet", "Conv2d", "Conv3d", "Deconv3d", "depth_regression",
+           "get_depth_range_samples", "get_cur_depth_range_samples", "cas_mvsnet_loss", "fold_bn"]
+
+
+def fold_bn(bn):
+    """Eval-mode BatchNorm as y = x*scale + shift."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return scale, bn.bias - bn.running_mean * scale
+
+
+def _versions(mod):
+    return tuple((p.data_ptr(), p._version) for p in list(mod.parameters()) + list(mod.buffers()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a1  homo_warping
+# ---------------------------------------------------------------------------------------------------------------
+class _HomoWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src_fea, rt, depth_values):
+        ctx.save_for_backward(rt, depth_values)
+        ctx.hw = src_fea.shape[2:]
+        return ops.homo_warp_fwd(src_fea, rt, depth_values)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rt, depth_values = ctx.saved_tensors
+        # the sampling grid is built under torch.no_grad() in the reference: gradient reaches src_fea only
+        return ops.homo_warp_bwd(grad_out.contiguous(), rt, depth_values, *ctx.hw), None, None
+
+
+def homo_warping(src_fea, src_proj, ref_proj, depth_values):
+    """src_fea [B,C,H,W], src_proj/ref_proj [B,4,4], depth_values [B,D] or [B,D,H,W] -> [B,C,D,H,W]."""
+    with torch.no_grad():
+        rt = ops.relative_projection_pair(src_proj.float().contiguous(), ref_proj.float().contiguous())
+        depth_values = depth_values.detach().float().contiguous()
+    return _HomoWarp.apply(src_fea.float().contiguous(), rt, depth_values)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-D / 3-D conv blocks (state_dict layout: <name>.conv.weight, <name>.bn.{weight,bias,running_mean,running_var,
+# num_batches_tracked})
+# ---------------------------------------------------------------------------------------------------------------
+class _ConvNormAct(nn.Module):
+    conv_cls = None
+    bn_cls = None
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 **kwargs):
+        super().__init__()
+        kwargs.pop("init_method", None)
+        kwargs.pop("norm", None)
+        kwargs.pop("num_groups", None)
+        assert stride in (1, 2)
+        self.out_channels, self.kernel_size, self.stride, self.relu = out_channels, kernel_size, stride, relu
+        self.conv = self.conv_cls(in_channels, out_channels, kernel_size, stride=stride, bias=not bn, **kwargs)
+        self.bn = self.bn_cls(out_channels, momentum=bn_momentum) if bn else None
+
+    def forward(self, x):
+        y = self.conv(x)
+        if self.bn is not None:
+            y = self.bn(y)
+        return F.relu(y, inplace=True) if self.relu else y
+
+
+class Conv2d(_ConvNormAct):
+    conv_cls, bn_cls = nn.Conv2d, nn.BatchNorm2d
+
+
+class Conv3d(_ConvNormAct):
+    conv_cls, bn_cls = nn.Conv3d, nn.BatchNorm3d
+
+
+class Deconv3d(_ConvNormAct):
+    conv_cls, bn_cls = nn.ConvTranspose3d, nn.BatchNorm3d
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FeatureNet (fpn) — SURVEY §8 row f1 ("next"): still library convolutions (cuDNN through torch), but run ONCE on
+# all V views as a batch with BatchNorm folded, and emitting channels-last maps the sweep kernel consumes directly.
+# ---------------------------------------------------------------------------------------------------------------
+class FeatureNet(nn.Module):
+    def __init__(self, base_channels, num_stage=3, stride=4, arch_mode="fpn"):
+        super().__init__()
+        if arch_mode != "fpn":
+            raise NotImplementedError("rcmvs FeatureNet implements arch_mode='fpn' (the reference default)")
+        assert num_stage in (2, 3)
+        c = base_channels
+        self.arch_mode, self.stride, self.base_channels, self.num_stage = arch_mode, stride, c, num_stage
+
+        def chain(*specs):
+            return nn.Sequential(*[Conv2d(i, o, k, s, padding=k // 2) for (i, o, k, s) in specs])
+
+        self.conv0 = chain((3, c, 3, 1), (c, c, 3, 1))
+        self.conv1 = chain((c, 2 * c, 5, 2), (2 * c, 2 * c, 3, 1), (2 * c, 2 * c, 3, 1))
+        self.conv2 = chain((2 * c, 4 * c, 5, 2), (4 * c, 4 * c, 3, 1), (4 * c, 4 * c, 3, 1))
+        self.out1 = nn.Conv2d(4 * c, 4 * c, 1, bias=False)
+        self.inner1 = nn.Conv2d(2 * c, 4 * c, 1, bias=True)
+        self.out_channels = [4 * c]
+        if num_stage == 3:
+            self.inner2 = nn.Conv2d(c, 4 * c, 1, bias=True)
+            self.out2 = nn.Conv2d(4 * c, 2 * c, 3, padding=1, bias=False)
+            self.out3 = nn.Conv2d(4 * c, c, 3, padding=1, bias=False)
+            self.out_channels += [2 * c, c]
+        else:
+            self.out2 = nn.Conv2d(4 * c, c, 3, padding=1, bias=False)
+            self.out_channels += [c]
+        self._folded = None
+
+    def _fold(self):
+        key = _versions(self)
+        if self._folded is None or self._folded[0] != key:
+            layers = {}
+            for name in ("conv0", "conv1", "conv2"):
+                seq = []
+                for blk in getattr(self, name):
+                    s, t = fold_bn(blk.bn)
+                    w = (blk.conv.weight * s.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+                    seq.append((w, t.contiguous(), blk.stride, blk.kernel_size // 2))
+                layers[name] = seq
+            self._folded = (key, layers)
+        return self._folded[1]
+
+    def _trunk(self, x, folded):
+        outs = []
+        for name in ("conv0", "conv1", "conv2"):
+            for (w, b, s, p) in folded[name]:
+                x = F.relu_(F.conv2d(x, w, b, stride=s, padding=p))
+            outs.append(x)
+        return outs
+
+    def forward(self, x):
+        """x [N,3,H,W] -> {"stage1": [N,4c,H/4,W/4], "stage2": [N,2c,H/2,W/2], "stage3": [N,c,H,W]}.
+        In eval mode the maps are returned in channels_last memory format (same logical NCHW shape)."""
+        if self.training:
+            c0 = self.conv0(x)
+            c1 = self.conv1(c0)
+            c2 = self.conv2(c1)
+        else:
+            c0, c1, c2 = self._trunk(x.contiguous(memory_format=torch.channels_last), self._fold())
+        out = {"stage1": self.out1(c2)}
+        intra = F.interpolate(c2, scale_factor=2, mode="nearest") + self.inner1(c1)
+        out["stage2"] = self.out2(intra)
+        if self.num_stage == 3:
+            intra = F.interpolate(intra, scale_factor=2, mode="nearest") + self.inner2(c0)
+            out["stage3"] = self.out3(intra)
+        return out
+
+
+def as_channels_last_views(feat):
+    """[N,C,h,w] (any memory format) -> contiguous [N,h,w,C] tensor (zero-copy if already channels_last)."""
+    p = feat.permute(0, 2, 3, 1)
+    return p if p.is_contiguous() else ops.to_channels_last(feat.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a3  CostRegNet
+# ---------------------------------------------------------------------------------------------------------------
+class CostRegNet(nn.Module):
+    """3-D U-Net regulariser.  Parameters/keys as the reference (modules.py:470-490); the eval-mode forward runs
+    librcmvs conv kernels on channels-last volumes with BatchNorm folded and bias+ReLU+skip fused."""
+
+    _LAYERS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11")
+
+    def __init__(self, in_channels, base_channels):
+        super().__init__()
+        c = base_channels
+        self.conv0 = Conv3d(in_channels, c, padding=1)
+        self.conv1 = Conv3d(c, 2 * c, stride=2, padding=1)
+        self.conv2 = Conv3d(2 * c, 2 * c, padding=1)
+        self.conv3 = Conv3d(2 * c, 4 * c, stride=2, padding=1)
+        self.conv4 = Conv3d(4 * c, 4 * c, padding=1)
+        self.conv5 = Conv3d(4 * c, 8 * c, stride=2, padding=1)
+        self.conv6 = Conv3d(8 * c, 8 * c, padding=1)
+        self.conv7 = Deconv3d(8 * c, 4 * c, stride=2, padding=1, output_padding=1)
+        self.conv9 = Deconv3d(4 * c, 2 * c, stride=2, padding=1, output_padding=1)
+        self.conv11 = Deconv3d(2 * c, c, stride=2, padding=1, output_padding=1)
+        self.prob = nn.Conv3d(c, 1, 3, stride=1, padding=1, bias=False)
+        self._packed = None
+
+    def packed(self):
+        """{layer: (packed_w [27,Cin,Cout], bias [Cout])}, rebuilt when any parameter/buffer changes."""
+        key = _versions(self)
+        if self._packed is None or self._packed[0] != key:
+            with torch.no_grad():
+                P = {}
+                for name in self._LAYERS:
+                    blk = getattr(self, name)
+                    scale, shift = fold_bn(blk.bn)
+                    tr = isinstance(blk.conv, nn.ConvTranspose3d)
+                    P[name] = (ops.pack_conv3d_weight(blk.conv.weight.detach().contiguous(), scale.contiguous(), tr),
+                               shift.contiguous())
+                P["prob"] = (ops.pack_conv3d_weight(self.prob.weight.detach().contiguous(), None, False), None)
+            self._packed = (key, P)
+        return self._packed[1]
+
+    def forward_cl(self, x_cl):
+        """x_cl [B,D,h,w,Cin] channels-last -> cost [B,D,h,w]."""
+        P = self.packed()
+        c0 = ops.conv3d(x_cl, *P["conv0"])
+        c2 = ops.conv3d(ops.conv3d(c0, *P["conv1"], stride=2), *P["conv2"])
+        c4 = ops.conv3d(ops.conv3d(c2, *P["conv3"], stride=2), *P["conv4"])
+        y = ops.conv3d(ops.conv3d(c4, *P["conv5"], stride=2), *P["conv6"])
+        y = ops.conv_transpose3d(y, *P["conv7"], skip=c4)       # conv4 + relu(bn(convT(x)))  (modules.py:497)
+        y = ops.conv_transpose3d(y, *P["conv9"], skip=c2)
+        y = ops.conv_transpose3d(y, *P["conv11"], skip=c0)
+        return ops.conv3d(y, P["prob"][0], None, relu=False).squeeze(-1)
+
+    def forward(self, x):
+        """x [B,C,D,h,w] -> [B,1,D,h,w] (reference signature)."""
+        if self.training or torch.is_grad_enabled() and x.requires_grad:
+            return self._forward_autograd(x)
+        with torch.no_grad():
+            return self.forward_cl(ops.to_channels_last(x.float().contiguous())).unsqueeze(1)
+
+    def _forward_autograd(self, x):
+        # Training path (train-mode BatchNorm statistics + backward) is not on the inference hot path yet:
+        # library ops keep train_rcmvsnet.py working until the fused train kernels land.
+        c0 = self.conv0(x)
+        c2 = self.conv2(self.conv1(c0))
+        c4 = self.conv4(self.conv3(c2))
+        y = self.conv6(self.conv5(c4))
+        y = c4 + self.conv7(y)
+        y = c2 + self.conv9(y)
+        y = c0 + self.conv11(y)
+        return self.prob(y)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a4 / a5 helpers with the reference signatures
+# ---------------------------------------------------------------------------------------------------------------
+def depth_regression(p, depth_values):
+    """Σ_d p[:,d]·depth_values[:,d]; kept as a torch expression for API parity (the fused CUDA regression used by
+    DepthNet is ops.softargmin_conf)."""
+    if depth_values.dim() <= 2:
+        depth_values = depth_values.view(*depth_values.shape, 1, 1)
+    return torch.sum(p * depth_values, 1)
+
+
+def get_cur_depth_range_samples(cur_depth, ndepth, depth_inteval_pixel, shape, max_depth=192.0, min_depth=0.0):
+    """cur_depth [B,H,W] -> [B,ndepth,H,W] planes at the SAME resolution (no resize): reference :549-566."""
+    assert cur_depth.shape == torch.Size(shape), "cur_depth:{}, input shape:{}".format(cur_depth.shape, shape)
+    B, H, W = cur_depth.shape
+    return ops.depth_hypotheses_next(cur_depth.float().contiguous(), ndepth, depth_inteval_pixel, H, W, H, W)
+
+
+def get_depth_range_samples(cur_depth, ndepth, depth_inteval_pixel, device, dtype, shape, max_depth=192.0,
+                            min_depth=0.0):
+    """cur_depth [B,D0] or [B,H,W] -> [B,ndepth,H,W]: reference :569-588."""
+    if cur_depth.dim() == 2:
+        planes = ops.depth_hypotheses_first(cur_depth.float().contiguous(), ndepth)
+        return planes.view(planes.shape[0], ndepth, 1, 1).expand(-1, -1, shape[1], shape[2]).contiguous()
+    return get_cur_depth_range_samples(cur_depth, ndepth, depth_inteval_pixel, shape, max_depth, min_depth)
+
+
+def cas_mvsnet_loss(inputs, depth_gt_ms, mask_ms, **kwargs):
+    """Supervised multi-stage smooth-L1 (reference :527-546); host glue, unchanged semantics."""
+    weights = kwargs.get("dlossw", None)
+    total = torch.tensor(0.0, dtype=torch.float32, device=mask_ms["stage1"].device)
+    depth_loss = None
+    for key in [k for k in inputs.keys() if "stage" in k]:
+        mask = mask_ms[key] > 0.5
+        depth_loss = F.smooth_l1_loss(inputs[key]["depth"][mask], depth_gt_ms[key][mask], reduction="mean")
+        wgt = weights[int(key.replace("stage", "")) - 1] if weights is not None else 1.0
+        total = total + wgt * depth_loss
+    return total, depth_loss

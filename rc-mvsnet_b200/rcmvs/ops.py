@@ -1,0 +1,169 @@
+"""Torch-facing wrappers over the C ABI: raw data_ptr() + the current CUDA stream, caller-allocated outputs.
+
+torch is plumbing here (device memory, streams); every function below enqueues hand-written sm_100a kernels from
+librcmvs.so and raises if the tensors are not CUDA fp32 contiguous — there is no eager fallback.
+"""
+import torch
+
+from . import _ffi
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("rcmvs: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("rcmvs: %s must be float32, got %s" % (name, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("rcmvs: %s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def _opt(t, name):
+    return None if t is None else _chk(t, name)
+
+
+# ---- layout ---------------------------------------------------------------------------------------------------
+def to_channels_last(x):
+    """[N,C,*spatial] contiguous -> [N,*spatial,C] contiguous."""
+    N, C = x.shape[:2]
+    S = x[0, 0].numel()
+    out = torch.empty((N,) + tuple(x.shape[2:]) + (C,), device=x.device, dtype=x.dtype)
+    _ffi.call("rcmvs_planar_to_cl", _chk(x, "x"), _chk(out, "out"), N, C, S, _stream())
+    return out
+
+
+def to_planar(x):
+    """[N,*spatial,C] contiguous -> [N,C,*spatial] contiguous."""
+    N, C = x.shape[0], x.shape[-1]
+    S = x[0, ..., 0].numel()
+    out = torch.empty((N, C) + tuple(x.shape[1:-1]), device=x.device, dtype=x.dtype)
+    _ffi.call("rcmvs_cl_to_planar", _chk(x, "x"), _chk(out, "out"), N, C, S, _stream())
+    return out
+
+
+# ---- projections ----------------------------------------------------------------------------------------------
+def relative_projections(proj):
+    """proj [B,V,2,4,4] -> rt [B,V-1,12]."""
+    B, V = proj.shape[:2]
+    rt = torch.empty((B, V - 1, 12), device=proj.device, dtype=torch.float32)
+    _ffi.call("rcmvs_relative_projections", _chk(proj, "proj"), _chk(rt, "rt"), B, V, _stream())
+    return rt
+
+
+def relative_projection_pair(src_proj, ref_proj):
+    B = src_proj.shape[0]
+    rt = torch.empty((B, 12), device=src_proj.device, dtype=torch.float32)
+    _ffi.call("rcmvs_relative_projection_pair", _chk(src_proj, "src_proj"), _chk(ref_proj, "ref_proj"),
+              _chk(rt, "rt"), B, _stream())
+    return rt
+
+
+# ---- hypotheses -----------------------------------------------------------------------------------------------
+def depth_hypotheses_first(depth_values, D):
+    B, Dv = depth_values.shape
+    planes = torch.empty((B, D), device=depth_values.device, dtype=torch.float32)
+    _ffi.call("rcmvs_depth_hypotheses_first", _chk(depth_values, "depth_values"), _chk(planes, "planes"), B, Dv, D,
+              _stream())
+    return planes
+
+
+def depth_hypotheses_next(prev_depth, D, interval_pixel, H, W, h, w):
+    B, hp, wp = prev_depth.shape
+    hyp = torch.empty((B, D, h, w), device=prev_depth.device, dtype=torch.float32)
+    _ffi.call("rcmvs_depth_hypotheses_next", _chk(prev_depth, "prev_depth"), _chk(hyp, "hyp"), B, hp, wp, H, W, h, w,
+              D, float(interval_pixel), _stream())
+    return hyp
+
+
+# ---- warp / cost volume ---------------------------------------------------------------------------------------
+def _depth_mode(depth, B, D_expected=None):
+    if depth.dim() == 2:
+        return 0
+    if depth.dim() == 4:
+        return 1
+    raise RuntimeError("rcmvs: depth must be [B,D] or [B,D,h,w]")
+
+
+def homo_warp_fwd(src_fea, rt, depth):
+    B, C, h, w = src_fea.shape
+    D = depth.shape[1]
+    out = torch.empty((B, C, D, h, w), device=src_fea.device, dtype=torch.float32)
+    _ffi.call("rcmvs_homo_warp_fwd", _chk(src_fea, "src_fea"), _chk(rt, "rt"), _chk(depth, "depth"),
+              _depth_mode(depth, B), _chk(out, "out"), B, C, D, h, w, _stream())
+    return out
+
+
+def homo_warp_bwd(grad_out, rt, depth, h, w):
+    B, C, D = grad_out.shape[:3]
+    gsrc = torch.zeros((B, C, h, w), device=grad_out.device, dtype=torch.float32)
+    _ffi.call("rcmvs_homo_warp_bwd", _chk(grad_out, "grad_out"), _chk(rt, "rt"), _chk(depth, "depth"),
+              _depth_mode(depth, B), _chk(gsrc, "grad_src"), B, C, D, h, w, _stream())
+    return gsrc
+
+
+def costvolume_variance(feats_cl, rt, depth, want_noref=False):
+    """feats_cl [B,V,h,w,C]; rt [B,V-1,12]; depth [B,D] or [B,D,h,w] -> var [B,D,h,w,C] (+ var_noref)."""
+    B, V, h, w, C = feats_cl.shape
+    D = depth.shape[1]
+    var = torch.empty((B, D, h, w, C), device=feats_cl.device, dtype=torch.float32)
+    noref = torch.empty_like(var) if want_noref else None
+    _ffi.call("rcmvs_costvolume_var_fwd", _chk(feats_cl, "feats"), _chk(rt, "rt"), _chk(depth, "depth"),
+              _depth_mode(depth, B), _chk(var, "var"), _opt(noref, "var_noref"), B, V, C, D, h, w, _stream())
+    return (var, noref) if want_noref else var
+
+
+# ---- conv3d ---------------------------------------------------------------------------------------------------
+def pack_conv3d_weight(w, scale=None, transposed=False):
+    """torch Conv3d [Cout,Cin,3,3,3] / ConvTranspose3d [Cin,Cout,3,3,3] weight (x BN scale) -> [27,Cin,Cout]."""
+    if transposed:
+        Cin, Cout = w.shape[:2]
+    else:
+        Cout, Cin = w.shape[:2]
+    packed = torch.empty((27, Cin, Cout), device=w.device, dtype=torch.float32)
+    _ffi.call("rcmvs_pack_conv3d_weight", _chk(w, "w"), _opt(scale, "scale"), _chk(packed, "packed"), Cout, Cin,
+              1 if transposed else 0, _stream())
+    return packed
+
+
+def conv3d(x_cl, packed_w, bias=None, skip=None, stride=1, relu=True):
+    """x_cl [B,D,H,W,Cin] -> [B,Do,Ho,Wo,Cout]: conv(k3,p1) + bias, ReLU, then + skip."""
+    B, D, H, W, Cin = x_cl.shape
+    Cout = packed_w.shape[2]
+    Do, Ho, Wo = (D - 1) // stride + 1, (H - 1) // stride + 1, (W - 1) // stride + 1
+    y = torch.empty((B, Do, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv3d_fwd", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"), _opt(skip, "skip"),
+              _chk(y, "y"), B, D, H, W, Cin, Cout, stride, 1 if relu else 0, _stream())
+    return y
+
+
+def conv_transpose3d(x_cl, packed_w, bias=None, skip=None, relu=True):
+    """x_cl [B,D,H,W,Cin] -> [B,2D,2H,2W,Cout] (k3, s2, p1, output_padding 1)."""
+    B, D, H, W, Cin = x_cl.shape
+    Cout = packed_w.shape[2]
+    y = torch.empty((B, 2 * D, 2 * H, 2 * W, Cout), device=x_cl.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv_transpose3d_fwd", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"),
+              _opt(skip, "skip"), _chk(y, "y"), B, D, H, W, Cin, Cout, 1 if relu else 0, _stream())
+    return y
+
+
+# ---- regression -----------------------------------------------------------------------------------------------
+def softargmin_conf(cost, planes, want_idx=False, want_prob=False):
+    """cost [B,D,h,w]; planes [B,D] or [B,D,h,w] -> depth [B,h,w], conf [B,h,w] (, idx int32, prob)."""
+    B, D, h, w = cost.shape
+    depth = torch.empty((B, h, w), device=cost.device, dtype=torch.float32)
+    conf = torch.empty_like(depth)
+    idx = torch.empty((B, h, w), device=cost.device, dtype=torch.int32) if want_idx else None
+    prob = torch.empty_like(cost) if want_prob else None
+    _ffi.call("rcmvs_softargmin_conf_fwd", _chk(cost, "cost"), _chk(planes, "planes"), _depth_mode(planes, B),
+              _chk(depth, "depth"), _chk(conf, "conf"), None if idx is None else idx.data_ptr(),
+              _opt(prob, "prob"), B, D, h, w, _stream())
+    out = [depth, conf]
+    if want_idx:
+        out.append(idx)
+    if want_prob:
+        out.append(prob)
+    return tuple(out)

@@ -108,7 +108,9 @@ save("mvs_small_noise.npz", **{k: v for k, v in a.items() if not (k.startswith("
 imgs, proj, dv = synth.mvs_inputs(4, 64, 64, kind="textured", seed=5)
 model = CascadeMVSNet(ndepths=[16, 8, 8])
 model.load_state_dict(ck, strict=True)
-model.eval()   # BN in eval mode, but DepthNet (train class) still returns volume_feature_no_ref
+model.eval()            # BatchNorm uses running statistics (deterministic fixture) ...
+model.DepthNet.train()  # ... but DepthNet follows its training branch (casmvsnet.py:86-90): the eval branch squares
+                        # warped_volume in place before the no-ref sums (:94-96) and its result is discarded upstream
 with torch.no_grad():
     out, vol = model(t(imgs), {k: t(v) for k, v in proj.items()}, t(dv))
 save("mvs_train_small.npz", imgs=imgs[0], depth_values=dv[0], **{"proj_" + k: v[0] for k, v in proj.items()},

@@ -78,3 +78,15 @@ def test_cascade_end_to_end(mvs):
         rel = np.abs(out[k]["depth"] - g["depth_" + k]).max() / np.abs(g["depth_" + k]).max()
         assert rel < 1e-5, (k, rel)
         np.testing.assert_allclose(out[k]["photometric_confidence"], g["conf_" + k], atol=1e-4)
+
+
+def test_torch_port_matches_numpy_oracle_and_golden(mvs):
+    """oracle/ref_torch.py (the multi-threaded port used as cpu_baseline) is pinned the same way."""
+    from oracle import ref_torch as T
+    g, P = mvs
+    proj = {k: g["proj_" + k] for k in ("stage1", "stage2", "stage3")}
+    out = T.cascade_forward_eval(g["imgs"], proj, g["depth_values"], P, ndepths=(16, 8, 8))
+    for k in ("stage1", "stage2", "stage3"):
+        rel = np.abs(out[k]["depth"] - g["depth_" + k]).max() / np.abs(g["depth_" + k]).max()
+        assert rel < 1e-5, (k, rel)
+        np.testing.assert_allclose(out[k]["photometric_confidence"], g["conf_" + k], atol=1e-4)
