@@ -116,3 +116,8 @@ with torch.no_grad():
 save("mvs_train_small.npz", imgs=imgs[0], depth_values=dv[0], **{"proj_" + k: v[0] for k, v in proj.items()},
      volume_feature_no_ref=vol[0].numpy(), depth_stage1=out["stage1"]["depth"][0].numpy(),
      depth_stage3=out["stage3"]["depth"][0].numpy())
+
+# ---- BASELINE configs[1] at full size, run by the reference itself: 5 views 512x640, D=192/64/8 ------------------
+a = run_eval(512, 640, 5, (192, 64, 8), "textured", 4)
+save("mvs_full_192_64_8.npz", **{k: v for k, v in a.items() if k.startswith("depth_stage")},
+     conf_stage3=a["conf_stage3"].astype(np.float16))
