@@ -89,6 +89,18 @@ int rcmvs_conv_transpose3d_fwd(const float* x, const float* packed_w, const floa
                                float* y, int B, int D, int H, int W, int Cin, int Cout, int relu,
                                rcmvs_stream_t stream);
 
+/* Tensor-core (tcgen05.mma kind::tf32, TMEM accumulators) path for the stride-1 convolutions, same semantics as
+ * rcmvs_conv3d_fwd with stride 1.  nsplit = 1: plain TF32 operands (the precision cuDNN uses for the reference on
+ * GPU by torch default); nsplit = 3: error-compensated 3xTF32, fp32-equivalent.  Cin in {8,16,32}, Cout in {1,8,16}.
+ * The weight image (operand layout of the kernel) is built once per checkpoint by rcmvs_conv3d_tc_pack from the
+ * torch [Cout][Cin][3][3][3] weight and the folded BatchNorm scale; its size in floats is
+ * rcmvs_conv3d_tc_weight_floats(). */
+int64_t rcmvs_conv3d_tc_weight_floats(int Cin, int Cout, int nsplit);
+int rcmvs_conv3d_tc_pack(const float* w, const float* scale, float* img, int Cout, int Cin, int nsplit,
+                         rcmvs_stream_t stream);
+int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const float* bias, const float* skip, float* y, int B,
+                        int D, int H, int W, int Cin, int Cout, int nsplit, int relu, rcmvs_stream_t stream);
+
 /* ---- a4 softmax + soft-argmin + photometric confidence: models/casmvsnet.py:111-122, modules.py:519-525 ------ */
 /* cost [B][D][h][w]; depth planes [B][D] (per_pixel=0) or [B][D][h][w]; -> depth [B][h][w], conf [B][h][w],
  * idx [B][h][w] int32 (optional, may be NULL: clamp(trunc(Σ p·i))), prob [B][D][h][w] (optional, may be NULL). */

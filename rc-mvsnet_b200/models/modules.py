@@ -15,6 +15,18 @@ __all__ = ["homo_warping", "CostRegNet", "FeatureNet", "Conv2d", "Conv3d", "Deco
            "get_depth_range_samples", "get_cur_depth_range_samples", "cas_mvsnet_loss", "fold_bn"]
 
 
+def conv_precision():
+    """RCMVS_CONV selects how CostRegNet's stride-1 convolutions run:
+         'tf32x3' (default) error-compensated 3xTF32 on tcgen05 tensor cores — fp32-equivalent accuracy;
+         'tf32'   single TF32 pass on tcgen05 (the precision cuDNN gives the reference on GPU by torch default);
+         'fp32'   exact fp32 FFMA direct-convolution kernels (no tensor cores)."""
+    import os
+    mode = os.environ.get("RCMVS_CONV", "tf32x3")
+    if mode not in ("tf32x3", "tf32", "fp32"):
+        raise ValueError("RCMVS_CONV must be tf32x3, tf32 or fp32")
+    return mode
+
+
 def fold_bn(bn):
     """Eval-mode BatchNorm as y = x*scale + shift."""
     scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
@@ -193,31 +205,49 @@ class CostRegNet(nn.Module):
 
     def packed(self):
         """{layer: (packed_w [27,Cin,Cout], bias [Cout])}, rebuilt when any parameter/buffer changes."""
-        key = _versions(self)
+        mode = conv_precision()
+        key = (_versions(self), mode)
         if self._packed is None or self._packed[0] != key:
+            nsplit = {"tf32x3": 3, "tf32": 1, "fp32": 0}[mode]
             with torch.no_grad():
                 P = {}
-                for name in self._LAYERS:
-                    blk = getattr(self, name)
-                    scale, shift = fold_bn(blk.bn)
-                    tr = isinstance(blk.conv, nn.ConvTranspose3d)
-                    P[name] = (ops.pack_conv3d_weight(blk.conv.weight.detach().contiguous(), scale.contiguous(), tr),
-                               shift.contiguous())
-                P["prob"] = (ops.pack_conv3d_weight(self.prob.weight.detach().contiguous(), None, False), None)
+                for name in self._LAYERS + ("prob",):
+                    if name == "prob":
+                        conv, scale, shift, tr = self.prob, None, None, False
+                    else:
+                        blk = getattr(self, name)
+                        conv = blk.conv
+                        scale, shift = (t.contiguous() for t in fold_bn(blk.bn))
+                        tr = isinstance(conv, nn.ConvTranspose3d)
+                    w = conv.weight.detach().contiguous()
+                    cout, cin = (w.shape[1], w.shape[0]) if tr else (w.shape[0], w.shape[1])
+                    use_tc = (nsplit > 0 and not tr and conv.stride[0] == 1 and cin in ops.TC_SUPPORTED_CIN
+                              and cout in ops.TC_SUPPORTED_COUT)
+                    if use_tc:
+                        P[name] = ("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit)
+                    else:
+                        P[name] = ("direct", ops.pack_conv3d_weight(w, scale, tr), shift)
             self._packed = (key, P)
         return self._packed[1]
 
+    @staticmethod
+    def _conv(x, spec, skip=None, stride=1, relu=True):
+        if spec[0] == "tc":
+            _, img, bias, cout, nsplit = spec
+            return ops.conv3d_tc(x, img, cout, bias, skip, nsplit, relu)
+        return ops.conv3d(x, spec[1], spec[2], skip, stride=stride, relu=relu)
+
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cin] channels-last -> cost [B,D,h,w]."""
-        P = self.packed()
-        c0 = ops.conv3d(x_cl, *P["conv0"])
-        c2 = ops.conv3d(ops.conv3d(c0, *P["conv1"], stride=2), *P["conv2"])
-        c4 = ops.conv3d(ops.conv3d(c2, *P["conv3"], stride=2), *P["conv4"])
-        y = ops.conv3d(ops.conv3d(c4, *P["conv5"], stride=2), *P["conv6"])
-        y = ops.conv_transpose3d(y, *P["conv7"], skip=c4)       # conv4 + relu(bn(convT(x)))  (modules.py:497)
-        y = ops.conv_transpose3d(y, *P["conv9"], skip=c2)
-        y = ops.conv_transpose3d(y, *P["conv11"], skip=c0)
-        return ops.conv3d(y, P["prob"][0], None, relu=False).squeeze(-1)
+        P, cv = self.packed(), self._conv
+        c0 = cv(x_cl, P["conv0"])
+        c2 = cv(cv(c0, P["conv1"], stride=2), P["conv2"])
+        c4 = cv(cv(c2, P["conv3"], stride=2), P["conv4"])
+        y = cv(cv(c4, P["conv5"], stride=2), P["conv6"])
+        y = ops.conv_transpose3d(y, *P["conv7"][1:3], skip=c4)      # conv4 + relu(bn(convT(x)))  (modules.py:497)
+        y = ops.conv_transpose3d(y, *P["conv9"][1:3], skip=c2)
+        y = ops.conv_transpose3d(y, *P["conv11"][1:3], skip=c0)
+        return cv(y, P["prob"], relu=False).squeeze(-1)
 
     def forward(self, x):
         """x [B,C,D,h,w] -> [B,1,D,h,w] (reference signature)."""

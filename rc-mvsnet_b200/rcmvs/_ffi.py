@@ -27,7 +27,7 @@ def declared_functions(header=HEADER):
     src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(int|const char\*)\s+(rcmvs_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"\b(int64_t|int|const char\*)\s+(rcmvs_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
@@ -35,7 +35,8 @@ def declared_functions(header=HEADER):
                 a = " ".join(a.split())
                 ty = a.rsplit(" ", 1)[0].replace(" *", "*")
                 argtypes.append(_CTYPES[ty])
-        out[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argtypes)
+        restype = {"int": ctypes.c_int, "int64_t": ctypes.c_int64}.get(ret, ctypes.c_char_p)
+        out[name] = (restype, argtypes)
     return out
 
 

@@ -150,6 +150,32 @@ def conv_transpose3d(x_cl, packed_w, bias=None, skip=None, relu=True):
     return y
 
 
+# ---- conv3d on the tensor cores (tcgen05 / TMEM) ----------------------------------------------------------------
+TC_SUPPORTED_CIN = (8, 16, 32)
+TC_SUPPORTED_COUT = (1, 8, 16)
+
+
+def conv3d_tc_pack(w, scale=None, nsplit=3):
+    """torch Conv3d weight [Cout,Cin,3,3,3] (x BN scale) -> operand image of the tcgen05 kernel."""
+    Cout, Cin = w.shape[:2]
+    n = _ffi.lib().rcmvs_conv3d_tc_weight_floats(Cin, Cout, nsplit)
+    img = torch.empty((n,), device=w.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv3d_tc_pack", _chk(w, "w"), _opt(scale, "scale"), _chk(img, "img"), Cout, Cin, nsplit,
+              _stream())
+    return img
+
+
+def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
+    """x_cl [B,D,H,W,Cin] -> [B,D,H,W,Cout]: stride-1 conv(k3,p1) + bias, ReLU, then + skip, on tcgen05.mma."""
+    B, D, H, W, Cin = x_cl.shape
+    y = torch.empty((B, D, H, W, Cout), device=x_cl.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv3d_tc_fwd", _chk(x_cl, "x"), _chk(img, "wimg"), _opt(bias, "bias"), _opt(skip, "skip"),
+              _chk(y, "y"), B, D, H, W, Cin, Cout, nsplit, 1 if relu else 0, _stream())
+    if Cin == 32 and nsplit == 3:
+        _ffi.launches += 1          # two channel-group launches inside the call
+    return y
+
+
 # ---- regression -----------------------------------------------------------------------------------------------
 def softargmin_conf(cost, planes, want_idx=False, want_prob=False):
     """cost [B,D,h,w]; planes [B,D] or [B,D,h,w] -> depth [B,h,w], conf [B,h,w] (, idx int32, prob)."""
