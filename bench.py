@@ -171,7 +171,7 @@ def kernel_rooflines(model, dev, inputs, pk):
             var = ops.costvolume_variance(feats[key], rt, hyp)
             cr = model.cost_regularization[s]
             P = cr.packed()
-            ms0 = time_kernel(lambda: ops.conv3d(var, *P["conv0"]), 5, stream)
+            ms0 = time_kernel(lambda: cr._conv(var, P["conv0"]), 5, stream)
             fl = conv_flops(C, 8, D * h * w)
             # conv0 is the dominant CostRegNet layer; tensor roofline = TF32 dense = half the measured bf16 peak
             tf32_peak = pk["bf16_tflops"] / 2
@@ -370,7 +370,7 @@ def main():
                    "batch_per_gpu": B, "parallelism": "view-sharded replicas x%d" % world,
                    "cache": "per-step working set %.0f MB of volumes >> 126 MB L2 (no explicit flush needed)"
                             % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6),
-                   "conv_precision": os.environ.get("RCMVS_CONV", "fp32")},
+                   "conv_precision": os.environ.get("RCMVS_CONV", "tf32x3")},
         "e2e": {"value": e2e_value, "unit": "ref-views/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,

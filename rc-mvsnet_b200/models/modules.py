@@ -157,18 +157,21 @@ class FeatureNet(nn.Module):
     def forward(self, x):
         """x [N,3,H,W] -> {"stage1": [N,4c,H/4,W/4], "stage2": [N,2c,H/2,W/2], "stage3": [N,c,H,W]}.
         In eval mode the maps are returned in channels_last memory format (same logical NCHW shape)."""
-        if self.training:
-            c0 = self.conv0(x)
-            c1 = self.conv1(c0)
-            c2 = self.conv2(c1)
-        else:
-            c0, c1, c2 = self._trunk(x.contiguous(memory_format=torch.channels_last), self._fold())
-        out = {"stage1": self.out1(c2)}
-        intra = F.interpolate(c2, scale_factor=2, mode="nearest") + self.inner1(c1)
-        out["stage2"] = self.out2(intra)
-        if self.num_stage == 3:
-            intra = F.interpolate(intra, scale_factor=2, mode="nearest") + self.inner2(c0)
-            out["stage3"] = self.out3(intra)
+        # library convolutions follow the selected precision: exact fp32 unless RCMVS_CONV=tf32
+        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                        allow_tf32=(conv_precision() == "tf32")):
+            if self.training:
+                c0 = self.conv0(x)
+                c1 = self.conv1(c0)
+                c2 = self.conv2(c1)
+            else:
+                c0, c1, c2 = self._trunk(x.contiguous(memory_format=torch.channels_last), self._fold())
+            out = {"stage1": self.out1(c2)}
+            intra = F.interpolate(c2, scale_factor=2, mode="nearest") + self.inner1(c1)
+            out["stage2"] = self.out2(intra)
+            if self.num_stage == 3:
+                intra = F.interpolate(intra, scale_factor=2, mode="nearest") + self.inner2(c0)
+                out["stage3"] = self.out3(intra)
         return out
 
 
