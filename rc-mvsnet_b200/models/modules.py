@@ -226,6 +226,10 @@ class CostRegNet(nn.Module):
                     cout, cin = (w.shape[1], w.shape[0]) if tr else (w.shape[0], w.shape[1])
                     use_tc = (nsplit > 0 and not tr and conv.stride[0] == 1 and cin in ops.TC_SUPPORTED_CIN
                               and cout in ops.TC_SUPPORTED_COUT)
+                    # measured on B200 (profiles/r01): the 3xTF32 kernel is shared-memory-operand bound (N<=16) and
+                    # only beats the FFMA direct kernel for Cin=8; plain TF32 wins for every supported layer.
+                    if nsplit == 3 and cin > 8:
+                        use_tc = False
                     if use_tc:
                         P[name] = ("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit)
                     else:
