@@ -104,3 +104,40 @@ def stage_projections(proj_stage):
     out = P[:, :, 0].copy()
     out[:, :, :3, :4] = np.matmul(P[:, :, 1, :3, :3], P[:, :, 0, :3, :4])
     return out
+
+
+# ---- renderer batch (reference datasets/dtu_train.py:352-364 keys) ---------------------------------------------
+IMAGENET_MEAN = np.array([0.485, 0.456, 0.406], np.float32)
+IMAGENET_STD = np.array([0.229, 0.224, 0.225], np.float32)
+
+
+def render_batch(H=64, W=64, seed=0, num_views=4):
+    """The NeRF-side entries of a training sample for V=4 views (1 ref + 3 src; the renderer is hard-wired to 3
+    sources, reference models/render_models.py:750): imgs (ImageNet-normalised), depths_h, w2cs, c2ws, near_fars,
+    intrinsics (full resolution), proj_mats; all with a leading batch dimension of 1, float32 numpy."""
+    proj = cameras(num_views, H, W)
+    ext = proj["stage3"][0, :, 0]                       # [V,4,4] world->cam
+    K = proj["stage3"][0, :, 1, :3, :3]                 # [V,3,3] full-res intrinsics
+    tex = textured_images(proj["stage3"], H, W, seed=seed)[0]              # roughly [-2,2]
+    rgb01 = np.clip(0.5 + 0.2 * tex, 0.0, 1.0)
+    imgs = (rgb01 - IMAGENET_MEAN[None, :, None, None]) / IMAGENET_STD[None, :, None, None]
+    rng = np.random.default_rng(seed + 7)
+    depths = (650.0 + 20.0 * rng.standard_normal((num_views, H, W))).astype(np.float32)
+    c2ws = np.stack([np.linalg.inv(ext[v].astype(np.float64)) for v in range(num_views)]).astype(np.float32)
+    near_fars = np.tile(np.array([[425.0, 425.0 + 2.65 * 192]], np.float32), (num_views, 1))
+    proj_mats = np.stack([np.eye(4)[:3]] + [(stage_projections(proj["stage3"])[0, v] @
+                                              np.linalg.inv(stage_projections(proj["stage3"])[0, 0]))[:3]
+                                             for v in range(1, num_views)]).astype(np.float32)
+    return {"imgs": imgs[None].astype(np.float32), "depths_h": depths[None], "w2cs": ext[None].astype(np.float32),
+            "c2ws": c2ws[None], "near_fars": near_fars[None], "intrinsics": K[None].astype(np.float32),
+            "proj_mats": proj_mats[None]}
+
+
+class RenderArgs:
+    """Defaults of train_rcmvsnet.py:74-120 for the NeRF branch."""
+    multires, i_embed, pts_dim, dir_dim = 10, 0, 3, 3
+    netdepth, netwidth, net_type, netchunk = 6, 128, "v0", 1024
+    ckpt, N_samples, N_importance, perturb = None, 128, 0, 1.0
+    use_viewdirs, white_bkgd, raw_noise_std = False, False, 0.0
+    pad, img_downscale, use_color_volume, use_disp = 0, 1.0, False, False
+    multires_views = 4
