@@ -56,7 +56,7 @@ def test_point_features_mlp_composite(g):
     raw = raw.reshape(len(sel), 128, 4)
     # the shipped NeRF weights drive activations to ~1e6-1e7 on synthetic input (sigma up to 1.3e7): compare sigma
     # relatively, rgb (post-sigmoid of O(1e5) logits) with an absolute tolerance that reflects fp32 cancellation there
-    np.testing.assert_allclose(raw[..., 3], g["raw"][..., 3], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(raw[..., 3], g["raw"][..., 3], rtol=1e-3, atol=1e-2)
     np.testing.assert_allclose(raw[..., :3], g["raw"][..., :3], atol=5e-3)
     rgb, depth, w, alpha = R.raw2outputs(g["raw"], g["depth_candidates"][sel])
     np.testing.assert_allclose(rgb, g["rgb"][sel], atol=1e-5)
