@@ -108,6 +108,52 @@ int rcmvs_softargmin_conf_fwd(const float* cost, const float* depth_planes, int 
                               float* conf, int32_t* idx, float* prob, int B, int D, int h, int w,
                               rcmvs_stream_t stream);
 
+/* ---- a7 Neural_Volume_Net resize: models/render_models.py:755-756 ------------------------------------------------ */
+/* x [B][D0][S][C] channels-last (S = h*w) -> y [B][D1][S][Cpad]: linear along D with align_corners=True, channels
+ * C..Cpad-1 zero-filled (the 41-channel volume is padded to 48 for the convolution kernels). */
+int rcmvs_resize_depth_cl(const float* x, float* y, int B, int D0, int D1, int64_t S, int C, int Cpad,
+                          rcmvs_stream_t stream);
+
+/* ---- a8 Gaussian-Uniform sampler + rays: models/render_utils.py:86-146, 149-243 ------------------------------------ */
+/* ray_depth [N] -> out [N][S] (S = 128): rays [0,n_gauss) ~ N(d, (min(|far-d|,|d-near|)/3)^2) sorted ascending,
+ * rays [n_gauss,N) stratified-uniform in [near,far].  Philox4x32-10 keyed by (seed, ray, lane). */
+int rcmvs_gu_sample(const float* ray_depth, float near, float far, uint64_t seed, float* out, int N, int n_gauss,
+                    int S, rcmvs_stream_t stream);
+/* ys, xs [N] pixel coordinates (float), K [3][3], c2w [4][4], w2c_ref [4][4], z [N][S] ->
+ * pts [N][S][3] = o + z*dir, ndc [N][S][3] = (pixel/(W-1,H-1), (z_cam-near)/(far-near)), dirs [N][3] (unnormalised). */
+int rcmvs_ray_points(const float* ys, const float* xs, const float* K, const float* c2w, const float* w2c_ref,
+                     const float* z, float near, float far, int W, int H, float* pts, float* ndc, float* dirs, int N,
+                     int S, rcmvs_stream_t stream);
+
+/* ---- a9 per-point features: models/render_utils.py:247-279, 304-330; models/renderer.py:154-166 --------------------- */
+/* vol_cl [D][h][w][8] channels-last, ndc/pts [P][3], imgs [3][3][H][W] (un-normalised source images),
+ * w2cs [3][4][4], Ks [3][3][3] (poses 0..2) -> out [P][20] = [8 trilinear (zeros padding), 3 x (RGB border-padded
+ * bilinear, in-bounds mask)]. */
+int rcmvs_point_features(const float* vol_cl, const float* ndc, const float* pts, const float* imgs,
+                         const float* w2cs, const float* Ks, float* out, int64_t P, int D, int h, int w, int H, int W,
+                         rcmvs_stream_t stream);
+
+/* ---- a10 embedding + Renderer_ours MLP: models/render_models.py:45-49, 192-220 --------------------------------------- */
+/* ndc [P][3], feat [P][20], dirs [P/S][3] (view direction per ray, reference-camera frame) -> out [P][4] = rgb, sigma.
+ * weights: 22 device pointers {pts_linears.0..5 (W^T [K][128], b), pts_bias (W^T [20][128], b), alpha_linear
+ * (w [128], b), feature_linear (W^T [128][128], b), views_linears.0 (W^T [131][64], b), rgb_linear (W^T [64][3], b)}. */
+int rcmvs_render_mlp(const float* ndc, const float* feat, const float* dirs, const float* const* weights, float* out,
+                     int64_t P, int S, rcmvs_stream_t stream);
+
+/* ---- a11 compositing: models/renderer.py:18-26, 65-93 ------------------------------------------------------------------ */
+/* raw [N][S][4], z [N][S] -> rgb [N][3], depth [N], weights [N][S], alpha [N][S]. */
+int rcmvs_composite(const float* raw, const float* z, float* rgb, float* depth, float* weights, float* alpha, int N,
+                    int S, rcmvs_stream_t stream);
+
+/* ---- a13 inverse_warping: losses/homography.py:6-200 ------------------------------------------------------------------- */
+/* img [B][h][w][C] (NHWC), cams [B][2][4][4], depth [B][h][w] -> warped [B][h][w][C], mask [B][h][w]. */
+int rcmvs_inverse_warp_fwd(const float* img, const float* left_cam, const float* right_cam, const float* depth,
+                           float* warped, float* mask, int B, int h, int w, int C, rcmvs_stream_t stream);
+/* gradient w.r.t. depth: grad_warped [B][h][w][C] -> grad_depth [B][h][w]. */
+int rcmvs_inverse_warp_bwd(const float* img, const float* left_cam, const float* right_cam, const float* depth,
+                           const float* grad_warped, float* grad_depth, int B, int h, int w, int C,
+                           rcmvs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

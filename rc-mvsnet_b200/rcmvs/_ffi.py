@@ -18,7 +18,7 @@ launches = 0          # number of C-ABI calls that enqueued a kernel (bench.py r
 _CTYPES = {
     "const float*": ctypes.c_void_p, "float*": ctypes.c_void_p, "int32_t*": ctypes.c_void_p,
     "int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
-    "rcmvs_stream_t": ctypes.c_void_p,
+    "rcmvs_stream_t": ctypes.c_void_p, "uint64_t": ctypes.c_uint64, "const float* const*": ctypes.c_void_p,
 }
 
 

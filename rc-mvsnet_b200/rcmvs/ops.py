@@ -193,3 +193,80 @@ def softargmin_conf(cost, planes, want_idx=False, want_prob=False):
     if want_prob:
         out.append(prob)
     return tuple(out)
+
+
+# ---- renderer (a7-a12) ------------------------------------------------------------------------------------------
+def resize_depth_cl(x_cl, D1, Cpad):
+    """x_cl [B,D0,h,w,C] -> [B,D1,h,w,Cpad] (linear along D, align_corners=True, zero-padded channels)."""
+    B, D0, h, w, C = x_cl.shape
+    y = torch.empty((B, D1, h, w, Cpad), device=x_cl.device, dtype=torch.float32)
+    _ffi.call("rcmvs_resize_depth_cl", _chk(x_cl, "x"), _chk(y, "y"), B, D0, D1, h * w, C, Cpad, _stream())
+    return y
+
+
+def gu_sample(ray_depth, near, far, seed, n_gauss, S=128):
+    N = ray_depth.shape[0]
+    out = torch.empty((N, S), device=ray_depth.device, dtype=torch.float32)
+    _ffi.call("rcmvs_gu_sample", _chk(ray_depth, "ray_depth"), float(near), float(far), int(seed) & (2 ** 64 - 1),
+              _chk(out, "out"), N, n_gauss, S, _stream())
+    return out
+
+
+def ray_points(ys, xs, K, c2w, w2c_ref, z, near, far, W, H):
+    N, S = z.shape
+    pts = torch.empty((N, S, 3), device=z.device, dtype=torch.float32)
+    ndc = torch.empty_like(pts)
+    dirs = torch.empty((N, 3), device=z.device, dtype=torch.float32)
+    _ffi.call("rcmvs_ray_points", _chk(ys, "ys"), _chk(xs, "xs"), _chk(K, "K"), _chk(c2w, "c2w"),
+              _chk(w2c_ref, "w2c_ref"), _chk(z, "z"), float(near), float(far), W, H, _chk(pts, "pts"),
+              _chk(ndc, "ndc"), _chk(dirs, "dirs"), N, S, _stream())
+    return pts, ndc, dirs
+
+
+def point_features(vol_cl, ndc, pts, imgs3, w2cs3, Ks3):
+    """vol_cl [D,h,w,8]; ndc/pts [N,S,3]; imgs3 [3,3,H,W]; w2cs3 [3,4,4]; Ks3 [3,3,3] -> [N,S,20]."""
+    D, h, w, _ = vol_cl.shape
+    H, W = imgs3.shape[-2:]
+    N, S = ndc.shape[:2]
+    out = torch.empty((N, S, 20), device=ndc.device, dtype=torch.float32)
+    _ffi.call("rcmvs_point_features", _chk(vol_cl, "vol"), _chk(ndc, "ndc"), _chk(pts, "pts"), _chk(imgs3, "imgs"),
+              _chk(w2cs3, "w2cs"), _chk(Ks3, "Ks"), _chk(out, "out"), N * S, D, h, w, H, W, _stream())
+    return out
+
+
+def render_mlp(ndc, feat, dirs, weight_ptrs):
+    """ndc [N,S,3], feat [N,S,20], dirs [N,3]; weight_ptrs: int64 CUDA... a HOST ctypes array of 22 device pointers."""
+    N, S = ndc.shape[:2]
+    out = torch.empty((N, S, 4), device=ndc.device, dtype=torch.float32)
+    _ffi.call("rcmvs_render_mlp", _chk(ndc, "ndc"), _chk(feat, "feat"), _chk(dirs, "dirs"), weight_ptrs,
+              _chk(out, "out"), N * S, S, _stream())
+    return out
+
+
+def composite(raw, z):
+    N, S = z.shape
+    rgb = torch.empty((N, 3), device=z.device, dtype=torch.float32)
+    depth = torch.empty((N,), device=z.device, dtype=torch.float32)
+    weights = torch.empty((N, S), device=z.device, dtype=torch.float32)
+    alpha = torch.empty_like(weights)
+    _ffi.call("rcmvs_composite", _chk(raw, "raw"), _chk(z, "z"), _chk(rgb, "rgb"), _chk(depth, "depth"),
+              _chk(weights, "weights"), _chk(alpha, "alpha"), N, S, _stream())
+    return rgb, depth, weights, alpha
+
+
+# ---- a13 ------------------------------------------------------------------------------------------------------------
+def inverse_warp_fwd(img, left_cam, right_cam, depth):
+    B, h, w, C = img.shape
+    warped = torch.empty_like(img)
+    mask = torch.empty((B, h, w, 1), device=img.device, dtype=torch.float32)
+    _ffi.call("rcmvs_inverse_warp_fwd", _chk(img, "img"), _chk(left_cam, "left_cam"), _chk(right_cam, "right_cam"),
+              _chk(depth, "depth"), _chk(warped, "warped"), _chk(mask, "mask"), B, h, w, C, _stream())
+    return warped, mask
+
+
+def inverse_warp_bwd(img, left_cam, right_cam, depth, grad_warped):
+    B, h, w, C = img.shape
+    gd = torch.empty((B, h, w), device=img.device, dtype=torch.float32)
+    _ffi.call("rcmvs_inverse_warp_bwd", _chk(img, "img"), _chk(left_cam, "left_cam"), _chk(right_cam, "right_cam"),
+              _chk(depth, "depth"), _chk(grad_warped, "grad_warped"), _chk(gd, "grad_depth"), B, h, w, C, _stream())
+    return gd
