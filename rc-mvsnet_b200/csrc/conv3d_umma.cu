@@ -1,26 +1,28 @@
 // a3 CostRegNet stride-1 3x3x3 convolutions on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in
 // TMEM), reference models/modules.py:118-163 (Conv3d = conv -> BN -> ReLU) and :490 (`prob`).
 //
-// Implicit GEMM without im2col:  out[voxel, cout] = Σ_tap Σ_cin x[voxel + off(tap), cin] · w[tap, cin, cout]
-//   M = 128 output voxels = a FLAT RUN of 128 consecutive positions of a zero-padded (rows x 32) input plane
-//       (4 rows of 30 real columns + 2 halo columns each; the 2 halo columns produce discarded garbage rows);
-//   N = Cout padded to 16/32;   K = 8 input channels per tcgen05.mma, 27 taps x Cin/8 K-steps accumulate in TMEM.
-// Because the run is flat, tap (kd,kh,kw) is nothing but a different START ADDRESS (+kh*32+kw voxels, slab kd) of
-// the same shared-memory slab: every input voxel is staged ONCE and consumed by all 27 taps.
+// v1 of this kernel (profiles/r01_conv3d_umma_v1_ncu.md) issued one M128xN16xK8 MMA per (tap, K-step): with N=16 every
+// MMA re-fetches its 4 KB A tile from shared memory, 27 x Cin/8 times per output tile, and the 128 B/clk shared-memory
+// operand path (not the tensor pipe, not HBM) bounded the kernel.  v2 folds the kd and kh taps into the N dimension:
 //
-// Shared-memory operand layout = UMMA canonical K-major, SWIZZLE_NONE: "core matrix" = 8 rows x 16 bytes contiguous.
-//   A slab : [Cin/4 channel-chunks][slab voxels][4 floats]  -> row (voxel) pitch 16 B, SBO = 128 B, LBO = plane size
-//   B image: [term][tap][K-step][2 chunks][NPAD rows][4 floats] (pre-packed in global memory, copied once per CTA)
-// cp.async (16 B, zero-fill outside the volume = the conv's zero padding) fills the slabs; a 4-deep ring of depth
-// slabs slides along d, so HBM/L2 traffic is ~1.33x the input once, and each output is written once.
+//   for one INPUT depth slab z and one kw:   E_z[m, (kd, kh, cout)] += Σ_cin x_z[m + kw, cin] · w[kd, kh, kw, cin, cout]
 //
-// Precision: NSPLIT=1 -> plain TF32 (what cuDNN does for the reference on GPU, torch allow_tf32 default);
-//            NSPLIT=3 -> error-compensated 3xTF32: x = x_hi + x_lo, w = w_hi + w_lo (hi = top 19 bits),
-//                        acc += x_lo·w_hi + x_hi·w_lo + x_hi·w_hi  — fp32-equivalent (~2^-21) for the parity bar.
+//   M = 128 input positions = a flat run of a zero-padded (rows x 32) plane (kw = +1 row of the run = +16 bytes of
+//       descriptor start address);  N = 3 (kd) x G, G = 3 (kh) x Cout rounded up to 16;  K = 8 channels per MMA.
+//   The three kd blocks of N are the accumulators of three different OUTPUT planes (z+1, z, z-1): TMEM holds a ring of
+//   per-plane column groups, so the sum over kd happens inside TMEM for free.  The sum over kh (contributions of input
+//   row r to output rows r, r-1, r-2) is done by the epilogue through a small shared-memory exchange.
+//   A is fetched 3 (kw) x Cin/8 times per slab instead of 27 x Cin/8 -> 9x less operand traffic; N grows to 96..144.
 //
-// Warp roles (224 threads): warps 0-3 epilogue (TMEM -> registers -> bias/ReLU/skip -> global), warps 4-5 slab
-// loaders (cp.async + hi/lo split + fence.proxy.async), warp 6 = single-thread MMA issuer.  mbarrier pipelines:
-// full/empty per slab buffer, acc_full/acc_empty per TMEM accumulator stage (double buffered).
+// Shared-memory operand layout = UMMA canonical K-major, SWIZZLE_NONE ("core matrix" = 8 rows x 16 bytes):
+//   A slab : [Cin/4 chunks][slab voxels][4 floats]   row pitch 16 B, SBO = 128 B, LBO = plane size
+//   B image: [term][kw][K-step][2 chunks][3 x G rows][4 floats], pre-packed in global memory, copied once per CTA
+// cp.async (16 B, zero-fill = the conv's zero padding) fills the slabs, double/triple buffered along d.
+//
+// Precision: NSPLIT=1 plain TF32 (what cuDNN gives the reference on GPU under torch defaults);
+//            NSPLIT=3 error-compensated 3xTF32: x = x_hi + x_lo, w = w_hi + w_lo, acc += x_lo·w_hi + x_hi·w_lo + x_hi·w_hi.
+//
+// Warp roles (224 threads): warps 0-3 epilogue, warps 4-5 slab loaders (cp.async + hi/lo split), warp 6 MMA issuer.
 #include "common.cuh"
 
 namespace rcmvs {
@@ -28,7 +30,6 @@ namespace umma {
 
 constexpr int PW = 32;           // padded plane width (voxels)
 constexpr int TW = 30;           // real output columns per tile
-constexpr int NS = 4;            // slab ring depth
 constexpr int kThreads = 224;
 constexpr int kLoaderThreads = 64;
 
@@ -68,6 +69,7 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4, [16,30) LBO>>4 (K-chunk stride), [32,46) SBO>>4 (8-row group stride), [46,48) version=1
@@ -105,22 +107,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int CIN, int NPAD, int NSPLIT, int KM>
+// COUT real output channels; G columns per (plane, M-tile) group = 3 kh blocks of COUT, rounded up to 16.
+template <int CIN, int COUT, int NSPLIT, int KM, int NS>
 struct Cfg {
-  static constexpr int KS = CIN / 8;                              // K-steps per tap
-  static constexpr int NCH = CIN / 4;                             // 16-byte channel chunks per voxel
-  static constexpr int TH = 4 * KM;                               // output rows per CTA tile
-  static constexpr int SLABV = (TH + 2) * PW + 8;                 // voxels per slab plane (+ overrun of the last tap)
-  static constexpr int PLANE_B = SLABV * 16;                      // bytes per channel-chunk plane
-  static constexpr int SLAB_B = NCH * PLANE_B;                    // one slab (hi part)
-  static constexpr int NPART = NSPLIT == 3 ? 2 : 1;               // hi (+ lo) slabs
+  static constexpr int CP = COUT < 8 ? 8 : COUT;                  // channel slots per kh block (Cout=1 -> 8)
+  static constexpr int G = ((3 * CP + 15) / 16) * 16;             // TMEM columns / B rows per plane block
+  static constexpr int KS = CIN / 8;
+  static constexpr int NCH = CIN / 4;
+  static constexpr int ROWS = 4 * KM;                             // input rows covered by the M-tiles
+  static constexpr int OROWS = ROWS - 2;                          // output rows per CTA tile
+  static constexpr int SLABV = ROWS * PW + 8;                     // voxels per slab plane (+ kw overrun)
+  static constexpr int PLANE_B = SLABV * 16;
+  static constexpr int SLAB_B = NCH * PLANE_B;
+  static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
   static constexpr int A_BYTES = NS * NPART * SLAB_B;
-  static constexpr int BTERM_B = 27 * KS * 2 * NPAD * 16;         // one term (hi or lo) of the weight image
+  static constexpr int BBLK_B = 2 * 3 * G * 16;                   // one (kw, K-step): 2 chunks x 3G rows x 16 B
+  static constexpr int BTERM_B = 3 * KS * BBLK_B;
   static constexpr int B_BYTES = NPART * BTERM_B;
-  static constexpr int ACC_COLS = KM * NPAD;                      // TMEM columns per accumulator stage
-  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256));
-  static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + 256; // + barriers / tmem slot
+  static constexpr int NG = 512 / (KM * G);                       // plane groups in the TMEM ring
+  static constexpr int EX_B = OROWS * PW * CP * 4;                // epilogue exchange buffer
+  static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + EX_B + 512;
+  static_assert(NG >= 4, "TMEM ring needs at least 4 plane groups");
 };
 
 struct Params {
@@ -129,48 +145,50 @@ struct Params {
   const float* bias;    // [Cout] or null
   const float* skip;    // [B][D][H][W][Cout] or null
   float* y;             // [B][D][H][W][Cout]
-  int D, H, W, cin_total, cin_off, Cout;
+  int D, H, W, cin_total, cin_off;
   int d_chunk, chunks;  // depth planes per CTA, chunks per batch item
   int accumulate_in;    // add the existing contents of y (partial sums of an earlier channel group)
   int finalize;         // apply bias / ReLU / skip (last channel group)
   int relu;
 };
 
-template <int CIN, int NPAD, int NSPLIT, int KM>
+template <int CIN, int COUT, int NSPLIT, int KM, int NS>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p) {
-  using C = Cfg<CIN, NPAD, NSPLIT, KM>;
+  using C = Cfg<CIN, COUT, NSPLIT, KM, NS>;
+  constexpr int G = C::G, NG = C::NG, CP = C::CP;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* a_smem = smem;
   unsigned char* b_smem = smem + C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::A_BYTES + C::B_BYTES);
-  uint64_t* full = bars;            // [NS]   loaders -> MMA
-  uint64_t* empty = bars + NS;      // [NS]   MMA -> loaders
-  uint64_t* acc_full = bars + 2 * NS;       // [2] MMA -> epilogue
-  uint64_t* acc_empty = bars + 2 * NS + 2;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+  float* ex = reinterpret_cast<float*>(smem + C::A_BYTES + C::B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::A_BYTES + C::B_BYTES + C::EX_B);
+  uint64_t* full = bars;                 // [NS]  loaders -> MMA
+  uint64_t* empty = bars + NS;           // [NS]  MMA -> loaders
+  uint64_t* grp_full = bars + 2 * NS;    // [NG]  MMA -> epilogue   (plane complete)
+  uint64_t* grp_free = grp_full + NG;    // [NG]  epilogue -> MMA   (group drained and zeroed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(grp_free + NG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * C::TH;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * C::OROWS;
   const int b = blockIdx.z / p.chunks;
   const int d0 = (blockIdx.z % p.chunks) * p.d_chunk;
   const int d1 = min(p.D, d0 + p.d_chunk);
-  const int nsteps = d1 - d0;            // output planes d0..d1-1 ; input slabs z = d0-1 .. d1  (nsteps + 2)
+  const int nplanes = d1 - d0;           // output planes d0..d1-1 ; input slabs z = d0-1 .. d1  (nplanes + 2)
+  const int nslabs = nplanes + 2;
   const int64_t vox_stride = p.cin_total;
   const float* xb = p.x + (int64_t)b * p.D * p.H * p.W * vox_stride + p.cin_off;
 
   // ---- one-time setup -------------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full + i, kLoaderThreads); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+    for (int i = 0; i < NG; ++i) { mbar_init(grp_full + i, 1); mbar_init(grp_free + i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // weight image -> shared memory (generic proxy writes, made visible to the tensor core by the proxy fence)
   {
     const float4* src = reinterpret_cast<const float4*>(p.wimg);
     float4* dst = reinterpret_cast<float4*>(b_smem);
@@ -181,21 +199,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {
+    // all accumulators start at zero: every MMA accumulates, a group is re-zeroed by the epilogue after it is drained
+    for (int c = 0; c < 512; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp >= 4 && warp < 6) {
     // =============================== slab loaders (64 threads) ===================================================
     const int t = threadIdx.x - 128;
-    constexpr int PIECES = (C::TH + 2) * PW * C::NCH;     // 16-byte pieces per slab (overrun tail stays garbage)
-    for (int i = 0; i <= nsteps + 2; ++i) {
-      if (i < nsteps + 2) {
+    constexpr int PIECES = C::ROWS * PW * C::NCH;
+    for (int i = 0; i <= nslabs; ++i) {
+      if (i < nslabs) {
         const int buf = i % NS;
         mbar_wait(empty + buf, ((i / NS) & 1) ^ 1);
         const int z = d0 - 1 + i;
         const bool zok = (z >= 0) && (z < p.D);
         const uint32_t slab = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
         for (int e = t; e < PIECES; e += kLoaderThreads) {
-          const int ch = e % C::NCH;                     // channel chunk fastest: contiguous global bytes per voxel
-          const int v = e / C::NCH;                      // voxel index in the padded plane
+          const int ch = e % C::NCH;
+          const int v = e / C::NCH;
           const int gy = y0 - 1 + v / PW, gx = x0 - 1 + (v % PW);
           const bool ok = zok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
           const float* src = ok ? xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4 : xb;
@@ -204,11 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
         cp_async_commit();
       }
       if (i >= 1) {
-        if (i < nsteps + 2) cp_async_wait<1>(); else cp_async_wait<0>();
-        const int j = i - 1;
-        const int buf = j % NS;
+        if (i < nslabs) cp_async_wait<1>(); else cp_async_wait<0>();
+        const int buf = (i - 1) % NS;
         if constexpr (NSPLIT == 3) {
-          // x = hi + lo with hi = x & 0xFFFFE000 (exactly representable in TF32); each thread splits its own pieces
           unsigned char* hi_p = a_smem + (size_t)buf * C::NPART * C::SLAB_B;
           unsigned char* lo_p = hi_p + C::SLAB_B;
           for (int e = t; e < PIECES; e += kLoaderThreads) {
@@ -230,76 +254,114 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
   } else if (warp == 6) {
     // =============================== MMA issuer (one thread) =====================================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, NPAD);
       const uint32_t b_base = smem_u32(b_smem);
-      for (int s = 0; s < nsteps; ++s) {
-        const int stage = s & 1;
-        mbar_wait(acc_empty + stage, ((s >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t acc = tmem_base + stage * C::ACC_COLS;
-        for (int kd = 0; kd < 3; ++kd) {
-          const int i = s + kd;
-          const int buf = i % NS;
-          mbar_wait(full + buf, (i / NS) & 1);
+      for (int i = 0; i < nslabs; ++i) {
+        // slab i = input plane z = d0-1+i contributes to output planes (relative) q = i-2+j, block j = 0,1,2 (kd = 2-j)
+        const int jlo = max(0, 2 - i), jhi = min(2, nplanes + 1 - i);       // valid blocks: 0 <= q < nplanes
+        const int qnew = i;                                                  // plane first touched by this slab (j=2)
+        if (qnew < nplanes && qnew >= NG) {                                  // its group must have been drained
+          mbar_wait(grp_free + (qnew % NG), ((qnew / NG) - 1) & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
+        }
+        const int buf = i % NS;
+        mbar_wait(full + buf, (i / NS) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
+        // split the valid block range into ring-contiguous runs
+        int run_j[2], run_n[2], nruns = 0;
+        {
+          int j = jlo;
+          while (j <= jhi) {
+            const int g = (i - 2 + j) % NG;
+            int n = 1;
+            while (j + n <= jhi && g + n < NG) ++n;
+            run_j[nruns] = j; run_n[nruns] = n; ++nruns;
+            j += n;
+          }
+        }
 #pragma unroll 1
-          for (int khw = 0; khw < 9; ++khw) {
-            const int kh = khw / 3, kw = khw % 3;
-            const int tap = kd * 9 + khw;
-            const uint32_t a_tap = a_hi + (kh * PW + kw) * 16;
+        for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-            for (int ks = 0; ks < C::KS; ++ks) {
-              const uint32_t b_hi = b_base + ((tap * C::KS + ks) * 2) * NPAD * 16;
-              const uint64_t bd_hi = make_desc(b_hi, NPAD * 16, 128);
+          for (int ks = 0; ks < C::KS; ++ks) {
+            const uint32_t b_blk = b_base + (kw * C::KS + ks) * C::BBLK_B;
 #pragma unroll
-              for (int mt = 0; mt < KM; ++mt) {
-                const uint32_t a_addr = a_tap + ks * 2 * C::PLANE_B + mt * 128 * 16;
-                const uint64_t ad_hi = make_desc(a_addr, C::PLANE_B, 128);
-                const uint32_t d = acc + mt * NPAD;
-                // the first MMA into each accumulator of this step overwrites, everything after accumulates
-                const uint32_t accf = (kd == 0 && khw == 0 && ks == 0) ? 0u : 1u;
+            for (int mt = 0; mt < KM; ++mt) {
+              const uint32_t a_addr = a_hi + ks * 2 * C::PLANE_B + (mt * 128 + kw) * 16;
+              const uint64_t ad_hi = make_desc(a_addr, C::PLANE_B, 128);
+              const uint64_t ad_lo = make_desc(a_addr + C::SLAB_B, C::PLANE_B, 128);
+              for (int r = 0; r < nruns; ++r) {
+                const int j = run_j[r], n = run_n[r];
+                const uint32_t idesc = make_idesc(128, n * G);
+                const uint32_t d = tmem_base + mt * (NG * G) + ((i - 2 + j) % NG) * G;
+                const uint32_t b_hi = b_blk + j * G * 16;
+                const uint64_t bd_hi = make_desc(b_hi, 3 * G * 16, 128);
                 if constexpr (NSPLIT == 3) {
-                  const uint64_t ad_lo = make_desc(a_addr + C::SLAB_B, C::PLANE_B, 128);
-                  const uint64_t bd_lo = make_desc(b_hi + C::BTERM_B, NPAD * 16, 128);
-                  umma_tf32(d, ad_lo, bd_hi, idesc, accf);              // small terms first
+                  const uint64_t bd_lo = make_desc(b_hi + C::BTERM_B, 3 * G * 16, 128);
+                  umma_tf32(d, ad_lo, bd_hi, idesc, 1u);              // small terms first
                   umma_tf32(d, ad_hi, bd_lo, idesc, 1u);
                   umma_tf32(d, ad_hi, bd_hi, idesc, 1u);
                 } else {
-                  umma_tf32(d, ad_hi, bd_hi, idesc, accf);
+                  umma_tf32(d, ad_hi, bd_hi, idesc, 1u);
                 }
               }
             }
           }
-          if (kd == 0) umma_commit(empty + buf);                 // slab d-1 is dead once these MMAs retire
         }
-        umma_commit(acc_full + stage);
+        umma_commit(empty + buf);                                   // slab consumed once these MMAs retire
+        if (i >= 2) umma_commit(grp_full + ((i - 2) % NG));         // output plane q = i-2 is complete (j = 0 was its last)
       }
     }
-  } else if (warp < 4) {
+  } else {
     // =============================== epilogue (128 threads) ======================================================
     const int gx = x0 + lane;
     const bool col_ok = lane < TW && gx < p.W;
-    for (int s = 0; s < nsteps; ++s) {
-      const int stage = s & 1;
-      mbar_wait(acc_full + stage, (s >> 1) & 1);
+    for (int q = 0; q < nplanes; ++q) {
+      const int g = q % NG;
+      mbar_wait(grp_full + g, (q / NG) & 1);
       tc_fence_after();
-      float v[KM][NPAD];
-#pragma unroll
-      for (int mt = 0; mt < KM; ++mt)
-#pragma unroll
-        for (int c0 = 0; c0 < NPAD; c0 += 16)
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + stage * C::ACC_COLS + mt * NPAD + c0, &v[mt][c0]);
-      tc_fence_before();
-      mbar_arrive(acc_empty + stage);                            // TMEM stage drained -> MMA may overwrite it
-      const int d = d0 + s;
+      float v[KM][G];
 #pragma unroll
       for (int mt = 0; mt < KM; ++mt) {
-        const int gy = y0 + mt * 4 + warp;
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + mt * (NG * G) + g * G;
+#pragma unroll
+        for (int c0 = 0; c0 < G; c0 += 16) tmem_ld16(ta + c0, &v[mt][c0]);
+#pragma unroll
+        for (int c0 = 0; c0 < G; c0 += 16) tmem_st16_zero(ta + c0);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(grp_free + g);
+      // ---- sum over kh: input row ri = 4*mt + warp contributes its kh block to output row j = ri - kh ----------
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int mt = 0; mt < KM; ++mt) {
+          const int j = 4 * mt + warp - kh;
+          if (j >= 0 && j < C::OROWS) {
+            float* e = ex + ((j * PW + lane) * CP);
+#pragma unroll
+            for (int c = 0; c < CP; c += 4) {
+              float4 val = make_float4(v[mt][kh * CP + c], v[mt][kh * CP + c + 1], v[mt][kh * CP + c + 2],
+                                       v[mt][kh * CP + c + 3]);
+              if (kh > 0) {
+                const float4 o = *reinterpret_cast<float4*>(e + c);
+                val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+              }
+              *reinterpret_cast<float4*>(e + c) = val;
+            }
+          }
+        }
+        epi_bar_sync();
+      }
+      // ---- bias / ReLU / skip, coalesced store: thread handles rows j = warp, warp+4, ... ------------------------
+      const int d = d0 + q;
+      for (int j = warp; j < C::OROWS; j += 4) {
+        const int gy = y0 + j;
         if (!col_ok || gy >= p.H) continue;
-        const int64_t o = ((((int64_t)b * p.D + d) * p.H + gy) * p.W + gx) * p.Cout;
-        if (p.Cout == 1) {
-          float r = v[mt][0];
+        const float* e = ex + ((j * PW + lane) * CP);
+        const int64_t o = ((((int64_t)b * p.D + d) * p.H + gy) * p.W + gx) * COUT;
+        if constexpr (COUT == 1) {
+          float r = e[0];
           if (p.accumulate_in) r += p.y[o];
           if (p.finalize) {
             if (p.bias) r += __ldg(p.bias);
@@ -307,30 +369,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
             if (p.skip) r += __ldg(p.skip + o);
           }
           p.y[o] = r;
-          continue;
-        }
+        } else {
 #pragma unroll
-        for (int c = 0; c < NPAD; c += 4) {                      // Cout is a multiple of 8 here
-          if (c >= p.Cout) break;
-          float4 r = make_float4(v[mt][c], v[mt][c + 1], v[mt][c + 2], v[mt][c + 3]);
-          if (p.accumulate_in) {
-            const float4 q = *reinterpret_cast<const float4*>(p.y + o + c);
-            r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
-          }
-          if (p.finalize) {
-            if (p.bias) {
-              const float4 q = ldg4(p.bias + c);
-              r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+          for (int c = 0; c < COUT; c += 4) {
+            float4 r = *reinterpret_cast<const float4*>(e + c);
+            if (p.accumulate_in) {
+              const float4 t4 = *reinterpret_cast<const float4*>(p.y + o + c);
+              r.x += t4.x; r.y += t4.y; r.z += t4.z; r.w += t4.w;
             }
-            if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-            if (p.skip) {
-              const float4 q = ldg4(p.skip + o + c);
-              r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+            if (p.finalize) {
+              if (p.bias) {
+                const float4 t4 = ldg4(p.bias + c);
+                r.x += t4.x; r.y += t4.y; r.z += t4.z; r.w += t4.w;
+              }
+              if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+              if (p.skip) {
+                const float4 t4 = ldg4(p.skip + o + c);
+                r.x += t4.x; r.y += t4.y; r.z += t4.z; r.w += t4.w;
+              }
             }
+            st4(p.y + o + c, r);
           }
-          st4(p.y + o + c, r);
         }
       }
+      epi_bar_sync();                              // exchange buffer is reused by the next plane
     }
   }
 
@@ -339,91 +401,99 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
-// Weight image: torch Conv3d weight [Cout][Cin_total][27] x BN scale -> for input channels [cin_off, cin_off+CIN):
-//   img[term][tap][ks][j][n][e] = split_term( w[n][cin_off + ks*8 + j*4 + e][tap] * scale[n] ), zero for n >= Cout
+// Weight image: torch Conv3d weight [Cout][Cin_total][27] x BN scale, for input channels [cin_off, cin_off+CIN):
+//   img[term][kw][ks][chunk][row = jblk*G + kh*CP + n][e],  kd = 2 - jblk,
+//   value = split_term( w[n][cin_off + ks*8 + chunk*4 + e][kd][kh][kw] * scale[n] ), zero for padded rows
 __global__ void pack_umma_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                         float* __restrict__ img, int Cout, int cin_total, int cin_off, int CIN,
-                                        int NPAD, int nsplit) {
-  const int per_term = 27 * CIN * NPAD;
+                                        int CP, int G, int nsplit) {
+  const int KS = CIN / 8;
+  const int per_term = 3 * KS * 2 * 3 * G * 4;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_term) return;
   const int e = i & 3;
   int r = i >> 2;
-  const int n = r % NPAD; r /= NPAD;
-  const int j = r & 1; r >>= 1;
-  const int KS = CIN / 8;
+  const int row = r % (3 * G); r /= (3 * G);
+  const int chunk = r & 1; r >>= 1;
   const int ks = r % KS;
-  const int tap = r / KS;
+  const int kw = r / KS;
+  const int jblk = row / G, rr = row % G;
+  const int kh = rr / CP, n = rr % CP;
   float v = 0.f;
-  if (n < Cout) {
-    const int ci = cin_off + ks * 8 + j * 4 + e;
-    v = w[((int64_t)n * cin_total + ci) * 27 + tap];
+  if (kh < 3 && n < Cout) {
+    const int kd = 2 - jblk;
+    const int ci = cin_off + ks * 8 + chunk * 4 + e;
+    v = w[((int64_t)n * cin_total + ci) * 27 + (kd * 9 + kh * 3 + kw)];
     if (scale) v *= scale[n];
   }
   if (nsplit == 3) {
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     img[i] = hi;
-    img[per_term + i] = v - hi;     // the tensor core drops the low 13 bits of this term: error ~2^-22·|w|
+    img[per_term + i] = v - hi;
   } else {
     img[i] = v;
   }
 }
 
-template <int CIN, int NPAD, int NSPLIT, int KM>
+template <int CIN, int COUT, int NSPLIT, int KM, int NS>
 static int launch(const Params& p, int B, cudaStream_t st) {
-  using C = Cfg<CIN, NPAD, NSPLIT, KM>;
+  using C = Cfg<CIN, COUT, NSPLIT, KM, NS>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = conv3d_umma_kernel<CIN, NPAD, NSPLIT, KM>;
+  auto kern = conv3d_umma_kernel<CIN, COUT, NSPLIT, KM, NS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid(ceil_div(p.W, TW), ceil_div(p.H, C::TH), B * p.chunks);
+  dim3 grid(ceil_div(p.W, TW), ceil_div(p.H, C::OROWS), B * p.chunks);
   RCMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_tc_fwd: grid too large");
   kern<<<grid, kThreads, C::SMEM, st>>>(p);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_tc_fwd");
   return RCMVS_OK;
 }
 
-// channel-group size processed per launch and tile height for a configuration
-static void plan(int Cin, int Cout, int nsplit, int& cin_k, int& npad, int& km) {
-  (void)Cout;
-  npad = 16;
-  km = 2;
-  cin_k = Cin;
-  if (nsplit == 3 && Cin == 32) cin_k = 16;      // hi+lo slabs of 32 channels do not fit: two channel groups
+// (Cin, Cout) pairs with an instantiated kernel: conv0 of every stage, conv2, prob
+static bool supported(int Cin, int Cout) {
+  return (Cout == 8 && (Cin == 8 || Cin == 16 || Cin == 32)) || (Cout == 1 && Cin == 8) || (Cout == 16 && Cin == 16);
+}
+
+struct Plan {
+  int cin_k, km, cp, g;
+};
+static Plan plan(int Cin, int Cout, int nsplit) {
+  Plan pl;
+  pl.cp = Cout < 8 ? 8 : Cout;
+  pl.g = ((3 * pl.cp + 15) / 16) * 16;
+  pl.cin_k = (nsplit == 3 && Cin == 32) ? 16 : Cin;     // hi+lo slabs of 32 channels do not fit: two channel groups
+  pl.km = Cout == 16 ? 2 : 3;
+  return pl;
 }
 
 }  // namespace umma
 }  // namespace rcmvs
 
 extern "C" int64_t rcmvs_conv3d_tc_weight_floats(int Cin, int Cout, int nsplit) {
-  int cin_k, npad, km;
-  rcmvs::umma::plan(Cin, Cout, nsplit, cin_k, npad, km);
-  return (int64_t)(nsplit == 3 ? 2 : 1) * 27 * Cin * npad;
+  const rcmvs::umma::Plan pl = rcmvs::umma::plan(Cin, Cout, nsplit);
+  return (int64_t)(nsplit == 3 ? 2 : 1) * 3 * (Cin / 8) * 2 * 3 * pl.g * 4;
 }
 
 extern "C" int rcmvs_conv3d_tc_pack(const float* w, const float* scale, float* img, int Cout, int Cin, int nsplit,
                                     rcmvs_stream_t stream) {
   using namespace rcmvs;
   RCMVS_REQUIRE(w && img, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_tc_pack: null pointer");
-  RCMVS_REQUIRE((Cin == 8 || Cin == 16 || Cin == 32) && (Cout == 1 || Cout == 8 || Cout == 16) &&
-                    (nsplit == 1 || nsplit == 3),
-                RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_tc_pack: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
-  int cin_k, npad, km;
-  umma::plan(Cin, Cout, nsplit, cin_k, npad, km);
+  RCMVS_REQUIRE(umma::supported(Cin, Cout) && (nsplit == 1 || nsplit == 3), RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv3d_tc_pack: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
+  const umma::Plan pl = umma::plan(Cin, Cout, nsplit);
   const int terms = nsplit == 3 ? 2 : 1;
-  for (int g = 0; g < Cin / cin_k; ++g) {
-    const int per_term = 27 * cin_k * npad;
+  const int per_term = 3 * (pl.cin_k / 8) * 2 * 3 * pl.g * 4;
+  for (int g = 0; g < Cin / pl.cin_k; ++g) {
     umma::pack_umma_weight_kernel<<<ceil_div(per_term, 256), 256, 0, as_stream(stream)>>>(
-        w, scale, img + (int64_t)g * terms * per_term, Cout, Cin, g * cin_k, cin_k, npad, nsplit);
+        w, scale, img + (int64_t)g * terms * per_term, Cout, Cin, g * pl.cin_k, pl.cin_k, pl.cp, pl.g, nsplit);
   }
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_tc_pack");
   return RCMVS_OK;
@@ -436,33 +506,34 @@ extern "C" int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const floa
   using namespace rcmvs::umma;
   RCMVS_REQUIRE(x && wimg && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_tc_fwd: null pointer");
   RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_tc_fwd: bad dims");
-  RCMVS_REQUIRE((Cin == 8 || Cin == 16 || Cin == 32) && (Cout == 1 || Cout == 8 || Cout == 16) &&
-                    (nsplit == 1 || nsplit == 3),
-                RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_tc_fwd: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
-  int cin_k, npad, km;
-  plan(Cin, Cout, nsplit, cin_k, npad, km);
-  const int th = 4 * km;
+  RCMVS_REQUIRE(umma::supported(Cin, Cout) && (nsplit == 1 || nsplit == 3), RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv3d_tc_fwd: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
+  const Plan pl = plan(Cin, Cout, nsplit);
+  const int orows = 4 * pl.km - 2;
   // depth chunks: enough CTAs for >= ~2 waves of 148 SMs, each chunk >= 8 planes (2 halo slabs of overhead)
-  const int cols = ceil_div(W, TW) * ceil_div(H, th) * B;
+  const int cols = ceil_div(W, TW) * ceil_div(H, orows) * B;
   int chunks = max(1, min(ceil_div(D, 8), ceil_div(2 * 148, cols)));
   const int d_chunk = ceil_div(D, chunks);
   chunks = ceil_div(D, d_chunk);
-  const int groups = Cin / cin_k;
+  const int groups = Cin / pl.cin_k;
   const int terms = nsplit == 3 ? 2 : 1;
+  const int per_term = 3 * (pl.cin_k / 8) * 2 * 3 * pl.g * 4;
   cudaStream_t st = as_stream(stream);
   for (int g = 0; g < groups; ++g) {
     Params p;
-    p.x = x; p.wimg = wimg + (int64_t)g * terms * 27 * cin_k * npad; p.bias = bias; p.skip = skip; p.y = y;
-    p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = g * cin_k; p.Cout = Cout;
+    p.x = x; p.wimg = wimg + (int64_t)g * terms * per_term; p.bias = bias; p.skip = skip; p.y = y;
+    p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = g * pl.cin_k;
     p.d_chunk = d_chunk; p.chunks = chunks;
     p.accumulate_in = g > 0; p.finalize = g == groups - 1; p.relu = relu;
     int rc = RCMVS_ERR_UNSUPPORTED;
-#define RCMVS_TC_CASE(CI, NP, NSP, KMV) \
-  if (cin_k == CI && npad == NP && nsplit == NSP && km == KMV) rc = launch<CI, NP, NSP, KMV>(p, B, st)
-    RCMVS_TC_CASE(8, 16, 1, 2); else RCMVS_TC_CASE(8, 16, 3, 2);
-    else RCMVS_TC_CASE(16, 16, 1, 2); else RCMVS_TC_CASE(16, 16, 3, 2);
-    else RCMVS_TC_CASE(32, 16, 1, 2);
-    else set_error("rcmvs_conv3d_tc_fwd: no kernel for cin_k=%d npad=%d nsplit=%d km=%d", cin_k, npad, nsplit, km);
+#define RCMVS_TC_CASE(CI, CO, NSP, KMV, NSV) \
+  if (pl.cin_k == CI && Cout == CO && nsplit == NSP) rc = launch<CI, CO, NSP, KMV, NSV>(p, B, st)
+    RCMVS_TC_CASE(8, 8, 1, 3, 3); else RCMVS_TC_CASE(8, 8, 3, 3, 3);
+    else RCMVS_TC_CASE(16, 8, 1, 3, 3); else RCMVS_TC_CASE(16, 8, 3, 3, 3);
+    else RCMVS_TC_CASE(32, 8, 1, 3, 3);
+    else RCMVS_TC_CASE(8, 1, 1, 3, 3); else RCMVS_TC_CASE(8, 1, 3, 3, 3);
+    else RCMVS_TC_CASE(16, 16, 1, 2, 3); else RCMVS_TC_CASE(16, 16, 3, 2, 3);
+    else set_error("rcmvs_conv3d_tc_fwd: no kernel for cin_k=%d Cout=%d nsplit=%d", pl.cin_k, Cout, nsplit);
 #undef RCMVS_TC_CASE
     if (rc != RCMVS_OK) return rc;
   }

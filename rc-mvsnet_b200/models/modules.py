@@ -5,6 +5,8 @@ Same public names, constructor arguments, state_dict keys and call signatures as
 get_depth_range_samples :569, get_cur_depth_range_samples :549), but the bodies enqueue the sm_100a kernels of
 librcmvs.so through rcmvs.ops.  CUDA tensors only — there is no CPU fallback.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -224,12 +226,8 @@ class CostRegNet(nn.Module):
                         tr = isinstance(conv, nn.ConvTranspose3d)
                     w = conv.weight.detach().contiguous()
                     cout, cin = (w.shape[1], w.shape[0]) if tr else (w.shape[0], w.shape[1])
-                    use_tc = (nsplit > 0 and not tr and conv.stride[0] == 1 and cin in ops.TC_SUPPORTED_CIN
-                              and cout in ops.TC_SUPPORTED_COUT)
-                    # measured on B200 (profiles/r01): the 3xTF32 kernel is shared-memory-operand bound (N<=16) and
-                    # only beats the FFMA direct kernel for Cin=8; plain TF32 wins for every supported layer.
-                    if nsplit == 3 and cin > 8:
-                        use_tc = False
+                    use_tc = (nsplit > 0 and not tr and conv.stride[0] == 1 and (cin, cout) in ops.TC_SUPPORTED
+                              and cin <= int(os.environ.get("RCMVS_TC_MAXCIN", "32")))
                     if use_tc:
                         P[name] = ("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit)
                     else:

@@ -151,8 +151,7 @@ def conv_transpose3d(x_cl, packed_w, bias=None, skip=None, relu=True):
 
 
 # ---- conv3d on the tensor cores (tcgen05 / TMEM) ----------------------------------------------------------------
-TC_SUPPORTED_CIN = (8, 16, 32)
-TC_SUPPORTED_COUT = (1, 8, 16)
+TC_SUPPORTED = {(8, 8), (16, 8), (32, 8), (8, 1), (16, 16)}      # (Cin, Cout) pairs of conv0 / prob / conv2
 
 
 def conv3d_tc_pack(w, scale=None, nsplit=3):

@@ -204,7 +204,7 @@ def test_conv3d_vs_oracle(dev, cin, cout, stride, dhw):
 @pytest.mark.parametrize("nsplit", [3, 1])
 @pytest.mark.parametrize("cin,cout,dhw", [
     (8, 8, (3, 9, 37)), (16, 8, (2, 8, 30)), (32, 8, (4, 17, 61)), (16, 16, (9, 5, 64)), (8, 1, (5, 12, 33)),
-    (8, 8, (1, 1, 1)), (32, 8, (20, 8, 31)),
+    (8, 8, (1, 1, 1)), (32, 8, (20, 8, 31)), (8, 8, (23, 21, 95)), (16, 16, (13, 14, 31)),
 ])
 def test_conv3d_tensor_core_vs_oracle(dev, cin, cout, dhw, nsplit):
     """tcgen05 implicit-GEMM path.  nsplit=3 (3xTF32) must be fp32-equivalent; nsplit=1 (plain TF32) carries
