@@ -91,6 +91,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Descriptors as (lo, hi) 32-bit halves: hi = SBO | version is constant, lo = (LBO>>4)<<16 | (addr>>4) and moving the
+// start address is a single 32-bit add — the MMA issue loop is latency-bound on one thread, so every instruction
+// between two tcgen05.mma counts (v2a spent ~360 cycles per MMA on 64-bit descriptor arithmetic, see profiles/).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+  return ((addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);     // SBO = 128 B at bits [32,46), version 1 at [46,48)
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(1u), "r"(kDescHi)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -252,64 +274,64 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
       }
     }
   } else if (warp == 6) {
-    // =============================== MMA issuer (one thread) =====================================================
-    if (lane == 0) {
-      const uint32_t b_base = smem_u32(b_smem);
-      for (int i = 0; i < nslabs; ++i) {
-        // slab i = input plane z = d0-1+i contributes to output planes (relative) q = i-2+j, block j = 0,1,2 (kd = 2-j)
-        const int jlo = max(0, 2 - i), jhi = min(2, nplanes + 1 - i);       // valid blocks: 0 <= q < nplanes
-        const int qnew = i;                                                  // plane first touched by this slab (j=2)
-        if (qnew < nplanes && qnew >= NG) {                                  // its group must have been drained
-          mbar_wait(grp_free + (qnew % NG), ((qnew / NG) - 1) & 1);
-          tc_fence_after();
-        }
-        const int buf = i % NS;
-        mbar_wait(full + buf, (i / NS) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
-        // split the valid block range into ring-contiguous runs
-        int run_j[2], run_n[2], nruns = 0;
-        {
-          int j = jlo;
-          while (j <= jhi) {
-            const int g = (i - 2 + j) % NG;
-            int n = 1;
-            while (j + n <= jhi && g + n < NG) ++n;
-            run_j[nruns] = j; run_n[nruns] = n; ++nruns;
-            j += n;
-          }
-        }
-#pragma unroll 1
-        for (int kw = 0; kw < 3; ++kw) {
+    // =============================== MMA issuer ==================================================================
+    // The whole warp runs the (warp-uniform) control flow so descriptor arithmetic stays on the uniform datapath;
+    // one elected lane issues tcgen05.mma / tcgen05.commit.
+    const bool leader = elect_one();
+    const uint32_t b_base = smem_u32(b_smem);
+    for (int i = 0; i < nslabs; ++i) {
+      // slab i = input plane z = d0-1+i contributes to output planes (relative) q = i-2+j, block j = 0,1,2 (kd = 2-j)
+      const int jlo = max(0, 2 - i), jhi = min(2, nplanes + 1 - i);       // valid blocks: 0 <= q < nplanes
+      const int qnew = i;                                                  // plane first touched by this slab (j=2)
+      if (qnew < nplanes && qnew >= NG) {                                  // its group must have been drained
+        mbar_wait(grp_free + (qnew % NG), ((qnew / NG) - 1) & 1);
+      }
+      const int buf = i % NS;
+      mbar_wait(full + buf, (i / NS) & 1);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
+      // split the valid block range into (at most two) ring-contiguous runs; per run: TMEM column, B row offset, N
+      const int g0 = (i - 2 + jlo + NG) % NG;
+      const int n_all = jhi - jlo + 1;
+      const int n0 = min(n_all, NG - g0), n1 = n_all - n0;                 // second run wraps to group 0
+      const uint32_t d0c = tmem_base + g0 * G, d1c = tmem_base;
+      const uint32_t idesc0 = make_idesc(128, n0 * G), idesc1 = make_idesc(128, (n1 > 0 ? n1 : 1) * G);
+      const uint32_t boff0 = (uint32_t)(jlo * G), boff1 = (uint32_t)((jlo + n0) * G);   // in 16-byte rows
+      const uint32_t a_lo0 = desc_lo(a_base, C::PLANE_B);                  // hi-part slab
+      const uint32_t b_lo0 = desc_lo(b_base, 3 * G * 16);
 #pragma unroll
-          for (int ks = 0; ks < C::KS; ++ks) {
-            const uint32_t b_blk = b_base + (kw * C::KS + ks) * C::BBLK_B;
+      for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-            for (int mt = 0; mt < KM; ++mt) {
-              const uint32_t a_addr = a_hi + ks * 2 * C::PLANE_B + (mt * 128 + kw) * 16;
-              const uint64_t ad_hi = make_desc(a_addr, C::PLANE_B, 128);
-              const uint64_t ad_lo = make_desc(a_addr + C::SLAB_B, C::PLANE_B, 128);
-              for (int r = 0; r < nruns; ++r) {
-                const int j = run_j[r], n = run_n[r];
-                const uint32_t idesc = make_idesc(128, n * G);
-                const uint32_t d = tmem_base + mt * (NG * G) + ((i - 2 + j) % NG) * G;
-                const uint32_t b_hi = b_blk + j * G * 16;
-                const uint64_t bd_hi = make_desc(b_hi, 3 * G * 16, 128);
-                if constexpr (NSPLIT == 3) {
-                  const uint64_t bd_lo = make_desc(b_hi + C::BTERM_B, 3 * G * 16, 128);
-                  umma_tf32(d, ad_lo, bd_hi, idesc, 1u);              // small terms first
-                  umma_tf32(d, ad_hi, bd_lo, idesc, 1u);
-                  umma_tf32(d, ad_hi, bd_hi, idesc, 1u);
-                } else {
-                  umma_tf32(d, ad_hi, bd_hi, idesc, 1u);
+        for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+          for (int mt = 0; mt < KM; ++mt) {
+            constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
+            const uint32_t a_hi_d = a_lo0 + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + kw);
+            const uint32_t b_blk_d = b_lo0 + (uint32_t)(((kw * C::KS + ks) * C::BBLK_B) >> 4);
+            const uint32_t dm = (uint32_t)(mt * (NG * G));
+            if (leader) {
+              if constexpr (NSPLIT == 3) {
+                umma_tf32_lohi(d0c + dm, a_hi_d + kLoOff, b_blk_d + boff0, idesc0);            // x_lo · w_hi
+                umma_tf32_lohi(d0c + dm, a_hi_d, b_blk_d + boff0 + kBLoOff, idesc0);           // x_hi · w_lo
+                umma_tf32_lohi(d0c + dm, a_hi_d, b_blk_d + boff0, idesc0);                     // x_hi · w_hi
+                if (n1 > 0) {
+                  umma_tf32_lohi(d1c + dm, a_hi_d + kLoOff, b_blk_d + boff1, idesc1);
+                  umma_tf32_lohi(d1c + dm, a_hi_d, b_blk_d + boff1 + kBLoOff, idesc1);
+                  umma_tf32_lohi(d1c + dm, a_hi_d, b_blk_d + boff1, idesc1);
                 }
+              } else {
+                umma_tf32_lohi(d0c + dm, a_hi_d, b_blk_d + boff0, idesc0);
+                if (n1 > 0) umma_tf32_lohi(d1c + dm, a_hi_d, b_blk_d + boff1, idesc1);
               }
             }
           }
         }
-        umma_commit(empty + buf);                                   // slab consumed once these MMAs retire
-        if (i >= 2) umma_commit(grp_full + ((i - 2) % NG));         // output plane q = i-2 is complete (j = 0 was its last)
       }
+      if (leader) {
+        umma_commit(empty + buf);                                   // slab consumed once these MMAs retire
+        if (i >= 2) umma_commit(grp_full + ((i - 2) % NG));         // output plane q = i-2 is complete
+      }
+      __syncwarp();
     }
   } else {
     // =============================== epilogue (128 threads) ======================================================
