@@ -532,9 +532,19 @@ extern "C" int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const floa
                 "rcmvs_conv3d_tc_fwd: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
   const Plan pl = plan(Cin, Cout, nsplit);
   const int orows = 4 * pl.km - 2;
-  // depth chunks: enough CTAs for >= ~2 waves of 148 SMs, each chunk >= 8 planes (2 halo slabs of overhead)
+  // depth chunks: one CTA per SM (shared memory), so pick the chunk count that minimises
+  //   waves(cols*chunks / 148) x slabs per CTA (planes + 2 halo slabs)
   const int cols = ceil_div(W, TW) * ceil_div(H, orows) * B;
-  int chunks = max(1, min(ceil_div(D, 8), ceil_div(2 * 148, cols)));
+  int chunks = 1;
+  {
+    long best = -1;
+    for (int c = 1; c <= max(1, D / 4); ++c) {
+      const int dc = ceil_div(D, c);
+      const int cc = ceil_div(D, dc);
+      const long cost = (long)ceil_div(cols * cc, 148) * (dc + 2);
+      if (best < 0 || cost < best) { best = cost; chunks = cc; }
+    }
+  }
   const int d_chunk = ceil_div(D, chunks);
   chunks = ceil_div(D, d_chunk);
   const int groups = Cin / pl.cin_k;
