@@ -144,6 +144,111 @@ costvolume_var_kernel(const float* __restrict__ feats, const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v2 of the fused sweep (eval path, no var_noref): ncu on v1 (profiles/r01_costvolume_v1_ncu.md) showed it is
+// instruction-issue bound — every one of the C/4 lanes of a pixel redid the projection, the IEEE divisions and the tap
+// setup for every (plane, view).  Here the LPP = C/4 lanes of a pixel each take ONE plane of a group of LPP planes,
+// compute its sample position once, and the group then walks the LPP planes broadcasting (tap base | flags, ax, ay)
+// with three width-LPP shuffles.  Σf, Σf² for the LPP planes stay in registers.
+// ------------------------------------------------------------------------------------------------------------------
+template <int C, bool PER_PIXEL>
+__global__ void __launch_bounds__(256)
+costvolume_var_v2_kernel(const float* __restrict__ feats, const float* __restrict__ rt_g,
+                         const float* __restrict__ depth, float* __restrict__ var, int V, int D, int h, int w,
+                         int d_chunk, int chunks_per_batch) {
+  constexpr int LPP = C / 4;
+  constexpr int PXB = 256 / LPP;
+  const int q = threadIdx.x % LPP;
+  const int xr = blockIdx.x * PXB + threadIdx.x / LPP;
+  const int x = min(xr, w - 1);                 // out-of-range lanes still take part in the shuffles
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / chunks_per_batch;
+  const int d_begin = (blockIdx.z % chunks_per_batch) * d_chunk;
+  const int d_end = min(D, d_begin + d_chunk);
+  __shared__ float rt_s[kMaxSrc * 12];
+  for (int i = threadIdx.x; i < (V - 1) * 12; i += 256) rt_s[i] = __ldg(rt_g + (int64_t)b * (V - 1) * 12 + i);
+  __syncthreads();
+
+  const int64_t hw = (int64_t)h * w;
+  feats += (int64_t)b * V * hw * C + q * 4;
+  var += (int64_t)b * D * hw * C + q * 4;
+  depth += PER_PIXEL ? (int64_t)b * D * hw + (int64_t)y * w + x : (int64_t)b * D;
+  const float4 ref = ldg4(feats + ((int64_t)y * w + x) * C);
+  const float4 ref2 = make_float4(ref.x * ref.x, ref.y * ref.y, ref.z * ref.z, ref.w * ref.w);
+  const float inv_v = 1.f / (float)V;
+  const float xf = (float)x, yf = (float)y;
+
+  for (int dg = d_begin; dg < d_end; dg += LPP) {
+    float4 s[LPP], s2[LPP];
+#pragma unroll
+    for (int j = 0; j < LPP; ++j) { s[j] = ref; s2[j] = ref2; }
+    const int my_d = min(dg + q, D - 1);
+    const float dep = PER_PIXEL ? __ldg(depth + (int64_t)my_d * hw) : __ldg(depth + my_d);
+    for (int v = 0; v < V - 1; ++v) {
+      const float* m = rt_s + v * 12;
+      // this lane's plane: p = rot·(x,y,1)·depth + trans ; (px,py) = p.xy / p.z   (modules.py:325-329)
+      const float rx = fmaf(m[0], xf, fmaf(m[1], yf, m[2]));
+      const float ry = fmaf(m[4], xf, fmaf(m[5], yf, m[6]));
+      const float rz = fmaf(m[8], xf, fmaf(m[9], yf, m[10]));
+      const float iz = __frcp_rn(fmaf(rz, dep, m[11]));
+      const float px = fmaf(rx, dep, m[3]) * iz, py = fmaf(ry, dep, m[7]) * iz;
+      const bool finite = (fabsf(px) < 1e8f) && (fabsf(py) < 1e8f);
+      const float fx = floorf(px), fy = floorf(py);
+      const float my_ax = px - fx, my_ay = py - fy;
+      const int x0 = finite ? (int)fx : -4, y0 = finite ? (int)fy : -4;
+      const bool vx0 = (x0 >= 0) && (x0 < w), vx1 = (x0 + 1 >= 0) && (x0 + 1 < w);
+      const bool vy0 = (y0 >= 0) && (y0 < h), vy1 = (y0 + 1 >= 0) && (y0 + 1 < h);
+      const int cx0 = min(max(x0, 0), w - 1), cx1 = min(max(x0 + 1, 0), w - 1);
+      const int cy0 = min(max(y0, 0), h - 1), cy1 = min(max(y0 + 1, 0), h - 1);
+      // tap base (< 2^24) | dx<<24 | dy<<25 | valid00<<26 | valid01<<27 | valid10<<28 | valid11<<29
+      const unsigned my_pk = (unsigned)(cy0 * w + cx0) | ((unsigned)(cx1 != cx0) << 24) | ((unsigned)(cy1 != cy0) << 25) |
+                             ((unsigned)(vx0 && vy0) << 26) | ((unsigned)(vx1 && vy0) << 27) |
+                             ((unsigned)(vx0 && vy1) << 28) | ((unsigned)(vx1 && vy1) << 29);
+      const float* src = feats + (int64_t)(v + 1) * hw * C;
+#pragma unroll
+      for (int j = 0; j < LPP; ++j) {
+        const unsigned pk = __shfl_sync(0xffffffffu, my_pk, j, LPP);
+        const float ax = __shfl_sync(0xffffffffu, my_ax, j, LPP);
+        const float ay = __shfl_sync(0xffffffffu, my_ay, j, LPP);
+        if (pk >> 26) {
+          const int base = (int)(pk & 0xFFFFFFu);
+          const int o01 = base + (int)((pk >> 24) & 1u);
+          const int o10 = base + (((pk >> 25) & 1u) ? w : 0);
+          const int o11 = o10 + (int)((pk >> 24) & 1u);
+          const float bx = 1.f - ax, by = 1.f - ay;
+          const float w00 = (pk & (1u << 26)) ? bx * by : 0.f, w01 = (pk & (1u << 27)) ? ax * by : 0.f;
+          const float w10 = (pk & (1u << 28)) ? bx * ay : 0.f, w11 = (pk & (1u << 29)) ? ax * ay : 0.f;
+          const float4 a = ldg4(src + (int64_t)base * C), bb = ldg4(src + (int64_t)o01 * C);
+          const float4 c = ldg4(src + (int64_t)o10 * C), e = ldg4(src + (int64_t)o11 * C);
+          float4 f;
+          f.x = fmaf(e.x, w11, fmaf(c.x, w10, fmaf(bb.x, w01, a.x * w00)));
+          f.y = fmaf(e.y, w11, fmaf(c.y, w10, fmaf(bb.y, w01, a.y * w00)));
+          f.z = fmaf(e.z, w11, fmaf(c.z, w10, fmaf(bb.z, w01, a.z * w00)));
+          f.w = fmaf(e.w, w11, fmaf(c.w, w10, fmaf(bb.w, w01, a.w * w00)));
+          s[j].x += f.x; s[j].y += f.y; s[j].z += f.z; s[j].w += f.w;
+          s2[j].x = fmaf(f.x, f.x, s2[j].x); s2[j].y = fmaf(f.y, f.y, s2[j].y);
+          s2[j].z = fmaf(f.z, f.z, s2[j].z); s2[j].w = fmaf(f.w, f.w, s2[j].w);
+        }
+      }
+    }
+    if (xr < w) {
+#pragma unroll
+      for (int j = 0; j < LPP; ++j) {
+        const int d = dg + j;
+        if (d < d_end) {
+          float4 o;
+          const float mx = s[j].x * inv_v, my = s[j].y * inv_v, mz = s[j].z * inv_v, mw = s[j].w * inv_v;
+          o.x = fmaf(-mx, mx, s2[j].x * inv_v);
+          o.y = fmaf(-my, my, s2[j].y * inv_v);
+          o.z = fmaf(-mz, mz, s2[j].z * inv_v);
+          o.w = fmaf(-mw, mw, s2[j].w * inv_v);
+          st4_stream(var + (((int64_t)d * h + y) * w + x) * C, o);
+        }
+      }
+    }
+  }
+}
+
 template <int C>
 static int launch_costvolume(const float* feats, const float* rt, const float* depth, int per_pixel, float* var,
                              float* var_noref, int B, int V, int D, int h, int w, cudaStream_t st) {
@@ -154,10 +259,19 @@ static int launch_costvolume(const float* feats, const float* rt, const float* d
   const int d_chunk = ceil_div(D, chunks);
   chunks = ceil_div(D, d_chunk);
   dim3 grid(ceil_div(w, PXB), h, B * chunks);
+  const bool hw_fits_24bit = (int64_t)h * w < (1 << 24);
 #define RCMVS_CV_LAUNCH(PP, NR)                                                                              \
   costvolume_var_kernel<C, PP, NR><<<grid, 256, 0, st>>>(feats, rt, depth, var, var_noref, V, D, h, w, d_chunk, \
                                                          chunks)
-  if (per_pixel) {
+  if (!var_noref && hw_fits_24bit) {
+    // eval path: plane-distributed v2 kernel; planes per CTA rounded to the group size
+    constexpr int LPP = C / 4;
+    const int dch = ceil_div(d_chunk, LPP) * LPP;
+    const int nch = ceil_div(D, dch);
+    dim3 grid2(ceil_div(w, PXB), h, B * nch);
+    if (per_pixel) costvolume_var_v2_kernel<C, true><<<grid2, 256, 0, st>>>(feats, rt, depth, var, V, D, h, w, dch, nch);
+    else costvolume_var_v2_kernel<C, false><<<grid2, 256, 0, st>>>(feats, rt, depth, var, V, D, h, w, dch, nch);
+  } else if (per_pixel) {
     if (var_noref) RCMVS_CV_LAUNCH(true, true); else RCMVS_CV_LAUNCH(true, false);
   } else {
     if (var_noref) RCMVS_CV_LAUNCH(false, true); else RCMVS_CV_LAUNCH(false, false);
