@@ -108,6 +108,17 @@ int rcmvs_softargmin_conf_fwd(const float* cost, const float* depth_planes, int 
                               float* conf, int32_t* idx, float* prob, int B, int D, int h, int w,
                               rcmvs_stream_t stream);
 
+/* ---- f1 FeatureNet building blocks: models/modules.py:28-62, 363-464 ------------------------------------------------ */
+/* img [N][C<=8][H][W] -> out [N][H][W][8] (zero-padded channels-last input of the first convolution). */
+int rcmvs_images_to_nhwc8(const float* img, float* out, int N, int C, int H, int W, rcmvs_stream_t stream);
+/* torch Conv2d weight [Cout][Cin][K][K] x folded BatchNorm scale[Cout] (NULL = 1) -> packed [K*K][Cin_pad][Cout]. */
+int rcmvs_pack_conv2d_weight(const float* w, const float* scale, float* packed, int Cout, int Cin, int Cin_pad, int K,
+                             rcmvs_stream_t stream);
+/* y = act(conv2d(x, K, pad K/2, stride) + bias) (+ nearest-2x-upsampled `up`);  x [N][H][W][Cin],
+ * y [N][Ho][Wo][Cout], up [N][Ho/2][Wo/2][Cout] or NULL.  (K,stride,Cout) in {(3,1,8|16|32),(5,2,16|32),(1,1,32)}. */
+int rcmvs_conv2d_fwd(const float* x, const float* packed_w, const float* bias, const float* up, float* y, int N, int H,
+                     int W, int Cin, int Cout, int K, int stride, int relu, rcmvs_stream_t stream);
+
 /* ---- a7 Neural_Volume_Net resize: models/render_models.py:755-756 ------------------------------------------------ */
 /* x [B][D0][S][C] channels-last (S = h*w) -> y [B][D1][S][Cpad]: linear along D with align_corners=True, channels
  * C..Cpad-1 zero-filled (the 41-channel volume is padded to 48 for the convolution kernels). */

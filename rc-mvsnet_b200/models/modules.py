@@ -103,8 +103,8 @@ class Deconv3d(_ConvNormAct):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# FeatureNet (fpn) — SURVEY §8 row f1 ("next"): still library convolutions (cuDNN through torch), but run ONCE on
-# all V views as a batch with BatchNorm folded, and emitting channels-last maps the sweep kernel consumes directly.
+# FeatureNet (fpn) — SURVEY §8 row f1: hand-written fp32 conv2d kernels (csrc/conv2d_direct.cu), run ONCE on all V
+# views as a batch with BatchNorm folded, emitting channels-last maps the sweep kernel consumes directly.
 # ---------------------------------------------------------------------------------------------------------------
 class FeatureNet(nn.Module):
     def __init__(self, base_channels, num_stage=3, stride=4, arch_mode="fpn"):
@@ -134,46 +134,62 @@ class FeatureNet(nn.Module):
             self.out_channels += [c]
         self._folded = None
 
-    def _fold(self):
+    def _packed(self):
+        """BN-folded, re-laid-out weights for the librcmvs conv2d kernels, rebuilt when parameters change."""
         key = _versions(self)
         if self._folded is None or self._folded[0] != key:
-            layers = {}
-            for name in ("conv0", "conv1", "conv2"):
-                seq = []
-                for blk in getattr(self, name):
-                    s, t = fold_bn(blk.bn)
-                    w = (blk.conv.weight * s.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
-                    seq.append((w, t.contiguous(), blk.stride, blk.kernel_size // 2))
-                layers[name] = seq
-            self._folded = (key, layers)
+            with torch.no_grad():
+                P = {}
+                for name in ("conv0", "conv1", "conv2"):
+                    for i, blk in enumerate(getattr(self, name)):
+                        scale, shift = (t.contiguous() for t in fold_bn(blk.bn))
+                        w = blk.conv.weight.detach().contiguous()
+                        cin_pad = (w.shape[1] + 7) // 8 * 8
+                        P["%s.%d" % (name, i)] = (ops.pack_conv2d_weight(w, scale, cin_pad), shift, blk.stride)
+                for name in ("out1", "inner1", "inner2", "out2", "out3"):
+                    conv = getattr(self, name, None)
+                    if conv is not None:
+                        b = conv.bias.detach().contiguous() if conv.bias is not None else None
+                        P[name] = (ops.pack_conv2d_weight(conv.weight.detach().contiguous(), None), b, 1)
+            self._folded = (key, P)
         return self._folded[1]
 
-    def _trunk(self, x, folded):
-        outs = []
-        for name in ("conv0", "conv1", "conv2"):
-            for (w, b, s, p) in folded[name]:
-                x = F.relu_(F.conv2d(x, w, b, stride=s, padding=p))
-            outs.append(x)
-        return outs
+    def forward_cl(self, x):
+        """x [N,3,H,W] -> {"stageK": [N,h,w,C] channels-last contiguous}; every layer is one librcmvs launch
+        (conv + folded BN + ReLU; the FPN's upsample+add is fused into the 1x1 lateral convolution)."""
+        P = self._packed()
+
+        def cbr(t, key):
+            w, b, stride = P[key]
+            return ops.conv2d(t, w, b, None, stride=stride, relu=True)
+        c0 = cbr(cbr(ops.images_to_nhwc8(x.float().contiguous()), "conv0.0"), "conv0.1")
+        c1 = cbr(cbr(cbr(c0, "conv1.0"), "conv1.1"), "conv1.2")
+        c2 = cbr(cbr(cbr(c1, "conv2.0"), "conv2.1"), "conv2.2")
+        out = {"stage1": ops.conv2d(c2, P["out1"][0], None, None, relu=False)}
+        intra = ops.conv2d(c1, P["inner1"][0], P["inner1"][1], c2, relu=False)      # up2(c2) + inner1(c1)
+        out["stage2"] = ops.conv2d(intra, P["out2"][0], None, None, relu=False)
+        if self.num_stage == 3:
+            intra = ops.conv2d(c0, P["inner2"][0], P["inner2"][1], intra, relu=False)
+            out["stage3"] = ops.conv2d(intra, P["out3"][0], None, None, relu=False)
+        return out
 
     def forward(self, x):
         """x [N,3,H,W] -> {"stage1": [N,4c,H/4,W/4], "stage2": [N,2c,H/2,W/2], "stage3": [N,c,H,W]}.
-        In eval mode the maps are returned in channels_last memory format (same logical NCHW shape)."""
-        # library convolutions follow the selected precision: exact fp32 unless RCMVS_CONV=tf32
-        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
-                                        allow_tf32=(conv_precision() == "tf32")):
-            if self.training:
-                c0 = self.conv0(x)
-                c1 = self.conv1(c0)
-                c2 = self.conv2(c1)
-            else:
-                c0, c1, c2 = self._trunk(x.contiguous(memory_format=torch.channels_last), self._fold())
-            out = {"stage1": self.out1(c2)}
-            intra = F.interpolate(c2, scale_factor=2, mode="nearest") + self.inner1(c1)
-            out["stage2"] = self.out2(intra)
-            if self.num_stage == 3:
-                intra = F.interpolate(intra, scale_factor=2, mode="nearest") + self.inner2(c0)
-                out["stage3"] = self.out3(intra)
+        Eval / no-grad: hand-written fp32 kernels, outputs are NCHW-shaped views of channels-last storage.
+        Training (batch-statistics BatchNorm + autograd): torch library ops."""
+        if not self.training and not (torch.is_grad_enabled() and x.requires_grad) and x.is_cuda \
+                and self.base_channels == 8:
+            with torch.no_grad():
+                return {k: v.permute(0, 3, 1, 2) for k, v in self.forward_cl(x).items()}
+        c0 = self.conv0(x)
+        c1 = self.conv1(c0)
+        c2 = self.conv2(c1)
+        out = {"stage1": self.out1(c2)}
+        intra = F.interpolate(c2, scale_factor=2, mode="nearest") + self.inner1(c1)
+        out["stage2"] = self.out2(intra)
+        if self.num_stage == 3:
+            intra = F.interpolate(intra, scale_factor=2, mode="nearest") + self.inner2(c0)
+            out["stage3"] = self.out3(intra)
         return out
 
 

@@ -269,3 +269,32 @@ def inverse_warp_bwd(img, left_cam, right_cam, depth, grad_warped):
     _ffi.call("rcmvs_inverse_warp_bwd", _chk(img, "img"), _chk(left_cam, "left_cam"), _chk(right_cam, "right_cam"),
               _chk(depth, "depth"), _chk(grad_warped, "grad_warped"), _chk(gd, "grad_depth"), B, h, w, C, _stream())
     return gd
+
+
+# ---- f1 FeatureNet ------------------------------------------------------------------------------------------------
+def images_to_nhwc8(img):
+    N, C, H, W = img.shape
+    out = torch.empty((N, H, W, 8), device=img.device, dtype=torch.float32)
+    _ffi.call("rcmvs_images_to_nhwc8", _chk(img, "img"), _chk(out, "out"), N, C, H, W, _stream())
+    return out
+
+
+def pack_conv2d_weight(w, scale=None, cin_pad=None):
+    Cout, Cin, K, _ = w.shape
+    cin_pad = cin_pad or Cin
+    packed = torch.empty((K * K, cin_pad, Cout), device=w.device, dtype=torch.float32)
+    _ffi.call("rcmvs_pack_conv2d_weight", _chk(w, "w"), _opt(scale, "scale"), _chk(packed, "packed"), Cout, Cin,
+              cin_pad, K, _stream())
+    return packed
+
+
+def conv2d(x_cl, packed_w, bias=None, up=None, stride=1, relu=True):
+    """x_cl [N,H,W,Cin] -> [N,Ho,Wo,Cout]: conv(K, pad K/2) + bias, ReLU, then + nearest-2x-upsampled `up`."""
+    N, H, W, Cin = x_cl.shape
+    KK, _, Cout = packed_w.shape
+    K = {1: 1, 9: 3, 25: 5}[KK]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    y = torch.empty((N, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv2d_fwd", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"), _opt(up, "up"),
+              _chk(y, "y"), N, H, W, Cin, Cout, K, stride, 1 if relu else 0, _stream())
+    return y

@@ -269,6 +269,42 @@ def test_costregnet_golden(dev, stage, mode, monkeypatch):
     np.testing.assert_allclose(cost[0, 0].cpu().numpy(), g["cost_" + k], atol=tol, rtol=1e-4 if mode != "tf32" else 1e-2)
 
 
+# ---- f1 FeatureNet -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,k,stride,hw", [(8, 8, 3, 1, (9, 37)), (8, 16, 5, 2, (20, 70)), (16, 16, 3, 1, (7, 33)),
+                                                  (16, 32, 5, 2, (18, 34)), (32, 32, 3, 1, (5, 40)), (32, 16, 3, 1, (6, 31)),
+                                                  (32, 8, 3, 1, (12, 65)), (16, 32, 1, 1, (8, 36)), (8, 32, 1, 1, (4, 34))])
+def test_conv2d_vs_oracle(dev, cin, cout, k, stride, hw):
+    from rcmvs import ops
+    rng = np.random.default_rng(cin * 100 + cout + k)
+    H, W = hw
+    x = rng.standard_normal((cin, H, W), dtype=np.float32)
+    w = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(k * k * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    want = np.maximum(O.conv2d(x, w * scale[:, None, None, None], bias, stride=stride, pad=k // 2), 0)
+    pw = ops.pack_conv2d_weight(cu(w, dev), cu(scale, dev))
+    got = ops.conv2d(cu(x.transpose(1, 2, 0)[None], dev), pw, cu(bias, dev), None, stride=stride, relu=True)
+    np.testing.assert_allclose(got[0].permute(2, 0, 1).cpu().numpy(), want, atol=2e-5, rtol=1e-5)
+    if stride == 1 and H % 2 == 0 and W % 2 == 0:
+        up = rng.standard_normal((cout, H // 2, W // 2), dtype=np.float32)
+        want_up = O.conv2d(x, w, None, pad=k // 2) + np.repeat(np.repeat(up, 2, 1), 2, 2)
+        got = ops.conv2d(cu(x.transpose(1, 2, 0)[None], dev), ops.pack_conv2d_weight(cu(w, dev)), None,
+                         cu(up.transpose(1, 2, 0)[None], dev), relu=False)
+        np.testing.assert_allclose(got[0].permute(2, 0, 1).cpu().numpy(), want_up, atol=2e-5, rtol=1e-5)
+
+
+def test_featurenet_golden(dev):
+    """Hand-written FeatureNet (conv2d_direct.cu) against the reference's per-view feature maps."""
+    g = load("mvs_small.npz")
+    m = _model(dev, (16, 8, 8))
+    with torch.no_grad():
+        f = m.feature(cu(g["imgs"], dev))                       # all views in one batch
+    for k in ("stage1", "stage2", "stage3"):
+        assert f[k].shape[1] == {"stage1": 32, "stage2": 16, "stage3": 8}[k]
+        for v in range(g["imgs"].shape[0]):
+            np.testing.assert_allclose(f[k][v].cpu().numpy(), g["feat_%s_v%d" % (k, v)], atol=3e-4, rtol=1e-4)
+
+
 # ---- a4 softmax / soft-argmin / confidence -------------------------------------------------------------------------
 @pytest.mark.parametrize("stage", [1, 2, 3])
 def test_softargmin_conf_golden(dev, stage):
