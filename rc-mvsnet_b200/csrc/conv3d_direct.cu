@@ -7,9 +7,11 @@
 // Mapping (direct convolution, register-blocked):
 //   CTA   = output tile 1(d) x TH(h) x 32(w), all Cout
 //   warp  = 32 consecutive w positions; thread = 4 output rows (h) x CO_T(<=8) output channels -> 32 accumulators
-//   smem  = input halo tile for CB=8 input channels at a time, stored [kd][row][c4][col] as float4 so that a warp's
-//           LDS.128 for one tap is 32 consecutive 16-byte words (conflict-free at stride 1), plus the 27xCBxCout
-//           weight slice (read as warp-uniform broadcasts).
+//   smem  = input halo tile for CB=8 input channels and ONE depth tap (kd) at a time, stored [row][c4][col] as float4
+//           so that a warp's LDS.128 for one tap is 32 consecutive 16-byte words (conflict-free at stride 1), plus
+//           the 9xCBxCOUT weight slice of that kd (warp-uniform broadcasts).  Small tiles (<= 36 KB) keep several
+//           CTAs resident per SM; layers with few output voxels additionally split Cout over CTAs (COUT = channels
+//           per CTA, grid.z carries the split) so that the 1/4- and 1/8-resolution levels still fill 148 SMs.
 //   Per (kd,kw,c4) a thread loads 6 input float4 and 24 weight float4 for 384 FMAs.
 // This is the fp32 reference-precision path; the tcgen05 implicit-GEMM path lives in conv3d_umma.cu.
 #include "common.cuh"
@@ -32,8 +34,8 @@ struct ConvSmem {
   using T = ConvTile<COUT>;
   static constexpr int IH = (T::TH - 1) * STRIDE + 3;
   static constexpr int IW = 31 * STRIDE + 3;
-  static constexpr int X_F4 = 3 * IH * 2 * IW;            // float4 count
-  static constexpr int W_F = 27 * CB * COUT;              // float count
+  static constexpr int X_F4 = IH * 2 * IW;                // float4 count: ONE depth slab (kd) at a time
+  static constexpr int W_F = 9 * CB * COUT;               // float count: the 9 in-plane taps of that kd
   static constexpr size_t BYTES = (size_t)X_F4 * 16 + (size_t)W_F * 4;
 };
 
@@ -41,7 +43,7 @@ template <int COUT, int STRIDE>
 __global__ void __launch_bounds__(ConvTile<COUT>::THREADS)
 conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
                      const float* __restrict__ skip, float* __restrict__ y, int D, int H, int W, int Cin, int Do,
-                     int Ho, int Wo, int relu) {
+                     int Ho, int Wo, int relu, int Ctot, int nsplit) {
   using T = ConvTile<COUT>;
   using S = ConvSmem<COUT, STRIDE>;
   constexpr int CO_T = T::CO_T, TH = T::TH, IH = S::IH, IW = S::IW;
@@ -54,7 +56,9 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
   const int hg = wid % T::NWH;
   const int cog = wid / T::NWH;
   const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * TH;
-  const int b = blockIdx.z / Do, od = blockIdx.z % Do;
+  const int co0 = (blockIdx.z % nsplit) * COUT;              // first output channel of this CTA
+  const int bz = blockIdx.z / nsplit;
+  const int b = bz / Do, od = bz % Do;
   const int iz0 = od * STRIDE - 1, iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
   x += (int64_t)b * D * H * W * Cin;
 
@@ -65,31 +69,31 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
     for (int c = 0; c < CO_T; ++c) acc[j][c] = 0.f;
 
   for (int cb0 = 0; cb0 < Cin; cb0 += CB) {
-    __syncthreads();
-    // ---- stage the input halo tile for channels [cb0, cb0+8): element e -> (kd, iy, ix, c4), c4 fastest ----
-    for (int e = threadIdx.x; e < S::X_F4; e += T::THREADS) {
-      const int c4 = e & 1;
-      int r = e >> 1;
-      const int ix = r % IW; r /= IW;
-      const int iy = r % IH;
-      const int kd = r / IH;
-      const int gz = iz0 + kd, gy = iy0 + iy, gx = ix0 + ix;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = ldg4(x + (((int64_t)gz * H + gy) * W + gx) * Cin + cb0 + c4 * 4);
-      xs[((kd * IH + iy) * 2 + c4) * IW + ix] = v;
-    }
-    // ---- stage the weight slice [27][CB][COUT] ----
-    for (int e = threadIdx.x; e < S::W_F; e += T::THREADS) {
-      const int co = e % COUT;
-      const int r = e / COUT;
-      const int ci = r % CB, tap = r / CB;
-      ws[e] = __ldg(wp + ((int64_t)tap * Cin + cb0 + ci) * COUT + co);
-    }
-    __syncthreads();
-
 #pragma unroll 1
     for (int kd = 0; kd < 3; ++kd) {
+      const int gz = iz0 + kd;
+      if (gz < 0 || gz >= D) continue;                       // zero padding in depth: nothing to accumulate (CTA-uniform)
+      __syncthreads();
+      // ---- stage the input halo slab for channels [cb0, cb0+8): element e -> (iy, ix, c4), c4 fastest ----
+      for (int e = threadIdx.x; e < S::X_F4; e += T::THREADS) {
+        const int c4 = e & 1;
+        const int r = e >> 1;
+        const int ix = r % IW, iy = r / IW;
+        const int gy = iy0 + iy, gx = ix0 + ix;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+          v = ldg4(x + (((int64_t)gz * H + gy) * W + gx) * Cin + cb0 + c4 * 4);
+        xs[(iy * 2 + c4) * IW + ix] = v;
+      }
+      // ---- stage the weight slice [9][CB][COUT] of this kd ----
+      for (int e = threadIdx.x; e < S::W_F; e += T::THREADS) {
+        const int co = e % COUT;
+        const int r = e / COUT;
+        const int ci = r % CB, tap = r / CB;
+        ws[e] = __ldg(wp + ((int64_t)(kd * 9 + tap) * Cin + cb0 + ci) * Ctot + co0 + co);
+      }
+      __syncthreads();
+
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
@@ -97,11 +101,10 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
           constexpr int NR = 3 * STRIDE + 3;  // distinct input rows touched by 4 output rows
           float4 xr[NR];
 #pragma unroll
-          for (int r = 0; r < NR; ++r)
-            xr[r] = xs[((kd * IH + hg * 4 * STRIDE + r) * 2 + c4) * IW + lane * STRIDE + kw];
+          for (int r = 0; r < NR; ++r) xr[r] = xs[((hg * 4 * STRIDE + r) * 2 + c4) * IW + lane * STRIDE + kw];
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const int tap = (kd * 3 + kh) * 3 + kw;
+            const int tap = kh * 3 + kw;
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
               float wv[CO_T];
@@ -134,12 +137,12 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
   if (ox >= Wo) return;
   float bv[CO_T];
 #pragma unroll
-  for (int c = 0; c < CO_T; ++c) bv[c] = bias ? __ldg(bias + cog * CO_T + c) : 0.f;
+  for (int c = 0; c < CO_T; ++c) bv[c] = bias ? __ldg(bias + co0 + cog * CO_T + c) : 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int oy = oy0 + hg * 4 + j;
     if (oy >= Ho) continue;
-    const int64_t o = ((((int64_t)b * Do + od) * Ho + oy) * Wo + ox) * COUT + cog * CO_T;
+    const int64_t o = ((((int64_t)b * Do + od) * Ho + oy) * Wo + ox) * Ctot + co0 + cog * CO_T;
     float v[CO_T];
 #pragma unroll
     for (int c = 0; c < CO_T; ++c) {
@@ -183,7 +186,7 @@ template <int COUT>
 __global__ void __launch_bounds__(TConvTile<COUT>::THREADS)
 conv_transpose3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                const float* __restrict__ bias, const float* __restrict__ skip, float* __restrict__ y,
-                               int D, int H, int W, int Cin, int relu) {
+                               int D, int H, int W, int Cin, int relu, int Ctot, int nsplit) {
   using T = TConvTile<COUT>;
   constexpr int IH = T::IH, IW = T::IW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -195,7 +198,9 @@ conv_transpose3d_direct_kernel(const float* __restrict__ x, const float* __restr
   const int hg = wid % T::NWH;
   const int cog = wid / T::NWH;
   const int ix0 = blockIdx.x * 32, iy0 = blockIdx.y * T::TH;
-  const int b = blockIdx.z / D, iz = blockIdx.z % D;
+  const int co0 = (blockIdx.z % nsplit) * COUT;
+  const int bz = blockIdx.z / nsplit;
+  const int b = bz / D, iz = bz % D;
   x += (int64_t)b * D * H * W * Cin;
 
   float acc[8][8];
@@ -221,7 +226,7 @@ conv_transpose3d_direct_kernel(const float* __restrict__ x, const float* __restr
       const int co = e % COUT;
       const int r = e / COUT;
       const int ci = r % CB, tap = r / CB;
-      ws[e] = __ldg(wp + ((int64_t)tap * Cin + cb0 + ci) * COUT + co);
+      ws[e] = __ldg(wp + ((int64_t)tap * Cin + cb0 + ci) * Ctot + co0 + co);
     }
     __syncthreads();
 
@@ -266,11 +271,11 @@ conv_transpose3d_direct_kernel(const float* __restrict__ x, const float* __restr
   const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
   float bv[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) bv[c] = bias ? __ldg(bias + cog * 8 + c) : 0.f;
+  for (int c = 0; c < 8; ++c) bv[c] = bias ? __ldg(bias + co0 + cog * 8 + c) : 0.f;
 #pragma unroll
   for (int o = 0; o < 8; ++o) {
     const int oz = 2 * iz + (o >> 2), oy = 2 * iy + ((o >> 1) & 1), ox = 2 * ix + (o & 1);
-    const int64_t off = ((((int64_t)b * Do + oz) * Ho + oy) * Wo + ox) * COUT + cog * 8;
+    const int64_t off = ((((int64_t)b * Do + oz) * Ho + oy) * Wo + ox) * Ctot + co0 + cog * 8;
     float v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -303,10 +308,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
 
 template <int COUT, int STRIDE>
 static int launch_conv(const float* x, const float* wp, const float* bias, const float* skip, float* y, int B, int D,
-                       int H, int W, int Cin, int relu, cudaStream_t st) {
+                       int H, int W, int Cin, int relu, int Ctot, cudaStream_t st) {
   using T = ConvTile<COUT>;
   using S = ConvSmem<COUT, STRIDE>;
   const int Do = (D - 1) / STRIDE + 1, Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
+  const int nsplit = Ctot / COUT;
   auto kern = conv3d_direct_kernel<COUT, STRIDE>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -314,18 +320,32 @@ static int launch_conv(const float* x, const float* wp, const float* bias, const
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  RCMVS_REQUIRE((int64_t)B * Do <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
+  RCMVS_REQUIRE((int64_t)B * Do * nsplit <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv3d_fwd: grid too large");
-  dim3 grid(ceil_div(Wo, 32), ceil_div(Ho, T::TH), B * Do);
-  kern<<<grid, T::THREADS, S::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, Do, Ho, Wo, relu);
+  dim3 grid(ceil_div(Wo, 32), ceil_div(Ho, T::TH), B * Do * nsplit);
+  kern<<<grid, T::THREADS, S::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, Do, Ho, Wo, relu, Ctot, nsplit);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_fwd");
   return RCMVS_OK;
 }
 
+// channels per CTA: all of Cout for the large layers; halved while the grid would not fill ~2 waves of 148 SMs
+static int pick_cout_per_cta(int Cout, int B, int D, int H, int W, int stride) {
+  if (Cout < 16) return Cout;
+  const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  int c = Cout;
+  auto ctas = [&](int cc) {
+    const int th = cc >= 32 ? 4 : (cc == 16 ? 8 : 16);
+    return (int64_t)ceil_div(Wo, 32) * ceil_div(Ho, th) * B * Do * (Cout / cc);
+  };
+  while (c > 8 && ctas(c) < 2 * 148) c /= 2;
+  return c;
+}
+
 template <int COUT>
 static int launch_tconv(const float* x, const float* wp, const float* bias, const float* skip, float* y, int B, int D,
-                        int H, int W, int Cin, int relu, cudaStream_t st) {
+                        int H, int W, int Cin, int relu, int Ctot, cudaStream_t st) {
   using T = TConvTile<COUT>;
+  const int nsplit = Ctot / COUT;
   auto kern = conv_transpose3d_direct_kernel<COUT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -334,10 +354,10 @@ static int launch_tconv(const float* x, const float* wp, const float* bias, cons
                   cudaGetErrorString(e));
     attr_set = true;
   }
-  RCMVS_REQUIRE((int64_t)B * D <= 65535 && ceil_div(H, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
+  RCMVS_REQUIRE((int64_t)B * D * nsplit <= 65535 && ceil_div(H, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv_transpose3d_fwd: grid too large");
-  dim3 grid(ceil_div(W, 32), ceil_div(H, T::TH), B * D);
-  kern<<<grid, T::THREADS, T::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, relu);
+  dim3 grid(ceil_div(W, 32), ceil_div(H, T::TH), B * D * nsplit);
+  kern<<<grid, T::THREADS, T::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, relu, Ctot, nsplit);
   RCMVS_CHECK_LAUNCH("rcmvs_conv_transpose3d_fwd");
   return RCMVS_OK;
 }
@@ -364,11 +384,14 @@ extern "C" int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const flo
   RCMVS_REQUIRE(Cin % 8 == 0 && Cin > 0, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_fwd: Cin=%d must be a multiple of 8", Cin);
   RCMVS_REQUIRE(stride == 1 || stride == 2, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_fwd: stride must be 1 or 2");
   cudaStream_t st = as_stream(stream);
-#define RCMVS_CONV_CASE(CO)                                                                       \
-  case CO:                                                                                        \
-    return stride == 1 ? launch_conv<CO, 1>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st) \
-                       : launch_conv<CO, 2>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st)
-  switch (Cout) {
+  RCMVS_REQUIRE(Cout == 1 || Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64, RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv3d_fwd: Cout=%d not in {1,8,16,32,64}", Cout);
+  const int cpc = pick_cout_per_cta(Cout, B, D, H, W, stride);
+#define RCMVS_CONV_CASE(CO)                                                                             \
+  case CO:                                                                                              \
+    return stride == 1 ? launch_conv<CO, 1>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, st) \
+                       : launch_conv<CO, 2>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, st)
+  switch (cpc) {
     RCMVS_CONV_CASE(1);
     RCMVS_CONV_CASE(8);
     RCMVS_CONV_CASE(16);
@@ -389,10 +412,21 @@ extern "C" int rcmvs_conv_transpose3d_fwd(const float* x, const float* packed_w,
   RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_fwd: bad dims");
   RCMVS_REQUIRE(Cin % 8 == 0 && Cin > 0, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_transpose3d_fwd: Cin=%d must be a multiple of 8", Cin);
   cudaStream_t st = as_stream(stream);
-  switch (Cout) {
-    case 8: return launch_tconv<8>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st);
-    case 16: return launch_tconv<16>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st);
-    case 32: return launch_tconv<32>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, st);
+  RCMVS_REQUIRE(Cout == 8 || Cout == 16 || Cout == 32, RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv_transpose3d_fwd: Cout=%d not in {8,16,32}", Cout);
+  // channels per CTA: halve while the grid does not fill ~2 waves (input-space tiles of 32 x TH voxels)
+  int cpc = Cout;
+  {
+    auto ctas = [&](int cc) {
+      const int th = cc >= 32 ? 1 : (cc == 16 ? 2 : 4);
+      return (int64_t)ceil_div(W, 32) * ceil_div(H, th) * B * D * (Cout / cc);
+    };
+    while (cpc > 8 && ctas(cpc) < 2 * 148) cpc /= 2;
+  }
+  switch (cpc) {
+    case 8: return launch_tconv<8>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, st);
+    case 16: return launch_tconv<16>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, st);
+    case 32: return launch_tconv<32>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, st);
     default: break;
   }
   set_error("rcmvs_conv_transpose3d_fwd: Cout=%d not in {8,16,32}", Cout);

@@ -1,0 +1,63 @@
+"""N>1 path on CPU: world_size-2 gloo processes exercise the view sharding, the max-over-ranks timing reduction and
+the result gathering that bench.py / a view-sharded evaluation use on NCCL (no data-path collective)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "rc-mvsnet_b200")]
+    from rcmvs import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_units = 7
+    mine = shard.shard_units(n_units, rank, world)
+    # stand-in for the per-view hot path: a deterministic function of the unit index
+    local = {i: torch.full((2, 3), float(i * i)) for i in mine}
+    ms = 10.0 + 5.0 * rank                                     # rank 1 is the slow one
+    ms_max = shard.max_over_ranks(ms)
+    total_units = shard.sum_over_ranks(len(mine))
+    allres = shard.gather_results(local, n_units, rank, world)
+    dist.barrier()
+    if rank == 0:
+        torch.save({"mine": mine, "ms_max": ms_max, "total": total_units,
+                    "vals": [float(t[0, 0]) for t in allres],
+                    "tput": shard.throughput(total_units, ms_max)}, out)
+    dist.destroy_process_group()
+
+
+def test_view_sharding_two_ranks_gloo(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["mine"] == [0, 2, 4, 6]
+    assert r["ms_max"] == 15.0                                 # max over ranks, never rank 0's own clock
+    assert r["total"] == 7.0
+    assert r["vals"] == [float(i * i) for i in range(7)]       # every unit exactly once, in order
+    assert abs(r["tput"] - 7 / 0.015) < 1e-6
+
+
+def test_shard_units_partition():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [os.path.join(root, "rc-mvsnet_b200")]
+    from rcmvs import shard
+    for world in (1, 2, 4, 8):
+        for n in (0, 1, 7, 8, 49):
+            parts = [shard.shard_units(n, r, world) for r in range(world)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
