@@ -101,6 +101,16 @@ int rcmvs_conv3d_tc_pack(const float* w, const float* scale, float* img, int Cou
 int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const float* bias, const float* skip, float* y, int B,
                         int D, int H, int W, int Cin, int Cout, int nsplit, int relu, rcmvs_stream_t stream);
 
+/* Tensor-core transposed convolution (k3, s2, p1, output_padding 1), same semantics as rcmvs_conv_transpose3d_fwd.
+ * (Cin, Cout) in {(16,8), (32,16)} = conv11 / conv9 of CostRegNet; the weight image is built from the torch
+ * ConvTranspose3d weight [Cin][Cout][3][3][3]. */
+int64_t rcmvs_conv_transpose3d_tc_weight_floats(int Cin, int Cout, int nsplit);
+int rcmvs_conv_transpose3d_tc_pack(const float* w, const float* scale, float* img, int Cout, int Cin, int nsplit,
+                                   rcmvs_stream_t stream);
+int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, const float* bias, const float* skip, float* y,
+                                  int B, int D, int H, int W, int Cin, int Cout, int nsplit, int relu,
+                                  rcmvs_stream_t stream);
+
 /* ---- a4 softmax + soft-argmin + photometric confidence: models/casmvsnet.py:111-122, modules.py:519-525 ------ */
 /* cost [B][D][h][w]; depth planes [B][D] (per_pixel=0) or [B][D][h][w]; -> depth [B][h][w], conf [B][h][w],
  * idx [B][h][w] int32 (optional, may be NULL: clamp(trunc(Σ p·i))), prob [B][D][h][w] (optional, may be NULL). */

@@ -105,6 +105,16 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const int tap = kh * 3 + kw;
+            if constexpr (COUT == 1) {
+              // single output channel (`prob`): the 4 input-channel weights of this tap are one float4
+              const float4 w4 = *reinterpret_cast<const float4*>(ws + (tap * CB) + c4 * 4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 xv4 = xr[j * STRIDE + kh];
+                acc[j][0] = fmaf(xv4.x, w4.x, fmaf(xv4.y, w4.y, fmaf(xv4.z, w4.z, fmaf(xv4.w, w4.w, acc[j][0]))));
+              }
+              continue;
+            }
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
               float wv[CO_T];

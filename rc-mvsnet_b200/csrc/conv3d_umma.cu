@@ -108,6 +108,17 @@ __device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, u
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(1u), "r"(kDescHi)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_lohi_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -496,6 +507,296 @@ static Plan plan(int Cin, int Cout, int nsplit) {
   return pl;
 }
 
+
+// ==================================================================================================================
+// ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) on tcgen05 (reference models/modules.py:166-210 Deconv3d;
+// conv7/9/11 of CostRegNet :484-488).  out[2i+a] per dimension: a=0 <- (k=1, i);  a=1 <- (k=2, i) + (k=0, i+1).
+// Every output parity class (a,b,c) is a small stride-1 convolution over the INPUT grid, so the same flat-run trick
+// applies in input space: M = 128 input positions, the 8 input shifts (dz,dy,dx) in {0,1}^3 are descriptor start
+// offsets (+dy*32+dx voxels, slab iz+dz), and N = 8 classes x Cout holds all parity classes at once (weights of
+// classes that do not use a shift are zero rows of B).  Accumulators: double-buffered TMEM stages; the epilogue
+// scatters the 8 classes of every input voxel to its 2x2x2 output block with bias / ReLU / skip fused.
+// ==================================================================================================================
+template <int CIN, int COUT, int NSPLIT, int KM, int NS>
+struct TCfg {
+  static constexpr int N = 8 * COUT;
+  static constexpr int KS = CIN / 8;
+  static constexpr int NCH = CIN / 4;
+  static constexpr int ROWS = 4 * KM;                              // input rows per CTA tile (all produce outputs)
+  static constexpr int TWI = 31;                                   // input columns per tile (col 31 = halo for dx=1)
+  static constexpr int SLABV = (ROWS + 1) * PW + 8;
+  static constexpr int PLANE_B = SLABV * 16;
+  static constexpr int SLAB_B = NCH * PLANE_B;
+  static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
+  static constexpr int A_BYTES = NS * NPART * SLAB_B;
+  static constexpr int BBLK_B = 2 * N * 16;                        // one (shift, K-step)
+  static constexpr int BTERM_B = 8 * KS * BBLK_B;
+  static constexpr int B_BYTES = NPART * BTERM_B;
+  static constexpr int TMEM_COLS = 2 * KM * N <= 256 ? 256 : 512;
+  static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + 512;
+  static_assert(2 * KM * N <= 512, "TMEM budget exceeded");
+};
+
+template <int CIN, int COUT, int NSPLIT, int KM, int NS>
+__global__ void __launch_bounds__(kThreads, 1) convT3d_umma_kernel(const Params p) {
+  using C = TCfg<CIN, COUT, NSPLIT, KM, NS>;
+  constexpr int N = C::N;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a_smem = smem;
+  unsigned char* b_smem = smem + C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::A_BYTES + C::B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NS;
+  uint64_t* acc_full = bars + 2 * NS;
+  uint64_t* acc_empty = bars + 2 * NS + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * C::TWI, y0 = blockIdx.y * C::ROWS;
+  const int b = blockIdx.z / p.chunks;
+  const int z0 = (blockIdx.z % p.chunks) * p.d_chunk;
+  const int z1 = min(p.D, z0 + p.d_chunk);
+  const int nsteps = z1 - z0;            // input planes z0..z1-1 ; slabs z0 .. z1  (nsteps + 1)
+  const int nslabs = nsteps + 1;
+  const int64_t vox_stride = p.cin_total;
+  const float* xb = p.x + (int64_t)b * p.D * p.H * p.W * vox_stride + p.cin_off;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, kLoaderThreads); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.wimg);
+    float4* dst = reinterpret_cast<float4*>(b_smem);
+    for (int i = threadIdx.x; i < C::B_BYTES / 16; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 6) {
+    // =============================== slab loaders ================================================================
+    const int t = threadIdx.x - 128;
+    constexpr int PIECES = (C::ROWS + 1) * PW * C::NCH;
+    for (int i = 0; i <= nslabs; ++i) {
+      if (i < nslabs) {
+        const int buf = i % NS;
+        mbar_wait(empty + buf, ((i / NS) & 1) ^ 1);
+        const int z = z0 + i;
+        const bool zok = z < p.D;
+        const uint32_t slab = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
+        for (int e = t; e < PIECES; e += kLoaderThreads) {
+          const int ch = e % C::NCH;
+          const int v = e / C::NCH;
+          const int gy = y0 + v / PW, gx = x0 + (v % PW);
+          const bool ok = zok && gy < p.H && gx < p.W;
+          const float* src = ok ? xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4 : xb;
+          cp_async16(slab + ch * C::PLANE_B + v * 16, src, ok);
+        }
+        cp_async_commit();
+      }
+      if (i >= 1) {
+        if (i < nslabs) cp_async_wait<1>(); else cp_async_wait<0>();
+        const int buf = (i - 1) % NS;
+        if constexpr (NSPLIT == 3) {
+          unsigned char* hi_p = a_smem + (size_t)buf * C::NPART * C::SLAB_B;
+          unsigned char* lo_p = hi_p + C::SLAB_B;
+          for (int e = t; e < PIECES; e += kLoaderThreads) {
+            const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
+            float4 v = *reinterpret_cast<float4*>(hi_p + off);
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            *reinterpret_cast<float4*>(hi_p + off) = h;
+            *reinterpret_cast<float4*>(lo_p + off) = l;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(full + buf);
+      }
+    }
+  } else if (warp == 6) {
+    // =============================== MMA issuer (warp-uniform, one elected lane issues) ============================
+    const bool leader = elect_one();
+    const uint32_t b_lo0 = desc_lo(smem_u32(b_smem), N * 16);
+    constexpr uint32_t idesc = make_idesc(128, N);
+    for (int s = 0; s < nsteps; ++s) {
+      const int stage = s & 1;
+      mbar_wait(acc_empty + stage, ((s >> 1) & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz) {
+        const int i = s + dz;
+        const int buf = i % NS;
+        mbar_wait(full + buf, (i / NS) & 1);
+        tc_fence_after();
+        const uint32_t a_lo0 = desc_lo(smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B), C::PLANE_B);
+#pragma unroll
+        for (int dyx = 0; dyx < 4; ++dyx) {
+          const int sh = dz * 4 + dyx;                                   // shift index (dz,dy,dx)
+#pragma unroll
+          for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+            for (int mt = 0; mt < KM; ++mt) {
+              constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
+              const uint32_t a_d = a_lo0 + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) +
+                                   (uint32_t)(mt * 128 + (dyx >> 1) * PW + (dyx & 1));
+              const uint32_t b_d = b_lo0 + (uint32_t)(((sh * C::KS + ks) * C::BBLK_B) >> 4);
+              const uint32_t d = tmem_base + (uint32_t)(stage * KM * N + mt * N);
+              const bool first = (dz == 0 && dyx == 0 && ks == 0);
+              if (leader) {
+                if constexpr (NSPLIT == 3) {
+                  umma_tf32_lohi_acc(d, a_d + kLoOff, b_d, idesc, first ? 0u : 1u);
+                  umma_tf32_lohi_acc(d, a_d, b_d + kBLoOff, idesc, 1u);
+                  umma_tf32_lohi_acc(d, a_d, b_d, idesc, 1u);
+                } else {
+                  umma_tf32_lohi_acc(d, a_d, b_d, idesc, first ? 0u : 1u);
+                }
+              }
+            }
+          }
+        }
+        if (dz == 0 && leader) umma_commit(empty + buf);                 // slab iz is not needed by later steps
+      }
+      if (leader) umma_commit(acc_full + stage);
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // =============================== epilogue ======================================================================
+    const int gx = x0 + lane;
+    const bool col_ok = lane < C::TWI && gx < p.W;
+    const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
+    for (int s = 0; s < nsteps; ++s) {
+      const int stage = s & 1;
+      mbar_wait(acc_full + stage, (s >> 1) & 1);
+      tc_fence_after();
+      const int iz = z0 + s;
+#pragma unroll 1
+      for (int mt = 0; mt < KM; ++mt) {
+        float v[N];
+#pragma unroll
+        for (int c0 = 0; c0 < N; c0 += 16)
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + stage * KM * N + mt * N + c0, &v[c0]);
+        if (mt == KM - 1) {
+          tc_fence_before();
+          mbar_arrive(acc_empty + stage);
+        }
+        const int gy = y0 + mt * 4 + warp;
+        if (!col_ok || gy >= p.H) continue;
+#pragma unroll
+        for (int cls = 0; cls < 8; ++cls) {
+          const int oz = 2 * iz + (cls >> 2), oy = 2 * gy + ((cls >> 1) & 1), ox = 2 * gx + (cls & 1);
+          const int64_t o = ((((int64_t)b * Do + oz) * Ho + oy) * Wo + ox) * COUT;
+#pragma unroll
+          for (int c = 0; c < COUT; c += 4) {
+            float4 r = make_float4(v[cls * COUT + c], v[cls * COUT + c + 1], v[cls * COUT + c + 2], v[cls * COUT + c + 3]);
+            if (p.accumulate_in) {
+              const float4 q = *reinterpret_cast<const float4*>(p.y + o + c);
+              r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+            }
+            if (p.finalize) {
+              if (p.bias) {
+                const float4 q = ldg4(p.bias + c);
+                r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+              }
+              if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+              if (p.skip) {
+                const float4 q = ldg4(p.skip + o + c);
+                r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+              }
+            }
+            st4(p.y + o + c, r);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// Weight image of the transposed convolution: torch ConvTranspose3d weight [Cin_total][Cout][27] x BN scale ->
+//   img[term][shift = dz*4+dy*2+dx][ks][chunk][row = cls*COUT + n][e]; per dimension the tap used by output parity a
+//   with input shift d is k = (a==0 ? (d==0 ? 1 : none) : (d==0 ? 2 : 0)).
+__global__ void pack_umma_tweight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                         float* __restrict__ img, int Cout, int cin_off, int CIN, int nsplit) {
+  const int KS = CIN / 8, N = 8 * Cout;
+  const int per_term = 8 * KS * 2 * N * 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_term) return;
+  const int e = i & 3;
+  int r = i >> 2;
+  const int row = r % N; r /= N;
+  const int chunk = r & 1; r >>= 1;
+  const int ks = r % KS;
+  const int sh = r / KS;
+  const int cls = row / Cout, n = row % Cout;
+  const int par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
+  const int dsh[3] = {sh >> 2, (sh >> 1) & 1, sh & 1};
+  int k[3];
+  bool used = true;
+  for (int a = 0; a < 3; ++a) {
+    if (par[a] == 0) { if (dsh[a] == 0) k[a] = 1; else used = false; }
+    else k[a] = dsh[a] == 0 ? 2 : 0;
+  }
+  float v = 0.f;
+  if (used) {
+    const int ci = cin_off + ks * 8 + chunk * 4 + e;
+    v = w[((int64_t)ci * Cout + n) * 27 + (k[0] * 9 + k[1] * 3 + k[2])];
+    if (scale) v *= scale[n];
+  }
+  if (nsplit == 3) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    img[i] = hi;
+    img[per_term + i] = v - hi;
+  } else {
+    img[i] = v;
+  }
+}
+
+template <int CIN, int COUT, int NSPLIT, int KM, int NS>
+static int launch_t(const Params& p, int B, cudaStream_t st) {
+  using C = TCfg<CIN, COUT, NSPLIT, KM, NS>;
+  static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
+  auto kern = convT3d_umma_kernel<CIN, COUT, NSPLIT, KM, NS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_transpose3d_tc_fwd: cudaFuncSetAttribute: %s",
+                  cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.W, C::TWI), ceil_div(p.H, C::ROWS), B * p.chunks);
+  RCMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_transpose3d_tc_fwd: grid too large");
+  kern<<<grid, kThreads, C::SMEM, st>>>(p);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv_transpose3d_tc_fwd");
+  return RCMVS_OK;
+}
+
+static bool t_supported(int Cin, int Cout) { return (Cin == 16 && Cout == 8) || (Cin == 32 && Cout == 16); }
+// channels per launch (channel groups accumulate through y): B image + slabs must fit 227 KB
+static int t_cin_k(int Cin, int Cout, int nsplit) {
+  if (Cout == 8) return 16;
+  return nsplit == 3 ? 8 : 16;
+}
+
 }  // namespace umma
 }  // namespace rcmvs
 
@@ -567,6 +868,70 @@ extern "C" int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const floa
     else RCMVS_TC_CASE(16, 16, 1, 2, 3); else RCMVS_TC_CASE(16, 16, 3, 2, 3);
     else set_error("rcmvs_conv3d_tc_fwd: no kernel for cin_k=%d Cout=%d nsplit=%d", pl.cin_k, Cout, nsplit);
 #undef RCMVS_TC_CASE
+    if (rc != RCMVS_OK) return rc;
+  }
+  return RCMVS_OK;
+}
+
+extern "C" int64_t rcmvs_conv_transpose3d_tc_weight_floats(int Cin, int Cout, int nsplit) {
+  return (int64_t)(nsplit == 3 ? 2 : 1) * 8 * (Cin / 8) * 2 * (8 * Cout) * 4;
+}
+
+extern "C" int rcmvs_conv_transpose3d_tc_pack(const float* w, const float* scale, float* img, int Cout, int Cin,
+                                              int nsplit, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(w && img, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_tc_pack: null pointer");
+  RCMVS_REQUIRE(umma::t_supported(Cin, Cout) && (nsplit == 1 || nsplit == 3), RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv_transpose3d_tc_pack: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
+  const int cin_k = umma::t_cin_k(Cin, Cout, nsplit);
+  const int terms = nsplit == 3 ? 2 : 1;
+  const int per_term = 8 * (cin_k / 8) * 2 * (8 * Cout) * 4;
+  for (int g = 0; g < Cin / cin_k; ++g)
+    umma::pack_umma_tweight_kernel<<<ceil_div(per_term, 256), 256, 0, as_stream(stream)>>>(
+        w, scale, img + (int64_t)g * terms * per_term, Cout, g * cin_k, cin_k, nsplit);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv_transpose3d_tc_pack");
+  return RCMVS_OK;
+}
+
+extern "C" int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, const float* bias, const float* skip,
+                                             float* y, int B, int D, int H, int W, int Cin, int Cout, int nsplit,
+                                             int relu, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  using namespace rcmvs::umma;
+  RCMVS_REQUIRE(x && wimg && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_tc_fwd: null pointer");
+  RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_tc_fwd: bad dims");
+  RCMVS_REQUIRE(t_supported(Cin, Cout) && (nsplit == 1 || nsplit == 3), RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv_transpose3d_tc_fwd: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
+  const int cin_k = t_cin_k(Cin, Cout, nsplit);
+  const int km = 2, rows = 4 * km;
+  const int cols = ceil_div(W, 31) * ceil_div(H, rows) * B;
+  int chunks = 1;
+  {
+    long best = -1;
+    for (int c = 1; c <= max(1, D / 2); ++c) {
+      const int dc = ceil_div(D, c);
+      const int cc = ceil_div(D, dc);
+      const long cost = (long)ceil_div(cols * cc, 148) * (dc + 1);
+      if (best < 0 || cost < best) { best = cost; chunks = cc; }
+    }
+  }
+  const int d_chunk = ceil_div(D, chunks);
+  chunks = ceil_div(D, d_chunk);
+  const int groups = Cin / cin_k;
+  const int terms = nsplit == 3 ? 2 : 1;
+  const int per_term = 8 * (cin_k / 8) * 2 * (8 * Cout) * 4;
+  cudaStream_t st = as_stream(stream);
+  for (int g = 0; g < groups; ++g) {
+    Params p;
+    p.x = x; p.wimg = wimg + (int64_t)g * terms * per_term; p.bias = bias; p.skip = skip; p.y = y;
+    p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = g * cin_k;
+    p.d_chunk = d_chunk; p.chunks = chunks;
+    p.accumulate_in = g > 0; p.finalize = g == groups - 1; p.relu = relu;
+    int rc = RCMVS_ERR_UNSUPPORTED;
+    if (Cout == 8 && nsplit == 1) rc = launch_t<16, 8, 1, 2, 3>(p, B, st);
+    else if (Cout == 8 && nsplit == 3) rc = launch_t<16, 8, 3, 2, 3>(p, B, st);
+    else if (Cout == 16 && nsplit == 1) rc = launch_t<16, 16, 1, 2, 3>(p, B, st);
+    else if (Cout == 16 && nsplit == 3) rc = launch_t<8, 16, 3, 2, 3>(p, B, st);
     if (rc != RCMVS_OK) return rc;
   }
   return RCMVS_OK;

@@ -244,7 +244,13 @@ class CostRegNet(nn.Module):
                     cout, cin = (w.shape[1], w.shape[0]) if tr else (w.shape[0], w.shape[1])
                     use_tc = (nsplit > 0 and not tr and conv.stride[0] == 1 and (cin, cout) in ops.TC_SUPPORTED
                               and cin <= int(os.environ.get("RCMVS_TC_MAXCIN", "32")))
-                    if use_tc:
+                    if cout == 1 and os.environ.get("RCMVS_PROB", "direct") == "direct":
+                        use_tc = False      # 8->1 `prob`: memory-bound, the fp32 FFMA kernel is faster (profiles/)
+                    use_tct = (nsplit > 0 and tr and (cin, cout) in ops.TCT_SUPPORTED
+                               and os.environ.get("RCMVS_TCT", "1") == "1")
+                    if use_tct:
+                        P[name] = ("tct", ops.conv_transpose3d_tc_pack(w, scale, nsplit), shift, cout, nsplit)
+                    elif use_tc:
                         P[name] = ("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit)
                     else:
                         P[name] = ("direct", ops.pack_conv3d_weight(w, scale, tr), shift)
@@ -265,9 +271,13 @@ class CostRegNet(nn.Module):
         c2 = cv(cv(c0, P["conv1"], stride=2), P["conv2"])
         c4 = cv(cv(c2, P["conv3"], stride=2), P["conv4"])
         y = cv(cv(c4, P["conv5"], stride=2), P["conv6"])
-        y = ops.conv_transpose3d(y, *P["conv7"][1:3], skip=c4)      # conv4 + relu(bn(convT(x)))  (modules.py:497)
-        y = ops.conv_transpose3d(y, *P["conv9"][1:3], skip=c2)
-        y = ops.conv_transpose3d(y, *P["conv11"][1:3], skip=c0)
+        def up(t, spec, skip):                                      # skip + relu(bn(convT(t)))  (modules.py:497-499)
+            if spec[0] == "tct":
+                return ops.conv_transpose3d_tc(t, spec[1], spec[3], spec[2], skip, spec[4], True)
+            return ops.conv_transpose3d(t, spec[1], spec[2], skip=skip)
+        y = up(y, P["conv7"], c4)
+        y = up(y, P["conv9"], c2)
+        y = up(y, P["conv11"], c0)
         return cv(y, P["prob"], relu=False).squeeze(-1)
 
     def forward(self, x):

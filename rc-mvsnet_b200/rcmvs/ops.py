@@ -175,6 +175,28 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     return y
 
 
+TCT_SUPPORTED = {(16, 8), (32, 16)}      # (Cin, Cout) of conv11 / conv9 (transposed)
+
+
+def conv_transpose3d_tc_pack(w, scale=None, nsplit=3):
+    """torch ConvTranspose3d weight [Cin,Cout,3,3,3] (x BN scale) -> operand image of the tcgen05 convT kernel."""
+    Cin, Cout = w.shape[:2]
+    n = _ffi.lib().rcmvs_conv_transpose3d_tc_weight_floats(Cin, Cout, nsplit)
+    img = torch.empty((n,), device=w.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv_transpose3d_tc_pack", _chk(w, "w"), _opt(scale, "scale"), _chk(img, "img"), Cout, Cin,
+              nsplit, _stream())
+    return img
+
+
+def conv_transpose3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
+    """x_cl [B,D,H,W,Cin] -> [B,2D,2H,2W,Cout] on tcgen05.mma (k3, s2, p1, output_padding 1)."""
+    B, D, H, W, Cin = x_cl.shape
+    y = torch.empty((B, 2 * D, 2 * H, 2 * W, Cout), device=x_cl.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv_transpose3d_tc_fwd", _chk(x_cl, "x"), _chk(img, "wimg"), _opt(bias, "bias"),
+              _opt(skip, "skip"), _chk(y, "y"), B, D, H, W, Cin, Cout, nsplit, 1 if relu else 0, _stream())
+    return y
+
+
 # ---- regression -----------------------------------------------------------------------------------------------
 def softargmin_conf(cost, planes, want_idx=False, want_prob=False):
     """cost [B,D,h,w]; planes [B,D] or [B,D,h,w] -> depth [B,h,w], conf [B,h,w] (, idx int32, prob)."""

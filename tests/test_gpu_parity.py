@@ -246,6 +246,27 @@ def test_conv_transpose3d_vs_oracle(dev, cin, cout, dhw):
     np.testing.assert_allclose(got[0].permute(3, 0, 1, 2).cpu().numpy(), want + skip, atol=2e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("nsplit", [3, 1])
+@pytest.mark.parametrize("cin,cout,dhw", [(16, 8, (3, 9, 35)), (16, 8, (1, 1, 1)), (16, 8, (7, 17, 62)),
+                                          (32, 16, (3, 6, 33)), (32, 16, (5, 12, 31))])
+def test_conv_transpose3d_tensor_core_vs_oracle(dev, cin, cout, dhw, nsplit):
+    from rcmvs import ops
+    rng = np.random.default_rng(cin * 7 + cout + nsplit)
+    D, H, W = dhw
+    x = rng.standard_normal((cin, D, H, W), dtype=np.float32)
+    w = (rng.standard_normal((cin, cout, 3, 3, 3)) / np.sqrt(27 * cin / 8)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    want = np.maximum(O.conv_transpose3d(x, w * scale[None, :, None, None, None]) + bias[:, None, None, None], 0)
+    skip = rng.standard_normal(want.shape, dtype=np.float32)
+    img = ops.conv_transpose3d_tc_pack(cu(w, dev), cu(scale, dev), nsplit)
+    got = ops.conv_transpose3d_tc(cu(x.transpose(1, 2, 3, 0)[None], dev), img, cout, cu(bias, dev),
+                                  cu(skip.transpose(1, 2, 3, 0)[None], dev), nsplit, True)
+    assert got.shape[1:4] == (2 * D, 2 * H, 2 * W)
+    tol = 3e-5 if nsplit == 3 else 6e-3
+    np.testing.assert_allclose(got[0].permute(3, 0, 1, 2).cpu().numpy(), want + skip, atol=tol, rtol=tol)
+
+
 def _model(dev, ndepths, cls_name="CascadeMVSNet_eval"):
     import models
     from rcmvs import weights
