@@ -171,7 +171,7 @@ def kernel_rooflines(model, dev, inputs, pk):
             var = ops.costvolume_variance(feats[key], rt, hyp)
             cr = model.cost_regularization[s]
             P = cr.packed()
-            ms0 = time_kernel(lambda: cr._conv(var, P["conv0"]), 5, stream)
+            ms0 = time_kernel(lambda: cr._run(P["conv0"], var), 5, stream)
             fl = conv_flops(C, 8, D * h * w)
             # conv0 is the dominant CostRegNet layer; tensor roofline = TF32 dense = half the measured bf16 peak
             tf32_peak = pk["bf16_tflops"] / 2
@@ -186,7 +186,9 @@ def kernel_rooflines(model, dev, inputs, pk):
             depth, _ = ops.softargmin_conf(cost, hyp)
             del var, cost
         msf = time_kernel(lambda: model.feature(imgs.reshape(V, 3, H, W)), 5, stream)
-        res["featurenet_library"] = {"ms": round(msf, 4)}
+        res["featurenet"] = {"ms": round(msf, 4)}
+        res["engines"] = {"stage%d" % (i + 1): {k: list(v.values())[0] for k, v in cr.engines().items() if v}
+                          for i, cr in enumerate(model.cost_regularization)}
     return res
 
 
@@ -357,7 +359,7 @@ def main():
     s1 = (roof_all or {}).get("costvolume_var_stage1")
     roofline = None
     if s1:
-        roofline = {"kernel": "costvolume_var_kernel<32> (stage 1, D=192, 128x160, V=5)", "bound": "hbm",
+        roofline = {"kernel": "costvolume_var_v2_kernel<32> (stage 1, D=192, 128x160, V=5)", "bound": "hbm",
                     "achieved": s1["achieved"], "peak": s1["peak"], "unit": "GB/s", "frac": s1["frac"],
                     "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": None}
     line = {

@@ -225,7 +225,10 @@ class CostRegNet(nn.Module):
         self._packed = None
 
     def packed(self):
-        """{layer: (packed_w [27,Cin,Cout], bias [Cout])}, rebuilt when any parameter/buffer changes."""
+        """{layer: [candidate engines]} rebuilt when any parameter/buffer or the precision mode changes.  Every
+        candidate computes the same layer (conv + folded BN + bias + ReLU + skip); which one runs is decided per
+        input shape by a one-off on-device timing (`_run`), because the winner depends on Cin/Cout/resolution:
+        the tcgen05 kernels win on the full/half-resolution layers, the FFMA kernels on tiny deep levels."""
         mode = conv_precision()
         key = (_versions(self), mode)
         if self._packed is None or self._packed[0] != key:
@@ -234,51 +237,79 @@ class CostRegNet(nn.Module):
                 P = {}
                 for name in self._LAYERS + ("prob",):
                     if name == "prob":
-                        conv, scale, shift, tr = self.prob, None, None, False
+                        conv, scale, shift, tr, relu = self.prob, None, None, False, False
                     else:
                         blk = getattr(self, name)
-                        conv = blk.conv
+                        conv, relu = blk.conv, True
                         scale, shift = (t.contiguous() for t in fold_bn(blk.bn))
                         tr = isinstance(conv, nn.ConvTranspose3d)
                     w = conv.weight.detach().contiguous()
                     cout, cin = (w.shape[1], w.shape[0]) if tr else (w.shape[0], w.shape[1])
-                    use_tc = (nsplit > 0 and not tr and conv.stride[0] == 1 and (cin, cout) in ops.TC_SUPPORTED
-                              and cin <= int(os.environ.get("RCMVS_TC_MAXCIN", "32")))
-                    if cout == 1 and os.environ.get("RCMVS_PROB", "direct") == "direct":
-                        use_tc = False      # 8->1 `prob`: memory-bound, the fp32 FFMA kernel is faster (profiles/)
-                    use_tct = (nsplit > 0 and tr and (cin, cout) in ops.TCT_SUPPORTED
-                               and os.environ.get("RCMVS_TCT", "1") == "1")
-                    if use_tct:
-                        P[name] = ("tct", ops.conv_transpose3d_tc_pack(w, scale, nsplit), shift, cout, nsplit)
-                    elif use_tc:
-                        P[name] = ("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit)
-                    else:
-                        P[name] = ("direct", ops.pack_conv3d_weight(w, scale, tr), shift)
+                    stride = conv.stride[0]
+                    cands = [("direct", ops.pack_conv3d_weight(w, scale, tr), shift)]
+                    if nsplit > 0 and tr and (cin, cout) in ops.TCT_SUPPORTED:
+                        cands.append(("tct", ops.conv_transpose3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
+                    if nsplit > 0 and not tr and stride == 1 and (cin, cout) in ops.TC_SUPPORTED:
+                        cands.append(("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
+                    P[name] = {"cands": cands, "tr": tr, "stride": stride, "relu": relu, "choice": {}}
             self._packed = (key, P)
         return self._packed[1]
 
     @staticmethod
-    def _conv(x, spec, skip=None, stride=1, relu=True):
-        if spec[0] == "tc":
-            _, img, bias, cout, nsplit = spec
-            return ops.conv3d_tc(x, img, cout, bias, skip, nsplit, relu)
-        return ops.conv3d(x, spec[1], spec[2], skip, stride=stride, relu=relu)
+    def _call(cand, layer, x, skip):
+        kind = cand[0]
+        if kind == "tc":
+            return ops.conv3d_tc(x, cand[1], cand[3], cand[2], skip, cand[4], layer["relu"])
+        if kind == "tct":
+            return ops.conv_transpose3d_tc(x, cand[1], cand[3], cand[2], skip, cand[4], layer["relu"])
+        if layer["tr"]:
+            return ops.conv_transpose3d(x, cand[1], cand[2], skip=skip, relu=layer["relu"])
+        return ops.conv3d(x, cand[1], cand[2], skip, stride=layer["stride"], relu=layer["relu"])
+
+    @classmethod
+    def _run(cls, layer, x, skip=None):
+        """Run a layer with the fastest engine for this input shape (timed once with CUDA events, then cached)."""
+        cands = layer["cands"]
+        if len(cands) == 1:
+            return cls._call(cands[0], layer, x, skip)
+        key = tuple(x.shape)
+        if key not in layer["choice"]:
+            forced = os.environ.get("RCMVS_ENGINE")            # 'direct' | 'tc' : disable the autotuner
+            if forced:
+                layer["choice"][key] = next((i for i, c in enumerate(cands) if c[0].startswith(forced)), 0)
+            else:
+                best, best_ms = 0, float("inf")
+                for i, c in enumerate(cands):
+                    cls._call(c, layer, x, skip)               # warm-up (sets kernel attributes)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(3):
+                        cls._call(c, layer, x, skip)
+                    e1.record()
+                    e1.synchronize()
+                    ms = e0.elapsed_time(e1)
+                    if ms < best_ms:
+                        best, best_ms = i, ms
+                layer["choice"][key] = best
+        return cls._call(cands[layer["choice"][key]], layer, x, skip)
+
+    def engines(self):
+        """{layer: {input shape: engine name}} chosen so far (bench.py reports it)."""
+        if self._packed is None:
+            return {}
+        return {n: {str(k): l["cands"][i][0] for k, i in l["choice"].items()} for n, l in self._packed[1].items()}
 
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cin] channels-last -> cost [B,D,h,w]."""
-        P, cv = self.packed(), self._conv
-        c0 = cv(x_cl, P["conv0"])
-        c2 = cv(cv(c0, P["conv1"], stride=2), P["conv2"])
-        c4 = cv(cv(c2, P["conv3"], stride=2), P["conv4"])
-        y = cv(cv(c4, P["conv5"], stride=2), P["conv6"])
-        def up(t, spec, skip):                                      # skip + relu(bn(convT(t)))  (modules.py:497-499)
-            if spec[0] == "tct":
-                return ops.conv_transpose3d_tc(t, spec[1], spec[3], spec[2], skip, spec[4], True)
-            return ops.conv_transpose3d(t, spec[1], spec[2], skip=skip)
-        y = up(y, P["conv7"], c4)
-        y = up(y, P["conv9"], c2)
-        y = up(y, P["conv11"], c0)
-        return cv(y, P["prob"], relu=False).squeeze(-1)
+        P, run = self.packed(), self._run
+        c0 = run(P["conv0"], x_cl)
+        c2 = run(P["conv2"], run(P["conv1"], c0))
+        c4 = run(P["conv4"], run(P["conv3"], c2))
+        y = run(P["conv6"], run(P["conv5"], c4))
+        y = run(P["conv7"], y, c4)                               # skip + relu(bn(convT(y)))  (modules.py:497-499)
+        y = run(P["conv9"], y, c2)
+        y = run(P["conv11"], y, c0)
+        return run(P["prob"], y).squeeze(-1)
 
     def forward(self, x):
         """x [B,C,D,h,w] -> [B,1,D,h,w] (reference signature)."""
