@@ -22,7 +22,7 @@
 // Precision: NSPLIT=1 plain TF32 (what cuDNN gives the reference on GPU under torch defaults);
 //            NSPLIT=3 error-compensated 3xTF32: x = x_hi + x_lo, w = w_hi + w_lo, acc += x_lo·w_hi + x_hi·w_lo + x_hi·w_hi.
 //
-// Warp roles (224 threads): warps 0-3 epilogue, warps 4-5 slab loaders (cp.async + hi/lo split), warp 6 MMA issuer.
+// Warp roles (288 threads): warps 0-3 epilogue, warps 4-7 slab loaders (cp.async + hi/lo split), warp 8 MMA issuer.
 #include "common.cuh"
 
 namespace rcmvs {
@@ -30,8 +30,8 @@ namespace umma {
 
 constexpr int PW = 32;           // padded plane width (voxels)
 constexpr int TW = 30;           // real output columns per tile
-constexpr int kThreads = 224;
-constexpr int kLoaderThreads = 64;
+constexpr int kThreads = 288;          // warps 0-3 epilogue, 4-7 loaders, 8 MMA issuer
+constexpr int kLoaderThreads = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -140,6 +140,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
   const uint32_t z = 0u;
   asm volatile(
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= 4 && warp < 6) {
+  if (warp >= 4 && warp < 8) {
     // =============================== slab loaders (64 threads) ===================================================
     const int t = threadIdx.x - 128;
     constexpr int PIECES = C::ROWS * PW * C::NCH;
@@ -252,13 +261,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
         const int z = d0 - 1 + i;
         const bool zok = (z >= 0) && (z < p.D);
         const uint32_t slab = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
-        for (int e = t; e < PIECES; e += kLoaderThreads) {
-          const int ch = e % C::NCH;
-          const int v = e / C::NCH;
-          const int gy = y0 - 1 + v / PW, gx = x0 - 1 + (v % PW);
-          const bool ok = zok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-          const float* src = ok ? xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4 : xb;
-          cp_async16(slab + ch * C::PLANE_B + v * 16, src, ok);
+        // thread -> fixed channel chunk `ch` and column phase; rows advance in the outer loop (no div/mod per piece)
+        {
+          constexpr int VSTEP = kLoaderThreads / C::NCH;          // voxels covered by the loader threads per pass
+          static_assert(VSTEP >= PW ? (VSTEP % PW == 0) : (PW % VSTEP == 0), "loader mapping");
+          const int ch = t % C::NCH, v0 = t / C::NCH;
+          const float* zbase = xb + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
+          const uint32_t dst0 = slab + ch * C::PLANE_B;
+          if constexpr (VSTEP >= PW) {
+            constexpr int RSTEP = VSTEP / PW;
+            const int col = v0 % PW, gx = x0 - 1 + col;
+            const bool xok = zok && gx >= 0 && gx < p.W;
+            for (int row = v0 / PW; row < C::ROWS; row += RSTEP) {
+              const int gy = y0 - 1 + row;
+              const bool ok = xok && gy >= 0 && gy < p.H;
+              const float* src = ok ? zbase + ((int64_t)gy * p.W + gx) * vox_stride : xb;
+              cp_async16(dst0 + (row * PW + col) * 16, src, ok);
+            }
+          } else {
+            for (int row = 0; row < C::ROWS; ++row) {
+              const int gy = y0 - 1 + row;
+              const bool yok = zok && gy >= 0 && gy < p.H;
+              const float* rbase = zbase + (int64_t)gy * p.W * vox_stride;
+#pragma unroll
+              for (int col = v0; col < PW; col += VSTEP) {
+                const int gx = x0 - 1 + col;
+                const bool ok = yok && gx >= 0 && gx < p.W;
+                const float* src = ok ? rbase + (int64_t)gx * vox_stride : xb;
+                cp_async16(dst0 + (row * PW + col) * 16, src, ok);
+              }
+            }
+          }
         }
         cp_async_commit();
       }
@@ -284,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
         mbar_arrive(full + buf);
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 8) {
     // =============================== MMA issuer ==================================================================
     // The whole warp runs the (warp-uniform) control flow so descriptor arithmetic stays on the uniform datapath;
     // one elected lane issues tcgen05.mma / tcgen05.commit.
@@ -352,15 +385,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
       const int g = q % NG;
       mbar_wait(grp_full + g, (q / NG) & 1);
       tc_fence_after();
-      float v[KM][G];
+      uint32_t vr[KM][G];
 #pragma unroll
       for (int mt = 0; mt < KM; ++mt) {
         const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + mt * (NG * G) + g * G;
 #pragma unroll
-        for (int c0 = 0; c0 < G; c0 += 16) tmem_ld16(ta + c0, &v[mt][c0]);
+        for (int c0 = 0; c0 < G; c0 += 16) tmem_ld16_nowait(ta + c0, &vr[mt][c0]);
+      }
+      tmem_ld_wait();                                            // one wait for all loads of this plane
+#pragma unroll
+      for (int mt = 0; mt < KM; ++mt) {
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + mt * (NG * G) + g * G;
 #pragma unroll
         for (int c0 = 0; c0 < G; c0 += 16) tmem_st16_zero(ta + c0);
       }
+      float v[KM][G];
+#pragma unroll
+      for (int mt = 0; mt < KM; ++mt)
+#pragma unroll
+        for (int c = 0; c < G; ++c) v[mt][c] = __uint_as_float(vr[mt][c]);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(grp_free + g);
@@ -583,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) convT3d_umma_kernel(const Params 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 6) {
+  if (warp >= 4 && warp < 8) {
     // =============================== slab loaders ================================================================
     const int t = threadIdx.x - 128;
     constexpr int PIECES = (C::ROWS + 1) * PW * C::NCH;
@@ -626,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) convT3d_umma_kernel(const Params 
         mbar_arrive(full + buf);
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 8) {
     // =============================== MMA issuer (warp-uniform, one elected lane issues) ============================
     const bool leader = elect_one();
     const uint32_t b_lo0 = desc_lo(smem_u32(b_smem), N * 16);
