@@ -22,7 +22,7 @@
 // Precision: NSPLIT=1 plain TF32 (what cuDNN gives the reference on GPU under torch defaults);
 //            NSPLIT=3 error-compensated 3xTF32: x = x_hi + x_lo, w = w_hi + w_lo, acc += x_lo·w_hi + x_hi·w_lo + x_hi·w_hi.
 //
-// Warp roles (288 threads): warps 0-3 epilogue, warps 4-7 slab loaders (cp.async + hi/lo split), warp 8 MMA issuer.
+// Warp roles: warps 0-3 epilogue, 2 loader warps per slab buffer (cp.async + hi/lo split), last warp MMA issuer.
 #include "common.cuh"
 
 namespace rcmvs {
@@ -30,8 +30,9 @@ namespace umma {
 
 constexpr int PW = 32;           // padded plane width (voxels)
 constexpr int TW = 30;           // real output columns per tile
-constexpr int kThreads = 288;          // warps 0-3 epilogue, 4-7 loaders, 8 MMA issuer
-constexpr int kLoaderThreads = 128;
+constexpr int kWPB = 2;                  // loader warps per slab buffer
+constexpr int kLoaderThreads = 32 * kWPB;   // threads filling ONE slab buffer (they own it for the whole kernel)
+__host__ __device__ constexpr int threads_for(int ns) { return 32 * (4 + kWPB * ns + 1); }   // epilogue + loaders + MMA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -195,7 +196,7 @@ struct Params {
 };
 
 template <int CIN, int COUT, int NSPLIT, int KM, int NS>
-__global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p) {
+__global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const Params p) {
   using C = Cfg<CIN, COUT, NSPLIT, KM, NS>;
   constexpr int G = C::G, NG = C::NG, CP = C::CP;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
   {
     const float4* src = reinterpret_cast<const float4*>(p.wimg);
     float4* dst = reinterpret_cast<float4*>(b_smem);
-    for (int i = threadIdx.x; i < C::B_BYTES / 16; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < C::B_BYTES / 16; i += threads_for(NS)) dst[i] = __ldg(src + i);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -250,74 +251,60 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= 4 && warp < 8) {
-    // =============================== slab loaders (64 threads) ===================================================
-    const int t = threadIdx.x - 128;
+  if (warp >= 4 && warp < 4 + kWPB * NS) {
+    // =============================== slab loaders ================================================================
+    // kWPB warps own one ring buffer each for the whole kernel: wait until the MMA warp released it, fill it with
+    // cp.async, wait for the data, (split hi/lo), publish.  The NS buffers run independent load->MMA->free cycles,
+    // so global-memory latency of one slab overlaps the MMAs of the others.
+    const int mybuf = (warp - 4) / kWPB;
+    const int t = (warp - 4) % kWPB * 32 + lane;
     constexpr int PIECES = C::ROWS * PW * C::NCH;
-    for (int i = 0; i <= nslabs; ++i) {
-      if (i < nslabs) {
-        const int buf = i % NS;
-        mbar_wait(empty + buf, ((i / NS) & 1) ^ 1);
-        const int z = d0 - 1 + i;
-        const bool zok = (z >= 0) && (z < p.D);
-        const uint32_t slab = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
-        // thread -> fixed channel chunk `ch` and column phase; rows advance in the outer loop (no div/mod per piece)
-        {
-          constexpr int VSTEP = kLoaderThreads / C::NCH;          // voxels covered by the loader threads per pass
-          static_assert(VSTEP >= PW ? (VSTEP % PW == 0) : (PW % VSTEP == 0), "loader mapping");
-          const int ch = t % C::NCH, v0 = t / C::NCH;
-          const float* zbase = xb + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
-          const uint32_t dst0 = slab + ch * C::PLANE_B;
-          if constexpr (VSTEP >= PW) {
-            constexpr int RSTEP = VSTEP / PW;
-            const int col = v0 % PW, gx = x0 - 1 + col;
-            const bool xok = zok && gx >= 0 && gx < p.W;
-            for (int row = v0 / PW; row < C::ROWS; row += RSTEP) {
-              const int gy = y0 - 1 + row;
-              const bool ok = xok && gy >= 0 && gy < p.H;
-              const float* src = ok ? zbase + ((int64_t)gy * p.W + gx) * vox_stride : xb;
-              cp_async16(dst0 + (row * PW + col) * 16, src, ok);
-            }
-          } else {
-            for (int row = 0; row < C::ROWS; ++row) {
-              const int gy = y0 - 1 + row;
-              const bool yok = zok && gy >= 0 && gy < p.H;
-              const float* rbase = zbase + (int64_t)gy * p.W * vox_stride;
+    const uint32_t slab = smem_u32(a_smem + (size_t)mybuf * C::NPART * C::SLAB_B);
+    for (int i = mybuf; i < nslabs; i += NS) {
+      mbar_wait(empty + mybuf, ((i / NS) & 1) ^ 1);
+      const int z = d0 - 1 + i;
+      const bool zok = (z >= 0) && (z < p.D);
+      {
+        constexpr int VSTEP = kLoaderThreads / C::NCH;          // voxels covered by the buffer's threads per pass
+        static_assert(PW % VSTEP == 0, "loader mapping");
+        const int ch = t % C::NCH, v0 = t / C::NCH;
+        const float* zbase = xb + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
+        const uint32_t dst0 = slab + ch * C::PLANE_B;
+        for (int row = 0; row < C::ROWS; ++row) {
+          const int gy = y0 - 1 + row;
+          const bool yok = zok && gy >= 0 && gy < p.H;
+          const float* rbase = zbase + (int64_t)gy * p.W * vox_stride;
 #pragma unroll
-              for (int col = v0; col < PW; col += VSTEP) {
-                const int gx = x0 - 1 + col;
-                const bool ok = yok && gx >= 0 && gx < p.W;
-                const float* src = ok ? rbase + (int64_t)gx * vox_stride : xb;
-                cp_async16(dst0 + (row * PW + col) * 16, src, ok);
-              }
-            }
+          for (int col = v0; col < PW; col += VSTEP) {
+            const int gx = x0 - 1 + col;
+            const bool ok = yok && gx >= 0 && gx < p.W;
+            const float* src = ok ? rbase + (int64_t)gx * vox_stride : xb;
+            cp_async16(dst0 + (row * PW + col) * 16, src, ok);
           }
         }
-        cp_async_commit();
       }
-      if (i >= 1) {
-        if (i < nslabs) cp_async_wait<1>(); else cp_async_wait<0>();
-        const int buf = (i - 1) % NS;
-        if constexpr (NSPLIT == 3) {
-          unsigned char* hi_p = a_smem + (size_t)buf * C::NPART * C::SLAB_B;
-          unsigned char* lo_p = hi_p + C::SLAB_B;
-          for (int e = t; e < PIECES; e += kLoaderThreads) {
-            const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
-            float4 v = *reinterpret_cast<float4*>(hi_p + off);
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-            *reinterpret_cast<float4*>(hi_p + off) = h;
-            *reinterpret_cast<float4*>(lo_p + off) = l;
-          }
+      cp_async_commit();
+      cp_async_wait<0>();
+      if constexpr (NSPLIT == 3) {
+        // x = hi + lo with hi = x & 0xFFFFE000 (exactly representable in TF32); each thread splits its own pieces
+        unsigned char* hi_p = a_smem + (size_t)mybuf * C::NPART * C::SLAB_B;
+        unsigned char* lo_p = hi_p + C::SLAB_B;
+        for (int e = t; e < PIECES; e += kLoaderThreads) {
+          const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
+          float4 v = *reinterpret_cast<float4*>(hi_p + off);
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          *reinterpret_cast<float4*>(hi_p + off) = h;
+          *reinterpret_cast<float4*>(lo_p + off) = l;
         }
-        fence_proxy_async();
-        mbar_arrive(full + buf);
       }
+      fence_proxy_async();
+      mbar_arrive(full + mybuf);
     }
-  } else if (warp == 8) {
+  } else if (warp == 4 + kWPB * NS) {
     // =============================== MMA issuer ==================================================================
     // The whole warp runs the (warp-uniform) control flow so descriptor arithmetic stays on the uniform datapath;
     // one elected lane issues tcgen05.mma / tcgen05.commit.
@@ -377,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_umma_kernel(const Params p
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp < 4) {
     // =============================== epilogue (128 threads) ======================================================
     const int gx = x0 + lane;
     const bool col_ok = lane < TW && gx < p.W;
@@ -528,7 +515,7 @@ static int launch(const Params& p, int B, cudaStream_t st) {
   }
   dim3 grid(ceil_div(p.W, TW), ceil_div(p.H, C::OROWS), B * p.chunks);
   RCMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_tc_fwd: grid too large");
-  kern<<<grid, kThreads, C::SMEM, st>>>(p);
+  kern<<<grid, threads_for(NS), C::SMEM, st>>>(p);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_tc_fwd");
   return RCMVS_OK;
 }
@@ -581,7 +568,7 @@ struct TCfg {
 };
 
 template <int CIN, int COUT, int NSPLIT, int KM, int NS>
-__global__ void __launch_bounds__(kThreads, 1) convT3d_umma_kernel(const Params p) {
+__global__ void __launch_bounds__(threads_for(NS), 1) convT3d_umma_kernel(const Params p) {
   using C = TCfg<CIN, COUT, NSPLIT, KM, NS>;
   constexpr int N = C::N;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -618,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) convT3d_umma_kernel(const Params 
   {
     const float4* src = reinterpret_cast<const float4*>(p.wimg);
     float4* dst = reinterpret_cast<float4*>(b_smem);
-    for (int i = threadIdx.x; i < C::B_BYTES / 16; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < C::B_BYTES / 16; i += threads_for(NS)) dst[i] = __ldg(src + i);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -626,50 +613,45 @@ __global__ void __launch_bounds__(kThreads, 1) convT3d_umma_kernel(const Params 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // =============================== slab loaders ================================================================
-    const int t = threadIdx.x - 128;
+  if (warp >= 4 && warp < 4 + kWPB * NS) {
+    // =============================== slab loaders (kWPB warps own one ring buffer each) ============================
+    const int mybuf = (warp - 4) / kWPB;
+    const int t = (warp - 4) % kWPB * 32 + lane;
     constexpr int PIECES = (C::ROWS + 1) * PW * C::NCH;
-    for (int i = 0; i <= nslabs; ++i) {
-      if (i < nslabs) {
-        const int buf = i % NS;
-        mbar_wait(empty + buf, ((i / NS) & 1) ^ 1);
-        const int z = z0 + i;
-        const bool zok = z < p.D;
-        const uint32_t slab = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
+    const uint32_t slab = smem_u32(a_smem + (size_t)mybuf * C::NPART * C::SLAB_B);
+    for (int i = mybuf; i < nslabs; i += NS) {
+      mbar_wait(empty + mybuf, ((i / NS) & 1) ^ 1);
+      const int z = z0 + i;
+      const bool zok = z < p.D;
+      for (int e = t; e < PIECES; e += kLoaderThreads) {
+        const int ch = e % C::NCH;
+        const int v = e / C::NCH;
+        const int gy = y0 + v / PW, gx = x0 + (v % PW);
+        const bool ok = zok && gy < p.H && gx < p.W;
+        const float* src = ok ? xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4 : xb;
+        cp_async16(slab + ch * C::PLANE_B + v * 16, src, ok);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      if constexpr (NSPLIT == 3) {
+        unsigned char* hi_p = a_smem + (size_t)mybuf * C::NPART * C::SLAB_B;
+        unsigned char* lo_p = hi_p + C::SLAB_B;
         for (int e = t; e < PIECES; e += kLoaderThreads) {
-          const int ch = e % C::NCH;
-          const int v = e / C::NCH;
-          const int gy = y0 + v / PW, gx = x0 + (v % PW);
-          const bool ok = zok && gy < p.H && gx < p.W;
-          const float* src = ok ? xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4 : xb;
-          cp_async16(slab + ch * C::PLANE_B + v * 16, src, ok);
+          const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
+          float4 v = *reinterpret_cast<float4*>(hi_p + off);
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          *reinterpret_cast<float4*>(hi_p + off) = h;
+          *reinterpret_cast<float4*>(lo_p + off) = l;
         }
-        cp_async_commit();
       }
-      if (i >= 1) {
-        if (i < nslabs) cp_async_wait<1>(); else cp_async_wait<0>();
-        const int buf = (i - 1) % NS;
-        if constexpr (NSPLIT == 3) {
-          unsigned char* hi_p = a_smem + (size_t)buf * C::NPART * C::SLAB_B;
-          unsigned char* lo_p = hi_p + C::SLAB_B;
-          for (int e = t; e < PIECES; e += kLoaderThreads) {
-            const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
-            float4 v = *reinterpret_cast<float4*>(hi_p + off);
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-            *reinterpret_cast<float4*>(hi_p + off) = h;
-            *reinterpret_cast<float4*>(lo_p + off) = l;
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(full + buf);
-      }
+      fence_proxy_async();
+      mbar_arrive(full + mybuf);
     }
-  } else if (warp == 8) {
+  } else if (warp == 4 + kWPB * NS) {
     // =============================== MMA issuer (warp-uniform, one elected lane issues) ============================
     const bool leader = elect_one();
     const uint32_t b_lo0 = desc_lo(smem_u32(b_smem), N * 16);
@@ -828,7 +810,7 @@ static int launch_t(const Params& p, int B, cudaStream_t st) {
   }
   dim3 grid(ceil_div(p.W, C::TWI), ceil_div(p.H, C::ROWS), B * p.chunks);
   RCMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_transpose3d_tc_fwd: grid too large");
-  kern<<<grid, kThreads, C::SMEM, st>>>(p);
+  kern<<<grid, threads_for(NS), C::SMEM, st>>>(p);
   RCMVS_CHECK_LAUNCH("rcmvs_conv_transpose3d_tc_fwd");
   return RCMVS_OK;
 }
@@ -904,11 +886,11 @@ extern "C" int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const floa
     int rc = RCMVS_ERR_UNSUPPORTED;
 #define RCMVS_TC_CASE(CI, CO, NSP, KMV, NSV) \
   if (pl.cin_k == CI && Cout == CO && nsplit == NSP) rc = launch<CI, CO, NSP, KMV, NSV>(p, B, st)
-    RCMVS_TC_CASE(8, 8, 1, 3, 3); else RCMVS_TC_CASE(8, 8, 3, 3, 3);
-    else RCMVS_TC_CASE(16, 8, 1, 3, 3); else RCMVS_TC_CASE(16, 8, 3, 3, 3);
+    RCMVS_TC_CASE(8, 8, 1, 3, 6); else RCMVS_TC_CASE(8, 8, 3, 3, 5);
+    else RCMVS_TC_CASE(16, 8, 1, 3, 5); else RCMVS_TC_CASE(16, 8, 3, 3, 3);
     else RCMVS_TC_CASE(32, 8, 1, 3, 3);
-    else RCMVS_TC_CASE(8, 1, 1, 3, 3); else RCMVS_TC_CASE(8, 1, 3, 3, 3);
-    else RCMVS_TC_CASE(16, 16, 1, 2, 3); else RCMVS_TC_CASE(16, 16, 3, 2, 3);
+    else RCMVS_TC_CASE(8, 1, 1, 3, 6); else RCMVS_TC_CASE(8, 1, 3, 3, 5);
+    else RCMVS_TC_CASE(16, 16, 1, 2, 5); else RCMVS_TC_CASE(16, 16, 3, 2, 3);
     else set_error("rcmvs_conv3d_tc_fwd: no kernel for cin_k=%d Cout=%d nsplit=%d", pl.cin_k, Cout, nsplit);
 #undef RCMVS_TC_CASE
     if (rc != RCMVS_OK) return rc;
@@ -971,10 +953,10 @@ extern "C" int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, 
     p.d_chunk = d_chunk; p.chunks = chunks;
     p.accumulate_in = g > 0; p.finalize = g == groups - 1; p.relu = relu;
     int rc = RCMVS_ERR_UNSUPPORTED;
-    if (Cout == 8 && nsplit == 1) rc = launch_t<16, 8, 1, 2, 3>(p, B, st);
+    if (Cout == 8 && nsplit == 1) rc = launch_t<16, 8, 1, 2, 5>(p, B, st);
     else if (Cout == 8 && nsplit == 3) rc = launch_t<16, 8, 3, 2, 3>(p, B, st);
-    else if (Cout == 16 && nsplit == 1) rc = launch_t<16, 16, 1, 2, 3>(p, B, st);
-    else if (Cout == 16 && nsplit == 3) rc = launch_t<8, 16, 3, 2, 3>(p, B, st);
+    else if (Cout == 16 && nsplit == 1) rc = launch_t<16, 16, 1, 2, 4>(p, B, st);
+    else if (Cout == 16 && nsplit == 3) rc = launch_t<8, 16, 3, 2, 4>(p, B, st);
     if (rc != RCMVS_OK) return rc;
   }
   return RCMVS_OK;
