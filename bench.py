@@ -119,6 +119,15 @@ def host_threads():
     return best, avail
 
 
+def ncu_traffic(key):
+    """dram bytes per launch from the committed `ncu --set full` capture (profiles/r01_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path))[key]["traffic_bytes"]
+    except Exception:
+        return None
+
+
 def algorithmic_bytes_costvolume(Vv, C, D, h, w, per_pixel):
     """4·(V·C·h·w + D·h·w + C·D·h·w) — features once, hypotheses once, variance written once."""
     hyp = D * h * w if per_pixel else D
@@ -361,7 +370,8 @@ def main():
     if s1:
         roofline = {"kernel": "costvolume_var_v2_kernel<32> (stage 1, D=192, 128x160, V=5)", "bound": "hbm",
                     "achieved": s1["achieved"], "peak": s1["peak"], "unit": "GB/s", "frac": s1["frac"],
-                    "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": None}
+                    "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                    "algorithmic_bytes": s1["bytes"], "traffic": ncu_traffic("costvolume_var_stage1")}
     line = {
         "metric": METRIC, "value": value, "unit": "ref-views/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
