@@ -84,6 +84,13 @@ int rcmvs_pack_conv3d_weight(const float* w, const float* scale, float* packed, 
  * bias/skip may be NULL; relu in {0,1}; stride in {1,2}.  The skip is added AFTER the ReLU (modules.py:497-499). */
 int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip, float* y, int B,
                      int D, int H, int W, int Cin, int Cout, int stride, int relu, rcmvs_stream_t stream);
+/* Same layer with a caller-provided workspace of rcmvs_conv3d_workspace_floats() floats (0 = not needed): lets the
+ * small 1/4- and 1/8-resolution layers split the input-channel reduction over more CTAs (deterministic split-K:
+ * per-slice partial sums + a fixed-order reduce that applies bias / ReLU / skip). */
+int64_t rcmvs_conv3d_workspace_floats(int B, int D, int H, int W, int Cin, int Cout, int stride);
+int rcmvs_conv3d_fwd_ws(const float* x, const float* packed_w, const float* bias, const float* skip, float* y,
+                        float* workspace, int B, int D, int H, int W, int Cin, int Cout, int stride, int relu,
+                        rcmvs_stream_t stream);
 /* ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1): x [B][D][H][W][Cin] -> y [B][2D][2H][2W][Cout]. */
 int rcmvs_conv_transpose3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip,
                                float* y, int B, int D, int H, int W, int Cin, int Cout, int relu,

@@ -43,7 +43,8 @@ template <int COUT, int STRIDE>
 __global__ void __launch_bounds__(ConvTile<COUT>::THREADS)
 conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
                      const float* __restrict__ skip, float* __restrict__ y, int D, int H, int W, int Cin, int Do,
-                     int Ho, int Wo, int relu, int Ctot, int nsplit) {
+                     int Ho, int Wo, int relu, int Ctot, int nsplit, int ksplit, float* __restrict__ wksp,
+                     int64_t ws_stride) {
   using T = ConvTile<COUT>;
   using S = ConvSmem<COUT, STRIDE>;
   constexpr int CO_T = T::CO_T, TH = T::TH, IH = S::IH, IW = S::IW;
@@ -56,9 +57,13 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
   const int hg = wid % T::NWH;
   const int cog = wid / T::NWH;
   const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * TH;
-  const int co0 = (blockIdx.z % nsplit) * COUT;              // first output channel of this CTA
-  const int bz = blockIdx.z / nsplit;
+  const int kidx = blockIdx.z % ksplit;                      // split-K slice (input-channel chunks) of this CTA
+  const int zz = blockIdx.z / ksplit;
+  const int co0 = (zz % nsplit) * COUT;                      // first output channel of this CTA
+  const int bz = zz / nsplit;
   const int b = bz / Do, od = bz % Do;
+  const int nchunks = Cin / CB, cper = (nchunks + ksplit - 1) / ksplit;
+  const int cb_begin = kidx * cper * CB, cb_end = min(Cin, (kidx + 1) * cper * CB);
   const int iz0 = od * STRIDE - 1, iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
   x += (int64_t)b * D * H * W * Cin;
 
@@ -68,7 +73,7 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
 #pragma unroll
     for (int c = 0; c < CO_T; ++c) acc[j][c] = 0.f;
 
-  for (int cb0 = 0; cb0 < Cin; cb0 += CB) {
+  for (int cb0 = cb_begin; cb0 < cb_end; cb0 += CB) {
 #pragma unroll 1
     for (int kd = 0; kd < 3; ++kd) {
       const int gz = iz0 + kd;
@@ -153,6 +158,13 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
     const int oy = oy0 + hg * 4 + j;
     if (oy >= Ho) continue;
     const int64_t o = ((((int64_t)b * Do + od) * Ho + oy) * Wo + ox) * Ctot + co0 + cog * CO_T;
+    if (ksplit > 1) {
+      // deterministic split-K: raw partial sums go to this slice's workspace; splitk_reduce_kernel finishes the layer
+      float* wsp = wksp + (int64_t)kidx * ws_stride + o;
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) wsp[c] = acc[j][c];
+      continue;
+    }
     float v[CO_T];
 #pragma unroll
     for (int c = 0; c < CO_T; ++c) {
@@ -316,13 +328,37 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
   packed[i] = scale ? v * scale[co] : v;
 }
 
+// y = act(Σ_k ws[k] + bias) (+ skip): fixed summation order -> deterministic
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, int64_t ws_stride,
+                                     const float* __restrict__ bias, const float* __restrict__ skip,
+                                     float* __restrict__ y, int64_t n4, int Ctot, int relu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = ldg4(ws + i * 4);
+  for (int k = 1; k < ksplit; ++k) {
+    const float4 q = ldg4(ws + (int64_t)k * ws_stride + i * 4);
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  if (bias) {
+    const float4 q = ldg4(bias + (int)((i * 4) % Ctot));
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+  if (skip) {
+    const float4 q = ldg4(skip + i * 4);
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  st4(y + i * 4, a);
+}
+
 template <int COUT, int STRIDE>
 static int launch_conv(const float* x, const float* wp, const float* bias, const float* skip, float* y, int B, int D,
-                       int H, int W, int Cin, int relu, int Ctot, cudaStream_t st) {
+                       int H, int W, int Cin, int relu, int Ctot, int ksplit, float* ws, cudaStream_t st) {
   using T = ConvTile<COUT>;
   using S = ConvSmem<COUT, STRIDE>;
   const int Do = (D - 1) / STRIDE + 1, Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
   const int nsplit = Ctot / COUT;
+  const int64_t out_elems = (int64_t)B * Do * Ho * Wo * Ctot;
   auto kern = conv3d_direct_kernel<COUT, STRIDE>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -330,12 +366,31 @@ static int launch_conv(const float* x, const float* wp, const float* bias, const
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  RCMVS_REQUIRE((int64_t)B * Do * nsplit <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
+  RCMVS_REQUIRE((int64_t)B * Do * nsplit * ksplit <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv3d_fwd: grid too large");
-  dim3 grid(ceil_div(Wo, 32), ceil_div(Ho, T::TH), B * Do * nsplit);
-  kern<<<grid, T::THREADS, S::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, Do, Ho, Wo, relu, Ctot, nsplit);
+  dim3 grid(ceil_div(Wo, 32), ceil_div(Ho, T::TH), B * Do * nsplit * ksplit);
+  kern<<<grid, T::THREADS, S::BYTES, st>>>(x, wp, bias, skip, y, D, H, W, Cin, Do, Ho, Wo, relu, Ctot, nsplit, ksplit,
+                                           ws, out_elems);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_fwd");
+  if (ksplit > 1) {
+    const int64_t n4 = out_elems / 4;
+    splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(ws, ksplit, out_elems, bias, skip, y, n4,
+                                                                             Ctot, relu);
+    RCMVS_CHECK_LAUNCH("rcmvs_conv3d_fwd(split-K reduce)");
+  }
   return RCMVS_OK;
+}
+
+// split-K factor: only for layers whose grid cannot fill ~2 waves even after the Cout split (tiny deep levels)
+static int pick_ksplit(int Cin, int Cout, int cpc, int B, int D, int H, int W, int stride) {
+  const int nchunks = Cin / CB;
+  if (nchunks < 2 || Cout % 4 != 0) return 1;
+  const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int th = cpc >= 32 ? 4 : (cpc == 16 ? 8 : 16);
+  const int64_t ctas = (int64_t)ceil_div(Wo, 32) * ceil_div(Ho, th) * B * Do * (Cout / cpc);
+  if (ctas >= 2 * 148) return 1;
+  int k = (int)(ceil_div<int64_t>(2 * 148, ctas) < nchunks ? ceil_div<int64_t>(2 * 148, ctas) : nchunks);
+  return max(1, min(k, 8));
 }
 
 // channels per CTA: all of Cout for the large layers; halved while the grid would not fill ~2 waves of 148 SMs
@@ -385,9 +440,20 @@ extern "C" int rcmvs_pack_conv3d_weight(const float* w, const float* scale, floa
   return RCMVS_OK;
 }
 
-extern "C" int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip, float* y,
-                                int B, int D, int H, int W, int Cin, int Cout, int stride, int relu,
-                                rcmvs_stream_t stream) {
+extern "C" int64_t rcmvs_conv3d_workspace_floats(int B, int D, int H, int W, int Cin, int Cout, int stride) {
+  using namespace rcmvs;
+  if (!(Cout == 1 || Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64) || Cin % 8 != 0 || (stride != 1 && stride != 2))
+    return 0;
+  const int cpc = pick_cout_per_cta(Cout, B, D, H, W, stride);
+  const int ks = pick_ksplit(Cin, Cout, cpc, B, D, H, W, stride);
+  if (ks <= 1) return 0;
+  const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  return (int64_t)ks * B * Do * Ho * Wo * Cout;
+}
+
+extern "C" int rcmvs_conv3d_fwd_ws(const float* x, const float* packed_w, const float* bias, const float* skip,
+                                   float* y, float* workspace, int B, int D, int H, int W, int Cin, int Cout,
+                                   int stride, int relu, rcmvs_stream_t stream) {
   using namespace rcmvs;
   RCMVS_REQUIRE(x && packed_w && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_fwd: null pointer");
   RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_fwd: bad dims");
@@ -397,10 +463,11 @@ extern "C" int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const flo
   RCMVS_REQUIRE(Cout == 1 || Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv3d_fwd: Cout=%d not in {1,8,16,32,64}", Cout);
   const int cpc = pick_cout_per_cta(Cout, B, D, H, W, stride);
-#define RCMVS_CONV_CASE(CO)                                                                             \
-  case CO:                                                                                              \
-    return stride == 1 ? launch_conv<CO, 1>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, st) \
-                       : launch_conv<CO, 2>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, st)
+  const int ksplit = workspace ? pick_ksplit(Cin, Cout, cpc, B, D, H, W, stride) : 1;
+#define RCMVS_CONV_CASE(CO)                                                                                           \
+  case CO:                                                                                                            \
+    return stride == 1 ? launch_conv<CO, 1>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, ksplit, workspace, st) \
+                       : launch_conv<CO, 2>(x, packed_w, bias, skip, y, B, D, H, W, Cin, relu, Cout, ksplit, workspace, st)
   switch (cpc) {
     RCMVS_CONV_CASE(1);
     RCMVS_CONV_CASE(8);
@@ -412,6 +479,12 @@ extern "C" int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const flo
 #undef RCMVS_CONV_CASE
   set_error("rcmvs_conv3d_fwd: Cout=%d not in {1,8,16,32,64}", Cout);
   return RCMVS_ERR_UNSUPPORTED;
+}
+
+extern "C" int rcmvs_conv3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip, float* y,
+                                int B, int D, int H, int W, int Cin, int Cout, int stride, int relu,
+                                rcmvs_stream_t stream) {
+  return rcmvs_conv3d_fwd_ws(x, packed_w, bias, skip, y, nullptr, B, D, H, W, Cin, Cout, stride, relu, stream);
 }
 
 extern "C" int rcmvs_conv_transpose3d_fwd(const float* x, const float* packed_w, const float* bias, const float* skip,

@@ -135,8 +135,12 @@ def conv3d(x_cl, packed_w, bias=None, skip=None, stride=1, relu=True):
     Cout = packed_w.shape[2]
     Do, Ho, Wo = (D - 1) // stride + 1, (H - 1) // stride + 1, (W - 1) // stride + 1
     y = torch.empty((B, Do, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32)
-    _ffi.call("rcmvs_conv3d_fwd", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"), _opt(skip, "skip"),
-              _chk(y, "y"), B, D, H, W, Cin, Cout, stride, 1 if relu else 0, _stream())
+    nws = _ffi.lib().rcmvs_conv3d_workspace_floats(B, D, H, W, Cin, Cout, stride)
+    ws = torch.empty((nws,), device=x_cl.device, dtype=torch.float32) if nws > 0 else None
+    _ffi.call("rcmvs_conv3d_fwd_ws", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"), _opt(skip, "skip"),
+              _chk(y, "y"), _opt(ws, "workspace"), B, D, H, W, Cin, Cout, stride, 1 if relu else 0, _stream())
+    if ws is not None:
+        _ffi.launches += 1          # conv + split-K reduce
     return y
 
 
