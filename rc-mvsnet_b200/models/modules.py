@@ -274,10 +274,10 @@ class CostRegNet(nn.Module):
             return cls._call(cands[0], layer, x, skip)
         key = tuple(x.shape)
         if key not in layer["choice"]:
-            forced = os.environ.get("RCMVS_ENGINE")            # 'direct' | 'tc' : disable the autotuner
+            forced = os.environ.get("RCMVS_ENGINE")            # 'direct' | 'tc': pin every layer to one engine
             if forced:
                 layer["choice"][key] = next((i for i, c in enumerate(cands) if c[0].startswith(forced)), 0)
-            else:
+            elif os.environ.get("RCMVS_AUTOTUNE", "0") == "1":
                 best, best_ms = 0, float("inf")
                 for i, c in enumerate(cands):
                     cls._call(c, layer, x, skip)               # warm-up (sets kernel attributes)
@@ -291,7 +291,27 @@ class CostRegNet(nn.Module):
                     if ms < best_ms:
                         best, best_ms = i, ms
                 layer["choice"][key] = best
+            else:
+                layer["choice"][key] = cls._default_engine(layer, cands, x)
         return cls._call(cands[layer["choice"][key]], layer, x, skip)
+
+    @staticmethod
+    def _default_engine(layer, cands, x):
+        """Static table distilled from RCMVS_AUTOTUNE=1 runs on B200 at DTU / BASELINE shapes (profiles/):
+        stride-1 conv0 / conv2 -> tcgen05 in both tensor modes; `prob` (8->1, memory-bound) -> FFMA kernel;
+        transposed conv11 -> tcgen05 when the input has >= 8 depth planes (3xTF32) or always (TF32);
+        transposed conv9 -> tcgen05 only with plain TF32 and >= 8 planes; everything else FFMA."""
+        kinds = [c[0] for c in cands]
+        nsplit = next((c[4] for c in cands if c[0] in ("tc", "tct")), 0)
+        cin, planes = x.shape[-1], x.shape[1]
+        if "tc" in kinds:
+            cout = cands[kinds.index("tc")][3]
+            return kinds.index("tc") if cout != 1 else 0
+        if "tct" in kinds:
+            if cin == 16:                                       # conv11
+                return kinds.index("tct") if (nsplit == 1 or planes >= 8) else 0
+            return kinds.index("tct") if (nsplit == 1 and planes >= 8) else 0      # conv9
+        return 0
 
     def engines(self):
         """{layer: {input shape: engine name}} chosen so far (bench.py reports it)."""
