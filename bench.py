@@ -201,6 +201,35 @@ def kernel_rooflines(model, dev, inputs, pk):
     return res
 
 
+def render_branch_timing(dev):
+    """BASELINE configs[2] (full RC-MVSNet forward + render), reported next to the headline: 4 views (the renderer is
+    hard-wired to 3 sources), 512x640, training-class CascadeMVSNet 48/32/8 (produces volume_feature_no_ref) followed by
+    Rendering_Consistency_Net (Neural_Volume_Net + 1024 rays x 128 samples), forward only, inputs resident."""
+    from rcmvs import synth, weights
+    import models
+    nerf_w = os.path.join(ROOT, "tests", "golden", "nerf_model_000014.npz")
+    cas = models.CascadeMVSNet(ndepths=[48, 32, 8])
+    weights.load_model(cas, GOLDEN_WEIGHTS)
+    cas.to(dev).eval()
+    nerf = models.Rendering_Consistency_Net(synth.RenderArgs())
+    nerf.load_state_dict(weights.load_npz_state_dict(nerf_w), strict=True)
+    nerf.to(dev).eval()
+    imgs, proj, dv = synth.mvs_inputs(4, H, W, kind="textured", seed=11)
+    batch = {k: torch.from_numpy(v).to(dev) for k, v in synth.render_batch(H, W, seed=3).items()}
+    imgs, proj, dv = torch.from_numpy(imgs).to(dev), {k: torch.from_numpy(v).to(dev) for k, v in proj.items()}, \
+        torch.from_numpy(dv).to(dev)
+    stream = torch.cuda.current_stream()
+    with torch.no_grad():
+        out, vol = cas(imgs, proj, dv)
+        ms_mvs = time_kernel(lambda: cas(imgs, proj, dv), 3, stream)
+        ms_render = time_kernel(lambda: nerf(vol, out["depth"], dict(batch)), 3, stream)
+        res = nerf(vol, out["depth"], dict(batch))
+    ok = bool(torch.isfinite(res[0]).all() and torch.isfinite(res[3]).all())
+    return {"workload": "configs[2]: CascadeMVSNet (train class, 4 views 512x640, D=48/32/8, volume_feature_no_ref) + "
+                        "Rendering_Consistency_Net (Neural_Volume_Net, 1024 rays x 128 samples), forward",
+            "mvs_forward_ms": round(ms_mvs, 3), "render_forward_ms": round(ms_render, 3), "finite": ok}
+
+
 def make_inputs(seed):
     from rcmvs import synth
     return synth.mvs_inputs(V, H, W, kind="textured", seed=seed)
@@ -249,6 +278,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="reference views per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the configs[2] renderer-branch timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -340,6 +370,9 @@ def main():
     roof_all, cpu_baseline = None, None
     if rank == 0 and not args.no_kernel_rooflines:
         roof_all = kernel_rooflines(model, dev, (imgs[:1], {k: v[:1] for k, v in proj.items()}, dv[:1]), pk)
+    render = None
+    if rank == 0 and world == 1 and not args.no_render and not args.no_kernel_rooflines:
+        render = render_branch_timing(dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import ref_torch as T
         from rcmvs import synth
@@ -390,6 +423,7 @@ def main():
         "roofline": roofline,
         "roofline_all": roof_all,
         "cpu_baseline": cpu_baseline,
+        "render_branch": render,
     }
     print(json.dumps(line), flush=True)
 
