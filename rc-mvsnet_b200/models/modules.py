@@ -321,6 +321,9 @@ class CostRegNet(nn.Module):
 
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cin] channels-last -> cost [B,D,h,w]."""
+        if any(int(v) % 8 for v in x_cl.shape[1:4]):
+            # three stride-2 levels: the reference fails at the first skip add (modules.py:497) for such shapes
+            raise ValueError("CostRegNet needs D, H, W divisible by 8, got %s" % (tuple(x_cl.shape[1:4]),))
         P, run = self.packed(), self._run
         c0 = run(P["conv0"], x_cl)
         c2 = run(P["conv2"], run(P["conv1"], c0))

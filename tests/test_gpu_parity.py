@@ -454,3 +454,28 @@ def test_train_class_volume_feature_no_ref(dev):
     np.testing.assert_allclose(vol[0].cpu().numpy(), g["volume_feature_no_ref"], atol=2e-3, rtol=1e-3)
     rel = np.abs(out["stage3"]["depth"][0].cpu().numpy() - g["depth_stage3"]).max() / g["depth_stage3"].max()
     assert rel < 1e-3
+
+
+def test_costregnet_rejects_shapes_not_divisible_by_8(dev):
+    m = _model(dev, (16, 8, 8))
+    with pytest.raises(ValueError, match="divisible by 8"):
+        with torch.no_grad():
+            m.cost_regularization[2](torch.zeros(1, 8, 12, 16, 16, device=dev))
+
+
+def test_tanks_shaped_eval_properties(dev):
+    """BASELINE configs[4] shape: 7 views, 1056x1920, cascade 48/32/8 — size-independent properties only (the CPU
+    oracle needs minutes here): finite, confidence in [0,1], stage-1 depth inside the swept range, deterministic."""
+    from rcmvs import synth
+    imgs, proj, dv = synth.mvs_inputs(7, 1056, 1920, kind="noise", seed=1)
+    m = _model(dev, (48, 32, 8))
+    args = (cu(imgs, dev), {k: cu(v, dev) for k, v in proj.items()}, cu(dv, dev))
+    with torch.no_grad():
+        out = m(*args)
+        out2 = m(*args)
+    assert out["depth"].shape == (1, 1056, 1920) and torch.isfinite(out["depth"]).all()
+    assert torch.equal(out["depth"], out2["depth"])
+    c = out["photometric_confidence"]
+    assert (c >= 0).all() and (c <= 1 + 1e-5).all()
+    s1 = out["stage1"]["depth"]
+    assert (s1 >= dv.min() - 1e-3).all() and (s1 <= dv.max() + 1e-3).all()
