@@ -177,7 +177,7 @@ struct Cfg {
   static constexpr int BTERM_B = 3 * KS * BBLK_B;
   static constexpr int B_BYTES = NPART * BTERM_B;
   static constexpr int NG = 512 / (KM * G);                       // plane groups in the TMEM ring
-  static constexpr int EX_B = OROWS * PW * CP * 4;                // epilogue exchange buffer
+  static constexpr int EX_B = 3 * OROWS * PW * CP * 4;            // epilogue exchange buffer: one plane per kh
   static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + EX_B + 512;
   static_assert(NG >= 4, "TMEM ring needs at least 4 plane groups");
 };
@@ -394,37 +394,33 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(grp_free + g);
-      // ---- sum over kh: input row ri = 4*mt + warp contributes its kh block to output row j = ri - kh ----------
+      // ---- sum over kh: input row ri = 4*mt + warp contributes its kh block to output row j = ri - kh.  Each kh
+      //      writes its own exchange plane (no read-modify-write), one barrier, then the store phase adds the three.
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
         for (int mt = 0; mt < KM; ++mt) {
           const int j = 4 * mt + warp - kh;
           if (j >= 0 && j < C::OROWS) {
-            float* e = ex + ((j * PW + lane) * CP);
+            float* e = ex + (((kh * C::OROWS + j) * PW + lane) * CP);
 #pragma unroll
-            for (int c = 0; c < CP; c += 4) {
-              float4 val = make_float4(v[mt][kh * CP + c], v[mt][kh * CP + c + 1], v[mt][kh * CP + c + 2],
-                                       v[mt][kh * CP + c + 3]);
-              if (kh > 0) {
-                const float4 o = *reinterpret_cast<float4*>(e + c);
-                val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
-              }
-              *reinterpret_cast<float4*>(e + c) = val;
-            }
+            for (int c = 0; c < CP; c += 4)
+              *reinterpret_cast<float4*>(e + c) = make_float4(v[mt][kh * CP + c], v[mt][kh * CP + c + 1],
+                                                              v[mt][kh * CP + c + 2], v[mt][kh * CP + c + 3]);
           }
         }
-        epi_bar_sync();
       }
+      epi_bar_sync();
       // ---- bias / ReLU / skip, coalesced store: thread handles rows j = warp, warp+4, ... ------------------------
       const int d = d0 + q;
       for (int j = warp; j < C::OROWS; j += 4) {
         const int gy = y0 + j;
         if (!col_ok || gy >= p.H) continue;
         const float* e = ex + ((j * PW + lane) * CP);
+        constexpr int EXP = C::OROWS * PW * CP;                  // floats per kh plane
         const int64_t o = ((((int64_t)b * p.D + d) * p.H + gy) * p.W + gx) * COUT;
         if constexpr (COUT == 1) {
-          float r = e[0];
+          float r = e[0] + e[EXP] + e[2 * EXP];
           if (p.accumulate_in) r += p.y[o];
           if (p.finalize) {
             if (p.bias) r += __ldg(p.bias);
@@ -436,6 +432,11 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
 #pragma unroll
           for (int c = 0; c < COUT; c += 4) {
             float4 r = *reinterpret_cast<const float4*>(e + c);
+            {
+              const float4 r1 = *reinterpret_cast<const float4*>(e + EXP + c);
+              const float4 r2 = *reinterpret_cast<const float4*>(e + 2 * EXP + c);
+              r.x += r1.x + r2.x; r.y += r1.y + r2.y; r.z += r1.z + r2.z; r.w += r1.w + r2.w;
+            }
             if (p.accumulate_in) {
               const float4 t4 = *reinterpret_cast<const float4*>(p.y + o + c);
               r.x += t4.x; r.y += t4.y; r.z += t4.z; r.w += t4.w;
