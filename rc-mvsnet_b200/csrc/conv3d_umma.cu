@@ -23,6 +23,8 @@
 //            NSPLIT=3 error-compensated 3xTF32: x = x_hi + x_lo, w = w_hi + w_lo, acc += x_lo·w_hi + x_hi·w_lo + x_hi·w_hi.
 //
 // Warp roles: warps 0-3 epilogue, 2 loader warps per slab buffer (cp.async + hi/lo split), last warp MMA issuer.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rcmvs {
@@ -193,6 +195,7 @@ struct Params {
   int accumulate_in;    // add the existing contents of y (partial sums of an earlier channel group)
   int finalize;         // apply bias / ReLU / skip (last channel group)
   int relu;
+  int dbg;              // development only (RCMVS_TC_DBG): 1 = skip MMA issue, 2 = skip epilogue math/stores, 4 = skip loads
 };
 
 template <int CIN, int COUT, int NSPLIT, int KM, int NS>
@@ -264,42 +267,68 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
       mbar_wait(empty + mybuf, ((i / NS) & 1) ^ 1);
       const int z = d0 - 1 + i;
       const bool zok = (z >= 0) && (z < p.D);
-      {
-        constexpr int VSTEP = kLoaderThreads / C::NCH;          // voxels covered by the buffer's threads per pass
+      if constexpr (NSPLIT == 3) {
+        // 3xTF32: plain loads into registers, split x = hi + lo (hi = x & 0xFFFFE000, exactly representable in TF32)
+        // on the way to shared memory — one pass instead of cp.async + re-read + two stores.  8 loads in flight per thread.
+        constexpr int VSTEP = kLoaderThreads / C::NCH;
         static_assert(PW % VSTEP == 0, "loader mapping");
+        constexpr int CPR = PW / VSTEP;                           // pieces per row per thread
+        constexpr int NP = C::ROWS * CPR;                         // pieces per thread
+        constexpr int BATCH = (NP % 8 == 0) ? 8 : (NP % 6 == 0 ? 6 : 4);
+        static_assert(NP % BATCH == 0, "loader batch");
         const int ch = t % C::NCH, v0 = t / C::NCH;
         const float* zbase = xb + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
-        const uint32_t dst0 = slab + ch * C::PLANE_B;
-        for (int row = 0; row < C::ROWS; ++row) {
-          const int gy = y0 - 1 + row;
-          const bool yok = zok && gy >= 0 && gy < p.H;
-          const float* rbase = zbase + (int64_t)gy * p.W * vox_stride;
+        unsigned char* hi_p = a_smem + (size_t)mybuf * C::NPART * C::SLAB_B + ch * C::PLANE_B;
+        unsigned char* lo_p = hi_p + C::SLAB_B;
+        if (!(p.dbg & 4)) {
+          for (int p0 = 0; p0 < NP; p0 += BATCH) {
+            float4 v[BATCH];
 #pragma unroll
-          for (int col = v0; col < PW; col += VSTEP) {
-            const int gx = x0 - 1 + col;
-            const bool ok = yok && gx >= 0 && gx < p.W;
-            const float* src = ok ? rbase + (int64_t)gx * vox_stride : xb;
-            cp_async16(dst0 + (row * PW + col) * 16, src, ok);
+            for (int u = 0; u < BATCH; ++u) {
+              const int pi = p0 + u;
+              const int row = pi / CPR, col = v0 + (pi % CPR) * VSTEP;
+              const int gy = y0 - 1 + row, gx = x0 - 1 + col;
+              const bool ok = pi < NP && zok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+              v[u] = ok ? ldg4(zbase + ((int64_t)gy * p.W + gx) * vox_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+              const int pi = p0 + u;
+              if (pi >= NP) break;
+              const int row = pi / CPR, col = v0 + (pi % CPR) * VSTEP;
+              const int off = (row * PW + col) * 16;
+              float4 h, l;
+              h.x = __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u); l.x = v[u].x - h.x;
+              h.y = __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u); l.y = v[u].y - h.y;
+              h.z = __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u); l.z = v[u].z - h.z;
+              h.w = __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u); l.w = v[u].w - h.w;
+              *reinterpret_cast<float4*>(hi_p + off) = h;
+              *reinterpret_cast<float4*>(lo_p + off) = l;
+            }
           }
         }
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-      if constexpr (NSPLIT == 3) {
-        // x = hi + lo with hi = x & 0xFFFFE000 (exactly representable in TF32); each thread splits its own pieces
-        unsigned char* hi_p = a_smem + (size_t)mybuf * C::NPART * C::SLAB_B;
-        unsigned char* lo_p = hi_p + C::SLAB_B;
-        for (int e = t; e < PIECES; e += kLoaderThreads) {
-          const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
-          float4 v = *reinterpret_cast<float4*>(hi_p + off);
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          *reinterpret_cast<float4*>(hi_p + off) = h;
-          *reinterpret_cast<float4*>(lo_p + off) = l;
+      } else {
+        if (!(p.dbg & 4)) {
+          constexpr int VSTEP = kLoaderThreads / C::NCH;          // voxels covered by the buffer's threads per pass
+          static_assert(PW % VSTEP == 0, "loader mapping");
+          const int ch = t % C::NCH, v0 = t / C::NCH;
+          const float* zbase = xb + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
+          const uint32_t dst0 = slab + ch * C::PLANE_B;
+          for (int row = 0; row < C::ROWS; ++row) {
+            const int gy = y0 - 1 + row;
+            const bool yok = zok && gy >= 0 && gy < p.H;
+            const float* rbase = zbase + (int64_t)gy * p.W * vox_stride;
+#pragma unroll
+            for (int col = v0; col < PW; col += VSTEP) {
+              const int gx = x0 - 1 + col;
+              const bool ok = yok && gx >= 0 && gx < p.W;
+              const float* src = ok ? rbase + (int64_t)gx * vox_stride : xb;
+              cp_async16(dst0 + (row * PW + col) * 16, src, ok);
+            }
+          }
         }
+        cp_async_commit();
+        cp_async_wait<0>();
       }
       fence_proxy_async();
       mbar_arrive(full + mybuf);
@@ -340,7 +369,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
             const uint32_t a_hi_d = a_lo0 + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + kw);
             const uint32_t b_blk_d = b_lo0 + (uint32_t)(((kw * C::KS + ks) * C::BBLK_B) >> 4);
             const uint32_t dm = (uint32_t)(mt * (NG * G));
-            if (leader) {
+            if (leader && !(p.dbg & 1)) {
               if constexpr (NSPLIT == 3) {
                 umma_tf32_lohi(d0c + dm, a_hi_d + kLoOff, b_blk_d + boff0, idesc0);            // x_lo · w_hi
                 umma_tf32_lohi(d0c + dm, a_hi_d, b_blk_d + boff0 + kBLoOff, idesc0);           // x_hi · w_lo
@@ -394,6 +423,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(grp_free + g);
+      if (p.dbg & 2) continue;
       // ---- sum over kh: input row ri = 4*mt + warp contributes its kh block to output row j = ri - kh.  Each kh
       //      writes its own exchange plane (no read-modify-write), one barrier, then the store phase adds the three.
 #pragma unroll
@@ -884,6 +914,7 @@ extern "C" int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const floa
     p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = g * pl.cin_k;
     p.d_chunk = d_chunk; p.chunks = chunks;
     p.accumulate_in = g > 0; p.finalize = g == groups - 1; p.relu = relu;
+    p.dbg = getenv("RCMVS_TC_DBG") ? atoi(getenv("RCMVS_TC_DBG")) : 0;
     int rc = RCMVS_ERR_UNSUPPORTED;
 #define RCMVS_TC_CASE(CI, CO, NSP, KMV, NSV) \
   if (pl.cin_k == CI && Cout == CO && nsplit == NSP) rc = launch<CI, CO, NSP, KMV, NSV>(p, B, st)
@@ -953,6 +984,7 @@ extern "C" int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, 
     p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = g * cin_k;
     p.d_chunk = d_chunk; p.chunks = chunks;
     p.accumulate_in = g > 0; p.finalize = g == groups - 1; p.relu = relu;
+    p.dbg = 0;
     int rc = RCMVS_ERR_UNSUPPORTED;
     if (Cout == 8 && nsplit == 1) rc = launch_t<16, 8, 1, 2, 5>(p, B, st);
     else if (Cout == 8 && nsplit == 3) rc = launch_t<16, 8, 3, 2, 3>(p, B, st);
