@@ -370,9 +370,18 @@ def main():
     roof_all, cpu_baseline = None, None
     if rank == 0 and not args.no_kernel_rooflines:
         roof_all = kernel_rooflines(model, dev, (imgs[:1], {k: v[:1] for k, v in proj.items()}, dv[:1]), pk)
-    render = None
+    render, batched = None, None
     if rank == 0 and world == 1 and not args.no_render and not args.no_kernel_rooflines:
         render = render_branch_timing(dev)
+        # same workload with 4 reference views per launch sequence (better fill of the small 1/4- and 1/8-scale layers)
+        b4 = [make_inputs(seed=1000 + i) for i in range(4)]
+        i4 = torch.from_numpy(np.concatenate([h[0] for h in b4])).to(dev)
+        p4 = {k: torch.from_numpy(np.concatenate([h[1][k] for h in b4])).to(dev) for k in b4[0][1]}
+        d4 = torch.from_numpy(np.concatenate([h[2] for h in b4])).to(dev)
+        with torch.no_grad():
+            ms4 = time_kernel(lambda: model(i4, p4, d4), 5, torch.cuda.current_stream())
+        batched = {"batch_per_gpu": 4, "value": round(4 / (ms4 * 1e-3), 1), "unit": "ref-views/s", "ms_per_step": round(ms4, 3)}
+        del i4, p4, d4
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import ref_torch as T
         from rcmvs import synth
@@ -424,6 +433,7 @@ def main():
         "roofline_all": roof_all,
         "cpu_baseline": cpu_baseline,
         "render_branch": render,
+        "batched": batched,
     }
     print(json.dumps(line), flush=True)
 
