@@ -1,6 +1,16 @@
-"""Drop-in for the reference's models/render_consist_net.py: Rendering_Consistency_Net(args).forward(
-volume_feature_warp, pseudo_depth, batch) -> (rgb, input_feat, weights, depth_pred, alpha, {}, rays_depth, target_s)
-(reference :54-76; the reference names the 2nd/3rd entries `disp, acc` but `rendering` returns input_feat, weights)."""
+"""Drop-in for the reference's models/render_consist_net.py.
+
+`Rendering_Consistency_Net(args)(volume_feature_warp, pseudo_depth, batch)` keeps the reference call signature and
+its 8-tuple result `(rgb, input_feat, weights, depth_pred, alpha, {}, rays_depth, target_s)` (reference :54-76 — the
+reference binds the 2nd/3rd entries to names `disp, acc`, but what `rendering` hands back there is the per-point
+feature tensor and the compositing weights).  State-dict keys are `MVSNet.cost_reg_2.*` and `network_fn.nerf.*`, so
+`pretrain/model_000014_nerf.ckpt` loads with strict=True.
+
+Under torch.no_grad() the whole branch runs on librcmvs kernels:
+    Neural_Volume_Net (resize + 3-D U-Net, channels-last)  ->  pixel pick + Gaussian-Uniform depth candidates
+    -> ray points / NDC -> per-point features -> fused embedding + MLP -> alpha compositing.
+With autograd enabled (training) the same math runs on differentiable torch ops; the sampler stays on CUDA.
+"""
 import torch
 import torch.nn as nn
 
@@ -10,54 +20,66 @@ from .renderer import rendering
 
 __all__ = ["Rendering_Consistency_Net"]
 
+_IMAGENET_MEAN = (0.485, 0.456, 0.406)
+_IMAGENET_STD = (0.229, 0.224, 0.225)
+_N_RAYS = 1024            # hard-coded in the reference forward (:68)
+
 
 class Rendering_Consistency_Net(nn.Module):
     def __init__(self, args):
         super().__init__()
-        self.args = args
-        self.args.feat_dim = 8 + 3 * 4
-        self.idx = 0
-        self.render_kwargs_train, self.render_kwargs_test, start, self.grad_vars = create_nerf_mvs(
+        args.feat_dim = 8 + 3 * 4                      # 8 volume channels + 3 views x (RGB + in-bounds mask)
+        self.args, self.idx = args, 0
+        train_kw, self.render_kwargs_test, _, self.grad_vars = create_nerf_mvs(
             args, use_mvs=True, dir_embedder=False, pts_embedder=True, share_warp=True)
-        filter_keys(self.render_kwargs_train)
-        kw = self.render_kwargs_train
-        self.MVSNet, self.network_fn = kw.pop("network_mvs"), kw.pop("network_fn")
-        self.network_query_fn, self.white_bkgd = kw.pop("network_query_fn"), kw.pop("white_bkgd")
-        kw["NDC_local"] = False
+        filter_keys(train_kw)
+        # sub-modules / callables the reference exposes as attributes (and whose names fix the state-dict keys)
+        self.MVSNet = train_kw.pop("network_mvs")
+        self.network_fn = train_kw.pop("network_fn")
+        self.network_query_fn = train_kw.pop("network_query_fn")
+        self.white_bkgd = train_kw.pop("white_bkgd")
+        train_kw["NDC_local"] = False
+        self.render_kwargs_train = train_kw
 
-    def decode_batch(self, batch, idx=list(range(4))):
-        device = next(self.parameters()).device           # the reference hard-codes cuda:0 (:8,:38)
-        data = sub_selete_data(batch, device, idx, filtKey=[])
-        pose_ref = {k: data[k].squeeze() for k in ("w2cs", "intrinsics", "c2ws", "near_fars")}
-        return data, pose_ref
+    # ---- helpers -----------------------------------------------------------------------------------------------------
+    def decode_batch(self, batch, idx=(0, 1, 2, 3)):
+        """NeRF-side tensors of a sample on this module's device + the squeezed pose dictionary."""
+        device = next(self.parameters()).device        # the reference pins a module-global cuda:0 instead
+        data = sub_selete_data(batch, device, list(idx), filtKey=[])
+        poses = {name: data[name].squeeze() for name in ("w2cs", "intrinsics", "c2ws", "near_fars")}
+        return data, poses
 
     @staticmethod
     def unpreprocess(data, shape=(1, 1, 3, 1, 1)):
-        mean = torch.tensor([-0.485 / 0.229, -0.456 / 0.224, -0.406 / 0.225], device=data.device).view(*shape)
-        std = torch.tensor([1 / 0.229, 1 / 0.224, 1 / 0.225], device=data.device).view(*shape)
-        return (data - mean) / std
+        """Undo the ImageNet normalisation: x*std + mean, written like the reference as (x - (-mean/std)) / (1/std)."""
+        shift = torch.tensor([-m / s for m, s in zip(_IMAGENET_MEAN, _IMAGENET_STD)], device=data.device).view(*shape)
+        scale = torch.tensor([1.0 / s for s in _IMAGENET_STD], device=data.device).view(*shape)
+        return (data - shift) / scale
 
-    def forward(self, volume_feature_warp, pseudo_depth, batch, samples=None):
-        batch.pop("scan", None)
-        data, pose_ref = self.decode_batch(batch)
-        imgs, near_fars, depths_h = data["imgs"], data["near_fars"], data["depths_h"]
-        _, V, H, W = depths_h.shape
-        pseudo_depth_h = pseudo_depth.expand(V, H, W).unsqueeze(0)
-        fused = not torch.is_grad_enabled()
-        volume_cl = None
+    def _encode(self, volume_feature_warp, fused):
+        """-> (NCDHW encoded volume or None, channels-last [128,h,w,8] volume or None)."""
         if fused:
-            vcl = self.MVSNet.forward_cl(volume_feature_warp)            # [1,128,h,w,8] channels-last
-            volume_cl, volume_feature = vcl[0], None
-        else:
-            volume_feature = self.MVSNet(volume_feature_warp, pad=self.args.pad)
-        imgs = self.unpreprocess(imgs)
-        N_rays, N_samples = 1024, self.args.N_samples
-        c2ws, w2cs, intrinsics = pose_ref["c2ws"], pose_ref["w2cs"], pose_ref["intrinsics"]
-        rays_pts, rays_dir, target_s, rays_NDC, depth_candidates, rays_o, rays_depth, _ = build_rays_norm(
-            imgs, pseudo_depth_h, pose_ref, w2cs, c2ws, intrinsics, near_fars, N_rays, N_samples, pad=self.args.pad,
-            samples=samples)
-        rgb, input_feat, weights, depth_pred, alpha, ret = rendering(
-            self.args, pose_ref, rays_pts, rays_NDC, depth_candidates, rays_o, rays_dir, volume_feature,
-            imgs[:, -3:], img_feat=None, network_fn=self.network_fn, network_query_fn=self.network_query_fn,
-            white_bkgd=self.white_bkgd, volume_cl=volume_cl)
-        return rgb, input_feat, weights, depth_pred, alpha, ret, rays_depth, target_s
+            return None, self.MVSNet.forward_cl(volume_feature_warp)[0]
+        return self.MVSNet(volume_feature_warp, pad=self.args.pad), None
+
+    # ---- forward -----------------------------------------------------------------------------------------------------
+    def forward(self, volume_feature_warp, pseudo_depth, batch, samples=None):
+        """`samples` (optional, not in the reference) injects {'pixel_coordinates', 'depth_candidates'} for parity tests."""
+        batch.pop("scan", None)
+        data, poses = self.decode_batch(batch)
+        n_views, height, width = data["depths_h"].shape[1:]
+        depth_per_view = pseudo_depth.expand(n_views, height, width).unsqueeze(0)      # same pseudo depth for every view
+
+        fused = not torch.is_grad_enabled()
+        volume, volume_cl = self._encode(volume_feature_warp, fused)
+        images = self.unpreprocess(data["imgs"])
+
+        pts, dirs, target_rgb, ndc, z_vals, origins, rays_depth, _ = build_rays_norm(
+            images, depth_per_view, poses, poses["w2cs"], poses["c2ws"], poses["intrinsics"], data["near_fars"],
+            _N_RAYS, self.args.N_samples, pad=self.args.pad, samples=samples)
+
+        rgb, point_feat, weights, depth_pred, alpha, extras = rendering(
+            self.args, poses, pts, ndc, z_vals, origins, dirs, volume, images[:, -3:], img_feat=None,
+            network_fn=self.network_fn, network_query_fn=self.network_query_fn, white_bkgd=self.white_bkgd,
+            volume_cl=volume_cl)
+        return rgb, point_feat, weights, depth_pred, alpha, extras, rays_depth, target_rgb
