@@ -162,7 +162,7 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // COUT real output channels; G columns per (plane, M-tile) group = 3 kh blocks of COUT, rounded up to 16.
-template <int CIN, int COUT, int NSPLIT, int KM, int NS>
+template <int CIN, int COUT, int NSPLIT, int KM, int NS, int NGRP = 1>
 struct Cfg {
   static constexpr int CP = COUT < 8 ? 8 : COUT;                  // channel slots per kh block (Cout=1 -> 8)
   static constexpr int G = ((3 * CP + 15) / 16) * 16;             // TMEM columns / B rows per plane block
@@ -177,7 +177,8 @@ struct Cfg {
   static constexpr int A_BYTES = NS * NPART * SLAB_B;
   static constexpr int BBLK_B = 2 * 3 * G * 16;                   // one (kw, K-step): 2 chunks x 3G rows x 16 B
   static constexpr int BTERM_B = 3 * KS * BBLK_B;
-  static constexpr int B_BYTES = NPART * BTERM_B;
+  static constexpr int BGRP_B = NPART * BTERM_B;                  // weight image of one input-channel group
+  static constexpr int B_BYTES = NGRP * BGRP_B;
   static constexpr int NG = 512 / (KM * G);                       // plane groups in the TMEM ring
   static constexpr int EX_B = 3 * OROWS * PW * CP * 4;            // epilogue exchange buffer: one plane per kh
   static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + EX_B + 512;
@@ -198,9 +199,12 @@ struct Params {
   int dbg;              // development only (RCMVS_TC_DBG): 1 = skip MMA issue, 2 = skip epilogue math/stores, 4 = skip loads
 };
 
-template <int CIN, int COUT, int NSPLIT, int KM, int NS>
+// NGRP > 1: the CTA walks NGRP input-channel groups of CIN channels per depth slab (each group is its own slab in
+// the ring and has its own weight image); all groups accumulate into the same TMEM plane groups, so a 32-channel
+// layer in 3xTF32 mode needs one launch and one epilogue instead of two launches chained through global memory.
+template <int CIN, int COUT, int NSPLIT, int KM, int NS, int NGRP>
 __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const Params p) {
-  using C = Cfg<CIN, COUT, NSPLIT, KM, NS>;
+  using C = Cfg<CIN, COUT, NSPLIT, KM, NS, NGRP>;
   constexpr int G = C::G, NG = C::NG, CP = C::CP;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* a_smem = smem;
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
   const int d1 = min(p.D, d0 + p.d_chunk);
   const int nplanes = d1 - d0;           // output planes d0..d1-1 ; input slabs z = d0-1 .. d1  (nplanes + 2)
   const int nslabs = nplanes + 2;
+  const int nstream = nslabs * NGRP;       // (slab, channel group) items flowing through the ring
   const int64_t vox_stride = p.cin_total;
   const float* xb = p.x + (int64_t)b * p.D * p.H * p.W * vox_stride + p.cin_off;
 
@@ -263,10 +268,12 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
     const int t = (warp - 4) % kWPB * 32 + lane;
     constexpr int PIECES = C::ROWS * PW * C::NCH;
     const uint32_t slab = smem_u32(a_smem + (size_t)mybuf * C::NPART * C::SLAB_B);
-    for (int i = mybuf; i < nslabs; i += NS) {
-      mbar_wait(empty + mybuf, ((i / NS) & 1) ^ 1);
+    for (int ii = mybuf; ii < nstream; ii += NS) {
+      mbar_wait(empty + mybuf, ((ii / NS) & 1) ^ 1);
+      const int i = ii / NGRP, grp = ii % NGRP;
       const int z = d0 - 1 + i;
       const bool zok = (z >= 0) && (z < p.D);
+      const float* xg = xb + grp * CIN;                          // this group's first channel
       if constexpr (NSPLIT == 3) {
         // 3xTF32: plain loads into registers, split x = hi + lo (hi = x & 0xFFFFE000, exactly representable in TF32)
         // on the way to shared memory — one pass instead of cp.async + re-read + two stores.  8 loads in flight per thread.
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
         constexpr int BATCH = (NP % 8 == 0) ? 8 : (NP % 6 == 0 ? 6 : 4);
         static_assert(NP % BATCH == 0, "loader batch");
         const int ch = t % C::NCH, v0 = t / C::NCH;
-        const float* zbase = xb + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
+        const float* zbase = xg + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
         unsigned char* hi_p = a_smem + (size_t)mybuf * C::NPART * C::SLAB_B + ch * C::PLANE_B;
         unsigned char* lo_p = hi_p + C::SLAB_B;
         if (!(p.dbg & 4)) {
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
           constexpr int VSTEP = kLoaderThreads / C::NCH;          // voxels covered by the buffer's threads per pass
           static_assert(PW % VSTEP == 0, "loader mapping");
           const int ch = t % C::NCH, v0 = t / C::NCH;
-          const float* zbase = xb + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
+          const float* zbase = xg + (int64_t)z * p.H * p.W * vox_stride + ch * 4;
           const uint32_t dst0 = slab + ch * C::PLANE_B;
           for (int row = 0; row < C::ROWS; ++row) {
             const int gy = y0 - 1 + row;
@@ -339,15 +346,16 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
     // one elected lane issues tcgen05.mma / tcgen05.commit.
     const bool leader = elect_one();
     const uint32_t b_base = smem_u32(b_smem);
-    for (int i = 0; i < nslabs; ++i) {
+    for (int ii = 0; ii < nstream; ++ii) {
+      const int i = ii / NGRP, grp = ii % NGRP;
       // slab i = input plane z = d0-1+i contributes to output planes (relative) q = i-2+j, block j = 0,1,2 (kd = 2-j)
       const int jlo = max(0, 2 - i), jhi = min(2, nplanes + 1 - i);       // valid blocks: 0 <= q < nplanes
       const int qnew = i;                                                  // plane first touched by this slab (j=2)
-      if (qnew < nplanes && qnew >= NG) {                                  // its group must have been drained
+      if (grp == 0 && qnew < nplanes && qnew >= NG) {                      // its group must have been drained
         mbar_wait(grp_free + (qnew % NG), ((qnew / NG) - 1) & 1);
       }
-      const int buf = i % NS;
-      mbar_wait(full + buf, (i / NS) & 1);
+      const int buf = ii % NS;
+      mbar_wait(full + buf, (ii / NS) & 1);
       tc_fence_after();
       const uint32_t a_base = smem_u32(a_smem + (size_t)buf * C::NPART * C::SLAB_B);
       // split the valid block range into (at most two) ring-contiguous runs; per run: TMEM column, B row offset, N
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
       const uint32_t idesc0 = make_idesc(128, n0 * G), idesc1 = make_idesc(128, (n1 > 0 ? n1 : 1) * G);
       const uint32_t boff0 = (uint32_t)(jlo * G), boff1 = (uint32_t)((jlo + n0) * G);   // in 16-byte rows
       const uint32_t a_lo0 = desc_lo(a_base, C::PLANE_B);                  // hi-part slab
-      const uint32_t b_lo0 = desc_lo(b_base, 3 * G * 16);
+      const uint32_t b_lo0 = desc_lo(b_base + grp * C::BGRP_B, 3 * G * 16);
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
       }
       if (leader) {
         umma_commit(empty + buf);                                   // slab consumed once these MMAs retire
-        if (i >= 2) umma_commit(grp_full + ((i - 2) % NG));         // output plane q = i-2 is complete
+        if (i >= 2 && grp == NGRP - 1) umma_commit(grp_full + ((i - 2) % NG));   // output plane q = i-2 is complete
       }
       __syncwarp();
     }
@@ -533,11 +541,11 @@ __global__ void pack_umma_weight_kernel(const float* __restrict__ w, const float
   }
 }
 
-template <int CIN, int COUT, int NSPLIT, int KM, int NS>
+template <int CIN, int COUT, int NSPLIT, int KM, int NS, int NGRP = 1>
 static int launch(const Params& p, int B, cudaStream_t st) {
-  using C = Cfg<CIN, COUT, NSPLIT, KM, NS>;
+  using C = Cfg<CIN, COUT, NSPLIT, KM, NS, NGRP>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = conv3d_umma_kernel<CIN, COUT, NSPLIT, KM, NS>;
+  auto kern = conv3d_umma_kernel<CIN, COUT, NSPLIT, KM, NS, NGRP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -563,8 +571,8 @@ static Plan plan(int Cin, int Cout, int nsplit) {
   Plan pl;
   pl.cp = Cout < 8 ? 8 : Cout;
   pl.g = ((3 * pl.cp + 15) / 16) * 16;
-  pl.cin_k = (nsplit == 3 && Cin == 32) ? 16 : Cin;     // hi+lo slabs of 32 channels do not fit: two channel groups
-  pl.km = Cout == 16 ? 2 : 3;
+  pl.cin_k = (nsplit == 3 && Cin == 32) ? 16 : Cin;     // hi+lo slabs of 32 channels do not fit: two channel groups,
+  pl.km = (Cout == 16 || (nsplit == 3 && Cin == 32)) ? 2 : 3;   // ... walked inside one launch (NGRP = 2)
   return pl;
 }
 
@@ -904,25 +912,22 @@ extern "C" int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const floa
   }
   const int d_chunk = ceil_div(D, chunks);
   chunks = ceil_div(D, d_chunk);
-  const int groups = Cin / pl.cin_k;
-  const int terms = nsplit == 3 ? 2 : 1;
-  const int per_term = 3 * (pl.cin_k / 8) * 2 * 3 * pl.g * 4;
   cudaStream_t st = as_stream(stream);
-  for (int g = 0; g < groups; ++g) {
+  {
     Params p;
-    p.x = x; p.wimg = wimg + (int64_t)g * terms * per_term; p.bias = bias; p.skip = skip; p.y = y;
-    p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = g * pl.cin_k;
+    p.x = x; p.wimg = wimg; p.bias = bias; p.skip = skip; p.y = y;
+    p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = 0;
     p.d_chunk = d_chunk; p.chunks = chunks;
-    p.accumulate_in = g > 0; p.finalize = g == groups - 1; p.relu = relu;
+    p.accumulate_in = 0; p.finalize = 1; p.relu = relu;
     p.dbg = getenv("RCMVS_TC_DBG") ? atoi(getenv("RCMVS_TC_DBG")) : 0;
     int rc = RCMVS_ERR_UNSUPPORTED;
-#define RCMVS_TC_CASE(CI, CO, NSP, KMV, NSV) \
-  if (pl.cin_k == CI && Cout == CO && nsplit == NSP) rc = launch<CI, CO, NSP, KMV, NSV>(p, B, st)
-    RCMVS_TC_CASE(8, 8, 1, 3, 6); else RCMVS_TC_CASE(8, 8, 3, 3, 5);
-    else RCMVS_TC_CASE(16, 8, 1, 3, 5); else RCMVS_TC_CASE(16, 8, 3, 3, 3);
-    else RCMVS_TC_CASE(32, 8, 1, 3, 3);
-    else RCMVS_TC_CASE(8, 1, 1, 3, 6); else RCMVS_TC_CASE(8, 1, 3, 3, 5);
-    else RCMVS_TC_CASE(16, 16, 1, 2, 5); else RCMVS_TC_CASE(16, 16, 3, 2, 3);
+#define RCMVS_TC_CASE(CI, CO, NSP, KMV, NSV, NGR) \
+  if (Cin == CI * NGR && pl.cin_k == CI && Cout == CO && nsplit == NSP) rc = launch<CI, CO, NSP, KMV, NSV, NGR>(p, B, st)
+    RCMVS_TC_CASE(8, 8, 1, 3, 6, 1); else RCMVS_TC_CASE(8, 8, 3, 3, 5, 1);
+    else RCMVS_TC_CASE(16, 8, 1, 3, 5, 1); else RCMVS_TC_CASE(16, 8, 3, 3, 3, 1);
+    else RCMVS_TC_CASE(32, 8, 1, 3, 3, 1); else RCMVS_TC_CASE(16, 8, 3, 2, 3, 2);
+    else RCMVS_TC_CASE(8, 1, 1, 3, 6, 1); else RCMVS_TC_CASE(8, 1, 3, 3, 5, 1);
+    else RCMVS_TC_CASE(16, 16, 1, 2, 5, 1); else RCMVS_TC_CASE(16, 16, 3, 2, 3, 1);
     else set_error("rcmvs_conv3d_tc_fwd: no kernel for cin_k=%d Cout=%d nsplit=%d", pl.cin_k, Cout, nsplit);
 #undef RCMVS_TC_CASE
     if (rc != RCMVS_OK) return rc;
