@@ -999,3 +999,297 @@ extern "C" int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, 
   }
   return RCMVS_OK;
 }
+
+// ==================================================================================================================
+// Gather implicit-GEMM on tcgen05 for the SMALL levels of the 3-D U-Net (1/4 and 1/8 resolution: conv3..conv6, conv7,
+// conv9; reference models/modules.py:478-486).  These layers have few voxels (7.7 k .. 61 k at stage 1) but many
+// channels (16..64): the slab kernels above cannot fill the machine there and the FFMA kernels are latency-bound
+// (0.1-0.2 ms per layer for 1-3 GFLOP).  Here M = 128 OUTPUT voxels taken from the flat (d,h,w) index space (no tile
+// shape, no width waste), N = Cout, and the K loop walks 27 taps x Cin/16 channel groups.  For every (tap, group) item
+// a loader warp GATHERS the 128 x 16-channel A tile straight from global/L2 (stride-1, stride-2 and transposed
+// convolutions differ only in the index arithmetic; out-of-range taps are zero-filled), splits hi/lo for 3xTF32 on the
+// way to shared memory, and copies the matching 16 x Cout weight block.  One loader warp per pipeline stage keeps
+// NS loads in flight; one thread issues the MMAs; accumulators stay in TMEM for the whole tile.
+// ==================================================================================================================
+namespace rcmvs {
+namespace umma {
+
+struct GParams {
+  const float* x;      // [B][D][H][W][Cin]
+  const float* wimg;   // [27][Cin/16][terms][2 ks][2 chunks][COUT][4]
+  const float* bias;
+  const float* skip;   // [B][Do][Ho][Wo][COUT] or null
+  float* y;            // [B][Do][Ho][Wo][COUT]
+  int D, H, W, Cin, Do, Ho, Wo;
+  int mode;            // 0: conv stride 1, 1: conv stride 2, 2: transposed conv (stride 2, output_padding 1)
+  int relu;
+};
+
+template <int COUT, int NSPLIT, int NS>
+struct GCfg {
+  static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
+  static constexpr int A_PART = 4 * 128 * 16;                       // 16 channels: 4 chunks x 128 rows x 16 B
+  static constexpr int B_PART = 2 * 2 * COUT * 16;                  // 2 K-steps x 2 chunks x COUT rows x 16 B
+  static constexpr int STAGE_B = NPART * (A_PART + B_PART);
+  static constexpr int TMEM_COLS = COUT <= 32 ? 32 : 64;
+  static constexpr size_t SMEM = (size_t)NS * STAGE_B + 256;
+  static constexpr int THREADS = 32 * (4 + NS + 1);
+};
+
+template <int COUT, int NSPLIT, int NS>
+__global__ void __launch_bounds__(GCfg<COUT, NSPLIT, NS>::THREADS, 1) conv3d_gather_umma_kernel(const GParams p) {
+  using C = GCfg<COUT, NSPLIT, NS>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * C::STAGE_B);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NS;
+  uint64_t* acc_full = bars + 2 * NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int64_t Mtot = (int64_t)p.Do * p.Ho * p.Wo;
+  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  const int ngroups = p.Cin / 16;
+  const int nitems = 27 * ngroups;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 4 + NS) {
+    // =============================== gather loaders: warp w owns pipeline stage w-4 ================================
+    const int st = warp - 4;
+    unsigned char* stage = smem + (size_t)st * C::STAGE_B;
+    // the lane's 4 rows (output voxels) are fixed for the whole tile
+    int oz[4], oy[4], ox[4];
+    bool rv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t m = m0 + lane + 32 * r;
+      rv[r] = m < Mtot;
+      const int64_t mm = rv[r] ? m : 0;
+      ox[r] = (int)(mm % p.Wo);
+      oy[r] = (int)((mm / p.Wo) % p.Ho);
+      oz[r] = (int)(mm / ((int64_t)p.Wo * p.Ho));
+    }
+    const float* xb = p.x + (int64_t)b * p.D * p.H * p.W * p.Cin;
+    for (int it = st; it < nitems; it += NS) {
+      mbar_wait(empty + st, ((it / NS) & 1) ^ 1);
+      const int tap = it / ngroups, grp = it % ngroups;
+      const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+      // ---- A: 4 rows x 4 chunks per lane --------------------------------------------------------------------------
+      float4 v[16];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int iz, iy, ix;
+        bool ok = rv[r];
+        if (p.mode == 2) {                       // transposed: i = (o + 1 - k) / 2 when that is an integer in range
+          const int tz = oz[r] + 1 - kd, ty = oy[r] + 1 - kh, tx = ox[r] + 1 - kw;
+          ok = ok && tz >= 0 && ty >= 0 && tx >= 0 && !((tz | ty | tx) & 1);
+          iz = tz >> 1; iy = ty >> 1; ix = tx >> 1;
+        } else {
+          const int s = p.mode == 1 ? 2 : 1;
+          iz = oz[r] * s + kd - 1; iy = oy[r] * s + kh - 1; ix = ox[r] * s + kw - 1;
+          ok = ok && iz >= 0 && iy >= 0 && ix >= 0;
+        }
+        ok = ok && iz < p.D && iy < p.H && ix < p.W;
+        const float* src = xb + (((int64_t)iz * p.H + iy) * p.W + ix) * p.Cin + grp * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r * 4 + c] = ok ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // ---- B: the (tap, group) weight block, NPART x B_PART bytes, copied as float4 -----------------------------------
+      const float4* wsrc = reinterpret_cast<const float4*>(p.wimg) + (int64_t)it * (C::NPART * C::B_PART / 16);
+      float4* wdst = reinterpret_cast<float4*>(stage + C::NPART * C::A_PART);
+      for (int e = lane; e < C::NPART * C::B_PART / 16; e += 32) wdst[e] = __ldg(wsrc + e);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int off = c * (128 * 16) + (lane + 32 * r) * 16;
+          const float4 x4 = v[r * 4 + c];
+          if constexpr (NSPLIT == 3) {
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u); l.x = x4.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(x4.y) & 0xFFFFE000u); l.y = x4.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(x4.z) & 0xFFFFE000u); l.z = x4.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(x4.w) & 0xFFFFE000u); l.w = x4.w - h.w;
+            *reinterpret_cast<float4*>(stage + off) = h;
+            *reinterpret_cast<float4*>(stage + C::A_PART + off) = l;
+          } else {
+            *reinterpret_cast<float4*>(stage + off) = x4;
+          }
+        }
+      fence_proxy_async();
+      mbar_arrive(full + st);
+    }
+  } else if (warp == 4 + NS) {
+    // =============================== MMA issuer ====================================================================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(128, COUT);
+    for (int it = 0; it < nitems; ++it) {
+      const int st = it % NS;
+      mbar_wait(full + st, (it / NS) & 1);
+      tc_fence_after();
+      const uint32_t sbase = smem_u32(smem + (size_t)st * C::STAGE_B);
+      const uint32_t a_lo0 = desc_lo(sbase, 128 * 16);
+      const uint32_t b_lo0 = desc_lo(sbase + C::NPART * C::A_PART, COUT * 16);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t a_d = a_lo0 + (uint32_t)((ks * 2 * 128 * 16) >> 4);
+        const uint32_t b_d = b_lo0 + (uint32_t)((ks * 2 * COUT * 16) >> 4);
+        const uint32_t acc = (it == 0 && ks == 0) ? 0u : 1u;
+        if (leader) {
+          if constexpr (NSPLIT == 3) {
+            umma_tf32_lohi_acc(tmem_base, a_d + (C::A_PART >> 4), b_d, idesc, acc);                 // x_lo · w_hi
+            umma_tf32_lohi_acc(tmem_base, a_d, b_d + (C::B_PART >> 4), idesc, 1u);                  // x_hi · w_lo
+            umma_tf32_lohi_acc(tmem_base, a_d, b_d, idesc, 1u);                                     // x_hi · w_hi
+          } else {
+            umma_tf32_lohi_acc(tmem_base, a_d, b_d, idesc, acc);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(empty + st);
+        if (it == nitems - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // =============================== epilogue =======================================================================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float v[COUT];
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, &v[c0]);
+    const int64_t m = m0 + warp * 32 + lane;
+    if (m < Mtot) {
+      const int64_t o = ((int64_t)b * Mtot + m) * COUT;
+#pragma unroll
+      for (int c = 0; c < COUT; c += 4) {
+        float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        if (p.bias) {
+          const float4 q = ldg4(p.bias + c);
+          r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+        }
+        if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+        if (p.skip) {
+          const float4 q = ldg4(p.skip + o + c);
+          r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+        }
+        st4(p.y + o + c, r);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// img[tap][grp][term][ks][chunk][n][e] = split_term( w(n, ci = grp*16 + ks*8 + chunk*4 + e, tap) * scale[n] )
+__global__ void pack_gather_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                          float* __restrict__ img, int Cout, int Cin, int transposed, int nsplit) {
+  const int terms = nsplit == 3 ? 2 : 1;
+  const int blk = 2 * 2 * Cout * 4;                 // floats per (tap, grp, term)
+  const int ngroups = Cin / 16;
+  const int total = 27 * ngroups * blk;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int e = i & 3;
+  int r = i >> 2;
+  const int n = r % Cout; r /= Cout;
+  const int chunk = r & 1; r >>= 1;
+  const int ks = r & 1; r >>= 1;
+  const int grp = r % ngroups;
+  const int tap = r / ngroups;
+  const int ci = grp * 16 + ks * 8 + chunk * 4 + e;
+  float v = transposed ? w[((int64_t)ci * Cout + n) * 27 + tap] : w[((int64_t)n * Cin + ci) * 27 + tap];
+  if (scale) v *= scale[n];
+  const int64_t base = ((int64_t)(tap * ngroups + grp) * terms) * blk + (((ks * 2 + chunk) * Cout + n) * 4 + e);
+  if (nsplit == 3) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    img[base] = hi;
+    img[base + blk] = v - hi;
+  } else {
+    img[base] = v;
+  }
+}
+
+template <int COUT, int NSPLIT, int NS>
+static int launch_g(const GParams& p, int B, cudaStream_t st) {
+  using C = GCfg<COUT, NSPLIT, NS>;
+  static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
+  auto kern = conv3d_gather_umma_kernel<COUT, NSPLIT, NS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_gemm_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t Mtot = (int64_t)p.Do * p.Ho * p.Wo;
+  dim3 grid((unsigned)ceil_div<int64_t>(Mtot, 128), B);
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(p);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv3d_gemm_tc_fwd");
+  return RCMVS_OK;
+}
+
+}  // namespace umma
+}  // namespace rcmvs
+
+extern "C" int64_t rcmvs_conv3d_gemm_tc_weight_floats(int Cin, int Cout, int nsplit) {
+  return (int64_t)27 * (Cin / 16) * (nsplit == 3 ? 2 : 1) * 2 * 2 * Cout * 4;
+}
+
+extern "C" int rcmvs_conv3d_gemm_tc_pack(const float* w, const float* scale, float* img, int Cout, int Cin,
+                                         int transposed, int nsplit, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(w && img, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_pack: null pointer");
+  RCMVS_REQUIRE(Cin % 16 == 0 && (Cout == 16 || Cout == 32 || Cout == 64) && (nsplit == 1 || nsplit == 3),
+                RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_gemm_tc_pack: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
+  const int total = 27 * (Cin / 16) * 2 * 2 * Cout * 4;
+  umma::pack_gather_weight_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, scale, img, Cout, Cin,
+                                                                                       transposed, nsplit);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv3d_gemm_tc_pack");
+  return RCMVS_OK;
+}
+
+extern "C" int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* wimg, const float* bias, const float* skip,
+                                        float* y, int B, int D, int H, int W, int Cin, int Cout, int mode, int nsplit,
+                                        int relu, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  using namespace rcmvs::umma;
+  RCMVS_REQUIRE(x && wimg && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_fwd: null pointer");
+  RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && B <= 65535, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_fwd: bad dims");
+  RCMVS_REQUIRE(Cin % 16 == 0 && (Cout == 16 || Cout == 32 || Cout == 64) && (nsplit == 1 || nsplit == 3) &&
+                    mode >= 0 && mode <= 2,
+                RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_gemm_tc_fwd: unsupported Cin=%d Cout=%d mode=%d nsplit=%d", Cin,
+                Cout, mode, nsplit);
+  GParams p;
+  p.x = x; p.wimg = wimg; p.bias = bias; p.skip = skip; p.y = y;
+  p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.mode = mode; p.relu = relu;
+  if (mode == 2) { p.Do = 2 * D; p.Ho = 2 * H; p.Wo = 2 * W; }
+  else if (mode == 1) { p.Do = (D - 1) / 2 + 1; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1; }
+  else { p.Do = D; p.Ho = H; p.Wo = W; }
+  cudaStream_t st = as_stream(stream);
+#define RCMVS_G_CASE(CO, NSP, NSV) if (Cout == CO && nsplit == NSP) return launch_g<CO, NSP, NSV>(p, B, st)
+  RCMVS_G_CASE(16, 1, 8); RCMVS_G_CASE(16, 3, 8);
+  RCMVS_G_CASE(32, 1, 8); RCMVS_G_CASE(32, 3, 8);
+  RCMVS_G_CASE(64, 1, 8); RCMVS_G_CASE(64, 3, 6);
+#undef RCMVS_G_CASE
+  return RCMVS_ERR_UNSUPPORTED;
+}

@@ -251,6 +251,9 @@ class CostRegNet(nn.Module):
                         cands.append(("tct", ops.conv_transpose3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
                     if nsplit > 0 and not tr and stride == 1 and (cin, cout) in ops.TC_SUPPORTED:
                         cands.append(("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
+                    if nsplit > 0 and ops.gemm_tc_supported(cin, cout):
+                        gmode = 2 if tr else (1 if stride == 2 else 0)
+                        cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, tr, nsplit), shift, cout, nsplit, gmode))
                     P[name] = {"cands": cands, "tr": tr, "stride": stride, "relu": relu, "choice": {}}
             self._packed = (key, P)
         return self._packed[1]
@@ -262,6 +265,8 @@ class CostRegNet(nn.Module):
             return ops.conv3d_tc(x, cand[1], cand[3], cand[2], skip, cand[4], layer["relu"])
         if kind == "tct":
             return ops.conv_transpose3d_tc(x, cand[1], cand[3], cand[2], skip, cand[4], layer["relu"])
+        if kind == "gemm":
+            return ops.conv3d_gemm_tc(x, cand[1], cand[3], cand[5], cand[2], skip, cand[4], layer["relu"])
         if layer["tr"]:
             return ops.conv_transpose3d(x, cand[1], cand[2], skip=skip, relu=layer["relu"])
         return ops.conv3d(x, cand[1], cand[2], skip, stride=layer["stride"], relu=layer["relu"])

@@ -174,8 +174,39 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     y = torch.empty((B, D, H, W, Cout), device=x_cl.device, dtype=torch.float32)
     _ffi.call("rcmvs_conv3d_tc_fwd", _chk(x_cl, "x"), _chk(img, "wimg"), _opt(bias, "bias"), _opt(skip, "skip"),
               _chk(y, "y"), B, D, H, W, Cin, Cout, nsplit, 1 if relu else 0, _stream())
-    if Cin == 32 and nsplit == 3:
-        _ffi.launches += 1          # two channel-group launches inside the call
+    return y
+
+
+def gemm_tc_supported(Cin, Cout):
+    """Layers the gather implicit-GEMM kernel takes (the 1/4- and 1/8-resolution levels)."""
+    return Cin % 16 == 0 and Cout in (16, 32, 64)
+
+
+def conv3d_gemm_tc_pack(w, scale=None, transposed=False, nsplit=3):
+    """torch Conv3d [Cout,Cin,27] / ConvTranspose3d [Cin,Cout,27] weight (x BN scale) -> gather-GEMM operand image."""
+    if transposed:
+        Cin, Cout = w.shape[:2]
+    else:
+        Cout, Cin = w.shape[:2]
+    n = _ffi.lib().rcmvs_conv3d_gemm_tc_weight_floats(Cin, Cout, nsplit)
+    img = torch.empty((n,), device=w.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv3d_gemm_tc_pack", _chk(w, "w"), _opt(scale, "scale"), _chk(img, "img"), Cout, Cin,
+              1 if transposed else 0, nsplit, _stream())
+    return img
+
+
+def conv3d_gemm_tc(x_cl, img, Cout, mode, bias=None, skip=None, nsplit=3, relu=True):
+    """x_cl [B,D,H,W,Cin]; mode 0 conv s1 / 1 conv s2 / 2 transposed conv -> [B,Do,Ho,Wo,Cout] on tcgen05.mma."""
+    B, D, H, W, Cin = x_cl.shape
+    if mode == 2:
+        Do, Ho, Wo = 2 * D, 2 * H, 2 * W
+    elif mode == 1:
+        Do, Ho, Wo = (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    else:
+        Do, Ho, Wo = D, H, W
+    y = torch.empty((B, Do, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32)
+    _ffi.call("rcmvs_conv3d_gemm_tc_fwd", _chk(x_cl, "x"), _chk(img, "wimg"), _opt(bias, "bias"), _opt(skip, "skip"),
+              _chk(y, "y"), B, D, H, W, Cin, Cout, mode, nsplit, 1 if relu else 0, _stream())
     return y
 
 

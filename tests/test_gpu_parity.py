@@ -267,6 +267,40 @@ def test_conv_transpose3d_tensor_core_vs_oracle(dev, cin, cout, dhw, nsplit):
     np.testing.assert_allclose(got[0].permute(3, 0, 1, 2).cpu().numpy(), want + skip, atol=tol, rtol=tol)
 
 
+@pytest.mark.parametrize("nsplit", [3, 1])
+@pytest.mark.parametrize("cin,cout,mode,dhw", [
+    (16, 16, 0, (5, 7, 33)), (16, 32, 1, (8, 10, 22)), (16, 32, 1, (7, 9, 21)), (32, 32, 0, (6, 8, 10)),
+    (32, 64, 1, (6, 8, 10)), (64, 64, 0, (3, 4, 5)), (64, 64, 0, (1, 1, 1)), (64, 32, 2, (3, 4, 5)),
+    (32, 16, 2, (3, 6, 11)), (32, 32, 0, (12, 16, 20)), (16, 16, 0, (1, 1, 129)),
+])
+def test_conv3d_gather_gemm_tensor_core_vs_oracle(dev, cin, cout, mode, dhw, nsplit):
+    """Gather implicit-GEMM tcgen05 kernel of the 1/4- and 1/8-resolution levels: stride-1, stride-2 and transposed
+    convolutions, ragged last M tile, batch 2."""
+    from rcmvs import ops
+    rng = np.random.default_rng(cin * 131 + cout * 7 + mode * 3 + nsplit)
+    D, H, W = dhw
+    xs = [rng.standard_normal((cin, D, H, W), dtype=np.float32) for _ in range(2)]
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    if mode == 2:
+        w = (rng.standard_normal((cin, cout, 3, 3, 3)) / np.sqrt(27 * cin / 8)).astype(np.float32)
+        lin = [O.conv_transpose3d(x, w * scale[None, :, None, None, None]) for x in xs]
+    else:
+        w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(27 * cin)).astype(np.float32)
+        lin = [O.conv3d(x, w * scale[:, None, None, None, None], stride=1 + mode) for x in xs]
+    lin = np.stack(lin)
+    want = np.maximum(lin + bias[None, :, None, None, None], 0)
+    skip = rng.standard_normal(want.shape, dtype=np.float32)
+    img = ops.conv3d_gemm_tc_pack(cu(w, dev), cu(scale, dev), mode == 2, nsplit)
+    x_cl = cu(np.stack(xs).transpose(0, 2, 3, 4, 1), dev)
+    got = ops.conv3d_gemm_tc(x_cl, img, cout, mode, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), nsplit, True)
+    assert tuple(got.shape) == (2,) + want.shape[2:] + (cout,)
+    tol = 3e-5 if nsplit == 3 else 6e-3
+    np.testing.assert_allclose(got.permute(0, 4, 1, 2, 3).cpu().numpy(), want + skip, atol=tol, rtol=tol)
+    got = ops.conv3d_gemm_tc(x_cl, img, cout, mode, None, None, nsplit, False)
+    np.testing.assert_allclose(got.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=tol, rtol=tol)
+
+
 def _model(dev, ndepths, cls_name="CascadeMVSNet_eval"):
     import models
     from rcmvs import weights
