@@ -118,16 +118,19 @@ int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, const float
                                   int B, int D, int H, int W, int Cin, int Cout, int nsplit, int relu,
                                   rcmvs_stream_t stream);
 
-/* Gather implicit-GEMM on tcgen05 for the small 1/4- and 1/8-resolution layers (conv3..conv7, conv9): any
- * D/H/W, Cin % 16 == 0, Cout in {16,32,64}; mode 0 = conv stride 1, 1 = conv stride 2, 2 = transposed conv
- * (k3, s2, p1, output_padding 1).  The weight image is built from the torch weight (Conv3d [Cout][Cin][27] or, with
- * transposed = 1, ConvTranspose3d [Cin][Cout][27]) and the folded BatchNorm scale. */
+/* Gather implicit-GEMM on tcgen05 for the small 1/4- and 1/8-resolution layers (conv3..conv7, conv9; reference
+ * models/modules.py:478-486): any D/H/W, Cin and Cout in {16,32,64}; mode 0 = conv stride 1, 1 = conv stride 2,
+ * 2 = transposed conv (k3, s2, p1, output_padding 1).  The weight image is built from the torch weight (Conv3d
+ * [Cout][Cin][27] or, with transposed = 1, ConvTranspose3d [Cin][Cout][27]) and the folded BatchNorm scale.
+ * With nsplit = 3 the input may come pre-split: x = hi half, x_lo = lo half (x_hi + x_lo == activation exactly), as
+ * written by the producing layer through y_hi / y_lo; x_lo = NULL makes the kernel split on the fly.  y may be NULL
+ * when only the split pair is wanted. */
 int64_t rcmvs_conv3d_gemm_tc_weight_floats(int Cin, int Cout, int nsplit);
 int rcmvs_conv3d_gemm_tc_pack(const float* w, const float* scale, float* img, int Cout, int Cin, int transposed,
                               int nsplit, rcmvs_stream_t stream);
-int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* wimg, const float* bias, const float* skip, float* y, int B,
-                             int D, int H, int W, int Cin, int Cout, int mode, int nsplit, int relu,
-                             rcmvs_stream_t stream);
+int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* x_lo, const float* wimg, const float* bias,
+                             const float* skip, float* y, float* y_hi, float* y_lo, int B, int D, int H, int W,
+                             int Cin, int Cout, int mode, int nsplit, int relu, rcmvs_stream_t stream);
 
 /* ---- a4 softmax + soft-argmin + photometric confidence: models/casmvsnet.py:111-122, modules.py:519-525 ------ */
 /* cost [B][D][h][w]; depth planes [B][D] (per_pixel=0) or [B][D][h][w]; -> depth [B][h][w], conf [B][h][w],

@@ -69,6 +69,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// the mbarrier receives this thread's arrival once all of its prior cp.async copies have landed (no thread blocks)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -1004,41 +1008,71 @@ extern "C" int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, 
 // Gather implicit-GEMM on tcgen05 for the SMALL levels of the 3-D U-Net (1/4 and 1/8 resolution: conv3..conv6, conv7,
 // conv9; reference models/modules.py:478-486).  These layers have few voxels (7.7 k .. 61 k at stage 1) but many
 // channels (16..64): the slab kernels above cannot fill the machine there and the FFMA kernels are latency-bound
-// (0.1-0.2 ms per layer for 1-3 GFLOP).  Here M = 128 OUTPUT voxels taken from the flat (d,h,w) index space (no tile
-// shape, no width waste), N = Cout, and the K loop walks 27 taps x Cin/16 channel groups.  For every (tap, group) item
-// a loader warp GATHERS the 128 x 16-channel A tile straight from global/L2 (stride-1, stride-2 and transposed
-// convolutions differ only in the index arithmetic; out-of-range taps are zero-filled), splits hi/lo for 3xTF32 on the
-// way to shared memory, and copies the matching 16 x Cout weight block.  One loader warp per pipeline stage keeps
-// NS loads in flight; one thread issues the MMAs; accumulators stay in TMEM for the whole tile.
+// (0.1-0.2 ms per layer for 1-3 GFLOP).  Here M = 128 OUTPUT voxels taken from a flat index space (no tile shape, no
+// width waste), N = Cout, and the K loop walks (tap, 16-channel group) items.  For every item a loader warp GATHERS
+// the 128 x 16-channel A tile straight from global/L2 and copies the matching 16 x Cout weight block; one loader warp
+// per pipeline stage keeps NS items in flight, one thread issues the MMAs, accumulators stay in TMEM for the tile.
+//   * stride-1 / stride-2 convolutions: rows = consecutive output voxels, 27 taps, input = s*o + k - 1.
+//   * transposed convolution (k3 s2 p1 op1): rows = 128 consecutive voxels of ONE output parity class (oz&1,oy&1,ox&1);
+//     a class only receives the taps whose parity matches (1, 2, 4 or 8 of the 27), so the K loop is 27/8 taps long on
+//     average instead of 27: input = j + d with o = 2j + parity.
+//   * 3xTF32: the hi/lo halves of the ACTIVATION are either produced on the fly by the loader (registers, `x_lo` null)
+//     or - cheaper, the split is done once instead of once per tap - read pre-split from the producing layer's epilogue
+//     (`y_hi`/`y_lo` outputs), in which case A and B both move with cp.async and the loader does no arithmetic.
 // ==================================================================================================================
 namespace rcmvs {
 namespace umma {
 
 struct GParams {
-  const float* x;      // [B][D][H][W][Cin]
+  const float* x;      // [B][D][H][W][Cin]  (the hi half when x_lo is given)
+  const float* x_lo;   // lo half of the pre-split input, or null
   const float* wimg;   // [27][Cin/16][terms][2 ks][2 chunks][COUT][4]
   const float* bias;
   const float* skip;   // [B][Do][Ho][Wo][COUT] or null
-  float* y;            // [B][Do][Ho][Wo][COUT]
-  int D, H, W, Cin, Do, Ho, Wo;
+  float* y;            // [B][Do][Ho][Wo][COUT] or null
+  float* y_hi;         // optional pre-split copy of the result for a following gather layer
+  float* y_lo;
+  int D, H, W, Cin, lg, Do, Ho, Wo;   // lg = log2(Cin/16)
   int mode;            // 0: conv stride 1, 1: conv stride 2, 2: transposed conv (stride 2, output_padding 1)
   int relu;
+  int tiles_per_class; // transposed: M tiles per parity class
 };
 
-template <int COUT, int NSPLIT, int NS>
+template <int COUT, int NSPLIT, bool PRESPLIT, int NS>
 struct GCfg {
   static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
+  static constexpr bool ASYNC_A = NSPLIT == 1 || PRESPLIT;          // A tile moves with cp.async (no arithmetic)
   static constexpr int A_PART = 4 * 128 * 16;                       // 16 channels: 4 chunks x 128 rows x 16 B
   static constexpr int B_PART = 2 * 2 * COUT * 16;                  // 2 K-steps x 2 chunks x COUT rows x 16 B
   static constexpr int STAGE_B = NPART * (A_PART + B_PART);
   static constexpr int TMEM_COLS = COUT <= 32 ? 32 : 64;
-  static constexpr size_t SMEM = (size_t)NS * STAGE_B + 256;
-  static constexpr int THREADS = 32 * (4 + NS + 1);
+  static constexpr size_t SMEM = (size_t)NS * STAGE_B + 256 + 128 * 8;      // stages | barriers | row table
+  // cp.async loaders never block on their own copies (the copies arrive on the mbarrier themselves), so 4 warps feed
+  // a ring of NS stages; the register path needs one warp per stage to keep NS gathers in flight
+  static constexpr int NLW = ASYNC_A ? 4 : NS;
+  static constexpr int THREADS = 32 * (4 + NLW + 1);
 };
 
-template <int COUT, int NSPLIT, int NS>
-__global__ void __launch_bounds__(GCfg<COUT, NSPLIT, NS>::THREADS, 1) conv3d_gather_umma_kernel(const GParams p) {
-  using C = GCfg<COUT, NSPLIT, NS>;
+// tap t of this tile -> weight tap index (kd*9+kh*3+kw) and input offset (dz,dy,dx) relative to the row's base voxel
+__device__ __forceinline__ void gather_tap(int mode, int t, int pz, int py, int px, int& wtap, int& dz, int& dy, int& dx) {
+  if (mode == 2) {
+    // per dimension: parity 0 -> k = 1, d = 0; parity 1 -> (k = 0, d = +1), (k = 2, d = 0)
+    const int nx = 1 + px, ny = 1 + py;
+    const int tx = t % nx, ty = (t / nx) % ny, tz = t / (nx * ny);
+    const int kw = px ? 2 * tx : 1, kh = py ? 2 * ty : 1, kd = pz ? 2 * tz : 1;
+    dx = px ? 1 - tx : 0; dy = py ? 1 - ty : 0; dz = pz ? 1 - tz : 0;
+    wtap = kd * 9 + kh * 3 + kw;
+  } else {
+    const int kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
+    dz = kd - 1; dy = kh - 1; dx = kw - 1;
+    wtap = t;
+  }
+}
+
+template <int COUT, int NSPLIT, bool PRESPLIT, int NS>
+__global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
+    conv3d_gather_umma_kernel(const GParams p) {
+  using C = GCfg<COUT, NSPLIT, PRESPLIT, NS>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * C::STAGE_B);
   uint64_t* full = bars;
@@ -1047,13 +1081,44 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, NS>::THREADS, 1) conv3d_gat
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int64_t Mtot = (int64_t)p.Do * p.Ho * p.Wo;
-  const int64_t m0 = (int64_t)blockIdx.x * 128;
-  const int ngroups = p.Cin / 16;
-  const int nitems = 27 * ngroups;
 
+  // ---- which rows this tile owns ---------------------------------------------------------------------------------
+  int pz = 0, py = 0, px = 0, tile = blockIdx.x, ntaps = 27;
+  int64_t Mspace;                       // size of the flat index space the rows are taken from
+  int Rh, Rw;                           // its (h, w) extents
+  if (p.mode == 2) {
+    const int cls = blockIdx.x / p.tiles_per_class;
+    tile = blockIdx.x - cls * p.tiles_per_class;
+    pz = (cls >> 2) & 1; py = (cls >> 1) & 1; px = cls & 1;
+    ntaps = (1 + pz) * (1 + py) * (1 + px);
+    Mspace = (int64_t)p.D * p.H * p.W; Rh = p.H; Rw = p.W;
+  } else {
+    Mspace = (int64_t)p.Do * p.Ho * p.Wo; Rh = p.Ho; Rw = p.Wo;
+  }
+  const int64_t m0 = (int64_t)tile * 128;
+  const int ngroups = 1 << p.lg;
+  const int nitems = ntaps << p.lg;
+
+  // ---- row table: element offset of each row's base input voxel + the set of taps that stay inside the volume --------
+  int2* geo = reinterpret_cast<int2*>(smem + (size_t)NS * C::STAGE_B + 256);
+  if (threadIdx.x < 128) {
+    const int s = p.mode == 1 ? 2 : 1;
+    const int64_t m = m0 + threadIdx.x;
+    int2 g = make_int2(0, 0);
+    if (m < Mspace) {
+      const int bx = (int)(m % Rw) * s, by = (int)((m / Rw) % Rh) * s, bz = (int)(m / ((int64_t)Rw * Rh)) * s;
+      g.x = ((bz * p.H + by) * p.W + bx) * p.Cin;
+      for (int t = 0; t < ntaps; ++t) {
+        int wtap, dz, dy, dx;
+        gather_tap(p.mode, t, pz, py, px, wtap, dz, dy, dx);
+        const int iz = bz + dz, iy = by + dy, ix = bx + dx;
+        if (iz >= 0 && iy >= 0 && ix >= 0 && iz < p.D && iy < p.H && ix < p.W) g.y |= 1 << t;
+      }
+    }
+    geo[threadIdx.x] = g;
+  }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, C::ASYNC_A ? 32 : 1); mbar_init(empty + i, 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1068,79 +1133,102 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, NS>::THREADS, 1) conv3d_gat
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 4 + NS) {
-    // =============================== gather loaders: warp w owns pipeline stage w-4 ================================
-    const int st = warp - 4;
-    unsigned char* stage = smem + (size_t)st * C::STAGE_B;
-    // the lane's 4 rows (output voxels) are fixed for the whole tile
-    int oz[4], oy[4], ox[4];
-    bool rv[4];
+  if (warp >= 4 && warp < 4 + C::NLW) {
+    // =============================== gather loaders ==================================================================
+    // 4 consecutive lanes fetch the 64 contiguous bytes (16 channels) of one row, so a warp instruction touches 8 cache
+    // lines instead of 32; a lane serves chunk c = lane&3 of rows (lane>>2) + 8j, j = 0..15.
+    const int lw = warp - 4;
+    const int c = lane & 3, row0 = lane >> 2;
+    const int64_t xbo = (int64_t)b * p.D * p.H * p.W * p.Cin;
+    const float* xb = p.x + xbo + c * 4;
+    const float* xlb = C::ASYNC_A && NSPLIT == 3 ? p.x_lo + xbo + c * 4 : nullptr;
+    constexpr int BV = C::NPART * C::B_PART / 16 / 32;              // 16-byte weight pieces per lane (2..16)
+    const uint32_t lane_dst = c * (128 * 16) + row0 * 16;           // + j * 128 per row step
+
+    auto item_geom = [&](int it, int& t, int& wblk, int& toff) {
+      t = it >> p.lg;
+      const int grp = it & (ngroups - 1);
+      int wtap, dz, dy, dx;
+      gather_tap(p.mode, t, pz, py, px, wtap, dz, dy, dx);
+      wblk = wtap * ngroups + grp;
+      toff = ((dz * p.H + dy) * p.W + dx) * p.Cin + grp * 16;
+    };
+    auto copy_weights = [&](int wblk, uint32_t stage_u) {
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wimg) + (int64_t)wblk * (C::NPART * C::B_PART);
+      const uint32_t wdst = stage_u + C::NPART * C::A_PART;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t m = m0 + lane + 32 * r;
-      rv[r] = m < Mtot;
-      const int64_t mm = rv[r] ? m : 0;
-      ox[r] = (int)(mm % p.Wo);
-      oy[r] = (int)((mm / p.Wo) % p.Ho);
-      oz[r] = (int)(mm / ((int64_t)p.Wo * p.Ho));
-    }
-    const float* xb = p.x + (int64_t)b * p.D * p.H * p.W * p.Cin;
-    for (int it = st; it < nitems; it += NS) {
-      mbar_wait(empty + st, ((it / NS) & 1) ^ 1);
-      const int tap = it / ngroups, grp = it % ngroups;
-      const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-      // ---- A: 4 rows x 4 chunks per lane --------------------------------------------------------------------------
-      float4 v[16];
+      for (int e = 0; e < BV; ++e) cp_async16(wdst + (lane + 32 * e) * 16, wsrc + (lane + 32 * e) * 16, true);
+    };
+
+    if constexpr (C::ASYNC_A) {
+      for (int it = lw; it < nitems; it += C::NLW) {
+        int t, wblk, toff;
+        item_geom(it, t, wblk, toff);
+        const int st = it % NS;
+        const uint32_t stage_u = smem_u32(smem + (size_t)st * C::STAGE_B);
+        mbar_wait(empty + st, ((it / NS) & 1) ^ 1);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        int iz, iy, ix;
-        bool ok = rv[r];
-        if (p.mode == 2) {                       // transposed: i = (o + 1 - k) / 2 when that is an integer in range
-          const int tz = oz[r] + 1 - kd, ty = oy[r] + 1 - kh, tx = ox[r] + 1 - kw;
-          ok = ok && tz >= 0 && ty >= 0 && tx >= 0 && !((tz | ty | tx) & 1);
-          iz = tz >> 1; iy = ty >> 1; ix = tx >> 1;
-        } else {
-          const int s = p.mode == 1 ? 2 : 1;
-          iz = oz[r] * s + kd - 1; iy = oy[r] * s + kh - 1; ix = ox[r] * s + kw - 1;
-          ok = ok && iz >= 0 && iy >= 0 && ix >= 0;
+        for (int j = 0; j < 16; ++j) {
+          const int2 g = geo[row0 + 8 * j];
+          const bool ok = (g.y >> t) & 1;
+          const int off = ok ? g.x + toff : 0;
+          const uint32_t dst = stage_u + lane_dst + j * 128;
+          cp_async16(dst, xb + off, ok);
+          if constexpr (NSPLIT == 3) cp_async16(dst + C::A_PART, xlb + off, ok);
         }
-        ok = ok && iz < p.D && iy < p.H && ix < p.W;
-        const float* src = xb + (((int64_t)iz * p.H + iy) * p.W + ix) * p.Cin + grp * 16;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[r * 4 + c] = ok ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        copy_weights(wblk, stage_u);
+        cp_async_mbar_arrive_noinc(full + st);
       }
-      // ---- B: the (tap, group) weight block, NPART x B_PART bytes, copied as float4 -----------------------------------
-      const float4* wsrc = reinterpret_cast<const float4*>(p.wimg) + (int64_t)it * (C::NPART * C::B_PART / 16);
-      float4* wdst = reinterpret_cast<float4*>(stage + C::NPART * C::A_PART);
-      for (int e = lane; e < C::NPART * C::B_PART / 16; e += 32) wdst[e] = __ldg(wsrc + e);
+      cp_async_commit();
+      cp_async_wait<0>();                 // nothing of this warp is in flight when the CTA tears down
+    } else {
+      // split-in-loader path: the A tile of the NEXT item is gathered into registers while this one is consumed
+      float4 v[16];
+      auto gather = [&](int it, int& wblk) {
+        int t, toff;
+        item_geom(it, t, wblk, toff);
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int off = c * (128 * 16) + (lane + 32 * r) * 16;
-          const float4 x4 = v[r * 4 + c];
-          if constexpr (NSPLIT == 3) {
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u); l.x = x4.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(x4.y) & 0xFFFFE000u); l.y = x4.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(x4.z) & 0xFFFFE000u); l.z = x4.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(x4.w) & 0xFFFFE000u); l.w = x4.w - h.w;
-            *reinterpret_cast<float4*>(stage + off) = h;
-            *reinterpret_cast<float4*>(stage + C::A_PART + off) = l;
-          } else {
-            *reinterpret_cast<float4*>(stage + off) = x4;
-          }
+        for (int j = 0; j < 16; ++j) {
+          const int2 g = geo[row0 + 8 * j];
+          const bool ok = (g.y >> t) & 1;
+          v[j] = ok ? ldg4(xb + g.x + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      fence_proxy_async();
-      mbar_arrive(full + st);
+      };
+      const int st = lw;                                            // this warp's pipeline stage
+      unsigned char* stage = smem + (size_t)st * C::STAGE_B;
+      int wblk = 0;
+      if (st < nitems) gather(st, wblk);
+      for (int it = st; it < nitems; it += NS) {
+        mbar_wait(empty + st, ((it / NS) & 1) ^ 1);
+        copy_weights(wblk, smem_u32(stage));
+        cp_async_commit();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t off = lane_dst + j * 128;
+          const float4 x4 = v[j];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u); l.x = x4.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x4.y) & 0xFFFFE000u); l.y = x4.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x4.z) & 0xFFFFE000u); l.z = x4.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x4.w) & 0xFFFFE000u); l.w = x4.w - h.w;
+          *reinterpret_cast<float4*>(stage + off) = h;
+          *reinterpret_cast<float4*>(stage + C::A_PART + off) = l;
+        }
+        if (it + NS < nitems) gather(it + NS, wblk);
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + st);
+      }
     }
-  } else if (warp == 4 + NS) {
+  } else if (warp == 4 + C::NLW) {
     // =============================== MMA issuer ====================================================================
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc(128, COUT);
     for (int it = 0; it < nitems; ++it) {
       const int st = it % NS;
       mbar_wait(full + st, (it / NS) & 1);
+      if constexpr (C::ASYNC_A) fence_proxy_async();       // cp.async data observed through the mbarrier -> async proxy
       tc_fence_after();
       const uint32_t sbase = smem_u32(smem + (size_t)st * C::STAGE_B);
       const uint32_t a_lo0 = desc_lo(sbase, 128 * 16);
@@ -1167,15 +1255,20 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, NS>::THREADS, 1) conv3d_gat
       __syncwarp();
     }
   } else if (warp < 4) {
-    // =============================== epilogue =======================================================================
+    // =============================== epilogue: one output voxel per thread ==========================================
+    const int64_t m = m0 + warp * 32 + lane;
+    int64_t ovox = m;
+    if (p.mode == 2 && m < Mspace) {
+      const int jx = (int)(m % p.W), jy = (int)((m / p.W) % p.H), jz = (int)(m / ((int64_t)p.W * p.H));
+      ovox = ((int64_t)(2 * jz + pz) * p.Ho + (2 * jy + py)) * p.Wo + (2 * jx + px);
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     float v[COUT];
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, &v[c0]);
-    const int64_t m = m0 + warp * 32 + lane;
-    if (m < Mtot) {
-      const int64_t o = ((int64_t)b * Mtot + m) * COUT;
+    if (m < Mspace) {
+      const int64_t o = ((int64_t)b * p.Do * p.Ho * p.Wo + ovox) * COUT;
 #pragma unroll
       for (int c = 0; c < COUT; c += 4) {
         float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
@@ -1188,7 +1281,16 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, NS>::THREADS, 1) conv3d_gat
           const float4 q = ldg4(p.skip + o + c);
           r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
         }
-        st4(p.y + o + c, r);
+        if (p.y) st4(p.y + o + c, r);
+        if (p.y_hi) {
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(r.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(r.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(r.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(r.w) & 0xFFFFE000u);
+          st4(p.y_hi + o + c, h);
+          st4(p.y_lo + o + c, make_float4(r.x - h.x, r.y - h.y, r.z - h.z, r.w - h.w));
+        }
       }
     }
   }
@@ -1230,19 +1332,20 @@ __global__ void pack_gather_weight_kernel(const float* __restrict__ w, const flo
   }
 }
 
-template <int COUT, int NSPLIT, int NS>
+template <int COUT, int NSPLIT, bool PRESPLIT, int NS>
 static int launch_g(const GParams& p, int B, cudaStream_t st) {
-  using C = GCfg<COUT, NSPLIT, NS>;
+  using C = GCfg<COUT, NSPLIT, PRESPLIT, NS>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = conv3d_gather_umma_kernel<COUT, NSPLIT, NS>;
+  auto kern = conv3d_gather_umma_kernel<COUT, NSPLIT, PRESPLIT, NS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_gemm_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int64_t Mtot = (int64_t)p.Do * p.Ho * p.Wo;
-  dim3 grid((unsigned)ceil_div<int64_t>(Mtot, 128), B);
+  const int64_t Mspace = p.mode == 2 ? (int64_t)p.D * p.H * p.W : (int64_t)p.Do * p.Ho * p.Wo;
+  const int64_t tiles = ceil_div<int64_t>(Mspace, 128);
+  dim3 grid((unsigned)(p.mode == 2 ? 8 * tiles : tiles), B);
   kern<<<grid, C::THREADS, C::SMEM, st>>>(p);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_gemm_tc_fwd");
   return RCMVS_OK;
@@ -1259,7 +1362,8 @@ extern "C" int rcmvs_conv3d_gemm_tc_pack(const float* w, const float* scale, flo
                                          int transposed, int nsplit, rcmvs_stream_t stream) {
   using namespace rcmvs;
   RCMVS_REQUIRE(w && img, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_pack: null pointer");
-  RCMVS_REQUIRE(Cin % 16 == 0 && (Cout == 16 || Cout == 32 || Cout == 64) && (nsplit == 1 || nsplit == 3),
+  RCMVS_REQUIRE((Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 16 || Cout == 32 || Cout == 64) &&
+                    (nsplit == 1 || nsplit == 3),
                 RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_gemm_tc_pack: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
   const int total = 27 * (Cin / 16) * 2 * 2 * Cout * 4;
   umma::pack_gather_weight_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, scale, img, Cout, Cin,
@@ -1268,28 +1372,37 @@ extern "C" int rcmvs_conv3d_gemm_tc_pack(const float* w, const float* scale, flo
   return RCMVS_OK;
 }
 
-extern "C" int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* wimg, const float* bias, const float* skip,
-                                        float* y, int B, int D, int H, int W, int Cin, int Cout, int mode, int nsplit,
-                                        int relu, rcmvs_stream_t stream) {
+extern "C" int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* x_lo, const float* wimg, const float* bias,
+                                        const float* skip, float* y, float* y_hi, float* y_lo, int B, int D, int H,
+                                        int W, int Cin, int Cout, int mode, int nsplit, int relu,
+                                        rcmvs_stream_t stream) {
   using namespace rcmvs;
   using namespace rcmvs::umma;
-  RCMVS_REQUIRE(x && wimg && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_fwd: null pointer");
+  RCMVS_REQUIRE(x && wimg && (y || y_hi), RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_fwd: null pointer");
+  RCMVS_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), RCMVS_ERR_BAD_ARG,
+                "rcmvs_conv3d_gemm_tc_fwd: y_hi and y_lo go together");
   RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && B <= 65535, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_fwd: bad dims");
-  RCMVS_REQUIRE(Cin % 16 == 0 && (Cout == 16 || Cout == 32 || Cout == 64) && (nsplit == 1 || nsplit == 3) &&
-                    mode >= 0 && mode <= 2,
+  RCMVS_REQUIRE((Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 16 || Cout == 32 || Cout == 64) &&
+                    (nsplit == 1 || nsplit == 3) && mode >= 0 && mode <= 2,
                 RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_gemm_tc_fwd: unsupported Cin=%d Cout=%d mode=%d nsplit=%d", Cin,
                 Cout, mode, nsplit);
+  RCMVS_REQUIRE(!(x_lo && nsplit == 1), RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_fwd: x_lo only with nsplit=3");
+  RCMVS_REQUIRE((int64_t)D * H * W * Cin < (int64_t)1 << 31, RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv3d_gemm_tc_fwd: one sample of the input must stay below 2^31 elements");
   GParams p;
-  p.x = x; p.wimg = wimg; p.bias = bias; p.skip = skip; p.y = y;
-  p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.mode = mode; p.relu = relu;
+  p.x = x; p.x_lo = x_lo; p.wimg = wimg; p.bias = bias; p.skip = skip; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo;
+  p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.lg = Cin == 16 ? 0 : (Cin == 32 ? 1 : 2); p.mode = mode; p.relu = relu;
   if (mode == 2) { p.Do = 2 * D; p.Ho = 2 * H; p.Wo = 2 * W; }
   else if (mode == 1) { p.Do = (D - 1) / 2 + 1; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1; }
   else { p.Do = D; p.Ho = H; p.Wo = W; }
+  p.tiles_per_class = (int)ceil_div<int64_t>((int64_t)D * H * W, 128);
   cudaStream_t st = as_stream(stream);
-#define RCMVS_G_CASE(CO, NSP, NSV) if (Cout == CO && nsplit == NSP) return launch_g<CO, NSP, NSV>(p, B, st)
-  RCMVS_G_CASE(16, 1, 8); RCMVS_G_CASE(16, 3, 8);
-  RCMVS_G_CASE(32, 1, 8); RCMVS_G_CASE(32, 3, 8);
-  RCMVS_G_CASE(64, 1, 8); RCMVS_G_CASE(64, 3, 6);
+  const bool pre = x_lo != nullptr;
+#define RCMVS_G_CASE(CO, NSP, PRE, NSV) \
+  if (Cout == CO && nsplit == NSP && pre == PRE) return launch_g<CO, NSP, PRE, NSV>(p, B, st)
+  RCMVS_G_CASE(16, 1, false, 8); RCMVS_G_CASE(16, 3, false, 8); RCMVS_G_CASE(16, 3, true, 8);
+  RCMVS_G_CASE(32, 1, false, 8); RCMVS_G_CASE(32, 3, false, 8); RCMVS_G_CASE(32, 3, true, 8);
+  RCMVS_G_CASE(64, 1, false, 8); RCMVS_G_CASE(64, 3, false, 6); RCMVS_G_CASE(64, 3, true, 8);
 #undef RCMVS_G_CASE
   return RCMVS_ERR_UNSUPPORTED;
 }

@@ -261,28 +261,28 @@ class CostRegNet(nn.Module):
     @staticmethod
     def _call(cand, layer, x, skip):
         kind = cand[0]
+        if kind == "gemm":
+            return ops.conv3d_gemm_tc(x, cand[1], cand[3], cand[5], cand[2], skip, cand[4], layer["relu"])
         if kind == "tc":
             return ops.conv3d_tc(x, cand[1], cand[3], cand[2], skip, cand[4], layer["relu"])
         if kind == "tct":
             return ops.conv_transpose3d_tc(x, cand[1], cand[3], cand[2], skip, cand[4], layer["relu"])
-        if kind == "gemm":
-            return ops.conv3d_gemm_tc(x, cand[1], cand[3], cand[5], cand[2], skip, cand[4], layer["relu"])
         if layer["tr"]:
             return ops.conv_transpose3d(x, cand[1], cand[2], skip=skip, relu=layer["relu"])
         return ops.conv3d(x, cand[1], cand[2], skip, stride=layer["stride"], relu=layer["relu"])
 
     @classmethod
-    def _run(cls, layer, x, skip=None):
-        """Run a layer with the fastest engine for this input shape (timed once with CUDA events, then cached)."""
+    def _choose(cls, layer, shape, x=None, skip=None):
+        """Index of the engine that runs `layer` for inputs of `shape` (cached per shape)."""
         cands = layer["cands"]
         if len(cands) == 1:
-            return cls._call(cands[0], layer, x, skip)
-        key = tuple(x.shape)
+            return 0
+        key = tuple(shape)
         if key not in layer["choice"]:
-            forced = os.environ.get("RCMVS_ENGINE")            # 'direct' | 'tc': pin every layer to one engine
+            forced = os.environ.get("RCMVS_ENGINE")            # 'direct' | 'tc' | 'gemm': pin every layer to one engine
             if forced:
                 layer["choice"][key] = next((i for i, c in enumerate(cands) if c[0].startswith(forced)), 0)
-            elif os.environ.get("RCMVS_AUTOTUNE", "0") == "1":
+            elif os.environ.get("RCMVS_AUTOTUNE", "0") == "1" and x is not None:
                 best, best_ms = 0, float("inf")
                 for i, c in enumerate(cands):
                     cls._call(c, layer, x, skip)               # warm-up (sets kernel attributes)
@@ -297,25 +297,32 @@ class CostRegNet(nn.Module):
                         best, best_ms = i, ms
                 layer["choice"][key] = best
             else:
-                layer["choice"][key] = cls._default_engine(layer, cands, x)
-        return cls._call(cands[layer["choice"][key]], layer, x, skip)
+                layer["choice"][key] = cls._default_engine(layer, cands, key)
+        return layer["choice"][key]
+
+    @classmethod
+    def _run(cls, layer, x, skip=None):
+        """Run a layer with the engine chosen for this input shape (static table, or timed once with CUDA events under
+        RCMVS_AUTOTUNE=1, then cached)."""
+        return cls._call(layer["cands"][cls._choose(layer, x.shape, x, skip)], layer, x, skip)
 
     @staticmethod
-    def _default_engine(layer, cands, x):
-        """Static table distilled from RCMVS_AUTOTUNE=1 runs on B200 at DTU / BASELINE shapes (profiles/):
-        stride-1 conv0 / conv2 -> tcgen05 in both tensor modes; `prob` (8->1, memory-bound) -> FFMA kernel;
-        transposed conv11 -> tcgen05 when the input has >= 8 depth planes (3xTF32) or always (TF32);
-        transposed conv9 -> tcgen05 only with plain TF32 and >= 8 planes; everything else FFMA."""
+    def _default_engine(layer, cands, shape):
+        """Static table distilled from RCMVS_AUTOTUNE=1 / tools/time_layers.py runs on B200 at DTU / BASELINE shapes
+        (profiles/): stride-1 conv0 / conv2 -> slab tcgen05 kernel; `prob` (8->1, memory-bound) -> FFMA kernel;
+        the 1/4- and 1/8-resolution levels conv3..conv7 -> gather-GEMM tcgen05 kernel; transposed conv9 -> FFMA;
+        transposed conv11 -> slab tcgen05 kernel when the input has >= 8 depth planes (3xTF32) or always (TF32);
+        everything else FFMA."""
         kinds = [c[0] for c in cands]
-        nsplit = next((c[4] for c in cands if c[0] in ("tc", "tct")), 0)
-        cin, planes = x.shape[-1], x.shape[1]
+        nsplit = next((c[4] for c in cands if c[0] in ("tc", "tct", "gemm")), 0)
+        cin, planes = shape[-1], shape[1]
         if "tc" in kinds:
             cout = cands[kinds.index("tc")][3]
             return kinds.index("tc") if cout != 1 else 0
+        if "gemm" in kinds and not (layer["tr"] and cin == 32):            # conv9 stays on the FFMA kernel
+            return kinds.index("gemm")
         if "tct" in kinds:
-            if cin == 16:                                       # conv11
-                return kinds.index("tct") if (nsplit == 1 or planes >= 8) else 0
-            return kinds.index("tct") if (nsplit == 1 and planes >= 8) else 0      # conv9
+            return kinds.index("tct") if (nsplit == 1 or planes >= 8) else 0      # conv11
         return 0
 
     def engines(self):

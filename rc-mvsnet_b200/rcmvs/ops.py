@@ -179,7 +179,7 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
 
 def gemm_tc_supported(Cin, Cout):
     """Layers the gather implicit-GEMM kernel takes (the 1/4- and 1/8-resolution levels)."""
-    return Cin % 16 == 0 and Cout in (16, 32, 64)
+    return Cin in (16, 32, 64) and Cout in (16, 32, 64)
 
 
 def conv3d_gemm_tc_pack(w, scale=None, transposed=False, nsplit=3):
@@ -195,8 +195,12 @@ def conv3d_gemm_tc_pack(w, scale=None, transposed=False, nsplit=3):
     return img
 
 
-def conv3d_gemm_tc(x_cl, img, Cout, mode, bias=None, skip=None, nsplit=3, relu=True):
-    """x_cl [B,D,H,W,Cin]; mode 0 conv s1 / 1 conv s2 / 2 transposed conv -> [B,Do,Ho,Wo,Cout] on tcgen05.mma."""
+def conv3d_gemm_tc(x_cl, img, Cout, mode, bias=None, skip=None, nsplit=3, relu=True, x_lo=None, want_y=True,
+                   want_split=False):
+    """x_cl [B,D,H,W,Cin]; mode 0 conv s1 / 1 conv s2 / 2 transposed conv -> [B,Do,Ho,Wo,Cout] on tcgen05.mma.
+
+    3xTF32 only: `x_lo` given -> (x_cl, x_lo) is the pre-split activation (hi, lo) written by the producing layer;
+    `want_split` -> also return the result pre-split for the next gather layer.  Returns y, or (y|None, hi, lo)."""
     B, D, H, W, Cin = x_cl.shape
     if mode == 2:
         Do, Ho, Wo = 2 * D, 2 * H, 2 * W
@@ -204,10 +208,13 @@ def conv3d_gemm_tc(x_cl, img, Cout, mode, bias=None, skip=None, nsplit=3, relu=T
         Do, Ho, Wo = (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
     else:
         Do, Ho, Wo = D, H, W
-    y = torch.empty((B, Do, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32)
-    _ffi.call("rcmvs_conv3d_gemm_tc_fwd", _chk(x_cl, "x"), _chk(img, "wimg"), _opt(bias, "bias"), _opt(skip, "skip"),
-              _chk(y, "y"), B, D, H, W, Cin, Cout, mode, nsplit, 1 if relu else 0, _stream())
-    return y
+    mk = lambda: torch.empty((B, Do, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32)
+    y = mk() if (want_y or not want_split) else None
+    hi, lo = (mk(), mk()) if want_split else (None, None)
+    _ffi.call("rcmvs_conv3d_gemm_tc_fwd", _chk(x_cl, "x"), _opt(x_lo, "x_lo"), _chk(img, "wimg"), _opt(bias, "bias"),
+              _opt(skip, "skip"), _opt(y, "y"), _opt(hi, "y_hi"), _opt(lo, "y_lo"), B, D, H, W, Cin, Cout, mode,
+              nsplit, 1 if relu else 0, _stream())
+    return (y, hi, lo) if want_split else y
 
 
 TCT_SUPPORTED = {(16, 8), (32, 16)}      # (Cin, Cout) of conv11 / conv9 (transposed)

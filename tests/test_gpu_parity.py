@@ -299,6 +299,16 @@ def test_conv3d_gather_gemm_tensor_core_vs_oracle(dev, cin, cout, mode, dhw, nsp
     np.testing.assert_allclose(got.permute(0, 4, 1, 2, 3).cpu().numpy(), want + skip, atol=tol, rtol=tol)
     got = ops.conv3d_gemm_tc(x_cl, img, cout, mode, None, None, nsplit, False)
     np.testing.assert_allclose(got.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=tol, rtol=tol)
+    if nsplit == 3:
+        # pre-split input (hi + lo == x exactly) and pre-split output: same numbers as the split-on-the-fly path
+        import torch
+        hi = (x_cl.view(torch.int32) & -8192).view(torch.float32)
+        y, y_hi, y_lo = ops.conv3d_gemm_tc(hi, img, cout, mode, None, None, 3, False, x_lo=x_cl - hi, want_split=True)
+        assert torch.equal(y, got)
+        assert torch.equal(y_hi + y_lo, y) and int((y_hi.view(torch.int32) & 8191).abs().max()) == 0
+        none_y, y_hi2, _ = ops.conv3d_gemm_tc(hi, img, cout, mode, None, None, 3, False, x_lo=x_cl - hi, want_y=False,
+                                              want_split=True)
+        assert none_y is None and torch.equal(y_hi2, y_hi)
 
 
 def _model(dev, ndepths, cls_name="CascadeMVSNet_eval"):
@@ -320,7 +330,7 @@ def test_costregnet_golden(dev, stage, mode, monkeypatch):
         cost = m.cost_regularization[stage - 1](cu(g["variance_" + k][None], dev))      # reference signature
     assert cost.shape[:2] == (1, 1)
     # logits of magnitude O(10); fp32 / 3xTF32: summation-order noise only; plain TF32: operand truncation
-    tol = 2e-2 if mode == "tf32" else 1e-3
+    tol = 5e-2 if mode == "tf32" else 1e-3
     np.testing.assert_allclose(cost[0, 0].cpu().numpy(), g["cost_" + k], atol=tol, rtol=1e-4 if mode != "tf32" else 1e-2)
 
 

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "rc-mvsnet_b200
 import torch
 from models.modules import CostRegNet
 
-SHAPES = {1: (32, 48, 128, 160), 2: (16, 32, 256, 320), 3: (8, 8, 512, 640)}
+SHAPES = {1: (32, 192, 128, 160), 2: (16, 64, 256, 320), 3: (8, 8, 512, 640)}     # BASELINE configs[1]
 
 
 def main():
