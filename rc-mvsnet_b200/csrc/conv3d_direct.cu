@@ -187,6 +187,138 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// `prob` layer (8 -> 1 channels, stride 1; reference models/modules.py:488): memory-bound, 27 x 8 MACs per output.
+// Input-stationary plane march: a CTA owns a 16 x 32 (h x w) column of the volume and walks a chunk of depth planes.
+// Every input plane is staged ONCE (cp.async, double-buffered) and scattered into the three output planes it touches
+// (kd = 0/1/2 -> out z+1 / z / z-1), whose partial sums stay in registers; plane z-1 is complete after plane z.
+// Per staged plane a thread does 36 LDS.128 of activations for 864 FMAs (the per-kd slab kernel above needs 3x that).
+// ------------------------------------------------------------------------------------------------------------------
+namespace march {
+constexpr int TH = 16, TW = 32, IH = TH + 2, IW = TW + 2;
+constexpr int PLANE_F4 = IH * 2 * IW;                        // float4 per staged plane: [iy][c4][ix]
+constexpr int THREADS = 128;
+constexpr size_t SMEM = (size_t)2 * PLANE_F4 * 16 + 27 * 8 * 4;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+}  // namespace march
+
+__global__ void __launch_bounds__(march::THREADS)
+conv3d_c8_to_c1_march_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                             const float* __restrict__ skip, float* __restrict__ y, int D, int H, int W, int relu,
+                             int planes_per_chunk, int nchunks) {
+  using namespace march;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* xs = reinterpret_cast<float4*>(smem_raw);
+  float* ws = reinterpret_cast<float*>(smem_raw + (size_t)2 * PLANE_F4 * 16);
+  const int lane = threadIdx.x & 31, hg = threadIdx.x >> 5;
+  const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+  const int b = blockIdx.z / nchunks, chunk = blockIdx.z % nchunks;
+  const int z0 = chunk * planes_per_chunk, z1 = min(D, z0 + planes_per_chunk);
+  x += (int64_t)b * D * H * W * 8;
+  const int64_t ybase = (int64_t)b * D * H * W;
+
+  for (int e = threadIdx.x; e < 27 * 8; e += THREADS) ws[e] = __ldg(wp + e);      // packed [27][8][1]
+
+  auto stage = [&](int z, int buf) {
+    // plane z of the halo tile -> xs[buf]; out-of-volume voxels (incl. whole planes z = -1, D) are zero-filled
+    const bool zin = z >= 0 && z < D;
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(xs + (size_t)buf * PLANE_F4);
+    for (int e = threadIdx.x; e < PLANE_F4; e += THREADS) {
+      const int c4 = e & 1, r = e >> 1;
+      const int ix = r % IW, iy = r / IW;
+      const int gy = oy0 - 1 + iy, gx = ox0 - 1 + ix;
+      const bool ok = zin && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* src = ok ? x + (((int64_t)z * H + gy) * W + gx) * 8 + c4 * 4 : x;
+      cp_async16_zfill(dst0 + ((iy * 2 + c4) * IW + ix) * 16, src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[3][4];                                   // [0]: out plane z-1, [1]: z, [2]: z+1 (z = plane being consumed)
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
+
+  const float bv = bias ? __ldg(bias) : 0.f;
+  const int ox = ox0 + lane;
+  stage(z0 - 1, 0);
+  int buf = 0;
+  for (int z = z0 - 1; z <= z1; ++z, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                 // plane z landed; everyone is done reading the other buffer
+    if (z < z1) stage(z + 1, buf ^ 1);
+    if (z >= 0 && z < D) {                           // CTA-uniform: padding planes contribute nothing
+      const float4* xp = xs + (size_t)buf * PLANE_F4;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+          float4 xr[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) xr[r] = xp[((hg * 4 + r) * 2 + c4) * IW + lane + kw];
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ws + ((kd * 9 + kh * 3 + kw) * 8) + c4 * 4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 v = xr[j + kh];
+                float& a = acc[2 - kd][j];           // input plane z feeds out plane z + 1 - kd
+                a = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, a))));
+              }
+            }
+          }
+        }
+      }
+    }
+    // out plane z-1 has now seen input planes z-2, z-1, z
+    const int oz = z - 1;
+    if (oz >= z0 && oz < z1 && ox < W) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int oy = oy0 + hg * 4 + j;
+        if (oy >= H) continue;
+        const int64_t o = ybase + ((int64_t)oz * H + oy) * W + ox;
+        float v = acc[0][j] + bv;
+        if (relu) v = fmaxf(v, 0.f);
+        if (skip) v += __ldg(skip + o);
+        y[o] = v;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[0][j] = acc[1][j]; acc[1][j] = acc[2][j]; acc[2][j] = 0.f; }
+  }
+}
+
+static int launch_march_c8_c1(const float* x, const float* wp, const float* bias, const float* skip, float* y, int B,
+                              int D, int H, int W, int relu, cudaStream_t st) {
+  using namespace march;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_c8_to_c1_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM);
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  // depth chunks: as long as possible (every chunk re-reads 2 halo planes) while the grid still covers ~3 waves
+  const int64_t tiles = (int64_t)ceil_div(W, TW) * ceil_div(H, TH) * B;
+  int ppc = D;
+  while (ppc > 8 && tiles * ceil_div(D, ppc) < 3 * 148) ppc = (ppc + 1) / 2;
+  const int nchunks = ceil_div(D, ppc);
+  RCMVS_REQUIRE((int64_t)B * nchunks <= 65535 && ceil_div(H, TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv3d_fwd: grid too large");
+  dim3 grid(ceil_div(W, TW), ceil_div(H, TH), B * nchunks);
+  conv3d_c8_to_c1_march_kernel<<<grid, THREADS, SMEM, st>>>(x, wp, bias, skip, y, D, H, W, relu, ppc, nchunks);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv3d_fwd(march)");
+  return RCMVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1): out[z] += x[i]·w[k] with z = 2i + k - 1.
 // Per dimension: even output (a=0) <- (k=1, i); odd output (a=1) <- (k=2, i) and (k=0, i+1).
 // Thread = one input-space voxel -> its 2x2x2 output block x 8 output channels (64 accumulators).
@@ -462,6 +594,7 @@ extern "C" int rcmvs_conv3d_fwd_ws(const float* x, const float* packed_w, const 
   cudaStream_t st = as_stream(stream);
   RCMVS_REQUIRE(Cout == 1 || Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv3d_fwd: Cout=%d not in {1,8,16,32,64}", Cout);
+  if (Cin == 8 && Cout == 1 && stride == 1) return launch_march_c8_c1(x, packed_w, bias, skip, y, B, D, H, W, relu, st);
   const int cpc = pick_cout_per_cta(Cout, B, D, H, W, stride);
   const int ksplit = workspace ? pick_ksplit(Cin, Cout, cpc, B, D, H, W, stride) : 1;
 #define RCMVS_CONV_CASE(CO)                                                                                           \

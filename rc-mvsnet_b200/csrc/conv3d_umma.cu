@@ -1097,10 +1097,12 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
   }
   const int64_t m0 = (int64_t)tile * 128;
   const int ngroups = 1 << p.lg;
-  const int nitems = ntaps << p.lg;
 
   // ---- row table: element offset of each row's base input voxel + the set of taps that stay inside the volume --------
   int2* geo = reinterpret_cast<int2*>(smem + (size_t)NS * C::STAGE_B + 256);
+  unsigned* tapmask = reinterpret_cast<unsigned*>(tmem_slot + 1);      // taps that reach at least one row of this tile
+  if (threadIdx.x == 128) *tapmask = 0u;
+  __syncthreads();
   if (threadIdx.x < 128) {
     const int s = p.mode == 1 ? 2 : 1;
     const int64_t m = m0 + threadIdx.x;
@@ -1116,6 +1118,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
       }
     }
     geo[threadIdx.x] = g;
+    if (g.y) atomicOr(tapmask, (unsigned)g.y);
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full + i, C::ASYNC_A ? 32 : 1); mbar_init(empty + i, 1); }
@@ -1132,6 +1135,9 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // taps that fall outside the volume for every row (shallow volumes: kd = 0 / 2 of a 1-plane input) are skipped
+  const unsigned tmask = *tapmask;
+  const int nitems = __popc(tmask) << p.lg;
 
   if (warp >= 4 && warp < 4 + C::NLW) {
     // =============================== gather loaders ==================================================================
@@ -1146,7 +1152,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
     const uint32_t lane_dst = c * (128 * 16) + row0 * 16;           // + j * 128 per row step
 
     auto item_geom = [&](int it, int& t, int& wblk, int& toff) {
-      t = it >> p.lg;
+      t = __fns(tmask, 0, (it >> p.lg) + 1);             // the (it / ngroups)-th tap that is live in this tile
       const int grp = it & (ngroups - 1);
       int wtap, dz, dy, dx;
       gather_tap(p.mode, t, pz, py, px, wtap, dz, dy, dx);

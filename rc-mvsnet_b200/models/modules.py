@@ -322,7 +322,9 @@ class CostRegNet(nn.Module):
         if "gemm" in kinds and not (layer["tr"] and cin == 32):            # conv9 stays on the FFMA kernel
             return kinds.index("gemm")
         if "tct" in kinds:
-            return kinds.index("tct") if (nsplit == 1 or planes >= 8) else 0      # conv11
+            if cin == 16:                                                  # conv11
+                return kinds.index("tct") if (nsplit == 1 or planes >= 8) else 0
+            return kinds.index("tct") if (nsplit == 1 and planes >= 8) else 0      # conv9
         return 0
 
     def engines(self):
