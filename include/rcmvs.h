@@ -119,7 +119,7 @@ int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, const float
                                   rcmvs_stream_t stream);
 
 /* Gather implicit-GEMM on tcgen05 for the small 1/4- and 1/8-resolution layers (conv3..conv7, conv9; reference
- * models/modules.py:478-486): any D/H/W, Cin and Cout in {16,32,64}; mode 0 = conv stride 1, 1 = conv stride 2,
+ * models/modules.py:478-486): any D/H/W, Cin and Cout in {16,32,64} (plus 8 -> 16, conv1); mode 0 = conv stride 1, 1 = conv stride 2,
  * 2 = transposed conv (k3, s2, p1, output_padding 1).  The weight image is built from the torch weight (Conv3d
  * [Cout][Cin][27] or, with transposed = 1, ConvTranspose3d [Cin][Cout][27]) and the folded BatchNorm scale.
  * With nsplit = 3 the input may come pre-split: x = hi half, x_lo = lo half (x_hi + x_lo == activation exactly), as

@@ -1036,9 +1036,10 @@ struct GParams {
   int mode;            // 0: conv stride 1, 1: conv stride 2, 2: transposed conv (stride 2, output_padding 1)
   int relu;
   int tiles_per_class; // transposed: M tiles per parity class
+  int dbg;             // development only (RCMVS_TC_DBG): 1 = skip MMA issue, 2 = skip A gather, 4 = skip weight copy
 };
 
-template <int COUT, int NSPLIT, bool PRESPLIT, int NS>
+template <int COUT, int NSPLIT, bool PRESPLIT, int NS, bool CIN8 = false>
 struct GCfg {
   static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
   static constexpr bool ASYNC_A = NSPLIT == 1 || PRESPLIT;          // A tile moves with cp.async (no arithmetic)
@@ -1046,11 +1047,14 @@ struct GCfg {
   static constexpr int B_PART = 2 * 2 * COUT * 16;                  // 2 K-steps x 2 chunks x COUT rows x 16 B
   static constexpr int STAGE_B = NPART * (A_PART + B_PART);
   static constexpr int TMEM_COLS = COUT <= 32 ? 32 : 64;
-  static constexpr size_t SMEM = (size_t)NS * STAGE_B + 256 + 128 * 8;      // stages | barriers | row table
+  static constexpr size_t SMEM = (size_t)NS * STAGE_B + 256 + 128 * 8 + 32 * 16;   // stages | barriers | rows | taps
   // cp.async loaders never block on their own copies (the copies arrive on the mbarrier themselves), so 4 warps feed
-  // a ring of NS stages; the register path needs one warp per stage to keep NS gathers in flight
-  static constexpr int NLW = ASYNC_A ? 4 : NS;
+  // a ring of NS stages; the register path puts TWO warps on every stage (64 rows each): the per-item instruction chain
+  // of a warp (gather, hi/lo split, 128-bit stores) is what bounds the ring's round trip
+  static constexpr int NLW = ASYNC_A ? 4 : 2 * NS;
   static constexpr int THREADS = 32 * (4 + NLW + 1);
+  // short rings fit twice on an SM: two CTAs = two MMA issue threads and two rings whose stalls interleave
+  static constexpr int MIN_CTAS = (SMEM <= 113 * 1024 && THREADS <= 512) ? 2 : 1;
 };
 
 // tap t of this tile -> weight tap index (kd*9+kh*3+kw) and input offset (dz,dy,dx) relative to the row's base voxel
@@ -1069,8 +1073,10 @@ __device__ __forceinline__ void gather_tap(int mode, int t, int pz, int py, int 
   }
 }
 
-template <int COUT, int NSPLIT, bool PRESPLIT, int NS>
-__global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
+// CIN8: 8-channel input (conv1, 8 -> 16 stride 2): one tap is a single K-step, so an item carries TWO live taps
+// (chunks 0-1 = first tap, chunks 2-3 = second tap; the weight image is per tap: [27][terms][2 chunks][COUT][4]).
+template <int COUT, int NSPLIT, bool PRESPLIT, int NS, bool CIN8>
+__global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, GCfg<COUT, NSPLIT, PRESPLIT, NS>::MIN_CTAS)
     conv3d_gather_umma_kernel(const GParams p) {
   using C = GCfg<COUT, NSPLIT, PRESPLIT, NS>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1121,7 +1127,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
     if (g.y) atomicOr(tapmask, (unsigned)g.y);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full + i, C::ASYNC_A ? 32 : 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, C::ASYNC_A ? 32 : 2); mbar_init(empty + i, 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1135,9 +1141,19 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // taps that fall outside the volume for every row (shallow volumes: kd = 0 / 2 of a 1-plane input) are skipped
+  // taps that fall outside the volume for every row (shallow volumes: kd = 0 / 2 of a 1-plane input) are skipped;
+  // the live ones are listed once: {bit in the row masks, weight tap kd*9+kh*3+kw, element offset of the tap}
   const unsigned tmask = *tapmask;
-  const int nitems = __popc(tmask) << p.lg;
+  const int nlive = __popc(tmask);
+  int4* taps = reinterpret_cast<int4*>(smem + (size_t)NS * C::STAGE_B + 256 + 128 * 8);
+  if (threadIdx.x < nlive) {
+    const int tt = __fns(tmask, 0, threadIdx.x + 1);
+    int wtap, dz, dy, dx;
+    gather_tap(p.mode, tt, pz, py, px, wtap, dz, dy, dx);
+    taps[threadIdx.x] = make_int4(tt, wtap, ((dz * p.H + dy) * p.W + dx) * p.Cin, 0);
+  }
+  __syncthreads();
+  const int nitems = CIN8 ? (nlive + 1) >> 1 : nlive << p.lg;
 
   if (warp >= 4 && warp < 4 + C::NLW) {
     // =============================== gather loaders ==================================================================
@@ -1146,29 +1162,59 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
     const int lw = warp - 4;
     const int c = lane & 3, row0 = lane >> 2;
     const int64_t xbo = (int64_t)b * p.D * p.H * p.W * p.Cin;
-    const float* xb = p.x + xbo + c * 4;
-    const float* xlb = C::ASYNC_A && NSPLIT == 3 ? p.x_lo + xbo + c * 4 : nullptr;
+    const int coff = CIN8 ? (c & 1) * 4 : c * 4;                    // this lane's channel offset inside the tap
+    const float* xb = p.x + xbo + coff;
+    const float* xlb = C::ASYNC_A && NSPLIT == 3 ? p.x_lo + xbo + coff : nullptr;
     constexpr int BV = C::NPART * C::B_PART / 16 / 32;              // 16-byte weight pieces per lane (2..16)
     const uint32_t lane_dst = c * (128 * 16) + row0 * 16;           // + j * 128 per row step
 
-    auto item_geom = [&](int it, int& t, int& wblk, int& toff) {
-      t = __fns(tmask, 0, (it >> p.lg) + 1);             // the (it / ngroups)-th tap that is live in this tile
-      const int grp = it & (ngroups - 1);
-      int wtap, dz, dy, dx;
-      gather_tap(p.mode, t, pz, py, px, wtap, dz, dy, dx);
-      wblk = wtap * ngroups + grp;
-      toff = ((dz * p.H + dy) * p.W + dx) * p.Cin + grp * 16;
+    // item -> (tap bit `t` of this lane in the row masks, weight block(s), element offset of the tap + channel group)
+    auto item_geom = [&](int it, int& t, int2& wblk, int& toff) {
+      if constexpr (CIN8) {
+        const int te = 2 * it + (c >> 1);                  // chunks 0-1: first tap of the pair, chunks 2-3: second
+        wblk = make_int2(taps[2 * it].y, 2 * it + 1 < nlive ? taps[2 * it + 1].y : -1);
+        if (te < nlive) {
+          const int4 q = taps[te];
+          t = q.x; toff = q.z;
+        } else {
+          t = 31; toff = 0;                                // bit 31 of a row mask is never set -> zero rows
+        }
+      } else {
+        const int4 q = taps[it >> p.lg];                   // the (it / ngroups)-th live tap of this tile
+        const int grp = it & (ngroups - 1);
+        t = q.x;
+        wblk = make_int2(q.y * ngroups + grp, 0);
+        toff = q.z + grp * 16;
+      }
     };
-    auto copy_weights = [&](int wblk, uint32_t stage_u) {
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wimg) + (int64_t)wblk * (C::NPART * C::B_PART);
+    constexpr int BV0 = C::ASYNC_A ? 0 : 1;                 // register path: warp `half` copies its half of the pieces
+    auto copy_weights = [&](int2 wblk, uint32_t stage_u, int half) {
       const uint32_t wdst = stage_u + C::NPART * C::A_PART;
+      if (p.dbg & 4) return;
+      if constexpr (CIN8) {
+        // smem [term][ks][chunk][COUT] <- per-tap image blocks [term][chunk][COUT]; ks 0/1 = first/second tap
+        const float4* wimg4 = reinterpret_cast<const float4*>(p.wimg);
 #pragma unroll
-      for (int e = 0; e < BV; ++e) cp_async16(wdst + (lane + 32 * e) * 16, wsrc + (lane + 32 * e) * 16, true);
+        for (int e = 0; e < BV; ++e) {
+          if (BV0 && (e & 1) != half) continue;
+          const int piece = lane + 32 * e;
+          const int term = piece / (4 * COUT), ks = (piece / (2 * COUT)) & 1, within = piece % (2 * COUT);
+          const int wt = ks ? wblk.y : wblk.x;
+          if (wt >= 0) cp_async16(wdst + piece * 16, wimg4 + ((int64_t)wt * C::NPART + term) * (2 * COUT) + within, true);
+        }
+      } else {
+        const unsigned char* wsrc =
+            reinterpret_cast<const unsigned char*>(p.wimg) + (int64_t)wblk.x * (C::NPART * C::B_PART);
+#pragma unroll
+        for (int e = 0; e < BV; ++e)
+          if (!BV0 || (e & 1) == half) cp_async16(wdst + (lane + 32 * e) * 16, wsrc + (lane + 32 * e) * 16, true);
+      }
     };
 
     if constexpr (C::ASYNC_A) {
       for (int it = lw; it < nitems; it += C::NLW) {
-        int t, wblk, toff;
+        int t, toff;
+        int2 wblk;
         item_geom(it, t, wblk, toff);
         const int st = it % NS;
         const uint32_t stage_u = smem_u32(smem + (size_t)st * C::STAGE_B);
@@ -1176,41 +1222,44 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int2 g = geo[row0 + 8 * j];
-          const bool ok = (g.y >> t) & 1;
+          const bool ok = ((g.y >> t) & 1) && !(p.dbg & 2);
           const int off = ok ? g.x + toff : 0;
           const uint32_t dst = stage_u + lane_dst + j * 128;
           cp_async16(dst, xb + off, ok);
           if constexpr (NSPLIT == 3) cp_async16(dst + C::A_PART, xlb + off, ok);
         }
-        copy_weights(wblk, stage_u);
+        copy_weights(wblk, stage_u, 0);
         cp_async_mbar_arrive_noinc(full + st);
       }
       cp_async_commit();
       cp_async_wait<0>();                 // nothing of this warp is in flight when the CTA tears down
     } else {
-      // split-in-loader path: the A tile of the NEXT item is gathered into registers while this one is consumed
-      float4 v[16];
-      auto gather = [&](int it, int& wblk) {
+      // split-in-loader path: two warps per stage (64 rows each); the A rows of the NEXT item are gathered into
+      // registers while this one is consumed
+      const int st = lw >> 1, half = lw & 1;
+      const int rbase = half * 64 + row0;
+      float4 v[8];
+      auto gather = [&](int it, int2& wblk) {
         int t, toff;
         item_geom(it, t, wblk, toff);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int2 g = geo[row0 + 8 * j];
-          const bool ok = (g.y >> t) & 1;
+        for (int j = 0; j < 8; ++j) {
+          const int2 g = geo[rbase + 8 * j];
+          const bool ok = ((g.y >> t) & 1) && !(p.dbg & 2);
           v[j] = ok ? ldg4(xb + g.x + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      const int st = lw;                                            // this warp's pipeline stage
       unsigned char* stage = smem + (size_t)st * C::STAGE_B;
-      int wblk = 0;
+      int2 wblk = make_int2(0, 0);
       if (st < nitems) gather(st, wblk);
       for (int it = st; it < nitems; it += NS) {
         mbar_wait(empty + st, ((it / NS) & 1) ^ 1);
-        copy_weights(wblk, smem_u32(stage));
+        copy_weights(wblk, smem_u32(stage), half);
         cp_async_commit();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t off = lane_dst + j * 128;
+        for (int j = 0; j < 8; ++j) {
+          if (p.dbg & 16) break;
+          const uint32_t off = c * (128 * 16) + (rbase + 8 * j) * 16;
           const float4 x4 = v[j];
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u); l.x = x4.x - h.x;
@@ -1222,7 +1271,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
         }
         if (it + NS < nitems) gather(it + NS, wblk);
         cp_async_wait<0>();
-        fence_proxy_async();
+        if (!(p.dbg & 8)) fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full + st);
       }
@@ -1239,12 +1288,13 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
       const uint32_t sbase = smem_u32(smem + (size_t)st * C::STAGE_B);
       const uint32_t a_lo0 = desc_lo(sbase, 128 * 16);
       const uint32_t b_lo0 = desc_lo(sbase + C::NPART * C::A_PART, COUT * 16);
+      const int nk = (CIN8 && it == nitems - 1 && (nlive & 1)) ? 1 : 2;     // odd tap count: last item is half full
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         const uint32_t a_d = a_lo0 + (uint32_t)((ks * 2 * 128 * 16) >> 4);
         const uint32_t b_d = b_lo0 + (uint32_t)((ks * 2 * COUT * 16) >> 4);
         const uint32_t acc = (it == 0 && ks == 0) ? 0u : 1u;
-        if (leader) {
+        if (leader && ks < nk && !(p.dbg & 1)) {
           if constexpr (NSPLIT == 3) {
             umma_tf32_lohi_acc(tmem_base, a_d + (C::A_PART >> 4), b_d, idesc, acc);                 // x_lo · w_hi
             umma_tf32_lohi_acc(tmem_base, a_d, b_d + (C::B_PART >> 4), idesc, 1u);                  // x_hi · w_lo
@@ -1268,7 +1318,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
       const int jx = (int)(m % p.W), jy = (int)((m / p.W) % p.H), jz = (int)(m / ((int64_t)p.W * p.H));
       ovox = ((int64_t)(2 * jz + pz) * p.Ho + (2 * jy + py)) * p.Wo + (2 * jx + px);
     }
-    mbar_wait(acc_full, 0);
+    while (!mbar_try_wait(acc_full, 0)) __nanosleep(512);      // idle for the whole main loop: stay off the issue ports
     tc_fence_after();
     float v[COUT];
 #pragma unroll
@@ -1313,10 +1363,23 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, 1)
 __global__ void pack_gather_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                           float* __restrict__ img, int Cout, int Cin, int transposed, int nsplit) {
   const int terms = nsplit == 3 ? 2 : 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (Cin == 8) {                                   // per-tap image: [tap][term][chunk][n][e], ci = chunk*4 + e
+    const int blk8 = 2 * Cout * 4;
+    if (i >= 27 * blk8) return;
+    const int e = i & 3, n = (i >> 2) % Cout, chunk = ((i >> 2) / Cout) & 1, tap = i / blk8;
+    const int ci = chunk * 4 + e;
+    float v = transposed ? w[((int64_t)ci * Cout + n) * 27 + tap] : w[((int64_t)n * Cin + ci) * 27 + tap];
+    if (scale) v *= scale[n];
+    const int64_t base = (int64_t)tap * terms * blk8 + ((chunk * Cout + n) * 4 + e);
+    const float hi = nsplit == 3 ? __uint_as_float(__float_as_uint(v) & 0xFFFFE000u) : v;
+    img[base] = hi;
+    if (nsplit == 3) img[base + blk8] = v - hi;
+    return;
+  }
   const int blk = 2 * 2 * Cout * 4;                 // floats per (tap, grp, term)
   const int ngroups = Cin / 16;
   const int total = 27 * ngroups * blk;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int e = i & 3;
   int r = i >> 2;
@@ -1338,11 +1401,11 @@ __global__ void pack_gather_weight_kernel(const float* __restrict__ w, const flo
   }
 }
 
-template <int COUT, int NSPLIT, bool PRESPLIT, int NS>
+template <int COUT, int NSPLIT, bool PRESPLIT, int NS, bool CIN8 = false>
 static int launch_g(const GParams& p, int B, cudaStream_t st) {
   using C = GCfg<COUT, NSPLIT, PRESPLIT, NS>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = conv3d_gather_umma_kernel<COUT, NSPLIT, PRESPLIT, NS>;
+  auto kern = conv3d_gather_umma_kernel<COUT, NSPLIT, PRESPLIT, NS, CIN8>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -1361,6 +1424,7 @@ static int launch_g(const GParams& p, int B, cudaStream_t st) {
 }  // namespace rcmvs
 
 extern "C" int64_t rcmvs_conv3d_gemm_tc_weight_floats(int Cin, int Cout, int nsplit) {
+  if (Cin == 8) return (int64_t)27 * (nsplit == 3 ? 2 : 1) * 2 * Cout * 4;
   return (int64_t)27 * (Cin / 16) * (nsplit == 3 ? 2 : 1) * 2 * 2 * Cout * 4;
 }
 
@@ -1368,10 +1432,11 @@ extern "C" int rcmvs_conv3d_gemm_tc_pack(const float* w, const float* scale, flo
                                          int transposed, int nsplit, rcmvs_stream_t stream) {
   using namespace rcmvs;
   RCMVS_REQUIRE(w && img, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_pack: null pointer");
-  RCMVS_REQUIRE((Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 16 || Cout == 32 || Cout == 64) &&
+  RCMVS_REQUIRE(((Cin == 8 && Cout == 16) ||
+                 ((Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 16 || Cout == 32 || Cout == 64))) &&
                     (nsplit == 1 || nsplit == 3),
                 RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_gemm_tc_pack: unsupported Cin=%d Cout=%d nsplit=%d", Cin, Cout, nsplit);
-  const int total = 27 * (Cin / 16) * 2 * 2 * Cout * 4;
+  const int total = Cin == 8 ? 27 * 2 * Cout * 4 : 27 * (Cin / 16) * 2 * 2 * Cout * 4;
   umma::pack_gather_weight_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, scale, img, Cout, Cin,
                                                                                        transposed, nsplit);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_gemm_tc_pack");
@@ -1388,7 +1453,8 @@ extern "C" int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* x_lo, const
   RCMVS_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), RCMVS_ERR_BAD_ARG,
                 "rcmvs_conv3d_gemm_tc_fwd: y_hi and y_lo go together");
   RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && B <= 65535, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_gemm_tc_fwd: bad dims");
-  RCMVS_REQUIRE((Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 16 || Cout == 32 || Cout == 64) &&
+  RCMVS_REQUIRE(((Cin == 8 && Cout == 16 && !x_lo) ||
+                 ((Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 16 || Cout == 32 || Cout == 64))) &&
                     (nsplit == 1 || nsplit == 3) && mode >= 0 && mode <= 2,
                 RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_gemm_tc_fwd: unsupported Cin=%d Cout=%d mode=%d nsplit=%d", Cin,
                 Cout, mode, nsplit);
@@ -1397,17 +1463,19 @@ extern "C" int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* x_lo, const
                 "rcmvs_conv3d_gemm_tc_fwd: one sample of the input must stay below 2^31 elements");
   GParams p;
   p.x = x; p.x_lo = x_lo; p.wimg = wimg; p.bias = bias; p.skip = skip; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo;
-  p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.lg = Cin == 16 ? 0 : (Cin == 32 ? 1 : 2); p.mode = mode; p.relu = relu;
+  p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.lg = Cin <= 16 ? 0 : (Cin == 32 ? 1 : 2); p.mode = mode; p.relu = relu;
   if (mode == 2) { p.Do = 2 * D; p.Ho = 2 * H; p.Wo = 2 * W; }
   else if (mode == 1) { p.Do = (D - 1) / 2 + 1; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1; }
   else { p.Do = D; p.Ho = H; p.Wo = W; }
   p.tiles_per_class = (int)ceil_div<int64_t>((int64_t)D * H * W, 128);
+  p.dbg = getenv("RCMVS_TC_DBG") ? atoi(getenv("RCMVS_TC_DBG")) : 0;
   cudaStream_t st = as_stream(stream);
   const bool pre = x_lo != nullptr;
+  if (Cin == 8) return nsplit == 3 ? launch_g<16, 3, false, 8, true>(p, B, st) : launch_g<16, 1, false, 8, true>(p, B, st);
 #define RCMVS_G_CASE(CO, NSP, PRE, NSV) \
   if (Cout == CO && nsplit == NSP && pre == PRE) return launch_g<CO, NSP, PRE, NSV>(p, B, st)
   RCMVS_G_CASE(16, 1, false, 8); RCMVS_G_CASE(16, 3, false, 8); RCMVS_G_CASE(16, 3, true, 8);
-  RCMVS_G_CASE(32, 1, false, 8); RCMVS_G_CASE(32, 3, false, 8); RCMVS_G_CASE(32, 3, true, 8);
+  RCMVS_G_CASE(32, 1, false, 8); RCMVS_G_CASE(32, 3, false, 4); RCMVS_G_CASE(32, 3, true, 8);
   RCMVS_G_CASE(64, 1, false, 8); RCMVS_G_CASE(64, 3, false, 6); RCMVS_G_CASE(64, 3, true, 8);
 #undef RCMVS_G_CASE
   return RCMVS_ERR_UNSUPPORTED;

@@ -319,7 +319,7 @@ class CostRegNet(nn.Module):
         if "tc" in kinds:
             cout = cands[kinds.index("tc")][3]
             return kinds.index("tc") if cout != 1 else 0
-        if "gemm" in kinds and not (layer["tr"] and cin == 32):            # conv9 stays on the FFMA kernel
+        if "gemm" in kinds and cin != 8 and not (layer["tr"] and cin == 32):   # conv1 / conv9 stay on the FFMA kernels
             return kinds.index("gemm")
         if "tct" in kinds:
             if cin == 16:                                                  # conv11

@@ -179,7 +179,7 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
 
 def gemm_tc_supported(Cin, Cout):
     """Layers the gather implicit-GEMM kernel takes (the 1/4- and 1/8-resolution levels)."""
-    return Cin in (16, 32, 64) and Cout in (16, 32, 64)
+    return (Cin in (16, 32, 64) and Cout in (16, 32, 64)) or (Cin == 8 and Cout == 16)
 
 
 def conv3d_gemm_tc_pack(w, scale=None, transposed=False, nsplit=3):

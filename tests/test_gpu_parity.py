@@ -271,7 +271,8 @@ def test_conv_transpose3d_tensor_core_vs_oracle(dev, cin, cout, dhw, nsplit):
 @pytest.mark.parametrize("cin,cout,mode,dhw", [
     (16, 16, 0, (5, 7, 33)), (16, 32, 1, (8, 10, 22)), (16, 32, 1, (7, 9, 21)), (32, 32, 0, (6, 8, 10)),
     (32, 64, 1, (6, 8, 10)), (64, 64, 0, (3, 4, 5)), (64, 64, 0, (1, 1, 1)), (64, 32, 2, (3, 4, 5)),
-    (32, 16, 2, (3, 6, 11)), (32, 32, 0, (12, 16, 20)), (16, 16, 0, (1, 1, 129)),
+    (32, 16, 2, (3, 6, 11)), (32, 32, 0, (12, 16, 20)), (16, 16, 0, (1, 1, 129)), (8, 16, 1, (8, 10, 22)),
+    (8, 16, 1, (1, 7, 9)), (8, 16, 0, (3, 5, 7)), (8, 16, 1, (16, 32, 40)),
 ])
 def test_conv3d_gather_gemm_tensor_core_vs_oracle(dev, cin, cout, mode, dhw, nsplit):
     """Gather implicit-GEMM tcgen05 kernel of the 1/4- and 1/8-resolution levels: stride-1, stride-2 and transposed
@@ -299,7 +300,7 @@ def test_conv3d_gather_gemm_tensor_core_vs_oracle(dev, cin, cout, mode, dhw, nsp
     np.testing.assert_allclose(got.permute(0, 4, 1, 2, 3).cpu().numpy(), want + skip, atol=tol, rtol=tol)
     got = ops.conv3d_gemm_tc(x_cl, img, cout, mode, None, None, nsplit, False)
     np.testing.assert_allclose(got.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=tol, rtol=tol)
-    if nsplit == 3:
+    if nsplit == 3 and cin != 8:
         # pre-split input (hi + lo == x exactly) and pre-split output: same numbers as the split-on-the-fly path
         import torch
         hi = (x_cl.view(torch.int32) & -8192).view(torch.float32)
