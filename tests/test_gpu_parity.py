@@ -180,6 +180,7 @@ def test_costvolume_variance_noref_and_oob_vs_oracle(dev):
     (8, 8, 1, (4, 9, 37)), (32, 8, 1, (3, 18, 34)), (16, 8, 1, (2, 5, 64)), (8, 16, 2, (6, 10, 44)),
     (16, 16, 1, (3, 8, 40)), (16, 32, 2, (4, 12, 20)), (32, 32, 1, (3, 6, 10)), (32, 64, 2, (6, 8, 12)),
     (64, 64, 1, (2, 4, 5)), (8, 1, 1, (5, 17, 33)), (8, 8, 2, (5, 7, 9)), (8, 1, 1, (1, 1, 1)), (8, 1, 1, (40, 33, 70)),
+    (8, 16, 2, (1, 1, 1)), (8, 16, 2, (5, 7, 9)), (8, 16, 2, (9, 17, 70)), (8, 16, 2, (24, 33, 129)),
 ])
 def test_conv3d_vs_oracle(dev, cin, cout, stride, dhw):
     from rcmvs import ops
