@@ -56,6 +56,12 @@ int rcmvs_depth_hypotheses_first(const float* depth_values, float* planes, int B
  * cur -/+ D/2*interval, D planes, then bilinear resize to (h,w). */
 int rcmvs_depth_hypotheses_next(const float* prev_depth, float* hyp, int B, int hp, int wp, int H, int W, int h,
                                 int w, int D, double interval_pixel, rcmvs_stream_t stream);
+/* Same, with the pixel interval derived on the device: interval_ratio * (depth_values[0][Dv-1] - depth_values[0][0])
+ * / Dv in double precision (the reference pulls min/max to the host, casmvsnet.py:172-174; this keeps the forward
+ * free of host synchronisation). */
+int rcmvs_depth_hypotheses_next_dev(const float* prev_depth, const float* depth_values, int Dv, double interval_ratio,
+                                    float* hyp, int B, int hp, int wp, int H, int W, int h, int w, int D,
+                                    rcmvs_stream_t stream);
 
 /* ---- a1 homo_warping: models/modules.py:304-339 ------------------------------------------------------------- */
 /* src_fea [B][C][h][w] (NCHW), rt [B][12], depth [B][D] (per_pixel=0) or [B][D][h][w] (per_pixel=1)

@@ -44,7 +44,14 @@ __device__ __forceinline__ float upsampled_prev(const float* __restrict__ prev, 
 }
 
 __global__ void hyp_next_kernel(const float* __restrict__ prev, float* __restrict__ hyp, int hp, int wp, int H,
-                                int W, int h, int w, int D, float half_range) {
+                                int W, int h, int w, int D, float half_range, const float* __restrict__ dv, int Dv,
+                                double ratio) {
+  if (dv) {
+    // depth_interval = (max - min) / Dv of batch item 0 in Python floats (casmvsnet.py:172-174), times the stage
+    // ratio (:203-204), times ndepth / 2 (modules.py:553-554), rounded to fp32 where it meets the tensor
+    const double interval = ((double)__ldg(dv + Dv - 1) - (double)__ldg(dv)) / (double)Dv;
+    half_range = (float)((double)D / 2.0 * (ratio * interval));
+  }
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -98,7 +105,23 @@ extern "C" int rcmvs_depth_hypotheses_next(const float* prev_depth, float* hyp, 
   // `ndepth / 2 * depth_inteval_pixel` is a Python float in the reference, rounded to fp32 when it meets the tensor
   float half_range = (float)((double)D / 2.0 * interval_pixel);
   dim3 grid(ceil_div(w, 128), h, B);
-  hyp_next_kernel<<<grid, 128, 0, as_stream(stream)>>>(prev_depth, hyp, hp, wp, H, W, h, w, D, half_range);
+  hyp_next_kernel<<<grid, 128, 0, as_stream(stream)>>>(prev_depth, hyp, hp, wp, H, W, h, w, D, half_range, nullptr, 0,
+                                                       0.0);
   RCMVS_CHECK_LAUNCH("rcmvs_depth_hypotheses_next");
+  return RCMVS_OK;
+}
+
+extern "C" int rcmvs_depth_hypotheses_next_dev(const float* prev_depth, const float* depth_values, int Dv,
+                                               double interval_ratio, float* hyp, int B, int hp, int wp, int H, int W,
+                                               int h, int w, int D, rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(prev_depth && hyp && depth_values, RCMVS_ERR_BAD_ARG, "rcmvs_depth_hypotheses_next_dev: null pointer");
+  RCMVS_REQUIRE(B > 0 && hp > 0 && wp > 0 && H > 0 && W > 0 && h > 0 && w > 0 && D > 1 && Dv > 1, RCMVS_ERR_BAD_ARG,
+                "rcmvs_depth_hypotheses_next_dev: bad dims");
+  RCMVS_REQUIRE(h <= 65535 && B <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_depth_hypotheses_next_dev: h or B too large");
+  dim3 grid(ceil_div(w, 128), h, B);
+  hyp_next_kernel<<<grid, 128, 0, as_stream(stream)>>>(prev_depth, hyp, hp, wp, H, W, h, w, D, 0.f, depth_values, Dv,
+                                                       interval_ratio);
+  RCMVS_CHECK_LAUNCH("rcmvs_depth_hypotheses_next_dev");
   return RCMVS_OK;
 }

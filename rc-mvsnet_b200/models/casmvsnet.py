@@ -156,13 +156,10 @@ class _CascadeBase(nn.Module):
         B, V, _, H, W = imgs.shape
         imgs = imgs.float()
         depth_values = depth_values.float().contiguous()
-        # (max-min)/192 of batch element 0, kept on the device (the reference pulls it to the host, :172-174)
-        interval = (depth_values[0, -1].double() - depth_values[0, 0].double()) / depth_values.size(1)
         per_view, stacked = self._features(imgs)
         fused = stacked is not None and (not torch.is_grad_enabled() or self.depthnet_cls is DepthNet_eval)
         if not fused and stacked is not None:
             per_view = [{k: stacked[k][:, v].permute(0, 3, 1, 2) for k in stacked} for v in range(V)]
-        interval_host = None
         outputs, depth = {}, None
         for s in range(self.num_stage):
             key = "stage%d" % (s + 1)
@@ -172,11 +169,11 @@ class _CascadeBase(nn.Module):
                 planes = ops.depth_hypotheses_first(depth_values, D)               # [B,D]: uniform per plane
                 hyp = planes
             else:
-                if interval_host is None:
-                    interval_host = float(interval)     # one scalar read-back per forward (after stage 1 is queued)
+                # depth_interval = (max - min) / Dv of batch element 0 is taken on the device (the reference pulls
+                # min/max to the host, :172-174): no host synchronisation anywhere in the forward
                 cur = depth.detach() if self.grad_method == "detach" else depth
-                hyp = ops.depth_hypotheses_next(cur.contiguous(), D, self.depth_interals_ratio[s] * interval_host,
-                                                H, W, h, w)
+                hyp = ops.depth_hypotheses_next_dev(cur.contiguous(), depth_values, D, self.depth_interals_ratio[s],
+                                                    H, W, h, w)
             if fused:
                 with torch.no_grad():
                     want_noref = self.depthnet_cls is DepthNet and s == 0

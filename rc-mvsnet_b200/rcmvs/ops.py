@@ -79,6 +79,15 @@ def depth_hypotheses_next(prev_depth, D, interval_pixel, H, W, h, w):
     return hyp
 
 
+def depth_hypotheses_next_dev(prev_depth, depth_values, D, interval_ratio, H, W, h, w):
+    """Like depth_hypotheses_next, the pixel interval = ratio * (max - min) / Dv of depth_values[0] taken on the device."""
+    B, hp, wp = prev_depth.shape
+    hyp = torch.empty((B, D, h, w), device=prev_depth.device, dtype=torch.float32)
+    _ffi.call("rcmvs_depth_hypotheses_next_dev", _chk(prev_depth, "prev_depth"), _chk(depth_values, "depth_values"),
+              depth_values.shape[1], float(interval_ratio), _chk(hyp, "hyp"), B, hp, wp, H, W, h, w, D, _stream())
+    return hyp
+
+
 # ---- warp / cost volume ---------------------------------------------------------------------------------------
 def _depth_mode(depth, B, D_expected=None):
     if depth.dim() == 2:

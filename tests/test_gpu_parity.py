@@ -130,6 +130,11 @@ def test_hypotheses_match_reference_golden(dev):
     np.testing.assert_allclose(h2.cpu().numpy()[0], g["hyp_stage2"], atol=1.3e-4, rtol=0)   # <= 2 ulp @ 650
     h3 = ops.depth_hypotheses_next(cu(g["depth_stage2"][None], dev), 8, 1 * interval, H, W, H, W)
     np.testing.assert_allclose(h3.cpu().numpy()[0], g["hyp_stage3"], atol=1.3e-4, rtol=0)
+    # interval derived on the device (what the cascade uses: no host read-back) == host-float path, bit for bit
+    dv = cu(g["depth_values"][None], dev)
+    h2d = ops.depth_hypotheses_next_dev(cu(g["depth_stage1"][None], dev), dv, 8, 2, H, W, H // 2, W // 2)
+    h3d = ops.depth_hypotheses_next_dev(cu(g["depth_stage2"][None], dev), dv, 8, 1, H, W, H, W)
+    assert torch.equal(h2d, h2) and torch.equal(h3d, h3)
 
 
 def test_hypotheses_api_functions(dev):
