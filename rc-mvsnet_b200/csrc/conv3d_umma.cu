@@ -174,7 +174,10 @@ struct Cfg {
   static constexpr int NCH = CIN / 4;
   static constexpr int ROWS = 4 * KM;                             // input rows covered by the M-tiles
   static constexpr int OROWS = ROWS - 2;                          // output rows per CTA tile
-  static constexpr int SLABV = ROWS * PW + 8;                     // voxels per slab plane (+ kw overrun)
+  // voxels per slab plane (+ kw overrun) + 8/NCH voxels of padding: the channel-chunk planes then start 128/NCH bytes
+  // apart modulo 128, so the NCH chunks x (8/NCH) voxels a quarter-warp of the loader stores with one 128-bit store
+  // instruction fall into distinct banks (a plane stride of 0 mod 128 made them collide NCH-fold)
+  static constexpr int SLABV = ROWS * PW + 8 + 8 / NCH;
   static constexpr int PLANE_B = SLABV * 16;
   static constexpr int SLAB_B = NCH * PLANE_B;
   static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
@@ -597,7 +600,7 @@ struct TCfg {
   static constexpr int NCH = CIN / 4;
   static constexpr int ROWS = 4 * KM;                              // input rows per CTA tile (all produce outputs)
   static constexpr int TWI = 31;                                   // input columns per tile (col 31 = halo for dx=1)
-  static constexpr int SLABV = (ROWS + 1) * PW + 8;
+  static constexpr int SLABV = (ROWS + 1) * PW + 8 + 8 / NCH;     // + bank-spreading pad, see Cfg
   static constexpr int PLANE_B = SLABV * 16;
   static constexpr int SLAB_B = NCH * PLANE_B;
   static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
@@ -1043,7 +1046,9 @@ template <int COUT, int NSPLIT, bool PRESPLIT, int NS, bool CIN8 = false>
 struct GCfg {
   static constexpr int NPART = NSPLIT == 3 ? 2 : 1;
   static constexpr bool ASYNC_A = NSPLIT == 1 || PRESPLIT;          // A tile moves with cp.async (no arithmetic)
-  static constexpr int A_PART = 4 * 128 * 16;                       // 16 channels: 4 chunks x 128 rows x 16 B
+  static constexpr int CHUNK_B = 128 * 16 + 32;                     // one 4-channel chunk plane: 128 rows x 16 B, +32 B
+                                                                    // so the 4 chunks a quarter-warp stores hit distinct banks
+  static constexpr int A_PART = 4 * CHUNK_B;                        // 16 channels
   static constexpr int B_PART = 2 * 2 * COUT * 16;                  // 2 K-steps x 2 chunks x COUT rows x 16 B
   static constexpr int STAGE_B = NPART * (A_PART + B_PART);
   static constexpr int TMEM_COLS = COUT <= 32 ? 32 : 64;
@@ -1166,7 +1171,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, GCf
     const float* xb = p.x + xbo + coff;
     const float* xlb = C::ASYNC_A && NSPLIT == 3 ? p.x_lo + xbo + coff : nullptr;
     constexpr int BV = C::NPART * C::B_PART / 16 / 32;              // 16-byte weight pieces per lane (2..16)
-    const uint32_t lane_dst = c * (128 * 16) + row0 * 16;           // + j * 128 per row step
+    const uint32_t lane_dst = c * C::CHUNK_B + row0 * 16;           // + j * 128 per row step
 
     // item -> (tap bit `t` of this lane in the row masks, weight block(s), element offset of the tap + channel group)
     auto item_geom = [&](int it, int& t, int2& wblk, int& toff) {
@@ -1259,7 +1264,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, GCf
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (p.dbg & 16) break;
-          const uint32_t off = c * (128 * 16) + (rbase + 8 * j) * 16;
+          const uint32_t off = c * C::CHUNK_B + (rbase + 8 * j) * 16;
           const float4 x4 = v[j];
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u); l.x = x4.x - h.x;
@@ -1286,12 +1291,12 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, GCf
       if constexpr (C::ASYNC_A) fence_proxy_async();       // cp.async data observed through the mbarrier -> async proxy
       tc_fence_after();
       const uint32_t sbase = smem_u32(smem + (size_t)st * C::STAGE_B);
-      const uint32_t a_lo0 = desc_lo(sbase, 128 * 16);
+      const uint32_t a_lo0 = desc_lo(sbase, C::CHUNK_B);
       const uint32_t b_lo0 = desc_lo(sbase + C::NPART * C::A_PART, COUT * 16);
       const int nk = (CIN8 && it == nitems - 1 && (nlive & 1)) ? 1 : 2;     // odd tap count: last item is half full
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        const uint32_t a_d = a_lo0 + (uint32_t)((ks * 2 * 128 * 16) >> 4);
+        const uint32_t a_d = a_lo0 + (uint32_t)((ks * 2 * C::CHUNK_B) >> 4);
         const uint32_t b_d = b_lo0 + (uint32_t)((ks * 2 * COUT * 16) >> 4);
         const uint32_t acc = (it == 0 && ks == 0) ? 0u : 1u;
         if (leader && ks < nk && !(p.dbg & 1)) {
@@ -1474,7 +1479,7 @@ extern "C" int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* x_lo, const
   if (Cin == 8) return nsplit == 3 ? launch_g<16, 3, false, 8, true>(p, B, st) : launch_g<16, 1, false, 8, true>(p, B, st);
 #define RCMVS_G_CASE(CO, NSP, PRE, NSV) \
   if (Cout == CO && nsplit == NSP && pre == PRE) return launch_g<CO, NSP, PRE, NSV>(p, B, st)
-  RCMVS_G_CASE(16, 1, false, 8); RCMVS_G_CASE(16, 3, false, 8); RCMVS_G_CASE(16, 3, true, 8);
+  RCMVS_G_CASE(16, 1, false, 8); RCMVS_G_CASE(16, 3, false, 4); RCMVS_G_CASE(16, 3, true, 8);
   RCMVS_G_CASE(32, 1, false, 8); RCMVS_G_CASE(32, 3, false, 4); RCMVS_G_CASE(32, 3, true, 8);
   RCMVS_G_CASE(64, 1, false, 8); RCMVS_G_CASE(64, 3, false, 6); RCMVS_G_CASE(64, 3, true, 8);
 #undef RCMVS_G_CASE
