@@ -447,11 +447,12 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
         for (int mt = 0; mt < KM; ++mt) {
           const int j = 4 * mt + warp - kh;
           if (j >= 0 && j < C::OROWS) {
-            float* e = ex + (((kh * C::OROWS + j) * PW + lane) * CP);
+            // exchange layout [kh][row][channel quad][lane][4]: a warp's 128-bit stores are dense (bank-conflict free)
+            float* e = ex + ((kh * C::OROWS + j) * (CP / 4) * PW + lane) * 4;
 #pragma unroll
             for (int c = 0; c < CP; c += 4)
-              *reinterpret_cast<float4*>(e + c) = make_float4(v[mt][kh * CP + c], v[mt][kh * CP + c + 1],
-                                                              v[mt][kh * CP + c + 2], v[mt][kh * CP + c + 3]);
+              *reinterpret_cast<float4*>(e + (c / 4) * PW * 4) =
+                  make_float4(v[mt][kh * CP + c], v[mt][kh * CP + c + 1], v[mt][kh * CP + c + 2], v[mt][kh * CP + c + 3]);
           }
         }
       }
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
       for (int j = warp; j < C::OROWS; j += 4) {
         const int gy = y0 + j;
         if (!col_ok || gy >= p.H) continue;
-        const float* e = ex + ((j * PW + lane) * CP);
+        const float* e = ex + (j * (CP / 4) * PW + lane) * 4;
         constexpr int EXP = C::OROWS * PW * CP;                  // floats per kh plane
         const int64_t o = ((((int64_t)b * p.D + d) * p.H + gy) * p.W + gx) * COUT;
         if constexpr (COUT == 1) {
@@ -476,10 +477,10 @@ __global__ void __launch_bounds__(threads_for(NS), 1) conv3d_umma_kernel(const P
         } else {
 #pragma unroll
           for (int c = 0; c < COUT; c += 4) {
-            float4 r = *reinterpret_cast<const float4*>(e + c);
+            float4 r = *reinterpret_cast<const float4*>(e + (c / 4) * PW * 4);
             {
-              const float4 r1 = *reinterpret_cast<const float4*>(e + EXP + c);
-              const float4 r2 = *reinterpret_cast<const float4*>(e + 2 * EXP + c);
+              const float4 r1 = *reinterpret_cast<const float4*>(e + EXP + (c / 4) * PW * 4);
+              const float4 r2 = *reinterpret_cast<const float4*>(e + 2 * EXP + (c / 4) * PW * 4);
               r.x += r1.x + r2.x; r.y += r1.y + r2.y; r.z += r1.z + r2.z; r.w += r1.w + r2.w;
             }
             if (p.accumulate_in) {
