@@ -64,7 +64,9 @@ conv2d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
       const int gy = iy0 + iy, gx = ix0 + ix;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = ldg4(x + ((int64_t)gy * W + gx) * Cin + cb0 + c4 * 4);
-      xs[(iy * 2 + c4) * IW + ix] = v;
+      // stride 2: columns de-interleaved by parity so a warp's reads of column 2*lane + kw are consecutive float4
+      const int slot = STRIDE == 2 ? ((ix & 1) ? (IW + 1) / 2 + (ix >> 1) : (ix >> 1)) : ix;
+      xs[(iy * 2 + c4) * IW + slot] = v;
     }
     for (int e = threadIdx.x; e < S::W_F; e += T::THREADS) {
       const int co = e % COUT;
@@ -81,7 +83,9 @@ conv2d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
         constexpr int NR = 3 * STRIDE + KS;
         float4 xr[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) xr[r] = xs[((hg * 4 * STRIDE + r) * 2 + c4) * IW + lane * STRIDE + kw];
+        for (int r = 0; r < NR; ++r)
+          xr[r] = xs[((hg * 4 * STRIDE + r) * 2 + c4) * IW +
+                     (STRIDE == 2 ? ((kw & 1) ? (IW + 1) / 2 + lane + (kw >> 1) : lane + (kw >> 1)) : lane + kw)];
 #pragma unroll
         for (int kh = 0; kh < KS; ++kh) {
           const int tap = kh * KS + kw;

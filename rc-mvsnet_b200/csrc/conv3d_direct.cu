@@ -88,7 +88,10 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gy >= 0 && gy < H && gx >= 0 && gx < W)
           v = ldg4(x + (((int64_t)gz * H + gy) * W + gx) * Cin + cb0 + c4 * 4);
-        xs[(iy * 2 + c4) * IW + ix] = v;
+        // stride 2: columns are stored de-interleaved by parity ([even 0,2,..][odd 1,3,..]) so that the lanes of a warp,
+        // which read column 2*lane + kw, touch consecutive float4 (no 2-way bank conflict on every activation load)
+        const int slot = STRIDE == 2 ? ((ix & 1) ? (IW + 1) / 2 + (ix >> 1) : (ix >> 1)) : ix;
+        xs[(iy * 2 + c4) * IW + slot] = v;
       }
       // ---- stage the weight slice [9][CB][COUT] of this kd ----
       for (int e = threadIdx.x; e < S::W_F; e += T::THREADS) {
@@ -106,7 +109,9 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
           constexpr int NR = 3 * STRIDE + 3;  // distinct input rows touched by 4 output rows
           float4 xr[NR];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) xr[r] = xs[((hg * 4 * STRIDE + r) * 2 + c4) * IW + lane * STRIDE + kw];
+          for (int r = 0; r < NR; ++r)
+            xr[r] = xs[((hg * 4 * STRIDE + r) * 2 + c4) * IW +
+                       (STRIDE == 2 ? ((kw & 1) ? (IW + 1) / 2 + lane : lane + (kw >> 1)) : lane + kw)];
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const int tap = kh * 3 + kw;
