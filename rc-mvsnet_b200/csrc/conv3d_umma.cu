@@ -30,6 +30,17 @@
 namespace rcmvs {
 namespace umma {
 
+// Stage-ablation mask for profiling (skip MMA issue / loads / stores ...): only in builds made with
+// RCMVS_BUILD_DEBUG_HOOKS=1 (-DRCMVS_TC_DEBUG_HOOKS); the shipped library ignores the environment.
+static inline int tc_debug_mask() {
+#ifdef RCMVS_TC_DEBUG_HOOKS
+  const char* s = getenv("RCMVS_TC_DBG");
+  return s ? atoi(s) : 0;
+#else
+  return 0;
+#endif
+}
+
 constexpr int PW = 32;           // padded plane width (voxels)
 constexpr int TW = 30;           // real output columns per tile
 constexpr int kWPB = 2;                  // loader warps per slab buffer
@@ -927,7 +938,7 @@ extern "C" int rcmvs_conv3d_tc_fwd(const float* x, const float* wimg, const floa
     p.D = D; p.H = H; p.W = W; p.cin_total = Cin; p.cin_off = 0;
     p.d_chunk = d_chunk; p.chunks = chunks;
     p.accumulate_in = 0; p.finalize = 1; p.relu = relu;
-    p.dbg = getenv("RCMVS_TC_DBG") ? atoi(getenv("RCMVS_TC_DBG")) : 0;
+    p.dbg = tc_debug_mask();
     int rc = RCMVS_ERR_UNSUPPORTED;
 #define RCMVS_TC_CASE(CI, CO, NSP, KMV, NSV, NGR) \
   if (Cin == CI * NGR && pl.cin_k == CI && Cout == CO && nsplit == NSP) rc = launch<CI, CO, NSP, KMV, NSV, NGR>(p, B, st)
@@ -1474,7 +1485,7 @@ extern "C" int rcmvs_conv3d_gemm_tc_fwd(const float* x, const float* x_lo, const
   else if (mode == 1) { p.Do = (D - 1) / 2 + 1; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1; }
   else { p.Do = D; p.Ho = H; p.Wo = W; }
   p.tiles_per_class = (int)ceil_div<int64_t>((int64_t)D * H * W, 128);
-  p.dbg = getenv("RCMVS_TC_DBG") ? atoi(getenv("RCMVS_TC_DBG")) : 0;
+  p.dbg = tc_debug_mask();
   cudaStream_t st = as_stream(stream);
   const bool pre = x_lo != nullptr;
   if (Cin == 8) return nsplit == 3 ? launch_g<16, 3, false, 8, true>(p, B, st) : launch_g<16, 1, false, 8, true>(p, B, st);

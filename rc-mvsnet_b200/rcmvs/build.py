@@ -12,6 +12,8 @@ LIB = os.path.join(HERE, "librcmvs.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("RCMVS_BUILD_DEBUG_HOOKS") == "1":        # profiling builds only: RCMVS_TC_DBG stage ablation
+    FLAGS.append("-DRCMVS_TC_DEBUG_HOOKS")
 
 
 def sources():
