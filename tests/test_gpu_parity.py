@@ -530,3 +530,27 @@ def test_tanks_shaped_eval_properties(dev):
     assert (c >= 0).all() and (c <= 1 + 1e-5).all()
     s1 = out["stage1"]["depth"]
     assert (s1 >= dv.min() - 1e-3).all() and (s1 <= dv.max() + 1e-3).all()
+
+
+def test_host_pipeline_matches_direct_calls(dev):
+    """rcmvs.pipeline.HostPipeline (copies on their own streams, two input slots) returns what a plain call returns,
+    for every submit of a sequence that reuses the slots."""
+    from rcmvs import synth
+    from rcmvs.pipeline import HostPipeline
+    m = _model(dev, (16, 8, 8))
+    pipe = HostPipeline(m, dev)
+    outs, want = [], []
+    for seed in range(5):
+        imgs, proj, dv = synth.mvs_inputs(3, 64, 64, seed=seed)
+        ih = torch.from_numpy(imgs).pin_memory()
+        ph = {k: torch.from_numpy(v).pin_memory() for k, v in proj.items()}
+        dh = torch.from_numpy(dv).pin_memory()
+        d_h = torch.empty((1, 64, 64)).pin_memory()
+        c_h = torch.empty((1, 64, 64)).pin_memory()
+        pipe.submit(ih, ph, dh, d_h, c_h)
+        outs.append((d_h, c_h, ih, ph, dh))
+    pipe.synchronize()
+    with torch.no_grad():
+        for d_h, c_h, ih, ph, dh in outs:
+            o = m(ih.to(dev), {k: v.to(dev) for k, v in ph.items()}, dh.to(dev))
+            assert torch.equal(o["depth"].cpu(), d_h) and torch.equal(o["photometric_confidence"].cpu(), c_h)
