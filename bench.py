@@ -14,7 +14,11 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally:
   roofline      — the fused plane-sweep + variance kernel of stage 1 (HBM-bound), algorithmic bytes / CUDA-event time
   roofline_all  — the same for every hot kernel of the step
   cpu_baseline  — the oracle port timed on this box's host cores on a bounded sample (N=1 only)
-  e2e           — same metric through the public API with pinned HOST buffers (H2D + D2H inside the timed region)
+  e2e           — same metric through the public API with pinned HOST buffers (rcmvs.pipeline.HostPipeline: every step
+                  copies its inputs host->device and its depth/confidence device->host inside the timed region; the
+                  copies run on their own streams, one reference view in flight on the device)
+  e2e_two_in_flight — the same loop with two reference views in flight (alternating compute streams)
+  render_branch / batched — configs[2] forward times and the 4-views-per-call throughput, for reference
 """
 import argparse
 import json
@@ -279,6 +283,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the configs[2] renderer-branch timing")
+    ap.add_argument("--e2e-streams", type=int, default=1,
+                    help="reference views in flight on the device in the e2e loop (rcmvs.pipeline.HostPipeline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -324,7 +330,7 @@ def main():
             return model(imgs, proj, dv)
 
     from rcmvs.pipeline import HostPipeline
-    pipe = HostPipeline(model, dev)
+    pipe = HostPipeline(model, dev, compute_streams=args.e2e_streams)
 
     def step_e2e():
         # host buffers in, host buffers out, every step: the H2D copy of this step's inputs and the D2H copy of its
@@ -363,6 +369,16 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, launches = timed(step_resident, args.steps)
     ms_e2e, _ = timed(step_e2e, args.steps)
+    # same loop with two reference views in flight on the device (alternating compute streams): reported beside e2e
+    e2e_two = None
+    if args.e2e_streams == 1:
+        pipe1, pipe = pipe, HostPipeline(model, dev, compute_streams=2)
+        for _ in range(args.warmup):
+            step_e2e()
+        ms2, _ = timed(step_e2e, args.steps)
+        e2e_two = {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "ref-views/s", "ms_per_step": ms2 / args.steps,
+                   "views_in_flight": 2}
+        pipe = pipe1
     clocks = sampler.stop() if sampler else None
 
     value = world * B * args.steps / (ms_total * 1e-3)
@@ -428,7 +444,8 @@ def main():
                             % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6),
                    "conv_precision": os.environ.get("RCMVS_CONV", "tf32x3")},
         "e2e": {"value": e2e_value, "unit": "ref-views/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "views_in_flight": args.e2e_streams},
+        "e2e_two_in_flight": e2e_two,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -11,9 +11,15 @@ __all__ = ["HostPipeline"]
 
 
 class HostPipeline:
-    def __init__(self, model, device, slots=2):
+    def __init__(self, model, device, slots=2, compute_streams=1):
+        """`compute_streams` > 1 runs consecutive submits on alternating CUDA streams: two reference views in flight
+        fill the SMs during the small 1/4- and 1/8-resolution layers and overlap one view's FFMA-bound FeatureNet with
+        the other's tensor-core-bound regularisation.  Results are identical; memory use doubles."""
+        slots = max(slots, compute_streams + 1)
         self.model, self.device, self.slots = model, torch.device(device), slots
         self.h2d, self.d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.compute = [torch.cuda.Stream(self.device) for _ in range(compute_streams)] if compute_streams > 1 else None
+        self._pending = []
         self._dev_in = [None] * slots            # per slot: (imgs, {stage: proj}, depth_values) on the device
         self._consumed = [None] * slots          # event: the forward that read slot s has been enqueued and finished
         self._n = 0
@@ -30,8 +36,9 @@ class HostPipeline:
         """Enqueue one batch of reference views; returns immediately.  `depth_out_h` / `conf_out_h` (pinned host
         tensors) are valid after `synchronize()` (or after the returned event completes)."""
         s = self._n % self.slots
+        caller = torch.cuda.current_stream(self.device)
+        main = self.compute[self._n % len(self.compute)] if self.compute else caller
         self._n += 1
-        main = torch.cuda.current_stream(self.device)
         imgs_d, proj_d, dv_d = self._slot_buffers(s, imgs_h, proj_h, dv_h)
         with torch.cuda.stream(self.h2d):
             if self._consumed[s] is not None:
@@ -43,7 +50,7 @@ class HostPipeline:
             ready = torch.cuda.Event()
             ready.record(self.h2d)
         main.wait_event(ready)
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.stream(main):
             out = self.model(imgs_d, proj_d, dv_d)
         if isinstance(out, tuple):
             out = out[0]
@@ -59,14 +66,17 @@ class HostPipeline:
             conf.record_stream(self.d2h)
             copied = torch.cuda.Event()
             copied.record(self.d2h)
-        self._last = copied
+        self._pending.append(copied)
+        if len(self._pending) > self.slots:
+            self._pending.pop(0)
         return copied
 
     def join(self):
         """Make the current stream wait for every copy enqueued so far (so an event recorded next covers them)."""
         main = torch.cuda.current_stream(self.device)
-        if getattr(self, "_last", None) is not None:
-            main.wait_event(self._last)
+        for ev in self._pending:
+            main.wait_event(ev)
+        self._pending = []
 
     def synchronize(self):
         self.join()
