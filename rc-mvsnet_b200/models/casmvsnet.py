@@ -145,18 +145,31 @@ class _CascadeBase(nn.Module):
         if self.training:
             per_view = [self.feature(imgs[:, v]) for v in range(V)]
             return per_view, None
-        out = self.feature(imgs.reshape(B * V, *imgs.shape[2:]))
+        flat = imgs.reshape(B * V, *imgs.shape[2:])
+        if flat.is_cuda and not torch.is_grad_enabled() and self.feature.base_channels == 8:
+            # stage-2/3 feature maps are produced on a side stream while stage 1 runs (joined in _run)
+            out = self.feature.forward_cl(flat, side_stream=self._side_stream(flat.device))
+            stacked = {k: (v if k == "_ready" else v.view(B, V, *v.shape[1:])) for k, v in out.items()}
+            return None, stacked
+        out = self.feature(flat)
         stacked = {}
         for k, f in out.items():
             cl = as_channels_last_views(f)                     # [B*V,h,w,C]
             stacked[k] = cl.view(B, V, *cl.shape[1:])
         return None, stacked
 
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        if device not in streams:
+            streams[device] = torch.cuda.Stream(device)
+        return streams[device]
+
     def _run(self, imgs, proj_matrices, depth_values):
         B, V, _, H, W = imgs.shape
         imgs = imgs.float()
         depth_values = depth_values.float().contiguous()
         per_view, stacked = self._features(imgs)
+        feats_ready = stacked.pop("_ready", None) if stacked is not None else None
         fused = stacked is not None and (not torch.is_grad_enabled() or self.depthnet_cls is DepthNet_eval)
         if not fused and stacked is not None:
             per_view = [{k: stacked[k][:, v].permute(0, 3, 1, 2) for k in stacked} for v in range(V)]
@@ -169,6 +182,9 @@ class _CascadeBase(nn.Module):
                 planes = ops.depth_hypotheses_first(depth_values, D)               # [B,D]: uniform per plane
                 hyp = planes
             else:
+                if feats_ready is not None:                # join the FeatureNet tail before its maps are first read
+                    torch.cuda.current_stream(imgs.device).wait_event(feats_ready)
+                    feats_ready = None
                 # depth_interval = (max - min) / Dv of batch element 0 is taken on the device (the reference pulls
                 # min/max to the host, :172-174): no host synchronisation anywhere in the forward
                 cur = depth.detach() if self.grad_method == "detach" else depth

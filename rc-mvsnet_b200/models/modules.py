@@ -154,23 +154,49 @@ class FeatureNet(nn.Module):
             self._folded = (key, P)
         return self._folded[1]
 
-    def forward_cl(self, x):
+    def forward_cl(self, x, side_stream=None):
         """x [N,3,H,W] -> {"stageK": [N,h,w,C] channels-last contiguous}; every layer is one librcmvs launch
-        (conv + folded BN + ReLU; the FPN's upsample+add is fused into the 1x1 lateral convolution)."""
+        (conv + folded BN + ReLU; the FPN's upsample+add is fused into the 1x1 lateral convolution).
+
+        With `side_stream` the FPN tail (the stage-2/3 feature maps, ~0.5 ms of FFMA work nobody needs before stage 2)
+        is enqueued on that stream and the result carries `"_ready"`, a CUDA event the consumer's stream must wait for
+        before it touches `stage2` / `stage3`; the caller's stream goes straight on with stage 1."""
         P = self._packed()
 
         def cbr(t, key):
             w, b, stride = P[key]
             return ops.conv2d(t, w, b, None, stride=stride, relu=True)
+
+        def tail(out):
+            intra = ops.conv2d(c1, P["inner1"][0], P["inner1"][1], c2, relu=False)      # up2(c2) + inner1(c1)
+            out["stage2"] = ops.conv2d(intra, P["out2"][0], None, None, relu=False)
+            if self.num_stage == 3:
+                intra = ops.conv2d(c0, P["inner2"][0], P["inner2"][1], intra, relu=False)
+                out["stage3"] = ops.conv2d(intra, P["out3"][0], None, None, relu=False)
+
         c0 = cbr(cbr(ops.images_to_nhwc8(x.float().contiguous()), "conv0.0"), "conv0.1")
         c1 = cbr(cbr(cbr(c0, "conv1.0"), "conv1.1"), "conv1.2")
         c2 = cbr(cbr(cbr(c1, "conv2.0"), "conv2.1"), "conv2.2")
-        out = {"stage1": ops.conv2d(c2, P["out1"][0], None, None, relu=False)}
-        intra = ops.conv2d(c1, P["inner1"][0], P["inner1"][1], c2, relu=False)      # up2(c2) + inner1(c1)
-        out["stage2"] = ops.conv2d(intra, P["out2"][0], None, None, relu=False)
-        if self.num_stage == 3:
-            intra = ops.conv2d(c0, P["inner2"][0], P["inner2"][1], intra, relu=False)
-            out["stage3"] = ops.conv2d(intra, P["out3"][0], None, None, relu=False)
+        out = {}
+        if side_stream is None:
+            out["stage1"] = ops.conv2d(c2, P["out1"][0], None, None, relu=False)
+            tail(out)
+            return out
+        main = torch.cuda.current_stream(x.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        out["stage1"] = ops.conv2d(c2, P["out1"][0], None, None, relu=False)
+        side_stream.wait_event(fork)
+        with torch.cuda.stream(side_stream):
+            tail(out)
+            ready = torch.cuda.Event()
+            ready.record(side_stream)
+        for t_ in (c0, c1, c2):
+            t_.record_stream(side_stream)          # read over there: do not recycle before the tail has run
+        for k in ("stage2", "stage3"):
+            if k in out:
+                out[k].record_stream(main)         # allocated over there, consumed on the caller's stream
+        out["_ready"] = ready
         return out
 
     def forward(self, x):
