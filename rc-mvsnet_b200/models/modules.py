@@ -225,6 +225,22 @@ def as_channels_last_views(feat):
     return p if p.is_contiguous() else ops.to_channels_last(feat.contiguous())
 
 
+def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit):
+    """One 3x3x3 (transposed) convolution + folded BatchNorm as a list of candidate engines (`CostRegNet._run` picks
+    one per input shape): the FFMA kernel always; with nsplit = 1 (TF32) or 3 (3xTF32) also the tcgen05 kernels that
+    support the layer's shape (slab kernel `tc` / `tct`, gather implicit-GEMM `gemm`)."""
+    cout, cin = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+    cands = [("direct", ops.pack_conv3d_weight(w, scale, transposed), shift)]
+    if nsplit > 0 and transposed and (cin, cout) in ops.TCT_SUPPORTED:
+        cands.append(("tct", ops.conv_transpose3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
+    if nsplit > 0 and not transposed and stride == 1 and (cin, cout) in ops.TC_SUPPORTED:
+        cands.append(("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
+    if nsplit > 0 and ops.gemm_tc_supported(cin, cout):
+        gmode = 2 if transposed else (1 if stride == 2 else 0)
+        cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, transposed, nsplit), shift, cout, nsplit, gmode))
+    return {"cands": cands, "tr": transposed, "stride": stride, "relu": relu, "choice": {}}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # a3  CostRegNet
 # ---------------------------------------------------------------------------------------------------------------
@@ -269,18 +285,8 @@ class CostRegNet(nn.Module):
                         conv, relu = blk.conv, True
                         scale, shift = (t.contiguous() for t in fold_bn(blk.bn))
                         tr = isinstance(conv, nn.ConvTranspose3d)
-                    w = conv.weight.detach().contiguous()
-                    cout, cin = (w.shape[1], w.shape[0]) if tr else (w.shape[0], w.shape[1])
-                    stride = conv.stride[0]
-                    cands = [("direct", ops.pack_conv3d_weight(w, scale, tr), shift)]
-                    if nsplit > 0 and tr and (cin, cout) in ops.TCT_SUPPORTED:
-                        cands.append(("tct", ops.conv_transpose3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
-                    if nsplit > 0 and not tr and stride == 1 and (cin, cout) in ops.TC_SUPPORTED:
-                        cands.append(("tc", ops.conv3d_tc_pack(w, scale, nsplit), shift, cout, nsplit))
-                    if nsplit > 0 and ops.gemm_tc_supported(cin, cout):
-                        gmode = 2 if tr else (1 if stride == 2 else 0)
-                        cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, tr, nsplit), shift, cout, nsplit, gmode))
-                    P[name] = {"cands": cands, "tr": tr, "stride": stride, "relu": relu, "choice": {}}
+                    P[name] = pack_conv3d_layer(conv.weight.detach().contiguous(), scale, shift, tr, conv.stride[0],
+                                                relu, nsplit)
             self._packed = (key, P)
         return self._packed[1]
 
