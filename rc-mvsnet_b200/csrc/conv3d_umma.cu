@@ -681,30 +681,49 @@ __global__ void __launch_bounds__(threads_for(NS), 1) convT3d_umma_kernel(const 
       mbar_wait(empty + mybuf, ((i / NS) & 1) ^ 1);
       const int z = z0 + i;
       const bool zok = z < p.D;
-      for (int e = t; e < PIECES; e += kLoaderThreads) {
-        const int ch = e % C::NCH;
-        const int v = e / C::NCH;
-        const int gy = y0 + v / PW, gx = x0 + (v % PW);
-        const bool ok = zok && gy < p.H && gx < p.W;
-        const float* src = ok ? xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4 : xb;
-        cp_async16(slab + ch * C::PLANE_B + v * 16, src, ok);
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
       if constexpr (NSPLIT == 3) {
+        // 3xTF32: plain loads into registers, split x = hi + lo on the way to shared memory (one pass instead of
+        // cp.async + re-read + two stores); BATCH loads in flight per thread
+        static_assert(PIECES % kLoaderThreads == 0, "loader mapping");
+        constexpr int NP = PIECES / kLoaderThreads;
+        constexpr int BATCH = NP % 6 == 0 ? 6 : (NP % 4 == 0 ? 4 : (NP % 3 == 0 ? 3 : 1));
         unsigned char* hi_p = a_smem + (size_t)mybuf * C::NPART * C::SLAB_B;
         unsigned char* lo_p = hi_p + C::SLAB_B;
-        for (int e = t; e < PIECES; e += kLoaderThreads) {
-          const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
-          float4 v = *reinterpret_cast<float4*>(hi_p + off);
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          *reinterpret_cast<float4*>(hi_p + off) = h;
-          *reinterpret_cast<float4*>(lo_p + off) = l;
+        for (int p0 = 0; p0 < NP; p0 += BATCH) {
+          float4 v[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            const int e = t + (p0 + u) * kLoaderThreads;
+            const int ch = e % C::NCH, vv = e / C::NCH;
+            const int gy = y0 + vv / PW, gx = x0 + (vv % PW);
+            const bool ok = zok && gy < p.H && gx < p.W;
+            v[u] = ok ? ldg4(xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            const int e = t + (p0 + u) * kLoaderThreads;
+            const int off = (e % C::NCH) * C::PLANE_B + (e / C::NCH) * 16;
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u); l.x = v[u].x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u); l.y = v[u].y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u); l.z = v[u].z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u); l.w = v[u].w - h.w;
+            *reinterpret_cast<float4*>(hi_p + off) = h;
+            *reinterpret_cast<float4*>(lo_p + off) = l;
+          }
         }
+      } else {
+        for (int e = t; e < PIECES; e += kLoaderThreads) {
+          const int ch = e % C::NCH;
+          const int v = e / C::NCH;
+          const int gy = y0 + v / PW, gx = x0 + (v % PW);
+          const bool ok = zok && gy < p.H && gx < p.W;
+          const float* src = ok ? xb + (((int64_t)z * p.H + gy) * p.W + gx) * vox_stride + ch * 4 : xb;
+          cp_async16(slab + ch * C::PLANE_B + v * 16, src, ok);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
       }
       fence_proxy_async();
       mbar_arrive(full + mybuf);
