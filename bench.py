@@ -11,7 +11,9 @@ cascade D=192/64/8, synthetic DTU-shaped cameras, the reference's shipped weight
 Multi-GPU = independent reference views per rank (weak scaling, no data-path collective).
 
 Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally:
-  roofline      — the fused plane-sweep + variance kernel of stage 1 (HBM-bound), algorithmic bytes / CUDA-event time
+  roofline      — the fused plane-sweep + variance kernel of stage 1 (the kernel north_star names; HBM-bound by bytes),
+                  algorithmic bytes / CUDA-event time
+  roofline_dominant — the largest kernel of the step by time share: conv0 of stage 1 on tcgen05 (tensor-bound)
   roofline_all  — the same for every hot kernel of the step
   cpu_baseline  — the oracle port timed on this box's host cores on a bounded sample (N=1 only)
   e2e           — same metric through the public API with pinned HOST buffers (rcmvs.pipeline.HostPipeline: every step
@@ -432,6 +434,16 @@ def main():
                     "achieved": s1["achieved"], "peak": s1["peak"], "unit": "GB/s", "frac": s1["frac"],
                     "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                     "algorithmic_bytes": s1["bytes"], "traffic": ncu_traffic("costvolume_var_stage1")}
+    # the single largest kernel of the step by time share (profiles/r01_launches_final.md) is tensor-bound: conv0 of
+    # stage 1 on the slab tcgen05 kernel.  FLOPs = 2*27*Cin*Cout*voxels of the fp32 convolution (the 3xTF32 mode issues
+    # three TF32 products per fp32 product; they are not counted), peak = dense TF32 = half the measured bf16 peak.
+    c0 = (roof_all or {}).get("conv0_stage1")
+    roofline_dominant = None
+    if c0:
+        roofline_dominant = {"kernel": "conv3d_umma_kernel (conv0 of stage 1: 32->8 channels, 192x128x160, 3xTF32)",
+                             "bound": "tensor", "achieved": c0["achieved"], "peak": c0["peak"], "unit": "TFLOP/s",
+                             "frac": c0["frac"], "ms": c0["ms"], "flops": c0["flops"],
+                             "traffic": ncu_traffic("conv0_stage1")}
     line = {
         "metric": METRIC, "value": value, "unit": "ref-views/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -449,6 +461,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_dominant": roofline_dominant,
         "roofline_all": roof_all,
         "cpu_baseline": cpu_baseline,
         "render_branch": render,
