@@ -779,11 +779,31 @@ __global__ void __launch_bounds__(threads_for(NS), 1) convT3d_umma_kernel(const 
     const int gx = x0 + lane;
     const bool col_ok = lane < C::TWI && gx < p.W;
     const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
+    // The skip tensor is as large as the output and every thread needs 8 x COUT of it per M-tile: with one CTA per SM
+    // the 4 epilogue warps cannot hide that latency, so (COUT = 8) the values are requested BEFORE the wait for the
+    // accumulators / right after the previous M-tile's stores instead of one load per class in front of its add.
+    constexpr bool kPrefetchSkip = COUT == 8;
+    float4 sk[kPrefetchSkip ? 16 : 1];
+    const bool use_skip = p.skip != nullptr && p.finalize;
+    auto load_skip = [&](int iz, int mt) {
+      if constexpr (kPrefetchSkip) {
+        const int gy = y0 + mt * 4 + warp;
+        const bool ok = use_skip && col_ok && gy < p.H && iz < p.D;
+#pragma unroll
+        for (int cls = 0; cls < 8; ++cls) {
+          const int oz = 2 * iz + (cls >> 2), oy = 2 * gy + ((cls >> 1) & 1), ox = 2 * gx + (cls & 1);
+          const int64_t o = ((((int64_t)b * Do + oz) * Ho + oy) * Wo + ox) * COUT;
+          sk[cls * 2] = ok ? ldg4(p.skip + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          sk[cls * 2 + 1] = ok ? ldg4(p.skip + o + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
     for (int s = 0; s < nsteps; ++s) {
       const int stage = s & 1;
+      const int iz = z0 + s;
+      load_skip(iz, 0);
       mbar_wait(acc_full + stage, (s >> 1) & 1);
       tc_fence_after();
-      const int iz = z0 + s;
 #pragma unroll 1
       for (int mt = 0; mt < KM; ++mt) {
         float v[N];
@@ -795,7 +815,10 @@ __global__ void __launch_bounds__(threads_for(NS), 1) convT3d_umma_kernel(const 
           mbar_arrive(acc_empty + stage);
         }
         const int gy = y0 + mt * 4 + warp;
-        if (!col_ok || gy >= p.H) continue;
+        if (!col_ok || gy >= p.H) {
+          if (mt + 1 < KM) load_skip(iz, mt + 1);
+          continue;
+        }
 #pragma unroll
         for (int cls = 0; cls < 8; ++cls) {
           const int oz = 2 * iz + (cls >> 2), oy = 2 * gy + ((cls >> 1) & 1), ox = 2 * gx + (cls & 1);
@@ -814,13 +837,14 @@ __global__ void __launch_bounds__(threads_for(NS), 1) convT3d_umma_kernel(const 
               }
               if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
               if (p.skip) {
-                const float4 q = ldg4(p.skip + o + c);
+                const float4 q = kPrefetchSkip ? sk[kPrefetchSkip ? cls * 2 + c / 4 : 0] : ldg4(p.skip + o + c);
                 r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
               }
             }
             st4(p.y + o + c, r);
           }
         }
+        if (mt + 1 < KM) load_skip(iz, mt + 1);
       }
     }
   }

@@ -343,18 +343,17 @@ class CostRegNet(nn.Module):
         """Static table distilled from RCMVS_AUTOTUNE=1 / tools/time_layers.py runs on B200 at DTU / BASELINE shapes
         (profiles/): stride-1 conv0 / conv2 -> slab tcgen05 kernel; `prob` (8->1, memory-bound) -> FFMA kernel;
         the 1/4- and 1/8-resolution levels conv3..conv7 and the transposed conv9 -> gather-GEMM tcgen05 kernel;
-        transposed conv11 -> slab tcgen05 kernel when the input has >= 8 depth planes (3xTF32) or always (TF32);
+        transposed conv11 -> slab tcgen05 kernel;
         everything else FFMA."""
         kinds = [c[0] for c in cands]
-        nsplit = next((c[4] for c in cands if c[0] in ("tc", "tct", "gemm")), 0)
-        cin, planes = shape[-1], shape[1]
+        cin = shape[-1]
         if "tc" in kinds:
             cout = cands[kinds.index("tc")][3]
             return kinds.index("tc") if cout != 1 else 0
         if "gemm" in kinds and cin != 8:                                   # conv1 (8 -> 16, stride 2) stays on FFMA
             return kinds.index("gemm")
         if "tct" in kinds:                                                 # conv11 (16 -> 8, to full resolution)
-            return kinds.index("tct") if (nsplit == 1 or planes >= 8) else 0
+            return kinds.index("tct")
         return 0
 
     def engines(self):
