@@ -1378,13 +1378,21 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, GCf
       const int jx = (int)(m % p.W), jy = (int)((m / p.W) % p.H), jz = (int)(m / ((int64_t)p.W * p.H));
       ovox = ((int64_t)(2 * jz + pz) * p.Ho + (2 * jy + py)) * p.Wo + (2 * jx + px);
     }
+    // the skip row is requested before the (long) wait for the accumulators, so its latency never shows
+    constexpr bool kPrefetchSkip = COUT <= 32;
+    const int64_t o = ((int64_t)b * p.Do * p.Ho * p.Wo + ovox) * COUT;
+    float4 sk[kPrefetchSkip ? COUT / 4 : 1];
+    if constexpr (kPrefetchSkip) {
+#pragma unroll
+      for (int c = 0; c < COUT; c += 4)
+        sk[c / 4] = (p.skip && m < Mspace) ? ldg4(p.skip + o + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     while (!mbar_try_wait(acc_full, 0)) __nanosleep(512);      // idle for the whole main loop: stay off the issue ports
     tc_fence_after();
     float v[COUT];
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, &v[c0]);
     if (m < Mspace) {
-      const int64_t o = ((int64_t)b * p.Do * p.Ho * p.Wo + ovox) * COUT;
 #pragma unroll
       for (int c = 0; c < COUT; c += 4) {
         float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
@@ -1394,7 +1402,7 @@ __global__ void __launch_bounds__(GCfg<COUT, NSPLIT, PRESPLIT, NS>::THREADS, GCf
         }
         if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
         if (p.skip) {
-          const float4 q = ldg4(p.skip + o + c);
+          const float4 q = kPrefetchSkip ? sk[kPrefetchSkip ? c / 4 : 0] : ldg4(p.skip + o + c);
           r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
         }
         if (p.y) st4(p.y + o + c, r);
