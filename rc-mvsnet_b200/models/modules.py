@@ -269,8 +269,8 @@ class CostRegNet(nn.Module):
     def packed(self):
         """{layer: [candidate engines]} rebuilt when any parameter/buffer or the precision mode changes.  Every
         candidate computes the same layer (conv + folded BN + bias + ReLU + skip); which one runs is decided per
-        input shape by a one-off on-device timing (`_run`), because the winner depends on Cin/Cout/resolution:
-        the tcgen05 kernels win on the full/half-resolution layers, the FFMA kernels on tiny deep levels."""
+        input shape by `_choose`: a static table (`_default_engine`) distilled from on-device timings, or a one-off
+        timing of the candidates under RCMVS_AUTOTUNE=1."""
         mode = conv_precision()
         key = (_versions(self), mode)
         if self._packed is None or self._packed[0] != key:
