@@ -202,6 +202,39 @@ int rcmvs_inverse_warp_bwd(const float* img, const float* left_cam, const float*
                            const float* grad_warped, float* grad_depth, int B, int h, int w, int C,
                            rcmvs_stream_t stream);
 
+/* ---- f2 unsupervised loss stack: losses/unsup_loss.py:9-94, losses/modules.py:6-82, losses/aug_loss.py, sl1loss.py ---- */
+/* imgs [N][3][H][W] -> out [N][H/step][W/step][3]: F.interpolate(scale_factor=1/step, nearest) + NCHW->NHWC
+ * (unsup_loss.py:27-33, 55-61). */
+int rcmvs_images_subsample_nhwc(const float* imgs, float* out, int N, int H, int W, int step, rcmvs_stream_t stream);
+/* UnSupLoss.forward of one stage, value AND gradient w.r.t. depth in one call: imgs [B][V][h][w][3] (stage-resolution
+ * NHWC images, view 0 = reference), cams [B][V][2][4][4], depth [B][h][w] -> terms[4] = {12·reconstr + 6·ssim +
+ * smooth_weight·smooth, reconstr, ssim, smooth} (device), grad_depth [B][h][w] = d terms[0] / d depth (may be NULL).
+ * workspace: rcmvs_unsup_loss_workspace_floats(B, V, h, w) floats. */
+int64_t rcmvs_unsup_loss_workspace_floats(int B, int V, int h, int w);
+int rcmvs_unsup_loss_fwd_bwd(const float* imgs, const float* cams, const float* depth, float smooth_weight,
+                             float* terms, float* grad_depth, float* workspace, int B, int V, int h, int w,
+                             rcmvs_stream_t stream);
+/* scale · mean over the selected elements of smooth-L1 (mode 0) or squared error (mode 1) of pred [B][h][w] against
+ * target [B][h·step][w·step] read at (y·step, x·step), + gradient w.r.t. pred (may be NULL).  mask_kind 0: all elements;
+ * 1: mask[b·mask_batch_stride + (y·step)·(w·step) + x·step] > 0.5; 2: target > 0.  AugLossMultiStage (aug_loss.py:41-58),
+ * SL1Loss (sl1loss.py:9-13), img2mse.  workspace: rcmvs_masked_loss_workspace_floats() floats. */
+int64_t rcmvs_masked_loss_workspace_floats(void);
+int rcmvs_masked_loss_fwd_bwd(const float* pred, const float* target, const float* mask, int64_t mask_batch_stride,
+                              int mask_kind, int mode, float scale, float* loss, float* grad, float* workspace, int B,
+                              int h, int w, int step, rcmvs_stream_t stream);
+
+/* ---- f3 geometric-consistency filter: eval_rcmvsnet_dtu.py:281-336 (reproject_with_depth,
+ * check_geometric_consistency) + :366-389 of filter_depth, all NS source views of one reference view per launch ---- */
+/* depth_ref [H][W], conf [H][W] or NULL, depth_src [NS][Hs][Ws]; pair_mats [NS][68] float32 per source:
+ * {inv(K_ref) 9, E_src·inv(E_ref) 16, K_src 9, inv(K_src) 9, E_ref·inv(E_src) 16, K_ref 9} (float32 on the host, as the
+ * reference computes them).  Outputs (each may be NULL): masks uint8 [NS][H][W], depth_reproj [NS][H][W] (0 where the
+ * mask is 0), xy_src [NS][2][H][W] (float32 source coordinates), geo_mask_sum int32 [H][W], depth_avg [H][W] =
+ * (Σ depth_reproj + depth_ref) / (geo_mask_sum + 1), final_mask uint8 [H][W] = conf > prob_thresh & sum >= num_consistent. */
+int rcmvs_geo_consistency(const float* depth_ref, const float* conf, const float* depth_src, const float* pair_mats,
+                          int NS, int H, int W, int Hs, int Ws, float img_dist_thresh, float depth_thresh,
+                          float prob_thresh, int num_consistent, uint8_t* masks, float* depth_reproj, float* xy_src,
+                          int32_t* geo_mask_sum, float* depth_avg, uint8_t* final_mask, rcmvs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,24 @@ inline cudaStream_t as_stream(rcmvs_stream_t s) { return reinterpret_cast<cudaSt
     }                                                                                    \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(function, device) property: remember it per device ordinal
+// (a process-wide flag would leave every GPU but the first at the 48 KB default -> "invalid argument" at launch).
+struct SmemAttrOnce {
+  unsigned long long done[4] = {0, 0, 0, 0};        // one bit per device ordinal (< 256)
+  template <typename K>
+  cudaError_t ensure(K kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    unsigned long long& word = done[(dev >> 6) & 3];
+    if (__atomic_load_n(&word, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) __atomic_fetch_or(&word, bit, __ATOMIC_RELEASE);
+    return e;
+  }
+};
+
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

@@ -173,11 +173,10 @@ static int launch_conv2d(const float* x, const float* wp, const float* bias, con
   using S = Conv2Smem<COUT, STRIDE, KS>;
   const int Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
   auto kern = conv2d_direct_kernel<COUT, STRIDE, KS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES);
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(kern, (int)S::BYTES);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv2d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   RCMVS_REQUIRE(N <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv2d_fwd: grid too large");
   dim3 grid(ceil_div(Wo, 32), ceil_div(Ho, T::TH), N);

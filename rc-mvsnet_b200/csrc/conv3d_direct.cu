@@ -303,12 +303,10 @@ conv3d_c8_to_c1_march_kernel(const float* __restrict__ x, const float* __restric
 static int launch_march_c8_c1(const float* x, const float* wp, const float* bias, const float* skip, float* y, int B,
                               int D, int H, int W, int relu, cudaStream_t st) {
   using namespace march;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_c8_to_c1_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM);
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(conv3d_c8_to_c1_march_kernel, (int)SMEM);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   // depth chunks: as long as possible (every chunk re-reads 2 halo planes) while the grid still covers ~3 waves
   const int64_t tiles = (int64_t)ceil_div(W, TW) * ceil_div(H, TH) * B;
@@ -497,11 +495,10 @@ static int launch_conv(const float* x, const float* wp, const float* bias, const
   const int nsplit = Ctot / COUT;
   const int64_t out_elems = (int64_t)B * Do * Ho * Wo * Ctot;
   auto kern = conv3d_direct_kernel<COUT, STRIDE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES);
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(kern, (int)S::BYTES);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   RCMVS_REQUIRE((int64_t)B * Do * nsplit * ksplit <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv3d_fwd: grid too large");
@@ -549,12 +546,10 @@ static int launch_tconv(const float* x, const float* wp, const float* bias, cons
   using T = TConvTile<COUT>;
   const int nsplit = Ctot / COUT;
   auto kern = conv_transpose3d_direct_kernel<COUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES);
-    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_transpose3d_fwd: cudaFuncSetAttribute: %s",
-                  cudaGetErrorString(e));
-    attr_set = true;
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(kern, (int)T::BYTES);
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_transpose3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   RCMVS_REQUIRE((int64_t)B * D * nsplit <= 65535 && ceil_div(H, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv_transpose3d_fwd: grid too large");

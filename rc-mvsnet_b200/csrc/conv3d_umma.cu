@@ -565,11 +565,10 @@ static int launch(const Params& p, int B, cudaStream_t st) {
   using C = Cfg<CIN, COUT, NSPLIT, KM, NS, NGRP>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
   auto kern = conv3d_umma_kernel<CIN, COUT, NSPLIT, KM, NS, NGRP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(kern, (int)C::SMEM);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   dim3 grid(ceil_div(p.W, TW), ceil_div(p.H, C::OROWS), B * p.chunks);
   RCMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_tc_fwd: grid too large");
@@ -902,12 +901,10 @@ static int launch_t(const Params& p, int B, cudaStream_t st) {
   using C = TCfg<CIN, COUT, NSPLIT, KM, NS>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
   auto kern = convT3d_umma_kernel<CIN, COUT, NSPLIT, KM, NS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_transpose3d_tc_fwd: cudaFuncSetAttribute: %s",
-                  cudaGetErrorString(e));
-    attr_set = true;
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(kern, (int)C::SMEM);
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_transpose3d_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   dim3 grid(ceil_div(p.W, C::TWI), ceil_div(p.H, C::ROWS), B * p.chunks);
   RCMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_transpose3d_tc_fwd: grid too large");
@@ -1474,11 +1471,10 @@ static int launch_g(const GParams& p, int B, cudaStream_t st) {
   using C = GCfg<COUT, NSPLIT, PRESPLIT, NS>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
   auto kern = conv3d_gather_umma_kernel<COUT, NSPLIT, PRESPLIT, NS, CIN8>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(kern, (int)C::SMEM);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_gemm_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const int64_t Mspace = p.mode == 2 ? (int64_t)p.D * p.H * p.W : (int64_t)p.Do * p.Ho * p.Wo;
   const int64_t tiles = ceil_div<int64_t>(Mspace, 128);

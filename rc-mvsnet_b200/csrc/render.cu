@@ -502,11 +502,10 @@ extern "C" int rcmvs_render_mlp(const float* ndc, const float* feat, const float
   W.wrgb = weights[20]; W.brgb = weights[21];
   for (int i = 0; i < 22; ++i) RCMVS_REQUIRE(weights[i], RCMVS_ERR_BAD_ARG, "rcmvs_render_mlp: null weight %d", i);
   const size_t smem = (size_t)(MLP_TP * MLP_LD + MLP_TP * MLP_PE + MLP_TP * 128 + MLP_TP * 4 + MLP_TP) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(render_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttrOnce smem_attr;
+  {
+    cudaError_t e = smem_attr.ensure(render_mlp_kernel, (int)smem);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_render_mlp: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   render_mlp_kernel<<<(unsigned)ceil_div<int64_t>(P, MLP_TP), 256, smem, as_stream(stream)>>>(ndc, feat, dirs, W, out,
                                                                                               P, S);

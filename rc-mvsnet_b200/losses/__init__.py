@@ -1,9 +1,7 @@
-"""Drop-in `losses` package: the hot-path entry (inverse_warping) runs on librcmvs; the remaining loss terms of the
-reference (SSIM, smoothness, top-k photometric, augmentation, smooth-L1: losses/unsup_loss.py, modules.py, aug_loss.py,
-sl1loss.py) are small 2-D torch expressions and stay in the reference tree ("next")."""
+"""Drop-in `losses` package (reference losses/): inverse_warping (homography.py), the unsupervised photometric loss
+stack (unsup_loss.py — SSIM, gradient smooth-L1, top-1 over views and depth smoothness fused into one value+gradient
+call per stage), the augmentation-consistency loss (aug_loss.py) and SL1Loss (sl1loss.py), all on librcmvs kernels."""
 from .homography import inverse_warping  # noqa: F401
-
-# Merge with a same-named package further down sys.path (the reference tree): `losses.unsup_loss`, `losses.aug_loss`,
-# `losses.sl1loss`, `losses.modules` keep resolving there, and their `from .homography import *` picks up this one.
-import pkgutil as _pkgutil
-__path__ = _pkgutil.extend_path(__path__, __name__)
+from .unsup_loss import *  # noqa: F401,F403
+from .aug_loss import random_image_mask, AugLossMultiStage, masked_loss  # noqa: F401
+from .sl1loss import SL1Loss  # noqa: F401

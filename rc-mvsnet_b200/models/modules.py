@@ -12,6 +12,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from rcmvs import ops
+from rcmvs.cache import PackedCache
+from rcmvs.strict import library_fallback
 
 __all__ = ["homo_warping", "CostRegNet", "FeatureNet", "Conv2d", "Conv3d", "Deconv3d", "depth_regression",
            "get_depth_range_samples", "get_cur_depth_range_samples", "cas_mvsnet_loss", "fold_bn"]
@@ -132,12 +134,12 @@ class FeatureNet(nn.Module):
         else:
             self.out2 = nn.Conv2d(4 * c, c, 3, padding=1, bias=False)
             self.out_channels += [c]
-        self._folded = None
+        self._folded = PackedCache()
 
     def _packed(self):
-        """BN-folded, re-laid-out weights for the librcmvs conv2d kernels, rebuilt when parameters change."""
-        key = _versions(self)
-        if self._folded is None or self._folded[0] != key:
+        """BN-folded, re-laid-out weights for the librcmvs conv2d kernels, rebuilt when parameters change (stream-safe:
+        a hit on another CUDA stream waits for the packing kernels, rcmvs/cache.py)."""
+        def build():
             with torch.no_grad():
                 P = {}
                 for name in ("conv0", "conv1", "conv2"):
@@ -151,8 +153,8 @@ class FeatureNet(nn.Module):
                     if conv is not None:
                         b = conv.bias.detach().contiguous() if conv.bias is not None else None
                         P[name] = (ops.pack_conv2d_weight(conv.weight.detach().contiguous(), None), b, 1)
-            self._folded = (key, P)
-        return self._folded[1]
+            return P
+        return self._folded.get(_versions(self), build)
 
     def forward_cl(self, x, side_stream=None):
         """x [N,3,H,W] -> {"stageK": [N,h,w,C] channels-last contiguous}; every layer is one librcmvs launch
@@ -264,7 +266,7 @@ class CostRegNet(nn.Module):
         self.conv9 = Deconv3d(4 * c, 2 * c, stride=2, padding=1, output_padding=1)
         self.conv11 = Deconv3d(2 * c, c, stride=2, padding=1, output_padding=1)
         self.prob = nn.Conv3d(c, 1, 3, stride=1, padding=1, bias=False)
-        self._packed = None
+        self._packed = PackedCache()
 
     def packed(self):
         """{layer: [candidate engines]} rebuilt when any parameter/buffer or the precision mode changes.  Every
@@ -272,8 +274,8 @@ class CostRegNet(nn.Module):
         input shape by `_choose`: a static table (`_default_engine`) distilled from on-device timings, or a one-off
         timing of the candidates under RCMVS_AUTOTUNE=1."""
         mode = conv_precision()
-        key = (_versions(self), mode)
-        if self._packed is None or self._packed[0] != key:
+
+        def build():
             nsplit = {"tf32x3": 3, "tf32": 1, "fp32": 0}[mode]
             with torch.no_grad():
                 P = {}
@@ -287,8 +289,8 @@ class CostRegNet(nn.Module):
                         tr = isinstance(conv, nn.ConvTranspose3d)
                     P[name] = pack_conv3d_layer(conv.weight.detach().contiguous(), scale, shift, tr, conv.stride[0],
                                                 relu, nsplit)
-            self._packed = (key, P)
-        return self._packed[1]
+            return P
+        return self._packed.get((_versions(self), mode), build)
 
     @staticmethod
     def _call(cand, layer, x, skip):
@@ -358,9 +360,9 @@ class CostRegNet(nn.Module):
 
     def engines(self):
         """{layer: {input shape: engine name}} chosen so far (bench.py reports it)."""
-        if self._packed is None:
+        if self._packed.last is None:
             return {}
-        return {n: {str(k): l["cands"][i][0] for k, i in l["choice"].items()} for n, l in self._packed[1].items()}
+        return {n: {str(k): l["cands"][i][0] for k, i in l["choice"].items()} for n, l in self._packed.last.items()}
 
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cin] channels-last -> cost [B,D,h,w]."""

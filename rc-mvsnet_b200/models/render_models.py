@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from rcmvs import ops
+from rcmvs.cache import PackedCache
 from .modules import fold_bn, _versions
 
 __all__ = ["Embedder", "get_embedder", "Renderer_ours", "RenderNet", "create_nerf_mvs", "CostReg",
@@ -73,7 +74,7 @@ class Renderer_ours(nn.Module):
         if use_viewdirs:
             for m in (self.feature_linear, self.alpha_linear, self.rgb_linear):
                 m.apply(weights_init)
-        self._packed = None
+        self._packed = PackedCache()
 
     def _trunk(self, input_pts, input_feats):
         h, bias = input_pts, self.pts_bias(input_feats)
@@ -106,8 +107,7 @@ class Renderer_ours(nn.Module):
 
     def packed(self):
         """Host array of 22 device pointers to transposed weights/biases (rcmvs_render_mlp), cached by version."""
-        key = _versions(self)
-        if self._packed is None or self._packed[0] != key:
+        def build():
             with torch.no_grad():
                 ts = []
                 for lin in self.pts_linears:
@@ -118,8 +118,8 @@ class Renderer_ours(nn.Module):
                        self.views_linears[0].weight.t().contiguous(), self.views_linears[0].bias.contiguous(),
                        self.rgb_linear.weight.t().contiguous(), self.rgb_linear.bias.contiguous()]
                 arr = (ctypes.c_void_p * 22)(*[t.data_ptr() for t in ts])
-            self._packed = (key, arr, ts)          # keep the tensors alive
-        return self._packed[1]
+            return arr, ts                         # keep the tensors alive
+        return self._packed.get(_versions(self), build)[0]
 
     def forward_cuda(self, ndc, feat, dirs):
         """ndc [N,S,3], feat [N,S,20], dirs [N,3] -> raw [N,S,4] (embedding fused in the kernel)."""
@@ -178,7 +178,7 @@ class CostReg(nn.Module):
             return nn.Sequential(nn.ConvTranspose3d(i, o, 3, padding=1, output_padding=1, stride=2, bias=False),
                                  norm_act(n))
         self.conv7, self.conv9, self.conv11 = up(8 * c, 4 * c, 32), up(4 * c, 2 * c, 16), up(2 * c, c, 8)
-        self._packed = None
+        self._packed = PackedCache()
 
     def forward(self, x):
         c0 = self.conv0(x)
@@ -190,8 +190,7 @@ class CostReg(nn.Module):
         return c0 + self.conv11(y)
 
     def packed(self, cin_pad):
-        key = (_versions(self), cin_pad)
-        if self._packed is None or self._packed[0] != key:
+        def build():
             with torch.no_grad():
                 P = {}
                 for name in ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6"):
@@ -205,8 +204,8 @@ class CostReg(nn.Module):
                     seq = getattr(self, name)
                     scale, shift = (t.contiguous() for t in fold_bn(seq[1]))
                     P[name] = (ops.pack_conv3d_weight(seq[0].weight.detach().contiguous(), scale, True), shift)
-            self._packed = (key, P)
-        return self._packed[1]
+            return P
+        return self._packed.get((_versions(self), cin_pad), build)
 
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cpad] -> [B,D,h,w,8]; eval-mode BN folded, no ReLU anywhere."""

@@ -3,6 +3,8 @@
 torch is plumbing here (device memory, streams); every function below enqueues hand-written sm_100a kernels from
 librcmvs.so and raises if the tensors are not CUDA fp32 contiguous — there is no eager fallback.
 """
+import functools
+
 import torch
 
 from . import _ffi
@@ -10,6 +12,22 @@ from . import _ffi
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Run `fn` with the device of its first tensor argument current (kernels launch on the CURRENT device and
+    `_stream()` is that device's current stream): a model living on cuda:1 while cuda:0 is current — DataParallel
+    replicas, as the reference's scripts wrap the model (eval_rcmvsnet_dtu.py:189) — must not enqueue on cuda:0."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
 
 
 def _chk(t, name):
@@ -27,6 +45,7 @@ def _opt(t, name):
 
 
 # ---- layout ---------------------------------------------------------------------------------------------------
+@_on_device
 def to_channels_last(x):
     """[N,C,*spatial] contiguous -> [N,*spatial,C] contiguous."""
     N, C = x.shape[:2]
@@ -36,6 +55,7 @@ def to_channels_last(x):
     return out
 
 
+@_on_device
 def to_planar(x):
     """[N,*spatial,C] contiguous -> [N,C,*spatial] contiguous."""
     N, C = x.shape[0], x.shape[-1]
@@ -46,6 +66,7 @@ def to_planar(x):
 
 
 # ---- projections ----------------------------------------------------------------------------------------------
+@_on_device
 def relative_projections(proj):
     """proj [B,V,2,4,4] -> rt [B,V-1,12]."""
     B, V = proj.shape[:2]
@@ -54,6 +75,7 @@ def relative_projections(proj):
     return rt
 
 
+@_on_device
 def relative_projection_pair(src_proj, ref_proj):
     B = src_proj.shape[0]
     rt = torch.empty((B, 12), device=src_proj.device, dtype=torch.float32)
@@ -63,6 +85,7 @@ def relative_projection_pair(src_proj, ref_proj):
 
 
 # ---- hypotheses -----------------------------------------------------------------------------------------------
+@_on_device
 def depth_hypotheses_first(depth_values, D):
     B, Dv = depth_values.shape
     planes = torch.empty((B, D), device=depth_values.device, dtype=torch.float32)
@@ -71,6 +94,7 @@ def depth_hypotheses_first(depth_values, D):
     return planes
 
 
+@_on_device
 def depth_hypotheses_next(prev_depth, D, interval_pixel, H, W, h, w):
     B, hp, wp = prev_depth.shape
     hyp = torch.empty((B, D, h, w), device=prev_depth.device, dtype=torch.float32)
@@ -79,6 +103,7 @@ def depth_hypotheses_next(prev_depth, D, interval_pixel, H, W, h, w):
     return hyp
 
 
+@_on_device
 def depth_hypotheses_next_dev(prev_depth, depth_values, D, interval_ratio, H, W, h, w):
     """Like depth_hypotheses_next, the pixel interval = ratio * (max - min) / Dv of depth_values[0] taken on the device."""
     B, hp, wp = prev_depth.shape
@@ -97,6 +122,7 @@ def _depth_mode(depth, B, D_expected=None):
     raise RuntimeError("rcmvs: depth must be [B,D] or [B,D,h,w]")
 
 
+@_on_device
 def homo_warp_fwd(src_fea, rt, depth):
     B, C, h, w = src_fea.shape
     D = depth.shape[1]
@@ -106,6 +132,7 @@ def homo_warp_fwd(src_fea, rt, depth):
     return out
 
 
+@_on_device
 def homo_warp_bwd(grad_out, rt, depth, h, w):
     B, C, D = grad_out.shape[:3]
     gsrc = torch.zeros((B, C, h, w), device=grad_out.device, dtype=torch.float32)
@@ -114,6 +141,7 @@ def homo_warp_bwd(grad_out, rt, depth, h, w):
     return gsrc
 
 
+@_on_device
 def costvolume_variance(feats_cl, rt, depth, want_noref=False):
     """feats_cl [B,V,h,w,C]; rt [B,V-1,12]; depth [B,D] or [B,D,h,w] -> var [B,D,h,w,C] (+ var_noref)."""
     B, V, h, w, C = feats_cl.shape
@@ -126,6 +154,7 @@ def costvolume_variance(feats_cl, rt, depth, want_noref=False):
 
 
 # ---- conv3d ---------------------------------------------------------------------------------------------------
+@_on_device
 def pack_conv3d_weight(w, scale=None, transposed=False):
     """torch Conv3d [Cout,Cin,3,3,3] / ConvTranspose3d [Cin,Cout,3,3,3] weight (x BN scale) -> [27,Cin,Cout]."""
     if transposed:
@@ -138,6 +167,7 @@ def pack_conv3d_weight(w, scale=None, transposed=False):
     return packed
 
 
+@_on_device
 def conv3d(x_cl, packed_w, bias=None, skip=None, stride=1, relu=True):
     """x_cl [B,D,H,W,Cin] -> [B,Do,Ho,Wo,Cout]: conv(k3,p1) + bias, ReLU, then + skip."""
     B, D, H, W, Cin = x_cl.shape
@@ -153,6 +183,7 @@ def conv3d(x_cl, packed_w, bias=None, skip=None, stride=1, relu=True):
     return y
 
 
+@_on_device
 def conv_transpose3d(x_cl, packed_w, bias=None, skip=None, relu=True):
     """x_cl [B,D,H,W,Cin] -> [B,2D,2H,2W,Cout] (k3, s2, p1, output_padding 1)."""
     B, D, H, W, Cin = x_cl.shape
@@ -167,6 +198,7 @@ def conv_transpose3d(x_cl, packed_w, bias=None, skip=None, relu=True):
 TC_SUPPORTED = {(8, 8), (16, 8), (32, 8), (8, 1), (16, 16)}      # (Cin, Cout) pairs of conv0 / prob / conv2
 
 
+@_on_device
 def conv3d_tc_pack(w, scale=None, nsplit=3):
     """torch Conv3d weight [Cout,Cin,3,3,3] (x BN scale) -> operand image of the tcgen05 kernel."""
     Cout, Cin = w.shape[:2]
@@ -177,6 +209,7 @@ def conv3d_tc_pack(w, scale=None, nsplit=3):
     return img
 
 
+@_on_device
 def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     """x_cl [B,D,H,W,Cin] -> [B,D,H,W,Cout]: stride-1 conv(k3,p1) + bias, ReLU, then + skip, on tcgen05.mma."""
     B, D, H, W, Cin = x_cl.shape
@@ -191,6 +224,7 @@ def gemm_tc_supported(Cin, Cout):
     return (Cin in (16, 32, 64) and Cout in (16, 32, 64)) or (Cin == 8 and Cout == 16)
 
 
+@_on_device
 def conv3d_gemm_tc_pack(w, scale=None, transposed=False, nsplit=3):
     """torch Conv3d [Cout,Cin,27] / ConvTranspose3d [Cin,Cout,27] weight (x BN scale) -> gather-GEMM operand image."""
     if transposed:
@@ -204,6 +238,7 @@ def conv3d_gemm_tc_pack(w, scale=None, transposed=False, nsplit=3):
     return img
 
 
+@_on_device
 def conv3d_gemm_tc(x_cl, img, Cout, mode, bias=None, skip=None, nsplit=3, relu=True, x_lo=None, want_y=True,
                    want_split=False):
     """x_cl [B,D,H,W,Cin]; mode 0 conv s1 / 1 conv s2 / 2 transposed conv -> [B,Do,Ho,Wo,Cout] on tcgen05.mma.
@@ -229,6 +264,7 @@ def conv3d_gemm_tc(x_cl, img, Cout, mode, bias=None, skip=None, nsplit=3, relu=T
 TCT_SUPPORTED = {(16, 8), (32, 16)}      # (Cin, Cout) of conv11 / conv9 (transposed)
 
 
+@_on_device
 def conv_transpose3d_tc_pack(w, scale=None, nsplit=3):
     """torch ConvTranspose3d weight [Cin,Cout,3,3,3] (x BN scale) -> operand image of the tcgen05 convT kernel."""
     Cin, Cout = w.shape[:2]
@@ -239,6 +275,7 @@ def conv_transpose3d_tc_pack(w, scale=None, nsplit=3):
     return img
 
 
+@_on_device
 def conv_transpose3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     """x_cl [B,D,H,W,Cin] -> [B,2D,2H,2W,Cout] on tcgen05.mma (k3, s2, p1, output_padding 1)."""
     B, D, H, W, Cin = x_cl.shape
@@ -249,6 +286,7 @@ def conv_transpose3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=Tr
 
 
 # ---- regression -----------------------------------------------------------------------------------------------
+@_on_device
 def softargmin_conf(cost, planes, want_idx=False, want_prob=False):
     """cost [B,D,h,w]; planes [B,D] or [B,D,h,w] -> depth [B,h,w], conf [B,h,w] (, idx int32, prob)."""
     B, D, h, w = cost.shape
@@ -268,6 +306,7 @@ def softargmin_conf(cost, planes, want_idx=False, want_prob=False):
 
 
 # ---- renderer (a7-a12) ------------------------------------------------------------------------------------------
+@_on_device
 def resize_depth_cl(x_cl, D1, Cpad):
     """x_cl [B,D0,h,w,C] -> [B,D1,h,w,Cpad] (linear along D, align_corners=True, zero-padded channels)."""
     B, D0, h, w, C = x_cl.shape
@@ -276,6 +315,7 @@ def resize_depth_cl(x_cl, D1, Cpad):
     return y
 
 
+@_on_device
 def gu_sample(ray_depth, near, far, seed, n_gauss, S=128):
     N = ray_depth.shape[0]
     out = torch.empty((N, S), device=ray_depth.device, dtype=torch.float32)
@@ -284,6 +324,7 @@ def gu_sample(ray_depth, near, far, seed, n_gauss, S=128):
     return out
 
 
+@_on_device
 def ray_points(ys, xs, K, c2w, w2c_ref, z, near, far, W, H):
     N, S = z.shape
     pts = torch.empty((N, S, 3), device=z.device, dtype=torch.float32)
@@ -295,6 +336,7 @@ def ray_points(ys, xs, K, c2w, w2c_ref, z, near, far, W, H):
     return pts, ndc, dirs
 
 
+@_on_device
 def point_features(vol_cl, ndc, pts, imgs3, w2cs3, Ks3):
     """vol_cl [D,h,w,8]; ndc/pts [N,S,3]; imgs3 [3,3,H,W]; w2cs3 [3,4,4]; Ks3 [3,3,3] -> [N,S,20]."""
     D, h, w, _ = vol_cl.shape
@@ -306,6 +348,7 @@ def point_features(vol_cl, ndc, pts, imgs3, w2cs3, Ks3):
     return out
 
 
+@_on_device
 def render_mlp(ndc, feat, dirs, weight_ptrs):
     """ndc [N,S,3], feat [N,S,20], dirs [N,3]; weight_ptrs: int64 CUDA... a HOST ctypes array of 22 device pointers."""
     N, S = ndc.shape[:2]
@@ -315,6 +358,7 @@ def render_mlp(ndc, feat, dirs, weight_ptrs):
     return out
 
 
+@_on_device
 def composite(raw, z):
     N, S = z.shape
     rgb = torch.empty((N, 3), device=z.device, dtype=torch.float32)
@@ -327,6 +371,7 @@ def composite(raw, z):
 
 
 # ---- a13 ------------------------------------------------------------------------------------------------------------
+@_on_device
 def inverse_warp_fwd(img, left_cam, right_cam, depth):
     B, h, w, C = img.shape
     warped = torch.empty_like(img)
@@ -336,6 +381,7 @@ def inverse_warp_fwd(img, left_cam, right_cam, depth):
     return warped, mask
 
 
+@_on_device
 def inverse_warp_bwd(img, left_cam, right_cam, depth, grad_warped):
     B, h, w, C = img.shape
     gd = torch.empty((B, h, w), device=img.device, dtype=torch.float32)
@@ -345,6 +391,7 @@ def inverse_warp_bwd(img, left_cam, right_cam, depth, grad_warped):
 
 
 # ---- f1 FeatureNet ------------------------------------------------------------------------------------------------
+@_on_device
 def images_to_nhwc8(img):
     N, C, H, W = img.shape
     out = torch.empty((N, H, W, 8), device=img.device, dtype=torch.float32)
@@ -352,6 +399,7 @@ def images_to_nhwc8(img):
     return out
 
 
+@_on_device
 def pack_conv2d_weight(w, scale=None, cin_pad=None):
     Cout, Cin, K, _ = w.shape
     cin_pad = cin_pad or Cin
@@ -361,6 +409,7 @@ def pack_conv2d_weight(w, scale=None, cin_pad=None):
     return packed
 
 
+@_on_device
 def conv2d(x_cl, packed_w, bias=None, up=None, stride=1, relu=True):
     """x_cl [N,H,W,Cin] -> [N,Ho,Wo,Cout]: conv(K, pad K/2) + bias, ReLU, then + nearest-2x-upsampled `up`."""
     N, H, W, Cin = x_cl.shape
@@ -371,3 +420,49 @@ def conv2d(x_cl, packed_w, bias=None, up=None, stride=1, relu=True):
     _ffi.call("rcmvs_conv2d_fwd", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"), _opt(up, "up"),
               _chk(y, "y"), N, H, W, Cin, Cout, K, stride, 1 if relu else 0, _stream())
     return y
+
+
+# ---- f2 unsupervised loss stack ---------------------------------------------------------------------------------------
+@_on_device
+def images_subsample_nhwc(imgs, step):
+    """imgs [N,3,H,W] -> [N,H/step,W/step,3]: nearest down-sampling by an integer factor + NCHW -> NHWC."""
+    N, C, H, W = imgs.shape
+    if C != 3:
+        raise RuntimeError("rcmvs: images_subsample_nhwc expects 3 channels")
+    out = torch.empty((N, H // step, W // step, 3), device=imgs.device, dtype=torch.float32)
+    _ffi.call("rcmvs_images_subsample_nhwc", _chk(imgs, "imgs"), _chk(out, "out"), N, H, W, step, _stream())
+    return out
+
+
+@_on_device
+def unsup_loss_fwd_bwd(imgs_nhwc, cams, depth, smooth_weight, want_grad=True):
+    """imgs_nhwc [B,V,h,w,3], cams [B,V,2,4,4], depth [B,h,w] -> (terms [4] = total, reconstr, ssim, smooth; grad_depth)."""
+    B, V, h, w, _ = imgs_nhwc.shape
+    terms = torch.empty((4,), device=depth.device, dtype=torch.float32)
+    grad = torch.empty((B, h, w), device=depth.device, dtype=torch.float32) if want_grad else None
+    nws = _ffi.lib().rcmvs_unsup_loss_workspace_floats(B, V, h, w)
+    ws = torch.empty((nws,), device=depth.device, dtype=torch.float32)
+    _ffi.call("rcmvs_unsup_loss_fwd_bwd", _chk(imgs_nhwc, "imgs"), _chk(cams, "cams"), _chk(depth, "depth"),
+              float(smooth_weight), _chk(terms, "terms"), _opt(grad, "grad_depth"), _chk(ws, "workspace"), B, V, h, w,
+              _stream())
+    _ffi.launches += 10 + 4 * (V - 1) - 1 if want_grad else 3 + 2 * (V - 1) - 1
+    return terms, grad
+
+
+@_on_device
+def masked_loss_fwd_bwd(pred, target, mask=None, mask_kind=0, mode=0, scale=1.0, step=1, want_grad=True):
+    """scale * mean over selected elements of smooth-L1 (mode 0) / squared error (mode 1) of pred [B,h,w] vs target
+    [B,h*step,w*step] sampled at stride `step`; mask_kind 0 all / 1 mask [B,(C,)H,W] (first channel) > 0.5 / 2 target > 0.
+    Returns (loss [1], grad [B,h,w] or None)."""
+    B, h, w = pred.shape
+    loss = torch.empty((1,), device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if want_grad else None
+    ws = torch.empty((_ffi.lib().rcmvs_masked_loss_workspace_floats(),), device=pred.device, dtype=torch.float32)
+    mstride = 0
+    if mask is not None:
+        mstride = mask.stride(0)
+    _ffi.call("rcmvs_masked_loss_fwd_bwd", _chk(pred, "pred"), _chk(target, "target"), _opt(mask, "mask"), mstride,
+              mask_kind, mode, float(scale), _chk(loss, "loss"), _opt(grad, "grad"), _chk(ws, "workspace"), B, h, w, step,
+              _stream())
+    _ffi.launches += 2 if want_grad else 1
+    return loss, grad

@@ -27,6 +27,9 @@ class HostPipeline:
     def _slot_buffers(self, s, imgs_h, proj_h, dv_h):
         cur = self._dev_in[s]
         if cur is None or cur[0].shape != imgs_h.shape or cur[2].shape != dv_h.shape:
+            if self._consumed[s] is not None:
+                self._consumed[s].synchronize()     # a forward in flight may still read the buffers being replaced
+                self._consumed[s] = None
             mk = lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device)
             cur = (mk(imgs_h), {k: mk(v) for k, v in proj_h.items()}, mk(dv_h))
             self._dev_in[s] = cur
