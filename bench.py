@@ -4,23 +4,29 @@
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on the host cores
+    python bench.py --impl reference ...      # the reference's algorithm (torch-CPU port of the oracle) on the host cores
 
-One step = one CascadeMVSNet_eval forward of one reference view (BASELINE configs[1]: 5 views, 512x640,
-cascade D=192/64/8, synthetic DTU-shaped cameras, the reference's shipped weights as a numpy fixture).
-Multi-GPU = independent reference views per rank (weak scaling, no data-path collective).
+One step = one CascadeMVSNet_eval forward of one reference view (BASELINE configs[1]: 5 views, 512x640, cascade
+D=192/64/8, synthetic DTU-shaped cameras, the reference's shipped weights as a numpy fixture).  Multi-GPU = independent
+reference views per rank (weak scaling, no data-path collective).
+
+Timing: after >= 1 s of spin-up the K-step loop is timed REPS (9) times, each repetition bracketed by barrier +
+synchronize and timed with CUDA events on the launching stream, max over ranks per repetition; the reported
+`ms_per_step` / `value` are the MEDIAN repetition (one cold repetition cannot move the number; all repetitions are
+listed under `timing`).  Two distinct input sets alternate inside the loop.
 
 Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally:
-  roofline      — the fused plane-sweep + variance kernel of stage 1 (the kernel north_star names; HBM-bound by bytes),
-                  algorithmic bytes / CUDA-event time
-  roofline_dominant — the largest kernel of the step by time share: conv0 of stage 1 on tcgen05 (tensor-bound)
-  roofline_all  — the same for every hot kernel of the step
-  cpu_baseline  — the oracle port timed on this box's host cores on a bounded sample (N=1 only)
-  e2e           — same metric through the public API with pinned HOST buffers (rcmvs.pipeline.HostPipeline: every step
-                  copies its inputs host->device and its depth/confidence device->host inside the timed region; the
-                  copies run on their own streams, one reference view in flight on the device)
-  e2e_two_in_flight — the same loop with two reference views in flight (alternating compute streams)
-  render_branch / batched — configs[2] forward times and the 4-views-per-call throughput, for reference
+  roofline           the fused plane-sweep + variance kernel of stage 1 (the kernel north_star names; HBM-bound by bytes)
+  roofline_dominant  the largest kernel of the step by time share: conv0 of stage 1 on tcgen05 (tensor-bound)
+  roofline_all       every hot kernel of the step + the standalone homo_warp of BASELINE configs[0] (homo_warp_cfg1)
+  cpu_baseline       the oracle's torch-CPU port (F.grid_sample variant = what the reference executes) on this box's
+                     host cores, FULL configuration, bounded number of passes (N=1 only)
+  stock_torch_gpu    the same port on THIS GPU (cuDNN conv3d + ATen grid_sampler_2d, cudnn.benchmark, TF32 convs as
+                     torch defaults): the kernel-for-kernel bar BASELINE.md §5.4 names
+  e2e                same metric through the public API with pinned HOST buffers (rcmvs.pipeline.HostPipeline: every
+                     step copies its inputs host->device and its depth/confidence device->host inside the timed region)
+  e2e_two_in_flight  the same loop with two reference views in flight (alternating compute streams)
+  render_branch / train_step / tanks / batched   configs[2] / configs[3] / configs[4] timings, for reference
 """
 import argparse
 import json
@@ -34,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "rc-mvsnet_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
+os.environ.setdefault("RCMVS_STRICT", "1")          # a torch-library fallback inside the product path raises
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -42,6 +49,7 @@ GOLDEN_WEIGHTS = os.path.join(ROOT, "tests", "golden", "cas_model_000014.npz")
 V, H, W = 5, 512, 640
 NDEPTHS = (192, 64, 8)
 METRIC = "ref-views/sec (5-view, 512x640, D=192/64/8 cascade)"
+REPS = 9
 
 
 def peaks():
@@ -126,8 +134,9 @@ def host_threads():
 
 
 def ncu_traffic(key):
-    """dram bytes per launch from the committed `ncu --set full` capture (profiles/r01_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """dram bytes per launch from the committed `ncu --set full` capture of the CURRENT kernels (profiles/r02_traffic.json
+    is regenerated with the profile whenever the kernel changes), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return json.load(open(path))[key]["traffic_bytes"]
     except Exception:
@@ -204,10 +213,22 @@ def kernel_rooflines(model, dev, inputs, pk):
         res["featurenet"] = {"ms": round(msf, 4)}
         res["engines"] = {"stage%d" % (i + 1): {k: list(v.values())[0] for k, v in cr.engines().items() if v}
                           for i, cr in enumerate(model.cost_regularization)}
+        # BASELINE configs[0] / the second half of the metric: the STANDALONE homo_warping kernel, one source view,
+        # C=32, 128x160, D=48, per-pixel hypotheses: 4·(C·h·w + D·h·w + C·D·h·w) = 132.4 MB per call
+        Cw, hw_, ww_, Dw = 32, 128, 160, 48
+        g = torch.Generator(device="cpu").manual_seed(7)
+        src = torch.randn(1, Cw, hw_, ww_, generator=g).to(dev)
+        rt1 = ops.relative_projections(proj["stage1"])[:, 0].contiguous()
+        dpp = (torch.linspace(425, 933.8, Dw).view(1, Dw, 1, 1) + 6 * torch.rand(1, Dw, hw_, ww_, generator=g)).to(dev)
+        msw = time_kernel(lambda: ops.homo_warp_fwd(src, rt1, dpp), 20, stream)
+        wb = 4 * (Cw * hw_ * ww_ + Dw * hw_ * ww_ + Cw * Dw * hw_ * ww_)
+        res["homo_warp_cfg1"] = {"bound": "hbm", "ms": round(msw, 4), "achieved": round(wb / (msw * 1e-3) / 1e9, 1),
+                                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(wb / (msw * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+                                 "bytes": wb, "note": "132 MB per call: output stays L2-resident across back-to-back calls"}
     return res
 
 
-def render_branch_timing(dev):
+def render_branch_timing(dev, pk):
     """BASELINE configs[2] (full RC-MVSNet forward + render), reported next to the headline: 4 views (the renderer is
     hard-wired to 3 sources), 512x640, training-class CascadeMVSNet 48/32/8 (produces volume_feature_no_ref) followed by
     Rendering_Consistency_Net (Neural_Volume_Net + 1024 rays x 128 samples), forward only, inputs resident."""
@@ -229,11 +250,50 @@ def render_branch_timing(dev):
         out, vol = cas(imgs, proj, dv)
         ms_mvs = time_kernel(lambda: cas(imgs, proj, dv), 3, stream)
         ms_render = time_kernel(lambda: nerf(vol, out["depth"], dict(batch)), 3, stream)
+        ms_vol = time_kernel(lambda: nerf.MVSNet.forward_cl(vol), 3, stream)
         res = nerf(vol, out["depth"], dict(batch))
     ok = bool(torch.isfinite(res[0]).all() and torch.isfinite(res[3]).all())
+    # Neural_Volume_Net 63 GFLOP + MLP 251 392 FLOP/pt x 131 072 pts = 33.0 GFLOP per render (forward)
+    flops = 63.0e9 + 251392 * 131072
+    tf = flops / (ms_render * 1e-3) / 1e12
     return {"workload": "configs[2]: CascadeMVSNet (train class, 4 views 512x640, D=48/32/8, volume_feature_no_ref) + "
                         "Rendering_Consistency_Net (Neural_Volume_Net, 1024 rays x 128 samples), forward",
-            "mvs_forward_ms": round(ms_mvs, 3), "render_forward_ms": round(ms_render, 3), "finite": ok}
+            "mvs_forward_ms": round(ms_mvs, 3), "render_forward_ms": round(ms_render, 3),
+            "neural_volume_net_ms": round(ms_vol, 3), "finite": ok,
+            "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": pk["bf16_tflops"] / 2, "unit": "TFLOP/s",
+                         "frac": round(tf / (pk["bf16_tflops"] / 2), 4), "flops": flops,
+                         "note": "96 GFLOP of dense fp32 contractions per render against the TF32 tensor peak"}}
+
+
+def tanks_timing(model_cls, dev):
+    """BASELINE configs[4] shape on one GPU: 7 views 1056x1920, cascade 48/32/8 (eval_rcmvsnet_tanks.py defaults)."""
+    from rcmvs import synth, weights
+    m = model_cls(ndepths=[48, 32, 8])
+    weights.load_model(m, GOLDEN_WEIGHTS)
+    m.to(dev).eval()
+    imgs, proj, dv = synth.mvs_inputs(7, 1056, 1920, kind="noise", seed=1)
+    a = (torch.from_numpy(imgs).to(dev), {k: torch.from_numpy(v).to(dev) for k, v in proj.items()}, torch.from_numpy(dv).to(dev))
+    with torch.no_grad():
+        ms = time_kernel(lambda: m(*a), 5, torch.cuda.current_stream())
+    return {"workload": "configs[4] shape: 7 views 1056x1920, D=48/32/8, one GPU", "ms_per_step": round(ms, 3),
+            "value": round(1e3 / ms, 2), "unit": "ref-views/s"}
+
+
+def stock_torch_gpu(dev, inputs_np):
+    """The reference's op sequence on stock torch kernels on THIS GPU (oracle/ref_torch.py with F.grid_sample, cuDNN
+    conv2d/conv3d/conv_transpose3d, cudnn.benchmark=True as eval_rcmvsnet_dtu.py:24, TF32 convolutions = torch default)."""
+    from oracle import ref_torch as T
+    imgs, proj, dv = inputs_np
+    P = {k: torch.from_numpy(v).to(dev) for k, v in np.load(GOLDEN_WEIGHTS).items()}
+    pr = {k: torch.from_numpy(v[0]).to(dev) for k, v in proj.items()}
+    im, d = torch.from_numpy(imgs[0]).to(dev), torch.from_numpy(dv[0]).to(dev)
+    run = lambda: T.cascade_forward_eval(im, pr, d, P, ndepths=NDEPTHS, device=dev, grid_sample=True, as_numpy=False)
+    for _ in range(3):
+        run()
+    ms = time_kernel(run, 5, torch.cuda.current_stream())
+    return {"value": round(1e3 / ms, 2), "unit": "ref-views/s", "ms_per_step": round(ms, 3),
+            "what": "oracle/ref_torch.py port on cuda: cuDNN %s convs (allow_tf32=%s, benchmark=True) + ATen grid_sampler_2d, "
+                    "eager, same config" % (torch.backends.cudnn.version(), torch.backends.cudnn.allow_tf32)}
 
 
 def make_inputs(seed):
@@ -241,34 +301,38 @@ def make_inputs(seed):
     return synth.mvs_inputs(V, H, W, kind="textured", seed=seed)
 
 
+def cpu_port_step_fn():
+    """One FULL-configuration forward of the reference algorithm on the host (torch-CPU port, F.grid_sample variant)."""
+    from oracle import ref_torch as T
+    from rcmvs import synth
+    P = {k: torch.from_numpy(v) for k, v in np.load(GOLDEN_WEIGHTS).items()}
+    imgs, proj, dv = synth.mvs_inputs(V, H, W, kind="textured", seed=0)
+    pr = {k: v[0] for k, v in proj.items()}
+    return lambda: T.cascade_forward_eval(imgs[0], pr, dv[0], P, ndepths=NDEPTHS, grid_sample=True)
+
+
 def run_reference_arm(args, rank, world):
-    """The reference's CPU algorithm (oracle port, all host threads) on a bounded sample of the same workload."""
+    """The reference's CPU algorithm (torch-CPU port of the oracle, all useful host threads), full configuration:
+    one step = one whole 5-view 512x640 D=192/64/8 forward."""
     if rank != 0:
         return
-    from oracle import ref_torch as T
     cores, avail = host_threads()
-    P = dict(np.load(GOLDEN_WEIGHTS))
-    from rcmvs import synth
-    sh, sw = H // 2, W // 2                      # 1/4-area crop: every op of the path is linear in pixel count
-    frac = (sh * sw) / float(H * W)
-    imgs, proj, dv = synth.mvs_inputs(V, sh, sw, kind="textured", seed=0)
-    pr = {k: v[0] for k, v in proj.items()}
-
-    def step():
-        T.cascade_forward_eval(imgs[0], pr, dv[0], P, ndepths=NDEPTHS)
+    step = cpu_port_step_fn()
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    value = args.steps * frac / dt
-    sample = "%dx%d crop (%.3g of a ref-view per step), full D=%s, %d views; value = frac/step_time; %d of %d host threads (fastest count)" % (
-        sh, sw, frac, "/".join(map(str, NDEPTHS)), V, cores, avail)
+    value = args.steps / dt
+    sample = ("full configuration, one whole ref-view per step (%d views %dx%d, D=%s), %d of %d host threads (fastest "
+              "count), torch-CPU port of the oracle incl. F.grid_sample as the reference calls it"
+              % (V, H, W, "/".join(map(str, NDEPTHS)), cores, avail))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "ref-views/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "CascadeMVSNet_eval forward, %d views %dx%d D=%s" % (V, H, W, "/".join(map(str, NDEPTHS)))},
+            "config": {"workload": "CascadeMVSNet_eval forward, %d views %dx%d D=%s" % (V, H, W, "/".join(map(str, NDEPTHS))),
+                       "class": "CPU port of the reference algorithm (the reference is Python and cannot travel to the box)"},
             "cpu_baseline": {"value": value, "unit": "ref-views/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "ref-views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -282,9 +346,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="rcmvs", choices=["rcmvs", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="reference views per step per GPU")
+    ap.add_argument("--reps", type=int, default=REPS, help="timed repetitions of the K-step loop (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
-    ap.add_argument("--no-render", action="store_true", help="skip the configs[2] renderer-branch timing")
+    ap.add_argument("--no-render", action="store_true", help="skip the configs[2]/[3]/[4] side timings")
+    ap.add_argument("--no-stock-torch", action="store_true")
     ap.add_argument("--e2e-streams", type=int, default=1,
                     help="reference views in flight on the device in the e2e loop (rcmvs.pipeline.HostPipeline)")
     args = ap.parse_args()
@@ -315,21 +381,28 @@ def main():
     model.to(dev).eval()
 
     B = args.batch
-    host = []
-    for b in range(B):
-        host.append(make_inputs(seed=rank * 131 + b))
-    imgs_h = torch.from_numpy(np.concatenate([h[0] for h in host])).pin_memory()
-    proj_h = {k: torch.from_numpy(np.concatenate([h[1][k] for h in host])).pin_memory() for k in host[0][1]}
-    dv_h = torch.from_numpy(np.concatenate([h[2] for h in host])).pin_memory()
-    imgs, proj, dv = imgs_h.to(dev), {k: v.to(dev) for k, v in proj_h.items()}, dv_h.to(dev)
+    NSETS = 2                                       # distinct input sets alternating inside the timed loops
+    sets_h, sets_d = [], []
+    for s in range(NSETS):
+        host = [make_inputs(seed=rank * 131 + s * 17 + b) for b in range(B)]
+        imgs_h = torch.from_numpy(np.concatenate([h[0] for h in host])).pin_memory()
+        proj_h = {k: torch.from_numpy(np.concatenate([h[1][k] for h in host])).pin_memory() for k in host[0][1]}
+        dv_h = torch.from_numpy(np.concatenate([h[2] for h in host])).pin_memory()
+        sets_h.append((imgs_h, proj_h, dv_h))
+        sets_d.append((imgs_h.to(dev), {k: v.to(dev) for k, v in proj_h.items()}, dv_h.to(dev)))
+        if s == 0:
+            first_np = host[0]
+    imgs_h, proj_h, dv_h = sets_h[0]
     depth_out_h = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
     conf_out_h = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
     h2d = imgs_h.numel() * 4 + sum(v.numel() for v in proj_h.values()) * 4 + dv_h.numel() * 4
     d2h = 2 * B * H * W * 4
+    counter = [0]
 
     def step_resident():
+        counter[0] += 1
         with torch.no_grad():
-            return model(imgs, proj, dv)
+            return model(*sets_d[counter[0] % NSETS])
 
     from rcmvs.pipeline import HostPipeline
     pipe = HostPipeline(model, dev, compute_streams=args.e2e_streams)
@@ -338,14 +411,16 @@ def main():
         # host buffers in, host buffers out, every step: the H2D copy of this step's inputs and the D2H copy of its
         # depth/confidence are inside the timed region; they run on their own streams and overlap the neighbouring
         # steps' kernels (rcmvs/pipeline.py)
-        pipe.submit(imgs_h, proj_h, dv_h, depth_out_h, conf_out_h)
+        counter[0] += 1
+        ih, ph, dh = sets_h[counter[0] % NSETS]
+        pipe.submit(ih, ph, dh, depth_out_h, conf_out_h)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed_once(fn, steps):
         barrier()
         stream = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -364,22 +439,37 @@ def main():
             ms = float(t.item())
         return ms, _ffi.launches - n0
 
+    def timed(fn, steps, reps):
+        """REPS repetitions of the K-step loop, each max-over-ranks; (median ms, launches of one repetition, all ms)."""
+        all_ms, launches = [], 0
+        for _ in range(reps):
+            ms, launches = timed_once(fn, steps)
+            all_ms.append(ms)
+        return float(np.median(all_ms)), launches, [round(m, 3) for m in all_ms]
+
     for _ in range(args.warmup):
         step_resident()
     for _ in range(args.warmup):
         step_e2e()
+    # spin-up: >= 1 s of the real workload so clocks and the allocator are in steady state before anything is timed
+    barrier()
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.0:
+        for _ in range(args.steps):
+            step_resident()
+        torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_total, launches = timed(step_resident, args.steps)
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_total, launches, reps_resident = timed(step_resident, args.steps, args.reps)
+    ms_e2e, _, reps_e2e = timed(step_e2e, args.steps, args.reps)
     # same loop with two reference views in flight on the device (alternating compute streams): reported beside e2e
     e2e_two = None
     if args.e2e_streams == 1:
         pipe1, pipe = pipe, HostPipeline(model, dev, compute_streams=2)
         for _ in range(args.warmup):
             step_e2e()
-        ms2, _ = timed(step_e2e, args.steps)
+        ms2, _, reps2 = timed(step_e2e, args.steps, max(3, args.reps // 3))
         e2e_two = {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "ref-views/s", "ms_per_step": ms2 / args.steps,
-                   "views_in_flight": 2}
+                   "views_in_flight": 2, "ms_per_rep": reps2}
         pipe = pipe1
     clocks = sampler.stop() if sampler else None
 
@@ -387,12 +477,20 @@ def main():
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     pk = peaks()
-    roof_all, cpu_baseline = None, None
+    roof_all, cpu_baseline, stock = None, None, None
+    side = rank == 0 and world == 1
     if rank == 0 and not args.no_kernel_rooflines:
-        roof_all = kernel_rooflines(model, dev, (imgs[:1], {k: v[:1] for k, v in proj.items()}, dv[:1]), pk)
-    render, batched = None, None
-    if rank == 0 and world == 1 and not args.no_render and not args.no_kernel_rooflines:
-        render = render_branch_timing(dev)
+        d0 = sets_d[0]
+        roof_all = kernel_rooflines(model, dev, (d0[0][:1], {k: v[:1] for k, v in d0[1].items()}, d0[2][:1]), pk)
+    render, batched, tanks, train = None, None, None, None
+    if side and not args.no_render and not args.no_kernel_rooflines:
+        render = render_branch_timing(dev, pk)
+        tanks = tanks_timing(CascadeMVSNet_eval, dev)
+        try:
+            from rcmvs import train as rtrain
+            train = rtrain.bench_train_step(dev, steps=5)
+        except ImportError:
+            train = None
         # same workload with 4 reference views per launch sequence (better fill of the small 1/4- and 1/8-scale layers)
         b4 = [make_inputs(seed=1000 + i) for i in range(4)]
         i4 = torch.from_numpy(np.concatenate([h[0] for h in b4])).to(dev)
@@ -402,25 +500,21 @@ def main():
             ms4 = time_kernel(lambda: model(i4, p4, d4), 5, torch.cuda.current_stream())
         batched = {"batch_per_gpu": 4, "value": round(4 / (ms4 * 1e-3), 1), "unit": "ref-views/s", "ms_per_step": round(ms4, 3)}
         del i4, p4, d4
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import ref_torch as T
-        from rcmvs import synth
+    if side and not args.no_stock_torch:
+        stock = stock_torch_gpu(dev, first_np)
+    if side and not args.no_cpu_baseline:
         cores, avail = host_threads()
-        P = dict(np.load(GOLDEN_WEIGHTS))
-        sh, sw = H // 2, W // 2
-        frac = (sh * sw) / float(H * W)
-        ci, cp, cd = synth.mvs_inputs(V, sh, sw, kind="textured", seed=0)
-        cpj = {k: v[0] for k, v in cp.items()}
-        T.cascade_forward_eval(ci[0], cpj, cd[0], P, ndepths=NDEPTHS)            # warm-up
-        reps = 3
+        step = cpu_port_step_fn()
+        step()                                                                     # warm-up
+        reps = 2
         t0 = time.perf_counter()
         for _ in range(reps):
-            T.cascade_forward_eval(ci[0], cpj, cd[0], P, ndepths=NDEPTHS)
+            step()
         dt = (time.perf_counter() - t0) / reps
-        cpu_baseline = {"value": frac / dt, "unit": "ref-views/s", "cores": cores, "kind": "port",
-                        "sample": "%dx%d crop = %.3g ref-view per pass, full D=%s, %d views, %d passes of %.1f s, "
-                                  "%d of %d host threads (fastest count)"
-                                  % (sh, sw, frac, "/".join(map(str, NDEPTHS)), V, reps, dt, cores, avail)}
+        cpu_baseline = {"value": 1.0 / dt, "unit": "ref-views/s", "cores": cores, "kind": "port",
+                        "sample": "FULL configuration (%d views %dx%d, D=%s), %d passes of %.1f s after 1 warm-up, %d of "
+                                  "%d host threads (fastest count), torch-CPU port incl. F.grid_sample as the reference "
+                                  "calls it" % (V, H, W, "/".join(map(str, NDEPTHS)), reps, dt, cores, avail)}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -430,17 +524,18 @@ def main():
     s1 = (roof_all or {}).get("costvolume_var_stage1")
     roofline = None
     if s1:
-        roofline = {"kernel": "costvolume_var_v2_kernel<32> (stage 1, D=192, 128x160, V=5)", "bound": "hbm",
+        roofline = {"kernel": "fused plane-sweep + variance (stage 1, D=192, 128x160, V=5, C=32)", "bound": "hbm",
                     "achieved": s1["achieved"], "peak": s1["peak"], "unit": "GB/s", "frac": s1["frac"],
                     "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                     "algorithmic_bytes": s1["bytes"], "traffic": ncu_traffic("costvolume_var_stage1")}
-    # the single largest kernel of the step by time share (profiles/r01_launches_final.md) is tensor-bound: conv0 of
-    # stage 1 on the slab tcgen05 kernel.  FLOPs = 2*27*Cin*Cout*voxels of the fp32 convolution (the 3xTF32 mode issues
-    # three TF32 products per fp32 product; they are not counted), peak = dense TF32 = half the measured bf16 peak.
+    # the single largest kernel of the step by time share (profiles/) is tensor-bound: conv0 of stage 1 on the slab
+    # tcgen05 kernel.  FLOPs = 2*27*Cin*Cout*voxels of the fp32 convolution (the 3xTF32 mode issues three TF32 products
+    # per fp32 product; they are not counted), peak = dense TF32 = half the measured bf16 peak.
     c0 = (roof_all or {}).get("conv0_stage1")
     roofline_dominant = None
     if c0:
-        roofline_dominant = {"kernel": "conv3d_umma_kernel (conv0 of stage 1: 32->8 channels, 192x128x160, 3xTF32)",
+        roofline_dominant = {"kernel": "conv3d tcgen05 slab kernel (conv0 of stage 1: 32->8 channels, 192x128x160, %s)"
+                                       % os.environ.get("RCMVS_CONV", "tf32x3"),
                              "bound": "tensor", "achieved": c0["achieved"], "peak": c0["peak"], "unit": "TFLOP/s",
                              "frac": c0["frac"], "ms": c0["ms"], "flops": c0["flops"],
                              "traffic": ncu_traffic("conv0_stage1")}
@@ -452,9 +547,11 @@ def main():
                                "reference pretrained weights (numpy fixture), synthetic DTU-shaped cameras"
                                % (V, H, W, "/".join(map(str, NDEPTHS))),
                    "batch_per_gpu": B, "parallelism": "view-sharded replicas x%d" % world,
-                   "cache": "per-step working set %.0f MB of volumes >> 126 MB L2 (no explicit flush needed)"
-                            % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6),
+                   "cache": "per-step working set %.0f MB of volumes >> 126 MB L2 (no explicit flush needed); %d input "
+                            "sets alternate" % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6, NSETS),
                    "conv_precision": os.environ.get("RCMVS_CONV", "tf32x3")},
+        "timing": {"stat": "median of %d repetitions of the %d-step loop after >= 1 s spin-up" % (args.reps, args.steps),
+                   "ms_per_rep_resident": reps_resident, "ms_per_rep_e2e": reps_e2e},
         "e2e": {"value": e2e_value, "unit": "ref-views/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "views_in_flight": args.e2e_streams},
         "e2e_two_in_flight": e2e_two,
@@ -464,7 +561,12 @@ def main():
         "roofline_dominant": roofline_dominant,
         "roofline_all": roof_all,
         "cpu_baseline": cpu_baseline,
+        "stock_torch_gpu": stock,
+        "vs_reference_note": "the --impl reference arm is a CPU port (GPU-vs-CPU, context only); the like-for-like bar is "
+                             "stock_torch_gpu (same GPU, library kernels)",
         "render_branch": render,
+        "train_step": train,
+        "tanks": tanks,
         "batched": batched,
     }
     print(json.dumps(line), flush=True)

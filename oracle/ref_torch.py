@@ -56,13 +56,34 @@ def homo_warp(src, src_proj, ref_proj, depth):
     return out.view(C, D, h, w)
 
 
-def costvolume_variance(features, projs, depth):
+def homo_warp_gs(src, src_proj, ref_proj, depth):
+    """Same function through the library call the reference itself makes (models/modules.py:315-337): the sample grid is
+    normalised to [-1,1] with (w-1)/2, (h-1)/2 and handed to F.grid_sample(bilinear, zeros, align_corners=True).  This is
+    the variant the baseline arms time (`bench.py --impl reference`, cpu_baseline, stock_torch_gpu): it is what the
+    reference executes, multi-threaded on CPU and ATen's grid_sampler_2d kernel on a GPU.  Runs on src's device."""
+    C, h, w = src.shape
+    D = depth.shape[0]
+    dev = src.device
+    proj = src_proj @ torch.inverse(ref_proj)
+    rot, trans = proj[:3, :3], proj[:3, 3:4]
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev),
+                            torch.arange(w, dtype=torch.float32, device=dev), indexing="ij")
+    xyz = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(h * w, device=dev)])
+    p = (rot @ xyz)[:, None, :] * depth.reshape(1, D, -1) + trans.view(3, 1, 1)
+    xy = p[:2] / p[2:3]
+    grid = torch.stack([xy[0] / ((w - 1) / 2) - 1, xy[1] / ((h - 1) / 2) - 1], dim=-1)         # [D, h*w, 2]
+    out = F.grid_sample(src[None], grid.view(1, D * h, w, 2), mode="bilinear", padding_mode="zeros", align_corners=True)
+    return out.view(C, D, h, w)
+
+
+def costvolume_variance(features, projs, depth, grid_sample=False):
     """features: list of V [C,h,w]; projs [V,4,4]; depth [D,h,w]  (reference models/casmvsnet.py:254-288)."""
     V, D = len(features), depth.shape[0]
     ref = features[0][:, None].expand(-1, D, -1, -1)
     vsum, vsq = ref.clone(), ref ** 2
+    warp = homo_warp_gs if grid_sample else homo_warp
     for v in range(1, V):
-        wv = homo_warp(features[v], projs[v], projs[0], depth)
+        wv = warp(features[v], projs[v], projs[0], depth)
         vsum += wv
         vsq += wv ** 2
     return vsq / V - (vsum / V) ** 2
@@ -97,7 +118,7 @@ def softargmin_conf(cost, depth):
     D = cost.shape[0]
     p = torch.softmax(cost, dim=0)
     d = (p * depth).sum(0)
-    idx = (p * torch.arange(D, dtype=torch.float32).view(D, 1, 1)).sum(0).long().clamp(0, D - 1)
+    idx = (p * torch.arange(D, dtype=torch.float32, device=p.device).view(D, 1, 1)).sum(0).long().clamp(0, D - 1)
     pp = F.pad(p, (0, 0, 0, 0, 1, 2))
     sum4 = pp[0:D] + pp[1:D + 1] + pp[2:D + 2] + pp[3:D + 3]
     return d, torch.gather(sum4, 0, idx[None])[0]
@@ -113,7 +134,7 @@ def depth_hypotheses_next(prev, D, interval_pixel, H, W, h, w):
     half = float(D / 2 * interval_pixel)
     cmin, cmax = cur - half, cur + half
     step = (cmax - cmin) / (D - 1)
-    s = cmin[None] + torch.arange(D, dtype=torch.float32).view(D, 1, 1) * step[None]
+    s = cmin[None] + torch.arange(D, dtype=torch.float32, device=prev.device).view(D, 1, 1) * step[None]
     return s if (h, w) == (H, W) else _resize(s, h, w)
 
 
@@ -132,17 +153,20 @@ def featurenet(imgs, P):
     return out
 
 
-def sub(P, prefix):
-    return {k[len(prefix):]: _t(v) for k, v in P.items() if k.startswith(prefix)}
+def sub(P, prefix, device="cpu"):
+    return {k[len(prefix):]: _t(v).to(device) for k, v in P.items() if k.startswith(prefix)}
 
 
 @torch.no_grad()
-def cascade_forward_eval(imgs, proj_matrices, depth_values, P, ndepths=(48, 32, 8), ratios=(4, 2, 1)):
-    """imgs [V,3,H,W]; proj_matrices {stageK: [V,2,4,4]}; depth_values [Dv]  (reference casmvsnet.py:356-417)."""
-    imgs, depth_values = _t(imgs).float(), _t(depth_values).float()
+def cascade_forward_eval(imgs, proj_matrices, depth_values, P, ndepths=(48, 32, 8), ratios=(4, 2, 1), device="cpu",
+                         grid_sample=False, as_numpy=True):
+    """imgs [V,3,H,W]; proj_matrices {stageK: [V,2,4,4]}; depth_values [Dv]  (reference casmvsnet.py:356-417).
+    `device` / `grid_sample`: the baseline arms run the same op sequence on a GPU and through F.grid_sample."""
+    imgs, depth_values = _t(imgs).float().to(device), _t(depth_values).float().to(device)
+    P = {k: (v if isinstance(v, torch.Tensor) and v.device == torch.device(device) else _t(v).to(device)) for k, v in P.items()}
     V, _, H, W = imgs.shape
     interval = (float(depth_values[-1]) - float(depth_values[0])) / depth_values.shape[0]
-    feats = featurenet(imgs, sub(P, "feature."))
+    feats = featurenet(imgs, sub(P, "feature.", device))
     out, depth = {}, None
     for s, D in enumerate(ndepths):
         key = "stage%d" % (s + 1)
@@ -150,12 +174,13 @@ def cascade_forward_eval(imgs, proj_matrices, depth_values, P, ndepths=(48, 32, 
         h, w = H // scale, W // scale
         if depth is None:
             step = (depth_values[-1] - depth_values[0]) / (D - 1)
-            hyp = (depth_values[0] + torch.arange(D, dtype=torch.float32) * step).view(D, 1, 1).expand(D, h, w)
+            hyp = (depth_values[0] + torch.arange(D, dtype=torch.float32, device=imgs.device) * step).view(D, 1, 1).expand(D, h, w)
         else:
             hyp = depth_hypotheses_next(depth, D, ratios[s] * interval, H, W, h, w)
-        projs = stage_projection(proj_matrices[key])
-        var = costvolume_variance([feats[key][v] for v in range(V)], projs, hyp)
-        cost = costregnet(var[None], sub(P, "cost_regularization.%d." % s))
+        projs = stage_projection(proj_matrices[key]).to(imgs.device)
+        var = costvolume_variance([feats[key][v] for v in range(V)], projs, hyp, grid_sample)
+        cost = costregnet(var[None], sub(P, "cost_regularization.%d." % s, device))
         depth, conf = softargmin_conf(cost, hyp)
-        out[key] = {"depth": depth.numpy(), "photometric_confidence": conf.numpy()}
+        out[key] = ({"depth": depth.cpu().numpy(), "photometric_confidence": conf.cpu().numpy()} if as_numpy else
+                    {"depth": depth, "photometric_confidence": conf})
     return out

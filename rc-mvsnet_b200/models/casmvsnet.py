@@ -13,6 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from rcmvs import ops
+from rcmvs.strict import library_fallback
 from .modules import CostRegNet, FeatureNet, as_channels_last_views, homo_warping
 
 Align_Corners_Range = False
@@ -82,6 +83,7 @@ class DepthNet(nn.Module):
     def _forward_autograd(self, features, proj_matrices, depth_values, num_depth, cost_regularization, imgs):
         """Differentiable path for train_rcmvsnet.py: CUDA warp (with its scatter-add backward) + library ops for
         the reductions and the 3-D CNN until the fused train-mode kernels land."""
+        library_fallback("DepthNet.forward (training / autograd)", "ATen reductions + softmax around the CUDA warp")
         B, V = imgs.shape[:2]
         C, h, w = features[0].shape[1:]
         projs = torch.unbind(proj_matrices, 1)

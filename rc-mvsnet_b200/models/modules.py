@@ -209,6 +209,7 @@ class FeatureNet(nn.Module):
                 and self.base_channels == 8:
             with torch.no_grad():
                 return {k: v.permute(0, 3, 1, 2) for k, v in self.forward_cl(x).items()}
+        library_fallback("FeatureNet.forward (training / autograd)", "cuDNN conv2d + batch_norm")
         c0 = self.conv0(x)
         c1 = self.conv1(c0)
         c2 = self.conv2(c1)
@@ -389,6 +390,7 @@ class CostRegNet(nn.Module):
     def _forward_autograd(self, x):
         # Training path (train-mode BatchNorm statistics + backward) is not on the inference hot path yet:
         # library ops keep train_rcmvsnet.py working until the fused train kernels land.
+        library_fallback("CostRegNet.forward (training / autograd)", "cuDNN conv3d + batch_norm")
         c0 = self.conv0(x)
         c2 = self.conv2(self.conv1(c0))
         c4 = self.conv4(self.conv3(c2))

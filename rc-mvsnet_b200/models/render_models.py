@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from rcmvs import ops
 from rcmvs.cache import PackedCache
+from rcmvs.strict import library_fallback
 from .modules import fold_bn, _versions
 
 __all__ = ["Embedder", "get_embedder", "Renderer_ours", "RenderNet", "create_nerf_mvs", "CostReg",
@@ -229,6 +230,7 @@ class Neural_Volume_Net(nn.Module):
         """volume_feature [B,41,D0,h,w] -> [1,B*8,128,h,w] (reference :753-760)."""
         B, C, _, H, W = volume_feature.shape
         if self.training or (torch.is_grad_enabled() and volume_feature.requires_grad):
+            library_fallback("Neural_Volume_Net.forward (training / autograd)", "cuDNN conv3d + batch_norm")
             v = F.interpolate(volume_feature, size=[128, H, W], mode="trilinear", align_corners=True)
             v = self.cost_reg_2(v)
             return v.reshape(1, -1, *v.shape[2:])

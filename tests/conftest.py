@@ -9,6 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "rc-mvsnet_b200")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+os.environ.setdefault("RCMVS_STRICT", "1")        # a silent torch-library fallback must fail a test, not pass it
 
 
 def pytest_configure(config):

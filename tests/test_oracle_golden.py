@@ -85,8 +85,9 @@ def test_torch_port_matches_numpy_oracle_and_golden(mvs):
     from oracle import ref_torch as T
     g, P = mvs
     proj = {k: g["proj_" + k] for k in ("stage1", "stage2", "stage3")}
-    out = T.cascade_forward_eval(g["imgs"], proj, g["depth_values"], P, ndepths=(16, 8, 8))
-    for k in ("stage1", "stage2", "stage3"):
-        rel = np.abs(out[k]["depth"] - g["depth_" + k]).max() / np.abs(g["depth_" + k]).max()
-        assert rel < 1e-5, (k, rel)
-        np.testing.assert_allclose(out[k]["photometric_confidence"], g["conf_" + k], atol=1e-4)
+    for gs in (False, True):          # explicit gather restatement, and the F.grid_sample variant the baseline arms time
+        out = T.cascade_forward_eval(g["imgs"], proj, g["depth_values"], P, ndepths=(16, 8, 8), grid_sample=gs)
+        for k in ("stage1", "stage2", "stage3"):
+            rel = np.abs(out[k]["depth"] - g["depth_" + k]).max() / np.abs(g["depth_" + k]).max()
+            assert rel < 1e-5, (k, rel, gs)
+            np.testing.assert_allclose(out[k]["photometric_confidence"], g["conf_" + k], atol=1e-4)
