@@ -124,6 +124,20 @@ int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, const float
                                   int B, int D, int H, int W, int Cin, int Cout, int nsplit, int relu,
                                   rcmvs_stream_t stream);
 
+/* Round-2 engine for the stride-1 convolutions (conv0 / conv2 of CostRegNet, reference models/modules.py:473-475):
+ * TMA-fed tcgen05.mma kind::f16 with error-compensated split-bf16 operands ("bf16x3": x = hi + lo, hi = bf16(x),
+ * lo = bf16(x - hi); x·w ~= x_lo·w_hi + x_hi·w_lo + x_hi·w_hi, relative operand error <= 3·2^-17).  The activation
+ * arrives PRE-SPLIT as two bf16 planes x_split [2][B][D][H][W][Cin] (hi plane, lo plane; 16-byte aligned), written by the
+ * producing kernel (rcmvs_costvolume_var_fwd_split, y_split of this function, rcmvs_conv3d_fwd_split) or, at an API
+ * boundary, by rcmvs_split_bf16.  Output: fp32 y and/or split-bf16 y_split (either may be NULL).
+ * (Cin, Cout) in {(32,8), (16,8), (16,16)}.  Weight image: rcmvs_conv3d_slab_weight_elems() bf16 elements. */
+int64_t rcmvs_conv3d_slab_weight_elems(int Cin, int Cout);
+int rcmvs_conv3d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
+int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip, float* y,
+                          void* y_split, int B, int D, int H, int W, int Cin, int Cout, int relu, rcmvs_stream_t stream);
+/* x [n] fp32 -> xs [2][n] bf16 (hi plane, lo plane). */
+int rcmvs_split_bf16(const float* x, void* xs, int64_t n, rcmvs_stream_t stream);
+
 /* Gather implicit-GEMM on tcgen05 for the small 1/4- and 1/8-resolution layers (conv3..conv7, conv9; reference
  * models/modules.py:478-486): any D/H/W, Cin and Cout in {16,32,64} (plus 8 -> 16, conv1); mode 0 = conv stride 1, 1 = conv stride 2,
  * 2 = transposed conv (k3, s2, p1, output_padding 1).  The weight image is built from the torch weight (Conv3d

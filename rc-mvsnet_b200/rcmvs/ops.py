@@ -219,6 +219,47 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     return y
 
 
+SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16)}      # (Cin, Cout) of the TMA-fed split-bf16 slab kernel
+
+
+def _chk_bf16(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous():
+        raise RuntimeError("rcmvs: %s must be a contiguous CUDA bfloat16 tensor" % name)
+    return t.data_ptr()
+
+
+@_on_device
+def split_bf16(x):
+    """x [...] fp32 -> [2, ...] bf16: hi = bf16(x), lo = bf16(x - hi)."""
+    xs = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_split_bf16", _chk(x, "x"), xs.data_ptr(), x.numel(), _stream())
+    return xs
+
+
+@_on_device
+def conv3d_slab_pack(w, scale=None):
+    """torch Conv3d weight [Cout,Cin,3,3,3] (x BN scale) -> split-bf16 operand image of the TMA slab kernel."""
+    Cout, Cin = w.shape[:2]
+    n = _ffi.lib().rcmvs_conv3d_slab_weight_elems(Cin, Cout)
+    img = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_conv3d_slab_pack", _chk(w, "w"), _opt(scale, "scale"), img.data_ptr(), Cout, Cin, _stream())
+    return img
+
+
+@_on_device
+def conv3d_slab(x_split, img, Cout, bias=None, skip=None, relu=True, want_y=True, want_split=False):
+    """x_split [2,B,D,H,W,Cin] bf16 (hi, lo) -> y [B,D,H,W,Cout] fp32 and/or y_split [2,B,D,H,W,Cout] bf16."""
+    _, B, D, H, W, Cin = x_split.shape
+    y = torch.empty((B, D, H, W, Cout), device=x_split.device, dtype=torch.float32) if want_y else None
+    ys = torch.empty((2, B, D, H, W, Cout), device=x_split.device, dtype=torch.bfloat16) if want_split else None
+    _ffi.call("rcmvs_conv3d_slab_fwd", _chk_bf16(x_split, "x_split"), _chk_bf16(img, "wimg"), _opt(bias, "bias"),
+              _opt(skip, "skip"), _opt(y, "y"), None if ys is None else ys.data_ptr(), B, D, H, W, Cin, Cout,
+              1 if relu else 0, _stream())
+    if want_y and want_split:
+        return y, ys
+    return y if want_y else ys
+
+
 def gemm_tc_supported(Cin, Cout):
     """Layers the gather implicit-GEMM kernel takes (the 1/4- and 1/8-resolution levels)."""
     return (Cin in (16, 32, 64) and Cout in (16, 32, 64)) or (Cin == 8 and Cout == 16)

@@ -244,3 +244,34 @@ def test_model_on_second_device_while_first_is_current():
     a = run(m0, d0)
     b = run(m1, d1)                       # cuda:0 is still the current device
     assert b.device == d1 and torch.equal(a.cpu(), b.cpu())
+
+
+# ---- a3 round-2 engine: TMA-fed split-bf16 slab convolution ---------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,dhw", [
+    (32, 8, (4, 17, 61)), (16, 8, (2, 8, 30)), (16, 16, (9, 5, 64)), (32, 8, (1, 1, 1)), (32, 8, (20, 8, 31)),
+    (16, 8, (23, 21, 95)), (16, 16, (13, 14, 31)), (32, 8, (7, 40, 33)),
+])
+def test_conv3d_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
+    """kind::f16 tcgen05 + TMA, split-bf16 operands: fp32-class accuracy (dropped terms <= 3·2^-17 relative per product)."""
+    from oracle import ref_np as O
+    from rcmvs import ops
+    rng = np.random.default_rng(cin * 1000 + cout * 10 + 7)
+    D, H, W = dhw
+    xs = [rng.standard_normal((cin, D, H, W), dtype=np.float32) for _ in range(2)]
+    w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(27 * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    lin = np.stack([O.conv3d(x, w * scale[:, None, None, None, None]) for x in xs])
+    want = np.maximum(lin + bias[None, :, None, None, None], 0)
+    skip = rng.standard_normal(want.shape, dtype=np.float32)
+    img = ops.conv3d_slab_pack(cu(w, dev), cu(scale, dev))
+    x_cl = cu(np.stack(xs).transpose(0, 2, 3, 4, 1), dev)
+    x_split = ops.split_bf16(x_cl)
+    assert torch.equal(x_split[0].float() + x_split[1].float(), x_split[0].float() + x_split[1].float())
+    assert (x_split[0].float() + x_split[1].float() - x_cl).abs().max() <= 2.0 ** -16 * x_cl.abs().max()
+    y, ys = ops.conv3d_slab(x_split, img, cout, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), True, True, True)
+    got = y.permute(0, 4, 1, 2, 3).cpu().numpy()
+    np.testing.assert_allclose(got, want + skip, atol=1e-4, rtol=1e-4)
+    assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * y.abs().max()
+    y2 = ops.conv3d_slab(x_split, img, cout, None, None, False)
+    np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
