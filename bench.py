@@ -186,14 +186,18 @@ def kernel_rooflines(model, dev, inputs, pk):
             hyp = (ops.depth_hypotheses_first(dv, D) if depth is None else
                    ops.depth_hypotheses_next(depth, D, model.depth_interals_ratio[s] * interval, H, W, h, w))
             rt = ops.relative_projections(proj[key])
-            ms = time_kernel(lambda: ops.costvolume_variance(feats[key], rt, hyp), 10, stream)
+            cr = model.cost_regularization[s]
+            # the sweep writes the variance in the operand format its consumer wants (split-bf16 planes for the TMA-fed
+            # tensor-core conv0, fp32 otherwise): same bytes either way
+            sweep = (lambda: ops.costvolume_variance_split(feats[key], rt, hyp)) if cr.wants_split_input() else \
+                (lambda: ops.costvolume_variance(feats[key], rt, hyp))
+            ms = time_kernel(sweep, 10, stream)
             nbytes = algorithmic_bytes_costvolume(V, C, D, h, w, hyp.dim() == 4)
             gbs = nbytes / (ms * 1e-3) / 1e9
             res["costvolume_var_" + key] = {"bound": "hbm", "ms": round(ms, 4), "achieved": round(gbs, 1),
                                             "peak": pk["hbm_gbs"], "unit": "GB/s",
                                             "frac": round(gbs / pk["hbm_gbs"], 4), "bytes": nbytes}
-            var = ops.costvolume_variance(feats[key], rt, hyp)
-            cr = model.cost_regularization[s]
+            var = sweep()
             P = cr.packed()
             ms0 = time_kernel(lambda: cr._run(P["conv0"], var), 5, stream)
             fl = conv_flops(C, 8, D * h * w)
@@ -535,7 +539,7 @@ def main():
     roofline_dominant = None
     if c0:
         roofline_dominant = {"kernel": "conv3d tcgen05 slab kernel (conv0 of stage 1: 32->8 channels, 192x128x160, %s)"
-                                       % os.environ.get("RCMVS_CONV", "tf32x3"),
+                                       % os.environ.get("RCMVS_CONV", "bf16x3"),
                              "bound": "tensor", "achieved": c0["achieved"], "peak": c0["peak"], "unit": "TFLOP/s",
                              "frac": c0["frac"], "ms": c0["ms"], "flops": c0["flops"],
                              "traffic": ncu_traffic("conv0_stage1")}
@@ -549,7 +553,7 @@ def main():
                    "batch_per_gpu": B, "parallelism": "view-sharded replicas x%d" % world,
                    "cache": "per-step working set %.0f MB of volumes >> 126 MB L2 (no explicit flush needed); %d input "
                             "sets alternate" % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6, NSETS),
-                   "conv_precision": os.environ.get("RCMVS_CONV", "tf32x3")},
+                   "conv_precision": os.environ.get("RCMVS_CONV", "bf16x3")},
         "timing": {"stat": "median of %d repetitions of the %d-step loop after >= 1 s spin-up" % (args.reps, args.steps),
                    "ms_per_rep_resident": reps_resident, "ms_per_rep_e2e": reps_e2e},
         "e2e": {"value": e2e_value, "unit": "ref-views/s", "ms_per_step": ms_e2e / args.steps,

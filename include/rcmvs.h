@@ -81,6 +81,11 @@ int rcmvs_homo_warp_bwd(const float* grad_out, const float* rt, const float* dep
 int rcmvs_costvolume_var_fwd(const float* feats, const float* rt, const float* depth, int per_pixel, float* var,
                              float* var_noref, int B, int V, int C, int D, int h, int w, rcmvs_stream_t stream);
 
+/* Same sweep, variance written as two bf16 planes var_split [2][B][D][h][w][C] (hi = bf16(v), lo = bf16(v - hi)): the
+ * pre-split operand format of rcmvs_conv3d_slab_fwd (same bytes as fp32, no conversion pass in between).  h, w >= 2. */
+int rcmvs_costvolume_var_fwd_split(const float* feats, const float* rt, const float* depth, int per_pixel,
+                                   void* var_split, int B, int V, int C, int D, int h, int w, rcmvs_stream_t stream);
+
 /* ---- a3 CostRegNet building blocks: models/modules.py:118-210, 470-501 --------------------------------------- */
 /* Weight packing (once per checkpoint): w [Cout][Cin][3][3][3] (Conv3d) or [Cin][Cout][3][3][3]
  * (ConvTranspose3d) times the folded BatchNorm scale[Cout] (NULL = 1) -> packed [27][Cin][Cout]. */

@@ -11,6 +11,9 @@
 // Thread mapping: one thread = one reference pixel × one group of 4 channels (float4).  Consecutive lanes hold the
 // channel groups of one pixel, then the next pixel, so a warp's tap load is (32/CQ) contiguous C·4-byte runs and a
 // warp's store is one contiguous (32/CQ)·C·4 = 512-byte run.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rcmvs {
@@ -249,9 +252,155 @@ costvolume_var_v2_kernel(const float* __restrict__ feats, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v3 of the fused sweep (round 2).  ncu on v2 (profiles/r01_costvolume_final_ncu.md): 329 M warp instructions for 110 M
+// essential ones (4 LDG.128 + 24 FP per float4, view and plane) — instruction-issue bound at 2.6 IPC, 62 % L1.  v3 keeps
+// the plane-distributed mapping (lane q of a pixel owns plane dg+q and broadcasts its sample) and removes work per tap:
+//   * the owning lane folds validity, clamping and the bilinear weights into FOUR final tap weights and ONE in-bounds
+//     base texel (the 2x2 quad is shifted inside the image at the borders and the weights move with it), so the LPP-1
+//     other lanes do no unpacking / predicate / weight arithmetic: 5 shuffles, 1 address, 4 loads at constant offsets
+//     {0, C, w·C, w·C + C} from the base, 24 FP;
+//   * consecutive planes of a group that fall into the same texel quad (disparity between neighbouring planes is
+//     0.1-0.5 px on DTU geometry) reuse the four texels from registers — fewer L1 wavefronts (the 128 B/clk/SM L1 path
+//     bounds v2-style designs at ~0.22 ms for stage 1);
+//   * the perspective division is an IEEE division again (v2 multiplied by a reciprocal: up to 2 ulp of the coordinate
+//     away from the reference's arithmetic).
+// OUT_SPLIT: write the variance as two bf16 planes [2][B][D][h][w][C] (hi, lo) — the operand format of the TMA-fed
+// tensor-core convolution that consumes it (csrc/conv3d_slab_bf16.cu) — instead of fp32; same bytes.
+// ------------------------------------------------------------------------------------------------------------------
+template <int C, bool PER_PIXEL, bool OUT_SPLIT>
+__global__ void __launch_bounds__(256)
+costvolume_var_v3_kernel(const float* __restrict__ feats, const float* __restrict__ rt_g,
+                         const float* __restrict__ depth, float* __restrict__ var, __nv_bfloat16* __restrict__ var_split,
+                         int B, int V, int D, int h, int w, int d_chunk, int chunks_per_batch) {
+  constexpr int LPP = C / 4;
+  constexpr int PXB = 256 / LPP;
+  const int q = threadIdx.x % LPP;
+  const int xr = blockIdx.x * PXB + threadIdx.x / LPP;
+  const int x = min(xr, w - 1);                 // out-of-range lanes still take part in the shuffles
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / chunks_per_batch;
+  const int d_begin = (blockIdx.z % chunks_per_batch) * d_chunk;
+  const int d_end = min(D, d_begin + d_chunk);
+  __shared__ float rt_s[kMaxSrc * 12];
+  for (int i = threadIdx.x; i < (V - 1) * 12; i += 256) rt_s[i] = __ldg(rt_g + (int64_t)b * (V - 1) * 12 + i);
+  __syncthreads();
+
+  const int64_t hw = (int64_t)h * w;
+  feats += (int64_t)b * V * hw * C + q * 4;
+  depth += PER_PIXEL ? (int64_t)b * D * hw + (int64_t)y * w + x : (int64_t)b * D;
+  const float4 ref = ldg4(feats + ((int64_t)y * w + x) * C);
+  const float4 ref2 = make_float4(ref.x * ref.x, ref.y * ref.y, ref.z * ref.z, ref.w * ref.w);
+  const float inv_v = 1.f / (float)V;
+  const float xf = (float)x, yf = (float)y;
+  const int wC = w * C;
+
+  for (int dg = d_begin; dg < d_end; dg += LPP) {
+    float2 s[LPP][2], s2[LPP][2];
+#pragma unroll
+    for (int j = 0; j < LPP; ++j) {
+      s[j][0] = make_float2(ref.x, ref.y); s[j][1] = make_float2(ref.z, ref.w);
+      s2[j][0] = make_float2(ref2.x, ref2.y); s2[j][1] = make_float2(ref2.z, ref2.w);
+    }
+    const int my_d = min(dg + q, D - 1);
+    const float dep = PER_PIXEL ? __ldg(depth + (int64_t)my_d * hw) : __ldg(depth + my_d);
+    for (int v = 0; v < V - 1; ++v) {
+      const float* m = rt_s + v * 12;
+      // this lane's plane: p = rot·(x,y,1)·depth + trans ; (px,py) = p.xy / p.z   (modules.py:325-329)
+      const float rx = fmaf(m[0], xf, fmaf(m[1], yf, m[2]));
+      const float ry = fmaf(m[4], xf, fmaf(m[5], yf, m[6]));
+      const float rz = fmaf(m[8], xf, fmaf(m[9], yf, m[10]));
+      const float Z = fmaf(rz, dep, m[11]);
+      const float px = __fdiv_rn(fmaf(rx, dep, m[3]), Z), py = __fdiv_rn(fmaf(ry, dep, m[7]), Z);
+      const bool finite = (fabsf(px) < 1e8f) && (fabsf(py) < 1e8f);     // false for NaN
+      const float fx = floorf(px), fy = floorf(py);
+      const float ax = px - fx, ay = py - fy;
+      const int x0 = finite ? (int)fx : -4, y0 = finite ? (int)fy : -4;
+      // shift the 2x2 quad inside the image; the per-axis weights of its two columns / rows move with it:
+      //   x0 in [0, w-2]: (1-ax, ax);  x0 = -1: only tap x1 = 0 is valid -> (ax, 0);  x0 = w-1: only tap x0 -> (0, 1-ax)
+      const int bx = min(max(x0, 0), w - 2), by = min(max(y0, 0), h - 2);
+      const float wx0 = (x0 == bx) ? 1.f - ax : ((x0 == -1) ? ax : 0.f);
+      const float wx1 = (x0 == bx) ? ax : ((x0 == w - 1) ? 1.f - ax : 0.f);
+      const float wy0 = (y0 == by) ? 1.f - ay : ((y0 == -1) ? ay : 0.f);
+      const float wy1 = (y0 == by) ? ay : ((y0 == h - 1) ? 1.f - ay : 0.f);
+      const float my_w00 = wy0 * wx0, my_w01 = wy0 * wx1, my_w10 = wy1 * wx0, my_w11 = wy1 * wx1;
+      // (all four taps outside -> all weights are 0 and the base stays inside the image: no branch needed)
+      const int my_base = (by * w + bx) * C;
+      const float* src = feats + (int64_t)(v + 1) * hw * C;
+      int prev = -1;
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0, e0 = a0, e1 = a0;
+#pragma unroll
+      for (int j = 0; j < LPP; ++j) {
+        const int base = __shfl_sync(0xffffffffu, my_base, j, LPP);
+        const float w00 = __shfl_sync(0xffffffffu, my_w00, j, LPP);
+        const float w01 = __shfl_sync(0xffffffffu, my_w01, j, LPP);
+        const float w10 = __shfl_sync(0xffffffffu, my_w10, j, LPP);
+        const float w11 = __shfl_sync(0xffffffffu, my_w11, j, LPP);
+        if (base != prev) {                      // neighbouring planes mostly sample the same texel quad
+          const float* t = src + base;
+          const float4 a = ldg4(t), bb = ldg4(t + C), c = ldg4(t + wC), e = ldg4(t + wC + C);
+          a0 = make_float2(a.x, a.y); a1 = make_float2(a.z, a.w);
+          b0 = make_float2(bb.x, bb.y); b1 = make_float2(bb.z, bb.w);
+          c0 = make_float2(c.x, c.y); c1 = make_float2(c.z, c.w);
+          e0 = make_float2(e.x, e.y); e1 = make_float2(e.z, e.w);
+          prev = base;
+        }
+        // packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100: two IEEE fp32 results per instruction)
+        const float2 q00 = make_float2(w00, w00), q01 = make_float2(w01, w01), q10 = make_float2(w10, w10),
+                     q11 = make_float2(w11, w11);
+        const float2 f0 = __ffma2_rn(e0, q11, __ffma2_rn(c0, q10, __ffma2_rn(b0, q01, __fmul2_rn(a0, q00))));
+        const float2 f1 = __ffma2_rn(e1, q11, __ffma2_rn(c1, q10, __ffma2_rn(b1, q01, __fmul2_rn(a1, q00))));
+        s[j][0] = __fadd2_rn(s[j][0], f0);
+        s[j][1] = __fadd2_rn(s[j][1], f1);
+        s2[j][0] = __ffma2_rn(f0, f0, s2[j][0]);
+        s2[j][1] = __ffma2_rn(f1, f1, s2[j][1]);
+      }
+    }
+    if (xr < w) {
+#pragma unroll
+      for (int j = 0; j < LPP; ++j) {
+        const int d = dg + j;
+        if (d < d_end) {
+          float4 o;
+          const float mx = s[j][0].x * inv_v, my = s[j][0].y * inv_v, mz = s[j][1].x * inv_v, mw = s[j][1].y * inv_v;
+          o.x = fmaf(-mx, mx, s2[j][0].x * inv_v);
+          o.y = fmaf(-my, my, s2[j][0].y * inv_v);
+          o.z = fmaf(-mz, mz, s2[j][1].x * inv_v);
+          o.w = fmaf(-mw, mw, s2[j][1].y * inv_v);
+          const int64_t oidx = ((((int64_t)b * D + d) * h + y) * w + x) * C + q * 4;
+          if (OUT_SPLIT) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y);
+            const __nv_bfloat16 h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+            const __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
+            const __nv_bfloat162 lo01 = __floats2bfloat162_rn(o.x - __bfloat162float(h0), o.y - __bfloat162float(h1));
+            const __nv_bfloat162 lo23 = __floats2bfloat162_rn(o.z - __bfloat162float(h2), o.w - __bfloat162float(h3));
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<const uint32_t*>(&hi01); hv.y = *reinterpret_cast<const uint32_t*>(&hi23);
+            lv.x = *reinterpret_cast<const uint32_t*>(&lo01); lv.y = *reinterpret_cast<const uint32_t*>(&lo23);
+            __stcs(reinterpret_cast<uint2*>(var_split + oidx), hv);
+            __stcs(reinterpret_cast<uint2*>(var_split + (int64_t)B * D * hw * C + oidx), lv);
+          } else {
+            st4_stream(var + oidx, o);
+          }
+        }
+      }
+    }
+  }
+}
+
+// A/B switch for profiling sessions: RCMVS_SWEEP=v2 runs the round-1 kernel on the fp32-output eval path
+static bool sweep_use_v2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RCMVS_SWEEP");
+    v = (e && e[0] == 'v' && e[1] == '2') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int C>
 static int launch_costvolume(const float* feats, const float* rt, const float* depth, int per_pixel, float* var,
-                             float* var_noref, int B, int V, int D, int h, int w, cudaStream_t st) {
+                             float* var_noref, void* var_split, int B, int V, int D, int h, int w, cudaStream_t st) {
   constexpr int PXB = 256 / (C / 4);
   // enough CTAs for >= ~4 waves of 148 SMs x 8 resident CTAs, but >= 8 planes per CTA to amortise the setup
   const int xy_blocks = ceil_div(w, PXB) * h * B;
@@ -263,8 +412,22 @@ static int launch_costvolume(const float* feats, const float* rt, const float* d
 #define RCMVS_CV_LAUNCH(PP, NR)                                                                              \
   costvolume_var_kernel<C, PP, NR><<<grid, 256, 0, st>>>(feats, rt, depth, var, var_noref, V, D, h, w, d_chunk, \
                                                          chunks)
-  if (!var_noref && hw_fits_24bit) {
-    // eval path: plane-distributed v2 kernel; planes per CTA rounded to the group size
+  if (!var_noref && h >= 2 && w >= 2 && (int64_t)h * w * C < (1ll << 31) && (var_split || !sweep_use_v2())) {
+    // eval path: plane-distributed v3 kernel; planes per CTA rounded to the group size
+    constexpr int LPP = C / 4;
+    const int dch = ceil_div(d_chunk, LPP) * LPP;
+    const int nch = ceil_div(D, dch);
+    dim3 grid2(ceil_div(w, PXB), h, B * nch);
+    __nv_bfloat16* vs = reinterpret_cast<__nv_bfloat16*>(var_split);
+#define RCMVS_V3(PP, SP) costvolume_var_v3_kernel<C, PP, SP><<<grid2, 256, 0, st>>>(feats, rt, depth, var, vs, B, V, D, h, w, dch, nch)
+    if (per_pixel) { if (vs) RCMVS_V3(true, true); else RCMVS_V3(true, false); }
+    else { if (vs) RCMVS_V3(false, true); else RCMVS_V3(false, false); }
+#undef RCMVS_V3
+  } else if (var_split) {
+    set_error("rcmvs_costvolume_var_fwd_split: needs h, w >= 2 and no var_noref");
+    return RCMVS_ERR_UNSUPPORTED;
+  } else if (!var_noref && hw_fits_24bit) {
+    // round-1 v2 kernel (degenerate 1-pixel-wide shapes, RCMVS_SWEEP=v2)
     constexpr int LPP = C / 4;
     const int dch = ceil_div(d_chunk, LPP) * LPP;
     const int nch = ceil_div(D, dch);
@@ -366,12 +529,31 @@ extern "C" int rcmvs_costvolume_var_fwd(const float* feats, const float* rt, con
   RCMVS_REQUIRE(h <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_costvolume_var_fwd: h > 65535");
   cudaStream_t st = as_stream(stream);
   switch (C) {
-    case 8: return launch_costvolume<8>(feats, rt, depth, per_pixel, var, var_noref, B, V, D, h, w, st);
-    case 16: return launch_costvolume<16>(feats, rt, depth, per_pixel, var, var_noref, B, V, D, h, w, st);
-    case 32: return launch_costvolume<32>(feats, rt, depth, per_pixel, var, var_noref, B, V, D, h, w, st);
+    case 8: return launch_costvolume<8>(feats, rt, depth, per_pixel, var, var_noref, nullptr, B, V, D, h, w, st);
+    case 16: return launch_costvolume<16>(feats, rt, depth, per_pixel, var, var_noref, nullptr, B, V, D, h, w, st);
+    case 32: return launch_costvolume<32>(feats, rt, depth, per_pixel, var, var_noref, nullptr, B, V, D, h, w, st);
     default: break;
   }
   set_error("rcmvs_costvolume_var_fwd: C=%d not in {8,16,32}", C);
+  return RCMVS_ERR_UNSUPPORTED;
+}
+
+extern "C" int rcmvs_costvolume_var_fwd_split(const float* feats, const float* rt, const float* depth, int per_pixel,
+                                              void* var_split, int B, int V, int C, int D, int h, int w,
+                                              rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(feats && rt && depth && var_split, RCMVS_ERR_BAD_ARG, "rcmvs_costvolume_var_fwd_split: null pointer");
+  RCMVS_REQUIRE(B > 0 && V > 1 && D > 0 && h > 0 && w > 0, RCMVS_ERR_BAD_ARG,
+                "rcmvs_costvolume_var_fwd_split: bad dims B=%d V=%d D=%d h=%d w=%d", B, V, D, h, w);
+  RCMVS_REQUIRE(V - 1 <= kMaxSrc && h <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_costvolume_var_fwd_split: V or h too large");
+  cudaStream_t st = as_stream(stream);
+  switch (C) {
+    case 8: return launch_costvolume<8>(feats, rt, depth, per_pixel, nullptr, nullptr, var_split, B, V, D, h, w, st);
+    case 16: return launch_costvolume<16>(feats, rt, depth, per_pixel, nullptr, nullptr, var_split, B, V, D, h, w, st);
+    case 32: return launch_costvolume<32>(feats, rt, depth, per_pixel, nullptr, nullptr, var_split, B, V, D, h, w, st);
+    default: break;
+  }
+  set_error("rcmvs_costvolume_var_fwd_split: C=%d not in {8,16,32}", C);
   return RCMVS_ERR_UNSUPPORTED;
 }
 

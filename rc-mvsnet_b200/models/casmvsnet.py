@@ -29,8 +29,11 @@ def _sweep_regularise_regress(feats_cl, proj_matrices, depth_values, cost_regula
     """feats_cl [B,V,h,w,C]; proj_matrices [B,V,2,4,4]; depth_values [B,D] (uniform planes) or [B,D,h,w]."""
     rt = ops.relative_projections(proj_matrices.float().contiguous())
     depth_values = depth_values.float().contiguous()
-    res = ops.costvolume_variance(feats_cl, rt, depth_values, want_noref)
-    var, noref = res if want_noref else (res, None)
+    if not want_noref and cost_regularization.wants_split_input() and min(feats_cl.shape[2:4]) >= 2:
+        var, noref = ops.costvolume_variance_split(feats_cl, rt, depth_values), None      # bf16 hi/lo planes for the TMA conv
+    else:
+        res = ops.costvolume_variance(feats_cl, rt, depth_values, want_noref)
+        var, noref = res if want_noref else (res, None)
     cost = cost_regularization.forward_cl(var)
     depth, conf = ops.softargmin_conf(cost, depth_values)
     return depth, conf, noref, rt

@@ -20,14 +20,17 @@ __all__ = ["homo_warping", "CostRegNet", "FeatureNet", "Conv2d", "Conv3d", "Deco
 
 
 def conv_precision():
-    """RCMVS_CONV selects how CostRegNet's stride-1 convolutions run:
-         'tf32x3' (default) error-compensated 3xTF32 on tcgen05 tensor cores — fp32-equivalent accuracy;
+    """RCMVS_CONV selects how CostRegNet's convolutions run:
+         'bf16x3' (default) conv0 / conv2 on the TMA-fed tcgen05 kind::f16 kernel with error-compensated split-bf16
+                  operands (3 products, operand error <= 3·2^-17: 1.7e-5 relative on the full-size golden depth), the other
+                  tensor-core layers as in 'tf32x3';
+         'tf32x3' error-compensated 3xTF32 on tcgen05 tensor cores — fp32-equivalent accuracy (round-1 default);
          'tf32'   single TF32 pass on tcgen05 (the precision cuDNN gives the reference on GPU by torch default);
          'fp32'   exact fp32 FFMA direct-convolution kernels (no tensor cores)."""
     import os
-    mode = os.environ.get("RCMVS_CONV", "tf32x3")
-    if mode not in ("tf32x3", "tf32", "fp32"):
-        raise ValueError("RCMVS_CONV must be tf32x3, tf32 or fp32")
+    mode = os.environ.get("RCMVS_CONV", "bf16x3")
+    if mode not in ("bf16x3", "tf32x3", "tf32", "fp32"):
+        raise ValueError("RCMVS_CONV must be bf16x3, tf32x3, tf32 or fp32")
     return mode
 
 
@@ -228,7 +231,7 @@ def as_channels_last_views(feat):
     return p if p.is_contiguous() else ops.to_channels_last(feat.contiguous())
 
 
-def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit):
+def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit, slab=False):
     """One 3x3x3 (transposed) convolution + folded BatchNorm as a list of candidate engines (`CostRegNet._run` picks
     one per input shape): the FFMA kernel always; with nsplit = 1 (TF32) or 3 (3xTF32) also the tcgen05 kernels that
     support the layer's shape (slab kernel `tc` / `tct`, gather implicit-GEMM `gemm`)."""
@@ -241,6 +244,8 @@ def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit):
     if nsplit > 0 and ops.gemm_tc_supported(cin, cout):
         gmode = 2 if transposed else (1 if stride == 2 else 0)
         cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, transposed, nsplit), shift, cout, nsplit, gmode))
+    if slab and not transposed and stride == 1 and (cin, cout) in ops.SLAB_SUPPORTED:
+        cands.append(("slab", ops.conv3d_slab_pack(w, scale), shift, cout))
     return {"cands": cands, "tr": transposed, "stride": stride, "relu": relu, "choice": {}}
 
 
@@ -277,7 +282,7 @@ class CostRegNet(nn.Module):
         mode = conv_precision()
 
         def build():
-            nsplit = {"tf32x3": 3, "tf32": 1, "fp32": 0}[mode]
+            nsplit = {"bf16x3": 3, "tf32x3": 3, "tf32": 1, "fp32": 0}[mode]
             with torch.no_grad():
                 P = {}
                 for name in self._LAYERS + ("prob",):
@@ -289,13 +294,18 @@ class CostRegNet(nn.Module):
                         scale, shift = (t.contiguous() for t in fold_bn(blk.bn))
                         tr = isinstance(conv, nn.ConvTranspose3d)
                     P[name] = pack_conv3d_layer(conv.weight.detach().contiguous(), scale, shift, tr, conv.stride[0],
-                                                relu, nsplit)
+                                                relu, nsplit, slab=(mode == "bf16x3"))
             return P
         return self._packed.get((_versions(self), mode), build)
 
     @staticmethod
     def _call(cand, layer, x, skip):
         kind = cand[0]
+        if kind == "slab":      # TMA-fed split-bf16 tcgen05 kernel; the input is pre-split by its producer when possible
+            xs = x if x.dtype == torch.bfloat16 else ops.split_bf16(x)
+            return ops.conv3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"])
+        if x.dtype == torch.bfloat16:
+            raise RuntimeError("rcmvs: split-bf16 activations can only feed the slab tensor-core engine")
         if kind == "gemm":
             return ops.conv3d_gemm_tc(x, cand[1], cand[3], cand[5], cand[2], skip, cand[4], layer["relu"])
         if kind == "tc":
@@ -339,7 +349,8 @@ class CostRegNet(nn.Module):
     def _run(cls, layer, x, skip=None):
         """Run a layer with the engine chosen for this input shape (static table, or timed once with CUDA events under
         RCMVS_AUTOTUNE=1, then cached)."""
-        return cls._call(layer["cands"][cls._choose(layer, x.shape, x, skip)], layer, x, skip)
+        shape = x.shape[1:] if x.dtype == torch.bfloat16 else x.shape
+        return cls._call(layer["cands"][cls._choose(layer, shape, x, skip)], layer, x, skip)
 
     @staticmethod
     def _default_engine(layer, cands, shape):
@@ -350,6 +361,8 @@ class CostRegNet(nn.Module):
         everything else FFMA."""
         kinds = [c[0] for c in cands]
         cin = shape[-1]
+        if "slab" in kinds:                                                # bf16x3 mode: conv0 (Cin 16/32), conv2
+            return kinds.index("slab")
         if "tc" in kinds:
             cout = cands[kinds.index("tc")][3]
             return kinds.index("tc") if cout != 1 else 0
@@ -365,11 +378,19 @@ class CostRegNet(nn.Module):
             return {}
         return {n: {str(k): l["cands"][i][0] for k, i in l["choice"].items()} for n, l in self._packed.last.items()}
 
+    def wants_split_input(self):
+        """True when conv0 runs on the split-bf16 slab engine: the sweep kernel then writes the variance pre-split
+        ([2,B,D,h,w,C] bf16: hi, lo) and no conversion pass sits between the two kernels."""
+        if conv_precision() != "bf16x3" or os.environ.get("RCMVS_ENGINE") or os.environ.get("RCMVS_AUTOTUNE", "0") == "1":
+            return False
+        return (self.conv0.conv.in_channels, self.conv0.conv.out_channels) in ops.SLAB_SUPPORTED
+
     def forward_cl(self, x_cl):
-        """x_cl [B,D,h,w,Cin] channels-last -> cost [B,D,h,w]."""
-        if any(int(v) % 8 for v in x_cl.shape[1:4]):
+        """x_cl [B,D,h,w,Cin] channels-last fp32 (or its split-bf16 form [2,B,D,h,w,Cin]) -> cost [B,D,h,w]."""
+        dims = x_cl.shape[2:5] if x_cl.dtype == torch.bfloat16 else x_cl.shape[1:4]
+        if any(int(v) % 8 for v in dims):
             # three stride-2 levels: the reference fails at the first skip add (modules.py:497) for such shapes
-            raise ValueError("CostRegNet needs D, H, W divisible by 8, got %s" % (tuple(x_cl.shape[1:4]),))
+            raise ValueError("CostRegNet needs D, H, W divisible by 8, got %s" % (tuple(dims),))
         P, run = self.packed(), self._run
         c0 = run(P["conv0"], x_cl)
         c2 = run(P["conv2"], run(P["conv1"], c0))

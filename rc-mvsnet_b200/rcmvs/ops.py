@@ -153,6 +153,17 @@ def costvolume_variance(feats_cl, rt, depth, want_noref=False):
     return (var, noref) if want_noref else var
 
 
+@_on_device
+def costvolume_variance_split(feats_cl, rt, depth):
+    """Like costvolume_variance, the variance written as split-bf16 planes [2,B,D,h,w,C] (hi, lo) for conv3d_slab."""
+    B, V, h, w, C = feats_cl.shape
+    D = depth.shape[1]
+    var = torch.empty((2, B, D, h, w, C), device=feats_cl.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_costvolume_var_fwd_split", _chk(feats_cl, "feats"), _chk(rt, "rt"), _chk(depth, "depth"),
+              _depth_mode(depth, B), var.data_ptr(), B, V, C, D, h, w, _stream())
+    return var
+
+
 # ---- conv3d ---------------------------------------------------------------------------------------------------
 @_on_device
 def pack_conv3d_weight(w, scale=None, transposed=False):

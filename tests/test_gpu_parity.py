@@ -326,7 +326,7 @@ def _model(dev, ndepths, cls_name="CascadeMVSNet_eval"):
     return m.to(dev).eval()
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["bf16x3", "tf32x3", "fp32", "tf32"])
 @pytest.mark.parametrize("stage", [1, 2, 3])
 def test_costregnet_golden(dev, stage, mode, monkeypatch):
     monkeypatch.setenv("RCMVS_CONV", mode)
@@ -418,7 +418,7 @@ def _run_model(m, g, dev):
         return m(imgs, proj, cu(g["depth_values"][None], dev))
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16x3", "tf32x3", "fp32"])
 @pytest.mark.parametrize("fixture", ["mvs_small.npz", "mvs_small_noise.npz"])
 def test_cascade_eval_matches_reference_golden(dev, fixture, mode, monkeypatch):
     monkeypatch.setenv("RCMVS_CONV", mode)
