@@ -1,62 +1,76 @@
-// Relative projections src·inverse(ref) (reference models/modules.py:315-317) on device, fp64, one thread each.
+// Relative projections src·inverse(ref) (reference models/modules.py:315-317) on device, one thread each, in the
+// reference's own fp32 arithmetic (see below).
 // Replaces torch.inverse (batched LU + host sync on `info`) + matmul + slicing: no host round trip, capturable.
 #include "common.cuh"
 
 namespace rcmvs {
 
-__device__ void kext_mul(const float* P /*[2][4][4]*/, double out[16]) {
-  // out = E with top 3x4 replaced by K[:3,:3] @ E[:3,:4]   (models/casmvsnet.py:78-81)
+// The reference forms these matrices in fp32: K·[R|t] by matmul (casmvsnet.py:78-81), inverse(ref_proj) by LAPACK-style LU
+// with partial pivoting (torch.inverse = getrf + getrs on the identity), then src_proj @ inverse by matmul
+// (modules.py:315).  The rounding of that fp32 path moves sample positions by up to 6e-4 px at 1920-px-wide inputs
+// relative to the exactly rounded matrices, and the cascade's soft-argmin amplifies such shifts ~10^3 x on ambiguous
+// pixels — so parity means reproducing the fp32 arithmetic, not improving on it (round 1 computed them in fp64).
+// This restatement matches torch-CPU's matmul bit for bit (fused multiply-add, ascending k) and its inverse to within
+// 3 ulp of the largest entry on DTU-like cameras (exactly when the reference camera is axis-aligned): right-looking LU,
+// pivot scaling by the reciprocal, FMA updates, forward / backward substitution of the permuted identity.
+__device__ void kext_mul(const float* P /*[2][4][4]*/, float out[16]) {
+  // out = E with top 3x4 replaced by K[:3,:3] @ E[:3,:4]
   const float* E = P;
   const float* K = P + 16;
-  for (int i = 0; i < 16; ++i) out[i] = (double)E[i];
+  for (int i = 0; i < 16; ++i) out[i] = E[i];
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 4; ++c) {
-      // the reference does this product in fp32; reproduce its rounding so both paths see the same matrix
-      float acc = 0.f;
-      for (int k = 0; k < 3; ++k) acc = fmaf(K[r * 4 + k], E[k * 4 + c], acc);
-      out[r * 4 + c] = (double)acc;
+      float acc = __fmul_rn(K[r * 4], E[c]);
+      for (int k = 1; k < 3; ++k) acc = __fmaf_rn(K[r * 4 + k], E[k * 4 + c], acc);
+      out[r * 4 + c] = acc;
     }
 }
 
-__device__ bool invert4(const double* A, double* inv) {
-  double m[4][8];
+__device__ bool invert4_f32(const float* Ain, float* inv) {
+  float A[4][4];
+  int piv[4] = {0, 1, 2, 3};
   for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) {
-      m[r][c] = A[r * 4 + c];
-      m[r][4 + c] = (r == c) ? 1.0 : 0.0;
+    for (int c = 0; c < 4; ++c) A[r][c] = Ain[r * 4 + c];
+  for (int k = 0; k < 4; ++k) {
+    int p = k;
+    float best = fabsf(A[k][k]);
+    for (int r = k + 1; r < 4; ++r)
+      if (fabsf(A[r][k]) > best) { best = fabsf(A[r][k]); p = r; }
+    if (!(best > 0.f)) return false;
+    if (p != k) {
+      for (int c = 0; c < 4; ++c) { const float t = A[k][c]; A[k][c] = A[p][c]; A[p][c] = t; }
+      const int t = piv[k]; piv[k] = piv[p]; piv[p] = t;
     }
-  for (int col = 0; col < 4; ++col) {
-    int piv = col;
-    double best = fabs(m[col][col]);
-    for (int r = col + 1; r < 4; ++r)
-      if (fabs(m[r][col]) > best) { best = fabs(m[r][col]); piv = r; }
-    if (best == 0.0) return false;
-    if (piv != col)
-      for (int c = 0; c < 8; ++c) { double t = m[col][c]; m[col][c] = m[piv][c]; m[piv][c] = t; }
-    double d = 1.0 / m[col][col];
-    for (int c = 0; c < 8; ++c) m[col][c] *= d;
-    for (int r = 0; r < 4; ++r)
-      if (r != col) {
-        double f = m[r][col];
-        for (int c = 0; c < 8; ++c) m[r][c] -= f * m[col][c];
-      }
+    const float rcp = __fdiv_rn(1.f, A[k][k]);
+    for (int i = k + 1; i < 4; ++i) A[i][k] = __fmul_rn(A[i][k], rcp);
+    for (int i = k + 1; i < 4; ++i)
+      for (int j = k + 1; j < 4; ++j) A[i][j] = __fmaf_rn(-A[i][k], A[k][j], A[i][j]);
   }
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) inv[r * 4 + c] = m[r][4 + c];
+  for (int c = 0; c < 4; ++c) {
+    float b[4];
+    for (int i = 0; i < 4; ++i) b[i] = (piv[i] == c) ? 1.f : 0.f;
+    for (int k = 0; k < 4; ++k)
+      for (int i = k + 1; i < 4; ++i) b[i] = __fmaf_rn(-A[i][k], b[k], b[i]);
+    for (int k = 3; k >= 0; --k) {
+      b[k] = __fmul_rn(b[k], __fdiv_rn(1.f, A[k][k]));
+      for (int i = 0; i < k; ++i) b[i] = __fmaf_rn(-A[i][k], b[k], b[i]);
+    }
+    for (int i = 0; i < 4; ++i) inv[i * 4 + c] = b[i];
+  }
   return true;
 }
 
-__device__ void rel_to_rt(const double* S, const double* R, float* rt) {
-  double inv[16];
-  if (!invert4(R, inv)) {
+__device__ void rel_to_rt(const float* S, const float* R, float* rt) {
+  float inv[16];
+  if (!invert4_f32(R, inv)) {
     for (int i = 0; i < 12; ++i) rt[i] = __int_as_float(0x7fc00000);  // NaN: singular reference projection
     return;
   }
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 4; ++c) {
-      double acc = 0.0;
-      for (int k = 0; k < 4; ++k) acc += S[r * 4 + k] * inv[k * 4 + c];
-      rt[r * 4 + c] = (float)acc;
+      float acc = __fmul_rn(S[r * 4], inv[c]);
+      for (int k = 1; k < 4; ++k) acc = __fmaf_rn(S[r * 4 + k], inv[k * 4 + c], acc);
+      rt[r * 4 + c] = acc;
     }
 }
 
@@ -64,7 +78,7 @@ __global__ void relative_projections_kernel(const float* __restrict__ proj, floa
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * (V - 1)) return;
   int b = i / (V - 1), v = i % (V - 1) + 1;
-  double R[16], S[16];
+  float R[16], S[16];
   kext_mul(proj + ((int64_t)b * V + 0) * 32, R);
   kext_mul(proj + ((int64_t)b * V + v) * 32, S);
   rel_to_rt(S, R, rt + (int64_t)i * 12);
@@ -74,7 +88,7 @@ __global__ void relative_pair_kernel(const float* __restrict__ src, const float*
                                      float* __restrict__ rt, int B) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  double R[16], S[16];
+  float R[16], S[16];
   for (int i = 0; i < 16; ++i) { R[i] = ref[b * 16 + i]; S[i] = src[b * 16 + i]; }
   rel_to_rt(S, R, rt + (int64_t)b * 12);
 }

@@ -293,7 +293,7 @@ costvolume_var_v3_kernel(const float* __restrict__ feats, const float* __restric
   const float4 ref2 = make_float4(ref.x * ref.x, ref.y * ref.y, ref.z * ref.z, ref.w * ref.w);
   const float inv_v = 1.f / (float)V;
   const float xf = (float)x, yf = (float)y;
-  const int wC = w * C;
+  const float* feats1 = feats + w * C;          // the quad's second row
 
   for (int dg = d_begin; dg < d_end; dg += LPP) {
     float2 s[LPP][2], s2[LPP][2];
@@ -325,20 +325,21 @@ costvolume_var_v3_kernel(const float* __restrict__ feats, const float* __restric
       const float wy1 = (y0 == by) ? ay : ((y0 == h - 1) ? 1.f - ay : 0.f);
       const float my_w00 = wy0 * wx0, my_w01 = wy0 * wx1, my_w10 = wy1 * wx0, my_w11 = wy1 * wx1;
       // (all four taps outside -> all weights are 0 and the base stays inside the image: no branch needed)
-      const int my_base = (by * w + bx) * C;
-      const float* src = feats + (int64_t)(v + 1) * hw * C;
-      int prev = -1;
+      // element offset of the quad's first texel from `feats` (the view offset is folded in: < 2^31, checked by the launcher)
+      const unsigned my_base = (unsigned)(v + 1) * (unsigned)hw * C + (unsigned)(by * w + bx) * C;
+      unsigned prev = 0xffffffffu;
       float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0, e0 = a0, e1 = a0;
 #pragma unroll
       for (int j = 0; j < LPP; ++j) {
-        const int base = __shfl_sync(0xffffffffu, my_base, j, LPP);
+        const unsigned base = __shfl_sync(0xffffffffu, my_base, j, LPP);
         const float w00 = __shfl_sync(0xffffffffu, my_w00, j, LPP);
         const float w01 = __shfl_sync(0xffffffffu, my_w01, j, LPP);
         const float w10 = __shfl_sync(0xffffffffu, my_w10, j, LPP);
         const float w11 = __shfl_sync(0xffffffffu, my_w11, j, LPP);
         if (base != prev) {                      // neighbouring planes mostly sample the same texel quad
-          const float* t = src + base;
-          const float4 a = ldg4(t), bb = ldg4(t + C), c = ldg4(t + wC), e = ldg4(t + wC + C);
+          const float* t = feats + base;         // two 64-bit address formations per reload (rows y0 and y0+1)
+          const float* t1 = feats1 + base;
+          const float4 a = ldg4(t), bb = ldg4(t + C), c = ldg4(t1), e = ldg4(t1 + C);
           a0 = make_float2(a.x, a.y); a1 = make_float2(a.z, a.w);
           b0 = make_float2(bb.x, bb.y); b1 = make_float2(bb.z, bb.w);
           c0 = make_float2(c.x, c.y); c1 = make_float2(c.z, c.w);

@@ -46,16 +46,40 @@ def test_layout_roundtrip_bit_exact(dev, shape):
 
 
 def test_relative_projections_match_oracle(dev):
+    """rot|trans = top 3x4 of src_proj @ inverse(ref_proj) in the reference's own fp32 arithmetic (modules.py:315-317):
+    bit-exact against torch-CPU (LAPACK LU + matmul) for the synthetic rigs, within a few ulp of the largest entry for
+    general DTU-like cameras (MKL's LU orders a few operations differently)."""
     from rcmvs import ops, synth
     proj = synth.cameras(5, 512, 640, batch=2)["stage2"]
     rt = ops.relative_projections(cu(proj, dev)).cpu().numpy()
     for b in range(2):
-        projs = O.stage_projection(proj[b])
+        projs = torch.from_numpy(O.stage_projection(proj[b]))
         for v in range(1, 5):
-            rot, trans = O.relative_projection(projs[v], projs[0])
-            want = np.concatenate([rot, trans[:, None]], 1).ravel()
-            # fp64-on-device vs the reference's fp32 LU: entries of magnitude up to ~1e5 agree to fp32 rounding
-            np.testing.assert_allclose(rt[b, v - 1], want, rtol=3e-6, atol=3e-6 * np.abs(want).max())
+            want = torch.matmul(projs[v], torch.inverse(projs[0]))[:3].numpy().ravel()
+            np.testing.assert_array_equal(rt[b, v - 1], want)
+            rot, trans = O.relative_projection(projs[v].numpy(), projs[0].numpy())
+            np.testing.assert_allclose(rt[b, v - 1], np.concatenate([rot, trans[:, None]], 1).ravel(), rtol=3e-6,
+                                       atol=3e-6 * np.abs(want).max())
+    rng = np.random.default_rng(0)
+
+    def rot3(a, bb, c):
+        ca, sa, cb, sb, cc, sc = np.cos(a), np.sin(a), np.cos(bb), np.sin(bb), np.cos(c), np.sin(c)
+        return (np.array([[1, 0, 0], [0, ca, -sa], [0, sa, ca]]) @ np.array([[cb, 0, sb], [0, 1, 0], [-sb, 0, cb]]) @
+                np.array([[cc, -sc, 0], [sc, cc, 0], [0, 0, 1]]))
+    P = np.zeros((64, 2, 2, 4, 4), np.float32)
+    for i in range(64):
+        for v in range(2):
+            E = np.eye(4)
+            E[:3, :3] = rot3(*rng.uniform(-0.6, 0.6, 3))
+            E[:3, 3] = rng.uniform(-400, 400, 3) + np.array([0, 0, 600])
+            P[i, v, 0] = E
+            P[i, v, 1, :3, :3] = [[361.5 * rng.uniform(0.8, 4.5), 0, 80 * rng.uniform(0.8, 8)],
+                                  [0, 361.5 * rng.uniform(0.8, 4.5), 64 * rng.uniform(0.8, 8)], [0, 0, 1]]
+    rt = ops.relative_projections(cu(P, dev)).cpu().numpy()
+    for i in range(64):
+        projs = torch.from_numpy(O.stage_projection(P[i]))
+        want = torch.matmul(projs[1], torch.inverse(projs[0]))[:3].numpy().ravel()
+        assert np.abs(rt[i, 0] - want).max() <= 4e-6 * np.abs(want).max()
 
 
 # ---- a1 homo_warping ---------------------------------------------------------------------------------------------
