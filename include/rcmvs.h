@@ -242,6 +242,55 @@ int rcmvs_masked_loss_fwd_bwd(const float* pred, const float* target, const floa
                               int mask_kind, int mode, float scale, float* loss, float* grad, float* workspace, int B,
                               int h, int w, int step, rcmvs_stream_t stream);
 
+/* ---- training path (BASELINE configs[3]; train_rcmvsnet.py:330-376, 397-445, 311): forward + backward of every
+ * conv -> BatchNorm(batch statistics) -> ReLU block (models/modules.py:28-62, 118-210), of the variance cost volume and of
+ * the soft-argmin, on own kernels.  All activations channels-last [M][C] / [B][D][H][W][C] / [N][H][W][C]. ---------------- */
+/* stats [2][C] double (zero-filled by the caller) += {Σ x, Σ x²} over the M rows of x [M][C]. */
+int rcmvs_bn_stats(const float* x, double* stats, int64_t M, int C, rcmvs_stream_t stream);
+/* mean, invstd [C] from stats; running_mean / running_var (may be NULL) updated with `momentum` (unbiased variance). */
+int rcmvs_bn_finalize(const double* stats, float* mean, float* invstd, float* running_mean, float* running_var, int64_t M,
+                      int C, float eps, float momentum, rcmvs_stream_t stream);
+/* z = act((x - mean)·invstd·gamma + beta) (+ skip, added after the ReLU: modules.py:497-499). */
+int rcmvs_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                   const float* skip, float* z, int64_t M, int C, int relu, rcmvs_stream_t stream);
+/* BatchNorm(+ReLU) backward: dz, x (the convolution output the forward normalised) -> dx (gradient w.r.t. x), dgamma,
+ * dbeta [C]; sums = 2·C doubles of zero-filled workspace.  frozen = 1: mean / invstd were running statistics (eval-mode
+ * BatchNorm under autograd), so the batch-statistic correction terms are dropped. */
+int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, double* sums, float* dx, float* dgamma, float* dbeta, int64_t M, int C, int relu,
+                 int frozen, rcmvs_stream_t stream);
+/* Weight gradient G[cs][cb][taps] += Σ_o S[o][cs]·Bg[stride·o + tap - pad][cb] (G zero-filled by the caller, torch weight
+ * layout): Conv: S = dy [B][Ds][Hs][Ws][Cs=Cout], Bg = x [B][Db][Hb][Wb][Cb=Cin] -> dW [Cout][Cin][taps];
+ * ConvTranspose(k3,s2,p1,op1): S = x (Cs = Cin), Bg = dy (Cb = Cout), stride 2 -> dW [Cin][Cout][27].
+ * dim3d = 1: 3x3x3; dim3d = 0: 2-D (Ds = Db = 1), k in {1,3,5}. */
+int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B, int Ds, int Hs, int Ws, int Cs, int Db, int Hb,
+                     int Wb, int Cb, int k, int stride, int dim3d, rcmvs_stream_t stream);
+/* 2-D data gradient: dy [N][Ho][Wo][Cout], torch weight w [Cout][Cin][k][k] -> dx [N][H][W][Cin] (Cin % 4 == 0: the
+ * 3-channel image layer needs none); wd_ws = k·k·Cout·Cin floats of workspace. */
+int rcmvs_conv2d_dgrad(const float* dy, const float* w, float* wd_ws, float* dx, int N, int H, int W, int Cin, int Cout,
+                       int k, int stride, rcmvs_stream_t stream);
+/* 3-D data gradients reuse the forward kernels: stride-1 conv -> rcmvs_conv3d_fwd with weights packed by
+ * rcmvs_pack_conv3d_dgrad_s1 ([27][Cout][Cin], taps flipped); stride-2 conv -> rcmvs_conv_transpose3d_fwd with
+ * rcmvs_pack_conv3d_weight(w, transposed = 1); transposed conv -> rcmvs_conv3d_fwd stride 2 with
+ * rcmvs_pack_conv3d_weight(w, transposed = 0).  The 1-output-channel `prob` layer: */
+int rcmvs_pack_conv3d_dgrad_s1(const float* w, float* packed, int Cout, int Cin, rcmvs_stream_t stream);
+int rcmvs_conv3d_c1_dgrad(const float* dcost, const float* w, float* dx, int B, int D, int H, int W, rcmvs_stream_t stream);
+/* Backward of rcmvs_costvolume_var_fwd: grad_var (and grad_noref, may be NULL) [B][D][h][w][C] -> grad_feats
+ * [B][V][h][w][C] (zero-filled by the caller; vector reductions).  At most 7 source views. */
+int rcmvs_costvolume_var_bwd(const float* feats, const float* rt, const float* depth, int per_pixel, const float* grad_var,
+                             const float* grad_noref, float* grad_feats, int B, int V, int C, int D, int h, int w,
+                             rcmvs_stream_t stream);
+/* Backward of softmax + depth regression: grad_cost[d] = grad_depth · p_d · (plane_d - depth). */
+int rcmvs_softargmin_bwd(const float* cost, const float* depth_planes, int per_pixel, const float* grad_depth,
+                         float* grad_cost, int B, int D, int h, int w, rcmvs_stream_t stream);
+/* FPN lateral (modules.py:451,455): out = a + nearest-2x-upsample(up); its backward w.r.t. up = 2x2 block sums. */
+int rcmvs_up2_add(const float* a, const float* up, float* out, int N, int H, int W, int C, rcmvs_stream_t stream);
+int rcmvs_sum2x2(const float* in, float* out, int N, int Ho, int Wo, int C, rcmvs_stream_t stream);
+/* Fused Adam (torch.optim.Adam semantics, train_rcmvsnet.py:537) over flat buffers; grads are multiplied by grad_scale
+ * first (1/world_size after the NCCL sum all-reduce). */
+int rcmvs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, rcmvs_stream_t stream);
+
 /* ---- f3 geometric-consistency filter: eval_rcmvsnet_dtu.py:281-336 (reproject_with_depth,
  * check_geometric_consistency) + :366-389 of filter_depth, all NS source views of one reference view per launch ---- */
 /* depth_ref [H][W], conf [H][W] or NULL, depth_src [NS][Hs][Ws]; pair_mats [NS][68] float32 per source:

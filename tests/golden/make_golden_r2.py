@@ -9,6 +9,7 @@
                48/32/8, 1024 rays x 128 samples; the sampled pixels / depth candidates are stored for injection
   geo          eval_rcmvsnet_dtu.py:281-338 reproject_with_depth / check_geometric_consistency on synthetic depth maps
   loss         losses/unsup_loss.py UnSupLoss (+ gradient w.r.t. depth) on a small synthetic case
+  tanks_sensitivity  (prints only) the reference re-run on ~1-ulp-perturbed images: its own conditioning at cfg 5
 
 Inputs always come from rcmvs.synth with the seeds written next to each case, so the GPU tests regenerate them.
 """
@@ -209,3 +210,22 @@ if "loss" in what:
     total, scalars = ms(inputs, t(imgs01), {k: t(v) for k, v in proj.items()}, dlossw=[0.5, 1.0, 2.0])
     res["multistage_total"] = np.float32(total.item())
     save("unsup_loss_small.npz", **res)
+
+# ---- tanks_sensitivity: how far does the REFERENCE move under ~1-ulp input noise? (justifies the cfg-5 tolerance) ------
+if "tanks_sensitivity" in what:
+    from models.casmvsnet import CascadeMVSNet_eval  # reference
+    V, H, W, nd = 7, 1056, 1920, (48, 32, 8)
+    imgs, proj, dv = synth.mvs_inputs(V, H, W, kind="textured", seed=21)
+    rng = np.random.default_rng(0)
+    imgs2 = (imgs.astype(np.float64) * (1 + 1e-7 * rng.standard_normal(imgs.shape))).astype(np.float32)
+    m = CascadeMVSNet_eval(ndepths=list(nd))
+    m.load_state_dict(ck_cas, strict=True)
+    m.eval()
+    with torch.no_grad():
+        out = m(t(imgs2), {k: t(v) for k, v in proj.items()}, t(dv))
+    g = dict(np.load(os.path.join(HERE, "tanks_7x1056x1920_48_32_8.npz")))
+    for k in ("stage1", "stage2", "stage3"):
+        d = out[k]["depth"][0].numpy()
+        err = np.abs(g["depth_" + k] - d) / np.abs(d).max()
+        print(k, "reference(x) vs reference(x·(1 + 1e-7·n)): rel L-inf %.3e, p99.9 %.3e" % (err.max(), np.percentile(err, 99.9)))
+    # measured in the authoring container: stage1 1.111e-06 / 7.1e-07, stage2 1.497e-05 / 6.9e-06, stage3 1.641e-04 / 2.2e-05

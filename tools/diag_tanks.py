@@ -9,7 +9,7 @@ G = os.path.join(ROOT, "tests", "golden")
 g = dict(np.load(os.path.join(G, "tanks_7x1056x1920_48_32_8.npz")))
 dev = torch.device("cuda:0")
 imgs, proj, dv = synth.mvs_inputs(7, 1056, 1920, kind="textured", seed=int(g["seed"]))
-for mode in ("tf32x3", "fp32"):
+for mode in ("bf16x3", "fp32"):
     os.environ["RCMVS_CONV"] = mode
     m = models.CascadeMVSNet_eval(ndepths=[48, 32, 8])
     weights.load_model(m, os.path.join(G, "cas_model_000014.npz"))
