@@ -490,11 +490,8 @@ def main():
     if side and not args.no_render and not args.no_kernel_rooflines:
         render = render_branch_timing(dev, pk)
         tanks = tanks_timing(CascadeMVSNet_eval, dev)
-        try:
-            from rcmvs import train as rtrain
-            train = rtrain.bench_train_step(dev, steps=5)
-        except ImportError:
-            train = None
+        from rcmvs import train as rtrain
+        train = rtrain.bench_train_step(dev, steps=5)
         # same workload with 4 reference views per launch sequence (better fill of the small 1/4- and 1/8-scale layers)
         b4 = [make_inputs(seed=1000 + i) for i in range(4)]
         i4 = torch.from_numpy(np.concatenate([h[0] for h in b4])).to(dev)
@@ -519,6 +516,11 @@ def main():
                         "sample": "FULL configuration (%d views %dx%d, D=%s), %d passes of %.1f s after 1 warm-up, %d of "
                                   "%d host threads (fastest count), torch-CPU port incl. F.grid_sample as the reference "
                                   "calls it" % (V, H, W, "/".join(map(str, NDEPTHS)), reps, dt, cores, avail)}
+    if dist is not None and not args.no_render:
+        # configs[3] under torchrun: every rank trains on its own reference view, one NCCL all-reduce of the flat gradient
+        # buffer + SyncBatchNorm statistics per step (device-timed, max over ranks inside bench_train_step)
+        from rcmvs import train as rtrain
+        train = rtrain.bench_train_step(dev, steps=5)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

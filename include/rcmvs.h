@@ -259,6 +259,12 @@ int rcmvs_bn_apply(const float* x, const float* mean, const float* invstd, const
 int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, const float* invstd, const float* gamma,
                  const float* beta, double* sums, float* dx, float* dgamma, float* dbeta, int64_t M, int C, int relu,
                  int frozen, rcmvs_stream_t stream);
+/* The same in two calls (SyncBatchNorm: all-reduce `sums` over the ranks in between; M_total = rows over all ranks). */
+int rcmvs_bn_bwd_reduce(const float* dz, const float* x, const float* mean, const float* invstd, const float* gamma,
+                        const float* beta, double* sums, int64_t M, int C, int relu, rcmvs_stream_t stream);
+int rcmvs_bn_bwd_apply(const float* dz, const float* x, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, const double* sums, float* dx, float* dgamma, float* dbeta, int64_t M,
+                       int64_t M_total, int C, int relu, int frozen, rcmvs_stream_t stream);
 /* Weight gradient G[cs][cb][taps] += Σ_o S[o][cs]·Bg[stride·o + tap - pad][cb] (G zero-filled by the caller, torch weight
  * layout): Conv: S = dy [B][Ds][Hs][Ws][Cs=Cout], Bg = x [B][Db][Hb][Wb][Cb=Cin] -> dW [Cout][Cin][taps];
  * ConvTranspose(k3,s2,p1,op1): S = x (Cs = Cin), Bg = dy (Cb = Cout), stride 2 -> dW [Cin][Cout][27].

@@ -553,6 +553,32 @@ extern "C" int rcmvs_bn_apply(const float* x, const float* mean, const float* in
   return RCMVS_OK;
 }
 
+// the two passes separately, for SyncBatchNorm: the caller all-reduces `sums` (and M) over the ranks in between
+extern "C" int rcmvs_bn_bwd_reduce(const float* dz, const float* x, const float* mean, const float* invstd,
+                                   const float* gamma, const float* beta, double* sums, int64_t M, int C, int relu,
+                                   rcmvs_stream_t stream) {
+  RCMVS_REQUIRE(dz && x && mean && invstd && gamma && beta && sums && M > 0 && C % 4 == 0 && C <= 256, RCMVS_ERR_BAD_ARG,
+                "rcmvs_bn_bwd_reduce: bad arguments");
+  const int rpc = rows_per_cta(M, 148 * 8);
+  bn_bwd_reduce_kernel<<<(unsigned)ceil_div<int64_t>(M, rpc), 256, 2 * C * sizeof(double), as_stream(stream)>>>(
+      dz, x, mean, invstd, gamma, beta, sums, M, C, relu, rpc);
+  RCMVS_CHECK_LAUNCH("rcmvs_bn_bwd_reduce");
+  return RCMVS_OK;
+}
+
+extern "C" int rcmvs_bn_bwd_apply(const float* dz, const float* x, const float* mean, const float* invstd,
+                                  const float* gamma, const float* beta, const double* sums, float* dx, float* dgamma,
+                                  float* dbeta, int64_t M, int64_t M_total, int C, int relu, int frozen,
+                                  rcmvs_stream_t stream) {
+  RCMVS_REQUIRE(dz && x && mean && invstd && gamma && beta && sums && dx && M > 0 && C % 4 == 0 && C <= 256, RCMVS_ERR_BAD_ARG,
+                "rcmvs_bn_bwd_apply: bad arguments");
+  const int64_t n4 = M * C / 4;
+  bn_bwd_apply_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, as_stream(stream)>>>(
+      dz, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, n4, (double)M_total, C, relu, frozen);
+  RCMVS_CHECK_LAUNCH("rcmvs_bn_bwd_apply");
+  return RCMVS_OK;
+}
+
 extern "C" int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, const float* invstd, const float* gamma,
                             const float* beta, double* sums, float* dx, float* dgamma, float* dbeta, int64_t M, int C,
                             int relu, int frozen, rcmvs_stream_t stream) {

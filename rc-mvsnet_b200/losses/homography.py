@@ -9,6 +9,10 @@ from rcmvs import ops
 class _InverseWarp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, left_cam, right_cam, depth):
+        if any(ctx.needs_input_grad[:3]):
+            # the reference's expression is differentiable w.r.t. img and the cameras too; no caller uses that (the loss
+            # warps input images), so only the depth gradient has a kernel: refuse instead of returning zeros
+            raise NotImplementedError("rcmvs: inverse_warping is differentiable w.r.t. depth only")
         warped, mask = ops.inverse_warp_fwd(img, left_cam, right_cam, depth)
         ctx.save_for_backward(img, left_cam, right_cam, depth)
         ctx.mark_non_differentiable(mask)

@@ -49,6 +49,10 @@ class DepthNet_eval(nn.Module):
             depth_values.shape[1], num_depth)
         if prob_volume_init is not None:
             raise NotImplementedError("prob_volume_init is never passed by the reference callers")
+        if cost_regularization.needs_autograd() or (torch.is_grad_enabled() and any(f.requires_grad for f in features)):
+            out = DepthNet._forward_autograd(self, features, proj_matrices, depth_values, num_depth, cost_regularization,
+                                             imgs)
+            return {"depth": out["depth"], "photometric_confidence": out["photometric_confidence"]}
         with torch.no_grad():
             depth, conf, _, _ = _sweep_regularise_regress(_stack_views_cl(features), proj_matrices, depth_values,
                                                           cost_regularization)
@@ -66,8 +70,9 @@ class DepthNet(nn.Module):
             depth_values.shape[1], num_depth)
         if prob_volume_init is not None:
             raise NotImplementedError("prob_volume_init is never passed by the reference callers")
-        needs_grad = torch.is_grad_enabled() and any(f.requires_grad for f in features)
-        if needs_grad:
+        needs_grad = torch.is_grad_enabled() and (any(f.requires_grad for f in features) or
+                                                  cost_regularization.needs_autograd())
+        if needs_grad or cost_regularization.training:
             return self._forward_autograd(features, proj_matrices, depth_values, num_depth, cost_regularization, imgs)
         B, V = imgs.shape[:2]
         C, h, w = features[0].shape[1:]
@@ -84,38 +89,25 @@ class DepthNet(nn.Module):
         return {"depth": depth, "photometric_confidence": conf, "volume_feature_no_ref": vol}
 
     def _forward_autograd(self, features, proj_matrices, depth_values, num_depth, cost_regularization, imgs):
-        """Differentiable path for train_rcmvsnet.py: CUDA warp (with its scatter-add backward) + library ops for
-        the reductions and the 3-D CNN until the fused train-mode kernels land."""
-        library_fallback("DepthNet.forward (training / autograd)", "ATen reductions + softmax around the CUDA warp")
+        """Differentiable path for train_rcmvsnet.py, all on own kernels (rcmvs.autograd): fused plane sweep + variance
+        (+ var_no_ref) with its hand-written backward into the V feature maps, CostRegNet with batch-statistics
+        BatchNorm, softmax + depth regression with its backward.  The hypotheses carry no gradient (the sample grid is
+        built under no_grad in the reference, modules.py:314, and grad_method='detach')."""
+        from rcmvs import autograd as A
         B, V = imgs.shape[:2]
         C, h, w = features[0].shape[1:]
-        projs = torch.unbind(proj_matrices, 1)
-
-        def kext(p):
-            q = p[:, 0].clone()
-            q[:, :3, :4] = torch.matmul(p[:, 1, :3, :3], p[:, 0, :3, :4])
-            return q
-        ref_proj = kext(projs[0])
-        small = F.interpolate(imgs.reshape(B * V, *imgs.shape[2:]), (h, w), mode="bilinear",
-                              align_corners=False).view(B, V, 3, h, w)
-        ref = features[0].unsqueeze(2)
-        vsum, vsq = ref.expand(-1, -1, num_depth, -1, -1), (ref ** 2).expand(-1, -1, num_depth, -1, -1)
-        nsum, nsq, rgb = 0, 0, []
-        for i in range(1, V):
-            sp = kext(projs[i])
-            rgb.append(homo_warping(small[:, i], sp, ref_proj, depth_values))
-            wv = homo_warping(features[i], sp, ref_proj, depth_values)
-            vsum, vsq = vsum + wv, vsq + wv ** 2
-            nsum, nsq = nsum + wv, nsq + wv ** 2
-        var = vsq / V - (vsum / V) ** 2
-        var_noref = nsq / V - (nsum / V) ** 2
-        prob = F.softmax(cost_regularization(var).squeeze(1), dim=1)
-        depth = torch.sum(prob * depth_values, 1)
         with torch.no_grad():
-            _, conf = ops.softargmin_conf(torch.log(prob.detach().clamp_min(1e-38)).contiguous(),
-                                          depth_values.float().contiguous())
+            rt = ops.relative_projections(proj_matrices.float().contiguous())
+            dv = depth_values.detach().float().contiguous()
+            small = F.interpolate(imgs.reshape(B * V, *imgs.shape[2:]).float(), (h, w), mode="bilinear",
+                                  align_corners=False).view(B, V, 3, h, w)
+            rgb = [ops.homo_warp_fwd(small[:, i + 1].contiguous(), rt[:, i].contiguous(), dv) for i in range(V - 1)]
+        feats_cl = torch.stack([as_channels_last_views(f) for f in features], dim=1)        # [B,V,h,w,C]
+        var, noref = A.costvolume_variance(feats_cl, rt, dv, True)
+        cost = cost_regularization.forward_cl_train(var)
+        depth, conf = A.softargmin(cost, dv)
         return {"depth": depth, "photometric_confidence": conf,
-                "volume_feature_no_ref": torch.cat(rgb + [var_noref], dim=1)}
+                "volume_feature_no_ref": torch.cat(rgb + [A.to_planar(noref)], dim=1)}
 
 
 class _CascadeBase(nn.Module):
@@ -173,6 +165,11 @@ class _CascadeBase(nn.Module):
         B, V, _, H, W = imgs.shape
         imgs = imgs.float()
         depth_values = depth_values.float().contiguous()
+        if self.grad_method != "detach" and torch.is_grad_enabled():
+            # 'undetach' (a train_rcmvsnet.py choice) differentiates the next stage's hypotheses w.r.t. this stage's depth;
+            # the hypothesis kernels carry no gradient, so refuse instead of silently dropping that term
+            raise NotImplementedError("rcmvs: grad_method='undetach' is not implemented on the CUDA path (use 'detach', "
+                                      "the reference default)")
         per_view, stacked = self._features(imgs)
         feats_ready = stacked.pop("_ready", None) if stacked is not None else None
         fused = stacked is not None and (not torch.is_grad_enabled() or self.depthnet_cls is DepthNet_eval)

@@ -208,11 +208,37 @@ class FeatureNet(nn.Module):
         """x [N,3,H,W] -> {"stage1": [N,4c,H/4,W/4], "stage2": [N,2c,H/2,W/2], "stage3": [N,c,H,W]}.
         Eval / no-grad: hand-written fp32 kernels, outputs are NCHW-shaped views of channels-last storage.
         Training (batch-statistics BatchNorm + autograd): torch library ops."""
-        if not self.training and not (torch.is_grad_enabled() and x.requires_grad) and x.is_cuda \
-                and self.base_channels == 8:
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not self.training and not needs_grad and x.is_cuda and self.base_channels == 8:
             with torch.no_grad():
                 return {k: v.permute(0, 3, 1, 2) for k, v in self.forward_cl(x).items()}
-        library_fallback("FeatureNet.forward (training / autograd)", "cuDNN conv2d + batch_norm")
+        if not x.is_cuda or self.base_channels != 8:
+            library_fallback("FeatureNet.forward (CPU tensor / non-default width)", "torch conv2d + batch_norm")
+            return self._forward_torch(x)
+        return {k: v.permute(0, 3, 1, 2) for k, v in self.forward_cl_train(x).items()}
+
+    def forward_cl_train(self, x):
+        """Differentiable forward on own kernels (rcmvs.autograd): batch-statistics BatchNorm when self.training, frozen
+        running statistics otherwise; every conv / BN / ReLU / FPN-add has a hand-written backward.  Channels-last maps."""
+        from rcmvs import autograd as A
+        tr = self.training
+
+        def chain(seq, t):
+            for blk in seq:
+                t = A.conv_block(t, blk.conv, blk.bn, relu=True, training=tr)
+            return t
+        c0 = chain(self.conv0, ops.images_to_nhwc8(x.float().contiguous()))
+        c1 = chain(self.conv1, c0)
+        c2 = chain(self.conv2, c1)
+        out = {"stage1": A.conv_block(c2, self.out1, None, relu=False)}
+        intra = A.up2_add(A.conv_block(c1, self.inner1, None, relu=False), c2)
+        out["stage2"] = A.conv_block(intra, self.out2, None, relu=False)
+        if self.num_stage == 3:
+            intra = A.up2_add(A.conv_block(c0, self.inner2, None, relu=False), intra)
+            out["stage3"] = A.conv_block(intra, self.out3, None, relu=False)
+        return out
+
+    def _forward_torch(self, x):
         c0 = self.conv0(x)
         c1 = self.conv1(c0)
         c2 = self.conv2(c1)
@@ -401,17 +427,42 @@ class CostRegNet(nn.Module):
         y = run(P["conv11"], y, c0)
         return run(P["prob"], y).squeeze(-1)
 
+    def needs_autograd(self, x=None):
+        """The fused inference kernels apply when nothing needs a gradient and BatchNorm runs on its running statistics."""
+        if self.training:
+            return True
+        return torch.is_grad_enabled() and ((x is not None and x.requires_grad) or
+                                            any(p.requires_grad for p in self.parameters()))
+
     def forward(self, x):
         """x [B,C,D,h,w] -> [B,1,D,h,w] (reference signature)."""
-        if self.training or torch.is_grad_enabled() and x.requires_grad:
-            return self._forward_autograd(x)
+        if self.needs_autograd(x):
+            if not x.is_cuda:
+                library_fallback("CostRegNet.forward (CPU tensor)", "torch conv3d + batch_norm")
+                return self._forward_torch(x)
+            from rcmvs import autograd as A
+            return self.forward_cl_train(A.to_channels_last(x)).unsqueeze(1)
         with torch.no_grad():
             return self.forward_cl(ops.to_channels_last(x.float().contiguous())).unsqueeze(1)
 
-    def _forward_autograd(self, x):
-        # Training path (train-mode BatchNorm statistics + backward) is not on the inference hot path yet:
-        # library ops keep train_rcmvsnet.py working until the fused train kernels land (DESIGN.md, row a3-train).
-        library_fallback("CostRegNet.forward (training / autograd)", "cuDNN conv3d + batch_norm")
+    def forward_cl_train(self, x_cl):
+        """Differentiable forward on own kernels: x_cl [B,D,h,w,Cin] -> cost [B,D,h,w].  conv -> BatchNorm (batch statistics
+        when self.training, running statistics otherwise) -> ReLU (+ skip after the ReLU, modules.py:497-499), `prob` plain."""
+        from rcmvs import autograd as A
+        if any(int(v) % 8 for v in x_cl.shape[1:4]):
+            raise ValueError("CostRegNet needs D, H, W divisible by 8, got %s" % (tuple(x_cl.shape[1:4]),))
+        tr = self.training
+        blk = lambda t, m, skip=None: A.conv_block(t, m.conv, m.bn, skip=skip, relu=True, training=tr)
+        c0 = blk(x_cl, self.conv0)
+        c2 = blk(blk(c0, self.conv1), self.conv2)
+        c4 = blk(blk(c2, self.conv3), self.conv4)
+        y = blk(blk(c4, self.conv5), self.conv6)
+        y = blk(y, self.conv7, c4)
+        y = blk(y, self.conv9, c2)
+        y = blk(y, self.conv11, c0)
+        return A.conv_block(y, self.prob, None, relu=False).squeeze(-1)
+
+    def _forward_torch(self, x):
         c0 = self.conv0(x)
         c2 = self.conv2(self.conv1(c0))
         c4 = self.conv4(self.conv3(c2))

@@ -16,8 +16,19 @@ from . import _ffi, ops
 from .ops import _chk, _opt, _stream, _on_device
 
 
+SYNC_BN = False      # True: batch statistics (forward) and their gradient sums (backward) are all-reduced over the ranks
+                     # of the default process group = nn.SyncBatchNorm semantics (train_rcmvsnet.py:524-525)
+
+
 def _f32c(t):
     return t.detach().float().contiguous()
+
+
+def _sync_world():
+    import torch.distributed as dist
+    if SYNC_BN and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_world_size()
+    return None, 1
 
 
 # ---- raw ops -------------------------------------------------------------------------------------------------------
@@ -27,11 +38,14 @@ def bn_batch_stats(x2d, running_mean, running_var, momentum, eps):
     M, C = x2d.shape
     stats = torch.zeros((2 * C,), device=x2d.device, dtype=torch.float64)
     _ffi.call("rcmvs_bn_stats", _chk(x2d, "x"), stats.data_ptr(), M, C, _stream())
+    dist, world = _sync_world()
+    if dist is not None:                                  # SyncBatchNorm: 2·C doubles over NCCL, equal rows per rank
+        dist.all_reduce(stats)
     mean = torch.empty((C,), device=x2d.device, dtype=torch.float32)
     invstd = torch.empty_like(mean)
     _ffi.call("rcmvs_bn_finalize", stats.data_ptr(), _chk(mean, "mean"), _chk(invstd, "invstd"),
-              _opt(running_mean, "running_mean"), _opt(running_var, "running_var"), M, C, float(eps), float(momentum),
-              _stream())
+              _opt(running_mean, "running_mean"), _opt(running_var, "running_var"), M * world, C, float(eps),
+              float(momentum), _stream())
     return mean, invstd, stats
 
 
@@ -51,11 +65,23 @@ def bn_backward(dz2d, x2d, mean, invstd, gamma, beta, relu, frozen):
     dx = torch.empty_like(x2d)
     dgamma = torch.empty((C,), device=x2d.device, dtype=torch.float32)
     dbeta = torch.empty_like(dgamma)
-    _ffi.call("rcmvs_bn_bwd", _chk(dz2d, "dz"), _chk(x2d, "x"), _chk(mean, "mean"), _chk(invstd, "invstd"),
-              _chk(gamma, "gamma"), _chk(beta, "beta"), sums.data_ptr(), _chk(dx, "dx"), _chk(dgamma, "dgamma"),
-              _chk(dbeta, "dbeta"), M, C, 1 if relu else 0, 1 if frozen else 0, _stream())
-    _ffi.launches += 1
-    return dx, dgamma, dbeta
+    dist, world = _sync_world()
+    if dist is None or frozen:
+        _ffi.call("rcmvs_bn_bwd", _chk(dz2d, "dz"), _chk(x2d, "x"), _chk(mean, "mean"), _chk(invstd, "invstd"),
+                  _chk(gamma, "gamma"), _chk(beta, "beta"), sums.data_ptr(), _chk(dx, "dx"), _chk(dgamma, "dgamma"),
+                  _chk(dbeta, "dbeta"), M, C, 1 if relu else 0, 1 if frozen else 0, _stream())
+        _ffi.launches += 1
+        return dx, dgamma, dbeta
+    # SyncBatchNorm backward: the correction terms use the sums over ALL ranks; dgamma / dbeta stay local (DDP's gradient
+    # all-reduce averages them like every other parameter gradient)
+    _ffi.call("rcmvs_bn_bwd_reduce", _chk(dz2d, "dz"), _chk(x2d, "x"), _chk(mean, "mean"), _chk(invstd, "invstd"),
+              _chk(gamma, "gamma"), _chk(beta, "beta"), sums.data_ptr(), M, C, 1 if relu else 0, _stream())
+    local = sums.clone()
+    dist.all_reduce(sums)
+    _ffi.call("rcmvs_bn_bwd_apply", _chk(dz2d, "dz"), _chk(x2d, "x"), _chk(mean, "mean"), _chk(invstd, "invstd"),
+              _chk(gamma, "gamma"), _chk(beta, "beta"), sums.data_ptr(), _chk(dx, "dx"), None, None, M, M * world, C,
+              1 if relu else 0, 0, _stream())
+    return dx, local[C:].float(), local[:C].float()
 
 
 @_on_device
@@ -192,8 +218,7 @@ def conv_block(x_cl, conv, bn=None, skip=None, relu=True, training=True):
     BatchNorm or None.  x_cl channels-last."""
     dim3d = conv.weight.dim() == 5
     transposed = isinstance(conv, torch.nn.ConvTranspose3d)
-    cfg = {"dim3d": dim3d, "transposed": transposed, "stride": conv.stride[0], "relu": relu and bn is not None or
-           (relu and bn is None and False), "batch_stats": bool(training), "momentum": 0.1, "eps": 1e-5,
+    cfg = {"dim3d": dim3d, "transposed": transposed, "stride": conv.stride[0], "relu": bool(relu) and bn is not None, "batch_stats": bool(training), "momentum": 0.1, "eps": 1e-5,
            "running_mean": None, "running_var": None}
     gamma = beta = None
     if bn is not None:

@@ -1,0 +1,153 @@
+"""One optimiser step of the reference's unsupervised training loop on own kernels (BASELINE configs[3]).
+
+The reference step (train_rcmvsnet.py:130-259) is: `train_sample` (CascadeMVSNet forward + UnsupLossMultiStage, :330-376)
+-> `train_sample_aug` (second forward on masked images + AugLossMultiStage against the detached first depth, :397-445)
+-> `train_render_net` (Rendering_Consistency_Net + image / depth losses, :279-325) -> ONE backward (:311) -> Adam step
+(:312), with DistributedDataParallel averaging the 1.36 M gradients over the ranks (one reference view per GPU, :567-578) and
+SyncBatchNorm sharing batch statistics (:524-525).
+
+`TrainStep` keeps that structure:
+  * parameters and gradients live in two FLAT fp32 buffers (the modules' .data / .grad are views), so the data-parallel
+    exchange is ONE NCCL all-reduce of 5.4 MB over NVLink and the optimiser is ONE fused Adam launch (csrc/train.cu);
+  * forward and backward run on librcmvs kernels through rcmvs.autograd (RCMVS_STRICT=1 raises on any library fallback);
+  * SyncBatchNorm semantics = `rcmvs.autograd.SYNC_BN` (2·C doubles per BatchNorm layer over NCCL).
+The rendering-consistency branch joins the step when `nerf` is given (its differentiable path is selected by the module).
+"""
+import torch
+import torch.distributed as dist
+
+from . import autograd as A
+
+
+class FlatParams:
+    """Re-homes the parameters of `modules` into one flat buffer (and their gradients into another)."""
+
+    def __init__(self, modules):
+        self.params = [p for m in modules for p in m.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty((n,), device=dev, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.flat)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:                       # autograd may have replaced .grad: re-attach the views
+            k = p.numel()
+            view = self.grad[off:off + k].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+            off += k
+
+    def all_reduce(self):
+        """Sum over ranks (the 1/world factor is folded into the Adam kernel's grad_scale)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad)
+            return dist.get_world_size()
+        return 1
+
+    def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world=1):
+        self.step_count += 1
+        A.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr, betas, eps, weight_decay,
+                    grad_scale=1.0 / world)
+
+
+class TrainStep:
+    def __init__(self, model, nerf=None, lr=1e-4, w_aug=0.01, dlossw=(0.5, 1.0, 2.0), sync_bn=None):
+        from losses import AugLossMultiStage, UnsupLossMultiStage, random_image_mask
+        self.model, self.nerf = model, nerf
+        self.unsup, self.aug, self.mask_fn = UnsupLossMultiStage(), AugLossMultiStage(), random_image_mask
+        self.lr, self.w_aug, self.dlossw = lr, w_aug, list(dlossw)
+        self.flat = FlatParams([model] + ([nerf] if nerf is not None else []))
+        if sync_bn is None:
+            sync_bn = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        A.SYNC_BN = bool(sync_bn)
+
+    def __call__(self, sample):
+        """sample: imgs [B,V,3,H,W] (normalised), center_imgs (the loss's images), imgs_aug, proj_matrices {stageK},
+        depth_values [B,Dv] — the keys the reference's loader produces (datasets/dtu_train.py:344-364)."""
+        m = self.model
+        m.train()
+        self.flat.zero_grad()
+        out, vol = m(sample["imgs"], sample["proj_matrices"], sample["depth_values"])
+        loss_base, scal = self.unsup(out, sample["center_imgs"], sample["proj_matrices"], dlossw=self.dlossw)
+        pseudo = out["depth"].detach()
+        imgs_aug = sample["imgs_aug"].clone()
+        ref, fmask = self.mask_fn(imgs_aug[:, 0], (imgs_aug.shape[3] // 3, imgs_aug.shape[4] // 3))
+        imgs_aug[:, 0] = ref
+        out_aug, _ = m(imgs_aug, sample["proj_matrices"], sample["depth_values"])
+        loss_aug, _ = self.aug(out_aug, pseudo, None, fmask, dlossw=self.dlossw)
+        loss = loss_base + self.w_aug * loss_aug
+        if self.nerf is not None:
+            loss = loss + self._render_losses(vol, pseudo, sample)
+        loss.backward()
+        world = self.flat.all_reduce()
+        self.flat.adam(self.lr, world=world)
+        return loss.detach(), {"loss_base": loss_base.detach(), "loss_aug": loss_aug.detach(), **{k: v.detach() for k, v in scal.items()}}
+
+    def _render_losses(self, vol, pseudo, sample):
+        from losses import SL1Loss, masked_loss
+        self.nerf.train()
+        rgb, _, _, depth_pred, _, _, rays_depth, target = self.nerf(vol, pseudo, dict(sample["render"]))
+        img_loss = masked_loss(rgb.reshape(1, 1, -1), target.reshape(1, 1, -1), None, mask_kind=0, mode=1)
+        return img_loss + SL1Loss()(depth_pred, rays_depth, rays_depth > 0)
+
+
+def synthetic_sample(dev, views=4, H=512, W=640, seed=0):
+    """A training sample with the reference loader's keys, from rcmvs.synth."""
+    import numpy as np
+    from . import synth
+    imgs, proj, dv = synth.mvs_inputs(views, H, W, kind="textured", seed=seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    center = (0.5 + 0.2 * imgs).clip(0, 1).astype(np.float32)
+    return {"imgs": t(imgs), "center_imgs": t(center), "imgs_aug": t(imgs * 0.9 + 0.05), "depth_values": t(dv),
+            "proj_matrices": {k: t(v) for k, v in proj.items()}}
+
+
+def bench_train_step(dev, steps=5, views=4, H=512, W=640, ndepths=(48, 32, 8)):
+    """ms per optimiser step (2 forwards + losses + backward + gradient all-reduce + fused Adam) of the MVS part of the
+    reference step at the default training shape (4 views 512x640, D=48/32/8, batch 1 per GPU), CUDA-event timed."""
+    import os
+    import numpy as np
+    import models
+    from . import weights
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    model = models.CascadeMVSNet(ndepths=list(ndepths))
+    weights.load_model(model, os.path.join(root, "tests", "golden", "cas_model_000014.npz"))
+    model.to(dev)
+    step = TrainStep(model)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    sample = synthetic_sample(dev, views, H, W, seed=rank)
+    np.random.seed(0)
+    for _ in range(2):
+        loss, _ = step(sample)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist.is_initialized():
+        dist.barrier()
+    e0.record()
+    for _ in range(steps):
+        loss, _ = step(sample)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if dist.is_initialized():
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    return {"workload": "configs[3] (MVS part): CascadeMVSNet.train() 2 forwards (%d views %dx%d, D=%s) + UnsupLossMultiStage + "
+                        "AugLossMultiStage + backward + flat-gradient all-reduce (%.2f MB) + fused Adam, batch 1 per GPU"
+                        % (views, H, W, "/".join(map(str, ndepths)), step.flat.grad.numel() * 4 / 1e6),
+            "ms_per_step": round(ms, 3), "value": round(world * 1e3 / ms, 2), "unit": "ref-views/s (training)",
+            "n_gpus": world, "sync_bn": bool(A.SYNC_BN), "loss": float(loss), "finite": bool(torch.isfinite(loss))}

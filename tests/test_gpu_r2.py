@@ -311,3 +311,264 @@ def test_sweep_v3_bitwise_equals_v1_and_split_output(dev):
             assert vs.shape == (2,) + tuple(v3.shape) and vs.dtype == torch.bfloat16
             assert (vs[0].float() + vs[1].float() - v3).abs().max() <= 2.0 ** -16 * v3.abs().max()
             assert torch.equal(vs[0], v3.bfloat16())
+
+
+# ---- training path: every backward kernel against torch autograd (library ops are the CHECKER here) -------------------------
+def _tconv_ref(x_cl, w, transposed, stride):
+    import torch.nn.functional as F
+    x = x_cl.permute(0, 4, 1, 2, 3)
+    y = F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1) if transposed else F.conv3d(x, w, stride=stride, padding=1)
+    return y.permute(0, 2, 3, 4, 1)
+
+
+@pytest.mark.parametrize("cin,cout,stride,transposed,dhw", [
+    (32, 8, 1, False, (4, 8, 12)), (8, 16, 2, False, (4, 8, 12)), (16, 16, 1, False, (2, 6, 10)), (16, 32, 2, False, (4, 8, 8)),
+    (64, 64, 1, False, (2, 2, 4)), (64, 32, 2, True, (2, 3, 4)), (32, 16, 2, True, (2, 4, 6)), (16, 8, 2, True, (3, 4, 10)),
+    (8, 8, 1, False, (3, 5, 33)),
+])
+def test_conv3d_bn_relu_block_forward_backward_vs_torch(dev, cin, cout, stride, transposed, dhw):
+    """conv -> BatchNorm3d (batch statistics) -> ReLU (+ skip): output, running statistics and all four gradients
+    (input, weight, gamma, beta, skip) against torch autograd in fp32 with TF32 disabled."""
+    import torch.nn as nn
+    from rcmvs import autograd as A
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(cin * 7 + cout + stride)
+    D, H, W = dhw
+    conv = (nn.ConvTranspose3d(cin, cout, 3, stride=2, padding=1, output_padding=1, bias=False) if transposed else
+            nn.Conv3d(cin, cout, 3, stride=stride, padding=1, bias=False)).to(dev)
+    bn = nn.BatchNorm3d(cout, momentum=0.1).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    x = torch.randn(2, D, H, W, cin, device=dev, requires_grad=True)
+    bn.train()
+    ref_bn = nn.BatchNorm3d(cout, momentum=0.1).to(dev)
+    ref_bn.load_state_dict(bn.state_dict())
+    ref_bn.train()
+    z_ref_lin = _tconv_ref(x, conv.weight, transposed, stride)
+    skip = torch.randn_like(z_ref_lin.detach()).requires_grad_(True)
+    z_ref = torch.relu(ref_bn(z_ref_lin.permute(0, 4, 1, 2, 3))).permute(0, 2, 3, 4, 1) + skip
+    g = torch.randn_like(z_ref)
+    gx, gw, gga, gbe, gs = torch.autograd.grad(z_ref, [x, conv.weight, ref_bn.weight, ref_bn.bias, skip], g)
+    x2 = x.detach().clone().requires_grad_(True)
+    skip2 = skip.detach().clone().requires_grad_(True)
+    z = A.conv_block(x2, conv, bn, skip=skip2, relu=True, training=True)
+    hx, hw, hga, hbe, hs = torch.autograd.grad(z, [x2, conv.weight, bn.weight, bn.bias, skip2], g)
+    tol = dict(rtol=2e-4, atol=2e-4)
+    assert torch.allclose(z, z_ref, **tol)
+    assert torch.allclose(bn.running_mean, ref_bn.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-4, atol=1e-5)
+    scale = lambda t: float(t.abs().max()) + 1e-6
+    assert (hx - gx).abs().max() <= 5e-4 * scale(gx)
+    assert (hw - gw).abs().max() <= 5e-4 * scale(gw)
+    assert (hga - gga).abs().max() <= 5e-4 * scale(gga) and (hbe - gbe).abs().max() <= 5e-4 * scale(gbe)
+    assert torch.equal(hs, gs)
+    # frozen statistics (eval-mode BatchNorm under autograd)
+    bn.eval(); ref_bn.eval()
+    ref_bn.load_state_dict(bn.state_dict())
+    z_ref = torch.relu(ref_bn(_tconv_ref(x, conv.weight, transposed, stride).permute(0, 4, 1, 2, 3))).permute(0, 2, 3, 4, 1)
+    gx, gw = torch.autograd.grad(z_ref, [x, conv.weight], g)
+    z = A.conv_block(x2, conv, bn, relu=True, training=False)
+    hx, hw = torch.autograd.grad(z, [x2, conv.weight], g)
+    assert torch.allclose(z, z_ref, **tol) and (hx - gx).abs().max() <= 5e-4 * scale(gx) and (hw - gw).abs().max() <= 5e-4 * scale(gw)
+
+
+def test_prob_conv_forward_backward_vs_torch(dev):
+    import torch.nn as nn
+    from rcmvs import autograd as A
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(3)
+    conv = nn.Conv3d(8, 1, 3, padding=1, bias=False).to(dev)
+    x = torch.randn(1, 8, 16, 24, 8, device=dev, requires_grad=True)
+    ref = _tconv_ref(x, conv.weight, False, 1)
+    g = torch.randn_like(ref)
+    gx, gw = torch.autograd.grad(ref, [x, conv.weight], g)
+    x2 = x.detach().clone().requires_grad_(True)
+    z = A.conv_block(x2, conv, None, relu=False)
+    hx, hw = torch.autograd.grad(z, [x2, conv.weight], g)
+    assert torch.allclose(z, ref, rtol=1e-4, atol=1e-4)
+    assert (hx - gx).abs().max() <= 5e-4 * float(gx.abs().max()) and (hw - gw).abs().max() <= 5e-4 * float(gw.abs().max())
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,bn,hw", [
+    (3, 8, 3, 1, True, (16, 24)), (8, 16, 5, 2, True, (16, 24)), (16, 32, 5, 2, True, (12, 20)), (32, 32, 3, 1, True, (6, 10)),
+    (32, 32, 1, 1, False, (6, 10)), (16, 32, 1, 1, False, (8, 12)), (8, 32, 1, 1, False, (8, 12)), (32, 16, 3, 1, False, (8, 12)),
+    (32, 8, 3, 1, False, (8, 34)),
+])
+def test_conv2d_block_forward_backward_vs_torch(dev, cin, cout, k, stride, bn, hw):
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from rcmvs import autograd as A, ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(cin + cout * 3 + k)
+    H, W = hw
+    conv = nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, bias=not bn).to(dev)
+    norm = nn.BatchNorm2d(cout).to(dev) if bn else None
+    x_nchw = torch.randn(2, cin, H, W, device=dev, requires_grad=cin != 3)
+    y = conv(x_nchw)
+    ref = (torch.relu(norm(y)) if bn else y).permute(0, 2, 3, 1)
+    g = torch.randn_like(ref)
+    wanted = [conv.weight] + ([norm.weight, norm.bias] if bn else [conv.bias]) + ([x_nchw] if cin != 3 else [])
+    grads = torch.autograd.grad(ref, wanted, g)
+    if cin == 3:
+        x_cl = ops.images_to_nhwc8(x_nchw.detach())
+    else:
+        x_cl = x_nchw.detach().permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    if bn:
+        norm2 = nn.BatchNorm2d(cout).to(dev)
+        z = A.conv_block(x_cl, conv, norm2, relu=True, training=True)
+        mine = torch.autograd.grad(z, [conv.weight, norm2.weight, norm2.bias] + ([x_cl] if cin != 3 else []), g)
+    else:
+        z = A.conv_block(x_cl, conv, None, relu=False)
+        mine = torch.autograd.grad(z, [conv.weight, conv.bias] + ([x_cl] if cin != 3 else []), g)
+    assert torch.allclose(z, ref, rtol=2e-4, atol=2e-4)
+    for a, b in zip(mine, grads):
+        if a.dim() == 4 and a.shape[-1] == cin and cin != 3 and a.shape != b.shape:
+            a = a.permute(0, 3, 1, 2)
+        assert (a - b).abs().max() <= 5e-4 * (float(b.abs().max()) + 1e-6), (a.shape, float((a - b).abs().max()), float(b.abs().max()))
+
+
+def test_up2_add_and_layout_adjoints(dev):
+    from rcmvs import autograd as A
+    a = torch.randn(2, 8, 12, 16, device=dev, requires_grad=True)
+    u = torch.randn(2, 4, 6, 16, device=dev, requires_grad=True)
+    out = A.up2_add(a, u)
+    want = a + u.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert torch.equal(out, want)
+    g = torch.randn_like(out)
+    ga, gu = torch.autograd.grad(out, [a, u], g)
+    wa, wu = torch.autograd.grad(want, [a, u], g)
+    assert torch.equal(ga, wa) and torch.allclose(gu, wu, rtol=1e-6, atol=1e-6)
+    x = torch.randn(1, 5 * 0 + 8, 3, 4, 5, device=dev, requires_grad=True)
+    y = A.to_planar(A.to_channels_last(x))
+    (gx,) = torch.autograd.grad(y, [x], torch.ones_like(y))
+    assert torch.equal(y, x) and torch.equal(gx, torch.ones_like(x))
+
+
+def test_costvolume_variance_backward_vs_torch(dev):
+    """Gradient of the fused sweep (+ var_no_ref) w.r.t. all feature maps against autograd through F.grid_sample on the
+    same sample positions."""
+    import torch.nn.functional as F
+    from oracle import ref_np as O
+    from rcmvs import autograd as A, ops, synth
+    rng = np.random.default_rng(5)
+    V, C, h, w, D = 4, 16, 20, 28, 6
+    proj = synth.cameras(V, 4 * h, 4 * w, baseline=90.0)["stage1"]
+    feats = cu(rng.standard_normal((1, V, h, w, C), dtype=np.float32), dev).requires_grad_(True)
+    depth = (np.linspace(400, 1000, D)[:, None, None] + rng.uniform(-5, 5, (D, h, w))).astype(np.float32)
+    rt = ops.relative_projections(cu(proj, dev))
+    var, noref = A.costvolume_variance(feats, rt, cu(depth[None], dev), True)
+    gv, gn = torch.randn_like(var), torch.randn_like(noref)
+    (gf,) = torch.autograd.grad([var, noref], [feats], [gv, gn])
+    # checker: torch grid_sample on coordinates from the numpy oracle
+    projs = O.stage_projection(proj[0])
+    f2 = feats.detach().clone().requires_grad_(True)
+    fn = f2[0].permute(0, 3, 1, 2)                                                # [V,C,h,w]
+    ref = fn[0][:, None].expand(-1, D, -1, -1)
+    s, s2, n, n2 = ref, ref ** 2, 0, 0
+    for v in range(1, V):
+        rot, trans = O.relative_projection(projs[v], projs[0])
+        ix, iy = O.warp_coords(rot, trans, depth, h, w)
+        grid = torch.stack([cu(ix, dev) / ((w - 1) / 2) - 1, cu(iy, dev) / ((h - 1) / 2) - 1], -1).view(1, D * h, w, 2)
+        wv = F.grid_sample(fn[v][None], grid, mode="bilinear", padding_mode="zeros", align_corners=True).view(C, D, h, w)
+        s, s2, n, n2 = s + wv, s2 + wv ** 2, n + wv, n2 + wv ** 2
+    var_r = (s2 / V - (s / V) ** 2).permute(1, 2, 3, 0)[None]
+    nr_r = (n2 / V - (n / V) ** 2).permute(1, 2, 3, 0)[None]
+    assert torch.allclose(var, var_r, atol=3e-3) and torch.allclose(noref, nr_r, atol=3e-3)
+    (gr,) = torch.autograd.grad([var_r, nr_r], [f2], [gv, gn])
+    assert (gf - gr).abs().max() <= 3e-3 * float(gr.abs().max())
+
+
+def test_softargmin_backward_vs_torch(dev):
+    from rcmvs import autograd as A
+    torch.manual_seed(1)
+    cost = torch.randn(2, 8, 6, 10, device=dev, requires_grad=True)
+    for planes in (torch.linspace(400, 900, 8, device=dev)[None].repeat(2, 1).contiguous(),
+                   (torch.linspace(400, 900, 8, device=dev).view(1, 8, 1, 1) + torch.rand(2, 8, 6, 10, device=dev)).contiguous()):
+        depth, conf = A.softargmin(cost, planes)
+        pl = planes if planes.dim() == 4 else planes.view(2, 8, 1, 1)
+        ref = (torch.softmax(cost, 1) * pl).sum(1)
+        g = torch.randn_like(ref)
+        (a,) = torch.autograd.grad(depth, [cost], g)
+        (b,) = torch.autograd.grad(ref, [cost], g)
+        assert torch.allclose(depth, ref, rtol=1e-5) and (a - b).abs().max() <= 1e-4 * float(b.abs().max())
+
+
+def test_fused_adam_matches_torch_adam(dev):
+    from rcmvs import autograd as A
+    torch.manual_seed(0)
+    p = torch.randn(10007, device=dev)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn_like(p)
+        ref.grad = g.clone()
+        opt.step()
+        A.adam_step(p, g, m, v, step, 1e-3, weight_decay=0.01)
+        assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_cascade_training_forward_backward_matches_torch_autograd(dev):
+    """Whole CascadeMVSNet in train() mode: outputs and the gradient of a scalar loss w.r.t. EVERY parameter, own kernels
+    (RCMVS_STRICT=1: no library fallback) against the same modules run on torch library ops (the round-1 path)."""
+    import models
+    from rcmvs import synth, weights
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    imgs, proj, dv = synth.mvs_inputs(3, 64, 64, kind="textured", seed=2)
+    args = (cu(imgs, dev), {k: cu(v, dev) for k, v in proj.items()}, cu(dv, dev))
+
+    def build():
+        m = models.CascadeMVSNet(ndepths=[16, 8, 8])
+        weights.load_model(m, os.path.join(G, "cas_model_000014.npz"))
+        return m.to(dev).train()
+    m1, m2 = build(), build()
+    out1, vol1 = m1(*args)
+    loss1 = sum(out1["stage%d" % s]["depth"].mean() for s in (1, 2, 3)) + 1e-3 * vol1[:, -32:].mean()
+    loss1.backward()
+    # checker: torch library ops, module by module (what the drop-in did in round 1)
+    feats = [m2.feature._forward_torch(args[0][:, v]) for v in range(3)]
+    depth, loss2 = None, 0
+    import torch.nn.functional as F
+    from models.modules import homo_warping
+    for s, key in enumerate(("stage1", "stage2", "stage3")):
+        with torch.no_grad():
+            hyp = out1[key]["hyp"] if "hyp" in out1[key] else None
+        D = [16, 8, 8][s]
+        sc = (4, 2, 1)[s]
+        h, w = 64 // sc, 64 // sc
+        from rcmvs import ops
+        hyp = ops.depth_hypotheses_first(args[2], D).view(1, D, 1, 1).expand(-1, -1, h, w).contiguous() if depth is None else \
+            ops.depth_hypotheses_next_dev(depth.detach().contiguous(), args[2], D, m2.depth_interals_ratio[s], 64, 64, h, w)
+        pm = proj[key]
+        P = cu(pm, dev)
+        def kext(p):
+            q = p[:, 0].clone()
+            q[:, :3, :4] = torch.matmul(p[:, 1, :3, :3], p[:, 0, :3, :4])
+            return q
+        ref_proj = kext(P[:, 0])
+        f0 = feats[0][key].unsqueeze(2)
+        vs, vq, ns, nq = f0.expand(-1, -1, D, -1, -1), (f0 ** 2).expand(-1, -1, D, -1, -1), 0, 0
+        for v in (1, 2):
+            wv = homo_warping(feats[v][key], kext(P[:, v]), ref_proj, hyp)
+            vs, vq, ns, nq = vs + wv, vq + wv ** 2, ns + wv, nq + wv ** 2
+        var = vq / 3 - (vs / 3) ** 2
+        nor = nq / 3 - (ns / 3) ** 2
+        prob = F.softmax(m2.cost_regularization[s]._forward_torch(var).squeeze(1), 1)
+        depth = (prob * hyp).sum(1)
+        loss2 = loss2 + depth.mean()
+        if s == 0:
+            loss2 = loss2 + 1e-3 * nor.mean()
+        assert torch.allclose(out1[key]["depth"], depth, rtol=2e-4, atol=2e-2), key
+    loss2.backward()
+    worst = 0.0
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert n1 == n2
+        if p2.grad is None:
+            assert p1.grad is None or float(p1.grad.abs().max()) == 0.0, n1
+            continue
+        rel = float((p1.grad - p2.grad).abs().max()) / (float(p2.grad.abs().max()) + 1e-12)
+        worst = max(worst, rel)
+        assert rel < 2e-2, (n1, rel)
+    print("worst relative parameter-gradient difference: %.2e" % worst)
