@@ -297,6 +297,30 @@ int rcmvs_sum2x2(const float* in, float* out, int N, int Ho, int Wo, int C, rcmv
 int rcmvs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale, rcmvs_stream_t stream);
 
+/* ---- training path of the rendering-consistency branch (train_rcmvsnet.py:279-325; models/render_models.py:192-220,
+ * models/renderer.py:65-93, models/render_utils.py:304-330) ---------------------------------------------------------------- */
+/* C[M][N] (+)= op(A)[M][K]·op(B)[K][N] (+ bias[N]): trans_a: A stored [K][M] (lda = M-stride); trans_b: B stored [N][K].
+ * splits > 1: split-K with atomic accumulation, C zero-filled by the caller.  The MLP's Linear layers: forward
+ * (X, W^T: trans_b = 1), data gradient (dY, W), weight gradient (dY^T, X: trans_a = 1, split-K). */
+int rcmvs_sgemm(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                int trans_a, int trans_b, int splits, rcmvs_stream_t stream);
+/* mode 0: h = relu(a·b) (multiplicative bias modulation, render_models.py:200); 1: relu(a); 2: sigmoid(a) — and backward
+ * (h = the forward output; db only for mode 0). */
+int rcmvs_act_fwd(const float* a, const float* b, float* h, int64_t n, int mode, rcmvs_stream_t stream);
+int rcmvs_act_bwd(const float* g, const float* a, const float* b, const float* h, float* da, float* db, int64_t n, int mode,
+                  rcmvs_stream_t stream);
+/* x [P][3] -> out[p][0..63) (row pitch ld): [x, sin(2^k x) k = 0..9, cos(2^k x)] (render_models.py:45-49). */
+int rcmvs_embed(const float* x, float* out, int64_t P, int ld, rcmvs_stream_t stream);
+/* grad_feat [P][ld] (first 8 columns = the trilinear volume features) -> grad_vol [D][h][w][8] (zero-filled by the caller). */
+int rcmvs_point_features_bwd(const float* ndc, const float* grad_feat, float* grad_vol, int64_t P, int ld, int D, int h, int w,
+                             rcmvs_stream_t stream);
+/* raw [N][S][4], z [N][S], grad_rgb [N][3], grad_depth [N], grad_weights [N][S] (each may be NULL) -> grad_raw [N][S][4]. */
+int rcmvs_composite_bwd(const float* raw, const float* z, const float* grad_rgb, const float* grad_depth,
+                        const float* grad_weights, float* grad_raw, int N, int S, rcmvs_stream_t stream);
+/* adjoint of rcmvs_resize_depth_cl: grad_y [B][D1][S][Cpad] -> grad_x [B][D0][S][C]. */
+int rcmvs_resize_depth_cl_bwd(const float* grad_y, float* grad_x, int B, int D0, int D1, int64_t S, int C, int Cpad,
+                              rcmvs_stream_t stream);
+
 /* ---- f3 geometric-consistency filter: eval_rcmvsnet_dtu.py:281-336 (reproject_with_depth,
  * check_geometric_consistency) + :366-389 of filter_depth, all NS source views of one reference view per launch ---- */
 /* depth_ref [H][W], conf [H][W] or NULL, depth_src [NS][Hs][Ws]; pair_mats [NS][68] float32 per source:

@@ -57,9 +57,13 @@ class Rendering_Consistency_Net(nn.Module):
         return (data - shift) / scale
 
     def _encode(self, volume_feature_warp, fused):
-        """-> (NCDHW encoded volume or None, channels-last [128,h,w,8] volume or None)."""
+        """-> (NCDHW encoded volume or None, channels-last [128,h,w,8] volume or None).  Both branches run on librcmvs
+        kernels: the fused inference kernels under no_grad with eval-mode BatchNorm, the differentiable ones
+        (rcmvs.autograd) otherwise — the mode the reference actually calls this module in (train_rcmvsnet.py:280-312)."""
         if fused:
             return None, self.MVSNet.forward_cl(volume_feature_warp)[0]
+        if volume_feature_warp.is_cuda:
+            return None, self.MVSNet.forward_cl_train(volume_feature_warp)[0]
         return self.MVSNet(volume_feature_warp, pad=self.args.pad), None
 
     # ---- forward -----------------------------------------------------------------------------------------------------
@@ -70,7 +74,7 @@ class Rendering_Consistency_Net(nn.Module):
         n_views, height, width = data["depths_h"].shape[1:]
         depth_per_view = pseudo_depth.expand(n_views, height, width).unsqueeze(0)      # same pseudo depth for every view
 
-        fused = not torch.is_grad_enabled()
+        fused = not torch.is_grad_enabled() and not self.MVSNet.training
         volume, volume_cl = self._encode(volume_feature_warp, fused)
         images = self.unpreprocess(data["imgs"])
 

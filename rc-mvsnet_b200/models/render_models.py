@@ -101,6 +101,29 @@ class Renderer_ours(nn.Module):
             h = F.relu(lin(h))
         return torch.cat([torch.sigmoid(self.rgb_linear(h)), alpha], -1)
 
+    def forward_train(self, ndc, feat, dirs):
+        """Differentiable forward on own kernels (rcmvs.autograd: SGEMM Linear layers, fused activation kernels, all with
+        hand-written backward): ndc [N,S,3] (no gradient), feat [N,S,20], dirs [N,3] -> raw [N,S,4] = (rgb, sigma).
+        Same math as forward(): multiplicative bias modulation (:200), skip concat after layer 4, relu'd density."""
+        from rcmvs import autograd as A
+        N, S = ndc.shape[:2]
+        M = N * S
+        pts = A.embed(ndc.reshape(M, 3))                                           # [M,63]
+        feats = feat.reshape(M, feat.shape[-1])
+        views = dirs[:, None].expand(N, S, dirs.shape[-1]).reshape(M, -1).contiguous()
+        bias = A.linear(feats, self.pts_bias)
+        h = pts
+        for i, lin in enumerate(self.pts_linears):
+            h = A.mul_relu(A.linear(h, lin), bias)
+            if i in self.skips:
+                h = torch.cat([pts, h], -1)
+        alpha = A.relu(A.linear(h, self.alpha_linear))
+        h2 = torch.cat([A.linear(h, self.feature_linear), views], -1)
+        for lin in self.views_linears:
+            h2 = A.relu(A.linear(h2, lin))
+        rgb = A.sigmoid(A.linear(h2, self.rgb_linear))
+        return torch.cat([rgb, alpha], -1).view(N, S, 4)
+
     # ---- CUDA path ------------------------------------------------------------------------------------------------
     def cuda_supported(self):
         return (self.use_viewdirs and self.D == 6 and self.W == 128 and self.in_ch_pts == 63 and self.in_ch_feat == 20
@@ -208,6 +231,20 @@ class CostReg(nn.Module):
             return P
         return self._packed.get((_versions(self), cin_pad), build)
 
+    def forward_cl_train(self, x_cl, training):
+        """Differentiable forward on own kernels: conv -> BatchNorm (batch statistics when `training`), NO ReLU
+        (reference :685-686), skip adds (:727-733)."""
+        from rcmvs import autograd as A
+        blk = lambda t, m: A.conv_block(t, m.conv, m.bn, relu=False, training=training)
+        up = lambda t, seq, skip: A.conv_block(t, seq[0], seq[1], skip=skip, relu=False, training=training)
+        c0 = blk(x_cl, self.conv0)
+        c2 = blk(blk(c0, self.conv1), self.conv2)
+        c4 = blk(blk(c2, self.conv3), self.conv4)
+        y = blk(blk(c4, self.conv5), self.conv6)
+        y = up(y, self.conv7, c4)
+        y = up(y, self.conv9, c2)
+        return up(y, self.conv11, c0)
+
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cpad] -> [B,D,h,w,8]; eval-mode BN folded, no ReLU anywhere."""
         P = self.packed(x_cl.shape[-1])
@@ -229,13 +266,30 @@ class Neural_Volume_Net(nn.Module):
     def forward(self, volume_feature, pad=0):
         """volume_feature [B,41,D0,h,w] -> [1,B*8,128,h,w] (reference :753-760)."""
         B, C, _, H, W = volume_feature.shape
-        if self.training or (torch.is_grad_enabled() and volume_feature.requires_grad):
-            library_fallback("Neural_Volume_Net.forward (training / autograd)", "cuDNN conv3d + batch_norm")
-            v = F.interpolate(volume_feature, size=[128, H, W], mode="trilinear", align_corners=True)
-            v = self.cost_reg_2(v)
-            return v.reshape(1, -1, *v.shape[2:])
+        if self.needs_autograd(volume_feature):
+            if not volume_feature.is_cuda:
+                library_fallback("Neural_Volume_Net.forward (CPU tensor)", "torch conv3d + batch_norm")
+                v = F.interpolate(volume_feature, size=[128, H, W], mode="trilinear", align_corners=True)
+                v = self.cost_reg_2(v)
+                return v.reshape(1, -1, *v.shape[2:])
+            from rcmvs import autograd as A
+            return A.to_planar(self.forward_cl_train(volume_feature)).reshape(1, -1, 128, H, W)
         with torch.no_grad():
             return ops.to_planar(self.forward_cl(volume_feature)).reshape(1, -1, 128, H, W)
+
+    def needs_autograd(self, x=None):
+        if self.training:
+            return True
+        return torch.is_grad_enabled() and ((x is not None and x.requires_grad) or
+                                            any(p.requires_grad for p in self.parameters()))
+
+    def forward_cl_train(self, volume_feature):
+        """Differentiable: NCDHW in -> channels-last encoded volume [B,128,h,w,8] (layout change, depth resize and the 3-D
+        U-Net all with hand-written backward)."""
+        from rcmvs import autograd as A
+        x = A.to_channels_last(volume_feature)
+        x = A.resize_depth_cl(x, 128, (x.shape[-1] + 7) // 8 * 8)
+        return self.cost_reg_2.forward_cl_train(x, self.training)
 
     def forward_cl(self, volume_feature):
         """NCDHW in -> channels-last encoded volume [B,128,h,w,8] (what the point-feature kernel consumes)."""

@@ -41,7 +41,11 @@ def run_network_mvs(pts, viewdirs, alpha_feat, fn, embed_fn, embeddirs_fn, netch
             and pts.is_cuda and hasattr(fn, "nerf") and fn.nerf.cuda_supported() and pts.dim() == 3):
         dirs = viewdirs if viewdirs.dim() == 2 else viewdirs[:, 0]
         return fn.nerf.forward_cuda(pts.float(), alpha_feat.float(), dirs.float())
-    library_fallback("run_network_mvs (training / autograd)", "cuBLAS linear layers")
+    if (viewdirs is not None and embeddirs_fn is None and alpha_feat is not None and pts.is_cuda and hasattr(fn, "nerf")
+            and fn.nerf.cuda_supported() and pts.dim() == 3):
+        dirs = viewdirs if viewdirs.dim() == 2 else viewdirs[:, 0]
+        return fn.nerf.forward_train(pts.float(), alpha_feat.float(), dirs.float())      # differentiable, own kernels
+    library_fallback("run_network_mvs (non-default network configuration)", "cuBLAS linear layers")
     if embed_fn is not None:
         pts = embed_fn(pts)
     if alpha_feat is not None:
@@ -59,8 +63,11 @@ def run_network_mvs(pts, viewdirs, alpha_feat, fn, embed_fn, embeddirs_fn, netch
 def raw2outputs(raw, z_vals, dists, white_bkgd=False, net_type="v2"):
     if not torch.is_grad_enabled() and raw.is_cuda and raw.shape[-1] == 4 and z_vals.shape[1] % 32 == 0:
         rgb_map, depth_map, weights, alpha = ops.composite(raw.float().contiguous(), z_vals.float().contiguous())
+    elif raw.is_cuda and raw.shape[-1] == 4 and z_vals.shape[1] % 32 == 0:
+        from rcmvs import autograd as A
+        rgb_map, depth_map, weights, alpha = A.composite(raw, z_vals)                   # differentiable, own kernels
     else:
-        library_fallback("raw2outputs (training / autograd)", "ATen cumprod / reductions")
+        library_fallback("raw2outputs (CPU tensor / unusual shape)", "ATen cumprod / reductions")
         alpha, weights, _ = raw2alpha(raw[..., 3], dists, net_type)
         rgb_map = torch.sum(weights[..., None] * raw[..., :3], -2)
         depth_map = torch.sum(weights * z_vals, -1)
@@ -83,7 +90,11 @@ def gen_pts_feats(imgs, volume_feature, rays_pts, pose_ref, rays_ndc, feat_dim, 
         return ops.point_features(volume_cl, rays_ndc.contiguous(), rays_pts.contiguous(), imgs[0].contiguous(),
                                   pose_ref["w2cs"][:3].float().contiguous(),
                                   pose_ref["intrinsics"][:3].float().contiguous())
-    library_fallback("gen_pts_feats (training / autograd)", "ATen grid_sample")
+    if volume_cl is not None:
+        from rcmvs import autograd as A
+        return A.point_features(volume_cl, rays_ndc.contiguous(), rays_pts.contiguous(), imgs[0].contiguous(),
+                                pose_ref["w2cs"][:3].float().contiguous(), pose_ref["intrinsics"][:3].float().contiguous())
+    library_fallback("gen_pts_feats (planar volume input)", "ATen grid_sample")
     ray_feats = index_point_feature(volume_feature, rays_ndc)
     return torch.cat([ray_feats, build_color_volume(rays_pts, pose_ref, imgs, img_feat, with_mask=True,
                                                     downscale=img_downscale)], -1)

@@ -138,6 +138,11 @@ def conv3d_dgrad(dy, w, transposed, stride):
         return dx
     packed = torch.empty((27, Cout, Cin), device=w.device, dtype=torch.float32)
     _ffi.call("rcmvs_pack_conv3d_dgrad_s1", _chk(w, "w"), _chk(packed, "packed"), Cout, Cin, _stream())
+    if Cin not in (1, 8, 16, 32, 64):                # e.g. 48: run with the output channels padded to 64, keep the first Cin
+        cpad = 64 if Cin < 64 else (Cin + 63) // 64 * 64
+        wide = torch.zeros((27, Cout, cpad), device=w.device, dtype=torch.float32)
+        wide[:, :, :Cin] = packed
+        return ops.conv3d(dy, wide, None, None, stride=1, relu=False)[..., :Cin].contiguous()
     return ops.conv3d(dy, packed, None, None, stride=1, relu=False)
 
 
@@ -228,7 +233,11 @@ def conv_block(x_cl, conv, bn=None, skip=None, relu=True, training=True):
         gamma, beta = bn.weight, bn.bias
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
-    return _ConvBNAct.apply(x_cl, conv.weight, conv.bias, gamma, beta, skip, cfg)
+    weight = conv.weight
+    if dim3d and not transposed and x_cl.shape[-1] > weight.shape[1]:
+        # zero-padded input channels (Neural_Volume_Net: 41 -> 48): pad the weight alike; autograd slices dW back
+        weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, 0, 0, x_cl.shape[-1] - weight.shape[1]))
+    return _ConvBNAct.apply(x_cl, weight, conv.bias, gamma, beta, skip, cfg)
 
 
 # ---- cost volume / regression ------------------------------------------------------------------------------------------
@@ -348,3 +357,162 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), 
     _ffi.call("rcmvs_adam_step", _chk(params, "params"), _chk(grads, "grads"), _chk(exp_avg, "exp_avg"),
               _chk(exp_avg_sq, "exp_avg_sq"), params.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
               float(weight_decay), int(step), float(grad_scale), _stream())
+
+
+# ---- rendering-consistency branch (training) ------------------------------------------------------------------------------
+@_on_device
+def sgemm(A, B, bias, M, N, K, trans_a, trans_b, splits=1, out=None):
+    C = out if out is not None else (torch.zeros if splits > 1 else torch.empty)((M, N), device=A.device, dtype=torch.float32)
+    _ffi.call("rcmvs_sgemm", _chk(A, "A"), _chk(B, "B"), _opt(bias, "bias"), _chk(C, "C"), M, N, K, A.stride(0), B.stride(0),
+              C.stride(0), 1 if trans_a else 0, 1 if trans_b else 0, splits, _stream())
+    return C
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b  (nn.Linear), x [M,K] row-major."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xc, w = _f32c(x), _f32c(weight)
+        ctx.save_for_backward(xc, w)
+        ctx.has_bias = bias is not None
+        M, K = xc.shape
+        return sgemm(xc, w, _f32c(bias) if bias is not None else None, M, w.shape[0], K, False, True)
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, w = ctx.saved_tensors
+        g = g.contiguous()
+        M, K = xc.shape
+        N = w.shape[0]
+        dx = sgemm(g, w, None, M, K, N, False, False) if ctx.needs_input_grad[0] else None
+        dw = sgemm(g, xc, None, N, K, M, True, False, splits=max(1, min(512, M // 512)))
+        db = channel_sums(g) if ctx.has_bias and N % 4 == 0 else (g.sum(0) if ctx.has_bias else None)
+        return dx, dw, db
+
+
+def linear(x, lin):
+    return _Linear.apply(x, lin.weight, lin.bias)
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, a, b, mode):
+        a = _f32c(a)
+        b = _f32c(b) if b is not None else None
+        h = torch.empty_like(a)
+        _ffi.call("rcmvs_act_fwd", _chk(a, "a"), _opt(b, "b"), _chk(h, "h"), a.numel(), mode, _stream())
+        ctx.mode = mode
+        ctx.save_for_backward(a, b, h) if mode == 0 else ctx.save_for_backward(h)
+        return h
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        g = g.contiguous()
+        if ctx.mode == 0:
+            a, b, h = ctx.saved_tensors
+            da, db = torch.empty_like(a), torch.empty_like(a)
+            _ffi.call("rcmvs_act_bwd", _chk(g, "g"), _chk(a, "a"), _chk(b, "b"), _chk(h, "h"), _chk(da, "da"), _chk(db, "db"),
+                      a.numel(), 0, _stream())
+            return da, db, None
+        (h,) = ctx.saved_tensors
+        da = torch.empty_like(h)
+        _ffi.call("rcmvs_act_bwd", _chk(g, "g"), None, None, _chk(h, "h"), _chk(da, "da"), None, h.numel(), ctx.mode, _stream())
+        return da, None, None
+
+
+def mul_relu(a, b):
+    return _Act.apply(a, b, 0)
+
+
+def relu(a):
+    return _Act.apply(a, None, 1)
+
+
+def sigmoid(a):
+    return _Act.apply(a, None, 2)
+
+
+@_on_device
+def embed(x, ld=63):
+    """x [P,3] (no gradient) -> [P,ld] with the 63-d positional embedding in the first columns."""
+    x = _f32c(x)
+    out = torch.empty((x.shape[0], ld), device=x.device, dtype=torch.float32)
+    _ffi.call("rcmvs_embed", _chk(x, "x"), _chk(out, "out"), x.shape[0], ld, _stream())
+    return out
+
+
+class _PointFeatures(torch.autograd.Function):
+    """[N,S,20] per-point features (csrc/render.cu point_features) with the gradient w.r.t. the encoded volume."""
+
+    @staticmethod
+    def forward(ctx, vol_cl, ndc, pts, imgs3, w2cs3, Ks3):
+        v = _f32c(vol_cl)
+        ndc = _f32c(ndc)
+        ctx.save_for_backward(ndc)
+        ctx.vshape = v.shape
+        return ops.point_features(v, ndc, _f32c(pts), _f32c(imgs3), _f32c(w2cs3), _f32c(Ks3))
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        (ndc,) = ctx.saved_tensors
+        g = g.contiguous()
+        D, h, w, _ = ctx.vshape
+        gv = torch.zeros(ctx.vshape, device=g.device, dtype=torch.float32)
+        P = ndc.shape[0] * ndc.shape[1]
+        _ffi.call("rcmvs_point_features_bwd", _chk(ndc, "ndc"), _chk(g, "grad_feat"), _chk(gv, "grad_vol"), P, g.shape[-1], D, h, w,
+                  _stream())
+        return gv, None, None, None, None, None
+
+
+def point_features(vol_cl, ndc, pts, imgs3, w2cs3, Ks3):
+    return _PointFeatures.apply(vol_cl, ndc, pts, imgs3, w2cs3, Ks3)
+
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z):
+        r, zz = _f32c(raw), _f32c(z)
+        rgb, depth, weights, alpha = ops.composite(r, zz)
+        ctx.save_for_backward(r, zz)
+        ctx.mark_non_differentiable(alpha)
+        return rgb, depth, weights, alpha
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g_rgb, g_depth, g_w, _g_alpha):
+        r, zz = ctx.saved_tensors
+        N, S = zz.shape
+        gr = torch.empty_like(r)
+        c = lambda t: None if t is None else _chk(t.contiguous(), "grad")
+        _ffi.call("rcmvs_composite_bwd", _chk(r, "raw"), _chk(zz, "z"), c(g_rgb), c(g_depth), c(g_w), _chk(gr, "grad_raw"), N, S,
+                  _stream())
+        return gr, None
+
+
+def composite(raw, z):
+    return _Composite.apply(raw, z)
+
+
+class _ResizeDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, D1, Cpad):
+        x = _f32c(x_cl)
+        ctx.shape, ctx.D1, ctx.Cpad = x.shape, D1, Cpad
+        return ops.resize_depth_cl(x, D1, Cpad)
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        B, D0, h, w, C = ctx.shape
+        g = g.contiguous()
+        gx = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        _ffi.call("rcmvs_resize_depth_cl_bwd", _chk(g, "grad_y"), _chk(gx, "grad_x"), B, D0, ctx.D1, h * w, C, ctx.Cpad, _stream())
+        return gx, None, None
+
+
+def resize_depth_cl(x_cl, D1, Cpad):
+    return _ResizeDepth.apply(x_cl, D1, Cpad)

@@ -572,3 +572,128 @@ def test_cascade_training_forward_backward_matches_torch_autograd(dev):
         worst = max(worst, rel)
         assert rel < 2e-2, (n1, rel)
     print("worst relative parameter-gradient difference: %.2e" % worst)
+
+
+# ---- rendering-consistency branch, training path (the mode the reference calls it in) ------------------------------------
+def test_sgemm_linear_forward_backward_vs_torch(dev):
+    import torch.nn as nn
+    from rcmvs import autograd as A
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    for (M, K, N) in ((1000, 63, 128), (777, 191, 128), (513, 128, 1), (640, 64, 3), (2048, 131, 64), (300, 20, 128)):
+        lin = nn.Linear(K, N).to(dev)
+        x = torch.randn(M, K, device=dev, requires_grad=True)
+        y_ref = lin(x)
+        g = torch.randn_like(y_ref)
+        gx, gw, gb = torch.autograd.grad(y_ref, [x, lin.weight, lin.bias], g)
+        x2 = x.detach().clone().requires_grad_(True)
+        y = A.linear(x2, lin)
+        hx, hw, hb = torch.autograd.grad(y, [x2, lin.weight, lin.bias], g)
+        assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-4)
+        for a, b in ((hx, gx), (hw, gw), (hb, gb)):
+            assert (a - b).abs().max() <= 2e-4 * (float(b.abs().max()) + 1e-6), (M, K, N)
+
+
+def test_render_mlp_training_path_vs_torch_module(dev):
+    """Renderer_ours.forward_train (own SGEMM / activation kernels + backward) against the module's torch forward."""
+    import models
+    from rcmvs import synth, weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = models.Rendering_Consistency_Net(synth.RenderArgs())
+    net.load_state_dict(weights.load_npz_state_dict(os.path.join(G, "nerf_model_000014.npz")), strict=True)
+    nerf = net.network_fn.nerf.to(dev)
+    with torch.no_grad():                      # tame the shipped weights (they saturate sigma on synthetic input)
+        for p in nerf.parameters():
+            p.mul_(0.5)
+    torch.manual_seed(1)
+    N, S = 24, 32
+    ndc = torch.rand(N, S, 3, device=dev)
+    feat = torch.randn(N, S, 20, device=dev, requires_grad=True)
+    dirs = torch.randn(N, 3, device=dev)
+    from models.render_models import get_embedder
+    emb, _ = get_embedder(10, 0, 3)
+    x = torch.cat([emb(ndc), feat, dirs[:, None].expand(N, S, 3)], -1).reshape(N * S, -1)
+    ref = nerf(x).view(N, S, 4)
+    g = torch.randn_like(ref)
+    params = list(nerf.parameters())
+    gref = torch.autograd.grad(ref, [feat] + params, g)
+    feat2 = feat.detach().clone().requires_grad_(True)
+    out = nerf.forward_train(ndc, feat2, dirs)
+    gmine = torch.autograd.grad(out, [feat2] + params, g)
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-4)
+    for a, b in zip(gmine, gref):
+        assert (a - b).abs().max() <= 2e-3 * (float(b.abs().max()) + 1e-9)
+
+
+def test_composite_point_features_resize_backward_vs_torch(dev):
+    import torch.nn.functional as F
+    from models.renderer import raw2alpha
+    from rcmvs import autograd as A
+    torch.manual_seed(2)
+    N, S = 40, 128
+    raw = torch.cat([torch.rand(N, S, 3, device=dev), torch.rand(N, S, 1, device=dev) * 0.3], -1).requires_grad_(True)
+    z = torch.sort(torch.rand(N, S, device=dev) * 500 + 400, -1)[0]
+    alpha, weights, _ = raw2alpha(raw[..., 3], None, "v0")
+    rgb_r, dep_r = (weights[..., None] * raw[..., :3]).sum(-2), (weights * z).sum(-1)
+    g1, g2, g3 = torch.randn_like(rgb_r), torch.randn_like(dep_r), torch.randn_like(weights)
+    (gr,) = torch.autograd.grad([rgb_r, dep_r, weights], [raw], [g1, g2, g3])
+    raw2 = raw.detach().clone().requires_grad_(True)
+    rgb, dep, w, a = A.composite(raw2, z)
+    (gm,) = torch.autograd.grad([rgb, dep, w], [raw2], [g1, g2, g3])
+    assert torch.allclose(rgb, rgb_r, atol=1e-5) and torch.allclose(dep, dep_r, rtol=1e-5)
+    assert (gm - gr).abs().max() <= 1e-3 * float(gr.abs().max())
+    # trilinear volume lookup
+    D, h, w_ = 12, 10, 14
+    vol = torch.randn(D, h, w_, 8, device=dev, requires_grad=True)
+    ndc = torch.rand(30, 16, 3, device=dev) * 1.1 - 0.05
+    grid = (ndc.view(1, 1, 30, 16, 3) * 2 - 1)
+    ref = F.grid_sample(vol.permute(3, 0, 1, 2)[None], grid, align_corners=True, mode="bilinear")[0, :, 0].permute(1, 2, 0)
+    gq = torch.randn_like(ref)
+    (gv_r,) = torch.autograd.grad(ref, [vol], gq)
+    vol2 = vol.detach().clone().requires_grad_(True)
+    imgs3 = torch.rand(3, 3, 32, 40, device=dev)
+    w2cs = torch.eye(4, device=dev)[None].repeat(3, 1, 1).contiguous()
+    Ks = torch.tensor([[30., 0, 20], [0, 30, 16], [0, 0, 1]], device=dev)[None].repeat(3, 1, 1).contiguous()
+    pts = torch.rand(30, 16, 3, device=dev) + torch.tensor([0., 0, 2], device=dev)
+    feat = A.point_features(vol2, ndc, pts, imgs3, w2cs, Ks)
+    assert torch.allclose(feat[..., :8], ref, atol=1e-5)
+    gfull = torch.zeros_like(feat)
+    gfull[..., :8] = gq
+    (gv_m,) = torch.autograd.grad(feat, [vol2], gfull)
+    assert (gv_m - gv_r).abs().max() <= 1e-4 * float(gv_r.abs().max())
+    # depth resize
+    x = torch.randn(1, 6, 5, 7, 41, device=dev, requires_grad=True)
+    yr = F.interpolate(x.permute(0, 4, 1, 2, 3), size=[16, 5, 7], mode="trilinear", align_corners=True).permute(0, 2, 3, 4, 1)
+    gy = torch.randn(1, 16, 5, 7, 48, device=dev)
+    (gx_r,) = torch.autograd.grad(yr, [x], gy[..., :41])
+    x2 = x.detach().clone().requires_grad_(True)
+    y = A.resize_depth_cl(x2, 16, 48)
+    (gx_m,) = torch.autograd.grad(y, [x2], gy)
+    assert torch.allclose(y[..., :41], yr, atol=1e-5) and (y[..., 41:] == 0).all()
+    assert (gx_m - gx_r).abs().max() <= 1e-5 * float(gx_r.abs().max()) + 1e-6
+
+
+def test_rendering_consistency_net_training_step_on_own_kernels(dev):
+    """model_nerf.train() + autograd, as train_rcmvsnet.py:279-312 calls it, with RCMVS_STRICT=1 (no library fallback):
+    finite losses, gradients reach the MLP, the volume network AND (through volume_feature_no_ref) the MVS FeatureNet."""
+    import models
+    from losses import SL1Loss, masked_loss
+    from rcmvs import synth, weights
+    H = W = 64
+    imgs, proj, dv = synth.mvs_inputs(4, H, W, kind="textured", seed=5)
+    batch = {k: cu(v, dev) for k, v in synth.render_batch(H, W, seed=0).items()}
+    cas = models.CascadeMVSNet(ndepths=[16, 8, 8])
+    weights.load_model(cas, os.path.join(G, "cas_model_000014.npz"))
+    cas.to(dev).train()
+    nerf = models.Rendering_Consistency_Net(synth.RenderArgs())
+    nerf.load_state_dict(weights.load_npz_state_dict(os.path.join(G, "nerf_model_000014.npz")), strict=True)
+    nerf.to(dev).train()
+    out, vol = cas(cu(imgs, dev), {k: cu(v, dev) for k, v in proj.items()}, cu(dv, dev))
+    rgb, feat, wts, depth_pred, alpha, ret, rays_depth, target = nerf(vol, out["depth"].detach(), batch)
+    loss = masked_loss(rgb.reshape(1, 1, -1), target.reshape(1, 1, -1), None, mask_kind=0, mode=1) + \
+        SL1Loss()(depth_pred, rays_depth, rays_depth > 0)
+    loss.backward()
+    assert torch.isfinite(loss)
+    gn = lambda m: sum(float(p.grad.abs().sum()) for p in m.parameters() if p.grad is not None)
+    assert gn(nerf.network_fn) > 0 and gn(nerf.MVSNet) > 0 and gn(cas.feature) > 0
+    assert all(torch.isfinite(p.grad).all() for p in list(nerf.parameters()) + list(cas.feature.parameters()) if p.grad is not None)
