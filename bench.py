@@ -25,7 +25,8 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally:
                      torch defaults): the kernel-for-kernel bar BASELINE.md §5.4 names
   e2e                same metric through the public API with pinned HOST buffers (rcmvs.pipeline.HostPipeline: every
                      step copies its inputs host->device and its depth/confidence device->host inside the timed region)
-  e2e_two_in_flight  the same loop with two reference views in flight (alternating compute streams)
+  single_stream      the same loops with one reference view at a time (per-view latency); the headline loops keep two
+                     reference views in flight per GPU on alternating CUDA streams (--in-flight)
   render_branch / train_step / tanks / batched   configs[2] / configs[3] / configs[4] timings, for reference
 """
 import argparse
@@ -355,8 +356,9 @@ def main():
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the configs[2]/[3]/[4] side timings")
     ap.add_argument("--no-stock-torch", action="store_true")
-    ap.add_argument("--e2e-streams", type=int, default=1,
-                    help="reference views in flight on the device in the e2e loop (rcmvs.pipeline.HostPipeline)")
+    ap.add_argument("--in-flight", type=int, default=2, dest="in_flight",
+                    help="reference views in flight per GPU (alternating CUDA streams) in the headline loops; the "
+                         "one-view-at-a-time numbers are reported under `single_stream`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -403,13 +405,26 @@ def main():
     d2h = 2 * B * H * W * 4
     counter = [0]
 
+    # Headline loops keep `in_flight` reference views in flight per GPU on alternating CUDA streams (a serving process
+    # does the same: the 1/4- and 1/8-resolution layers of one view leave SMs idle that the next view's kernels fill).
+    nfl = max(1, args.in_flight)
+    lanes = [torch.cuda.Stream(dev) for _ in range(nfl)] if nfl > 1 else None
+
     def step_resident():
+        counter[0] += 1
+        with torch.no_grad():
+            if lanes is None:
+                return model(*sets_d[counter[0] % NSETS])
+            with torch.cuda.stream(lanes[counter[0] % nfl]):
+                return model(*sets_d[counter[0] % NSETS])
+
+    def step_single():
         counter[0] += 1
         with torch.no_grad():
             return model(*sets_d[counter[0] % NSETS])
 
     from rcmvs.pipeline import HostPipeline
-    pipe = HostPipeline(model, dev, compute_streams=args.e2e_streams)
+    pipe = HostPipeline(model, dev, compute_streams=nfl)
 
     def step_e2e():
         # host buffers in, host buffers out, every step: the H2D copy of this step's inputs and the D2H copy of its
@@ -430,10 +445,16 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _ffi.launches
         e0.record(stream)
+        if fn is step_resident and lanes is not None:
+            for ln in lanes:
+                ln.wait_event(e0)             # the lanes start after e0 ...
         for _ in range(steps):
             fn()
         if fn is step_e2e:
             pipe.join()                       # the last step's device->host copies end before e1
+        if fn is step_resident and lanes is not None:
+            for ln in lanes:
+                stream.wait_stream(ln)        # ... and e1 is recorded after every lane has drained
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -465,16 +486,18 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, launches, reps_resident = timed(step_resident, args.steps, args.reps)
     ms_e2e, _, reps_e2e = timed(step_e2e, args.steps, args.reps)
-    # same loop with two reference views in flight on the device (alternating compute streams): reported beside e2e
-    e2e_two = None
-    if args.e2e_streams == 1:
-        pipe1, pipe = pipe, HostPipeline(model, dev, compute_streams=2)
+    # the same loops with ONE reference view at a time (single stream): the per-view latency
+    single = None
+    if nfl > 1:
+        ms1, _, _ = timed(step_single, args.steps, max(3, args.reps // 3))
+        pipe_n, pipe = pipe, HostPipeline(model, dev, compute_streams=1)
         for _ in range(args.warmup):
             step_e2e()
-        ms2, _, reps2 = timed(step_e2e, args.steps, max(3, args.reps // 3))
-        e2e_two = {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "ref-views/s", "ms_per_step": ms2 / args.steps,
-                   "views_in_flight": 2, "ms_per_rep": reps2}
-        pipe = pipe1
+        ms1e, _, _ = timed(step_e2e, args.steps, max(3, args.reps // 3))
+        pipe = pipe_n
+        single = {"value": world * B * args.steps / (ms1 * 1e-3), "ms_per_step": ms1 / args.steps,
+                  "e2e_value": world * B * args.steps / (ms1e * 1e-3), "e2e_ms_per_step": ms1e / args.steps,
+                  "unit": "ref-views/s", "views_in_flight": 1}
     clocks = sampler.stop() if sampler else None
 
     value = world * B * args.steps / (ms_total * 1e-3)
@@ -552,15 +575,16 @@ def main():
         "config": {"workload": "CascadeMVSNet_eval forward: %d views, %dx%d, D=%s (BASELINE configs[1]); "
                                "reference pretrained weights (numpy fixture), synthetic DTU-shaped cameras"
                                % (V, H, W, "/".join(map(str, NDEPTHS))),
-                   "batch_per_gpu": B, "parallelism": "view-sharded replicas x%d" % world,
+                   "batch_per_gpu": B, "views_in_flight_per_gpu": nfl,
+                   "parallelism": "view-sharded replicas x%d" % world,
                    "cache": "per-step working set %.0f MB of volumes >> 126 MB L2 (no explicit flush needed); %d input "
                             "sets alternate" % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6, NSETS),
                    "conv_precision": os.environ.get("RCMVS_CONV", "bf16x3")},
         "timing": {"stat": "median of %d repetitions of the %d-step loop after >= 1 s spin-up" % (args.reps, args.steps),
                    "ms_per_rep_resident": reps_resident, "ms_per_rep_e2e": reps_e2e},
         "e2e": {"value": e2e_value, "unit": "ref-views/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "views_in_flight": args.e2e_streams},
-        "e2e_two_in_flight": e2e_two,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "views_in_flight": nfl},
+        "single_stream": single,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -135,7 +135,7 @@ int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, const float
  * arrives PRE-SPLIT as two bf16 planes x_split [2][B][D][H][W][Cin] (hi plane, lo plane; 16-byte aligned), written by the
  * producing kernel (rcmvs_costvolume_var_fwd_split, y_split of this function, rcmvs_conv3d_fwd_split) or, at an API
  * boundary, by rcmvs_split_bf16.  Output: fp32 y and/or split-bf16 y_split (either may be NULL).
- * (Cin, Cout) in {(32,8), (16,8), (16,16)}.  Weight image: rcmvs_conv3d_slab_weight_elems() bf16 elements. */
+ * (Cin, Cout) in {(32,8), (16,8), (16,16), (48,8)}.  Weight image: rcmvs_conv3d_slab_weight_elems() bf16 elements. */
 int64_t rcmvs_conv3d_slab_weight_elems(int Cin, int Cout);
 int rcmvs_conv3d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
 int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip, float* y,
@@ -180,6 +180,10 @@ int rcmvs_conv2d_fwd(const float* x, const float* packed_w, const float* bias, c
  * C..Cpad-1 zero-filled (the 41-channel volume is padded to 48 for the convolution kernels). */
 int rcmvs_resize_depth_cl(const float* x, float* y, int B, int D0, int D1, int64_t S, int C, int Cpad,
                           rcmvs_stream_t stream);
+
+/* Same, written as split-bf16 planes y_split [2][B][D1][S][Cpad] for rcmvs_conv3d_slab_fwd (Cin = 48, Cout = 8). */
+int rcmvs_resize_depth_cl_split(const float* x, void* y_split, int B, int D0, int D1, int64_t S, int C, int Cpad,
+                                rcmvs_stream_t stream);
 
 /* ---- a8 Gaussian-Uniform sampler + rays: models/render_utils.py:86-146, 149-243 ------------------------------------ */
 /* ray_depth [N] -> out [N][S] (S = 128): rays [0,n_gauss) ~ N(d, (min(|far-d|,|d-near|)/3)^2) sorted ascending,

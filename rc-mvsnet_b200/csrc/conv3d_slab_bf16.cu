@@ -435,14 +435,14 @@ static int launch(const void* x, const Params& p, cudaStream_t st) {
 }
 
 static bool supported(int Cin, int Cout) {
-  return (Cout == 8 && (Cin == 16 || Cin == 32)) || (Cout == 16 && Cin == 16);
+  return (Cout == 8 && (Cin == 16 || Cin == 32 || Cin == 48)) || (Cout == 16 && Cin == 16);
 }
 
 // depth chunks + M-tiles per CTA: one CTA per SM (shared memory), so minimise
 //   waves(tiles x chunks / 148) x slabs per CTA (planes + 2 halo slabs) x KM
-static void plan(int B, int D, int H, int W, int Cout, int& km, int& chunks) {
+static void plan(int B, int D, int H, int W, int Cin, int Cout, int& km, int& chunks) {
   long best = -1;
-  const int km_lo = 2, km_hi = Cout == 16 ? 2 : 3;
+  const int km_lo = 2, km_hi = (Cout == 16 || Cin == 48) ? 2 : 3;        // shared-memory budget
   for (int k = km_lo; k <= km_hi; ++k) {
     const int tiles = ceil_div(W, TW) * ceil_div(H, 4 * k - 2) * B;
     for (int c = 1; c <= max(1, D / 4); ++c) {
@@ -503,12 +503,13 @@ extern "C" int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, cons
   p.bias = bias; p.skip = skip; p.y = y; p.ys = reinterpret_cast<__nv_bfloat16*>(y_split);
   p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu;
   int km = 2, chunks = 1;
-  plan(B, D, H, W, Cout, km, chunks);
+  plan(B, D, H, W, Cin, Cout, km, chunks);
   p.d_chunk = ceil_div(D, chunks);
   p.chunks = ceil_div(D, p.d_chunk);
   cudaStream_t st = as_stream(stream);
   if (Cin == 32 && Cout == 8) return km == 3 ? launch<32, 8, 3, 3>(x_split, p, st) : launch<32, 8, 2, 4>(x_split, p, st);
   if (Cin == 16 && Cout == 8) return km == 3 ? launch<16, 8, 3, 5>(x_split, p, st) : launch<16, 8, 2, 6>(x_split, p, st);
   if (Cin == 16 && Cout == 16) return launch<16, 16, 2, 5>(x_split, p, st);
+  if (Cin == 48 && Cout == 8) return launch<48, 8, 2, 3>(x_split, p, st);      // Neural_Volume_Net conv0 (41 -> 48 padded)
   return RCMVS_ERR_UNSUPPORTED;
 }

@@ -9,6 +9,7 @@
 //   render_mlp           positional embedding + Renderer_ours MLP fused per 128-point tile, activations in shared
 //                        memory, fp32 FFMA (render_models.py:45-49, 192-220)
 //   composite            alpha compositing per ray with a warp scan (renderer.py:18-26, 65-93)
+#include <cuda_bf16.h>
 #include <curand_kernel.h>
 
 #include "common.cuh"
@@ -37,6 +38,32 @@ __global__ void resize_depth_cl_kernel(const float* __restrict__ x, float* __res
     v = l0 * __ldg(xb + ((int64_t)i0 * S + s) * C + c) + l1 * __ldg(xb + ((int64_t)i1 * S + s) * C + c);
   }
   y[(int64_t)b * total + i] = v;
+}
+
+// Same resize, written as split-bf16 planes [2][B][D1][S][Cpad] (hi, lo): the operand format of the TMA-fed tensor-core
+// convolution (csrc/conv3d_slab_bf16.cu) that runs Neural_Volume_Net's conv0, the largest layer of the renderer.
+__global__ void resize_depth_cl_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int D0,
+                                             int D1, int64_t S, int C, int Cpad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)D1 * S * Cpad;
+  if (i >= total) return;
+  const int c = (int)(i % Cpad);
+  const int64_t s = (i / Cpad) % S;
+  const int d = (int)(i / ((int64_t)Cpad * S));
+  const int b = blockIdx.y;
+  float v = 0.f;
+  if (c < C) {
+    const float scale = D1 > 1 ? (float)(D0 - 1) / (float)(D1 - 1) : 0.f;
+    const float src = scale * (float)d;
+    const int i0 = min((int)src, D0 - 1);
+    const int i1 = min(i0 + 1, D0 - 1);
+    const float l1 = src - (float)i0, l0 = 1.f - l1;
+    const float* xb = x + (int64_t)b * D0 * S * C;
+    v = l0 * __ldg(xb + ((int64_t)i0 * S + s) * C + c) + l1 * __ldg(xb + ((int64_t)i1 * S + s) * C + c);
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  y[(int64_t)b * total + i] = h;
+  y[((int64_t)B + b) * total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -437,6 +464,19 @@ __global__ void __launch_bounds__(128) composite_kernel(const float* __restrict_
 }
 
 }  // namespace rcmvs
+
+extern "C" int rcmvs_resize_depth_cl_split(const float* x, void* y_split, int B, int D0, int D1, int64_t S, int C, int Cpad,
+                                           rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(x && y_split && B > 0 && D0 > 0 && D1 > 0 && S > 0 && C > 0 && Cpad >= C && B <= 65535, RCMVS_ERR_BAD_ARG,
+                "rcmvs_resize_depth_cl_split: bad arguments");
+  const int64_t total = (int64_t)D1 * S * Cpad;
+  dim3 grid((unsigned)ceil_div<int64_t>(total, 256), B);
+  resize_depth_cl_split_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y_split), B, D0, D1, S,
+                                                                    C, Cpad);
+  RCMVS_CHECK_LAUNCH("rcmvs_resize_depth_cl_split");
+  return RCMVS_OK;
+}
 
 extern "C" int rcmvs_resize_depth_cl(const float* x, float* y, int B, int D0, int D1, int64_t S, int C, int Cpad,
                                      rcmvs_stream_t stream) {

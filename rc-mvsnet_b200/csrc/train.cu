@@ -174,18 +174,21 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ x, c
 template <int KD, int K, int STRIDE>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* __restrict__ G, int B, int Ds, int Hs,
-             int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int cbb) {
+             int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int cbb, int csb) {
   constexpr int TAPS = KD * K * K, PAD = K / 2, PADD = KD / 2;
-  const int cb_l = threadIdx.x % cbb, cs_l = threadIdx.x / cbb, cs_per = 256 / cbb;
-  const int cs = blockIdx.y * cs_per + cs_l, cb = blockIdx.z * cbb + cb_l;
-  const bool active = cs < Cs && cb < Cb && cs_l < cs_per;
+  // 256 threads = `groups` x csb x cbb: few-channel layers (the full-resolution ones) do not fill a CTA with (cs, cb)
+  // pairs, so the remaining threads form further groups that take every groups-th row of the CTA's row range
+  const int cb_l = threadIdx.x % cbb, cs_l = (threadIdx.x / cbb) % csb, grp = threadIdx.x / (cbb * csb);
+  const int groups = 256 / (cbb * csb);
+  const int cs = blockIdx.y * csb + cs_l, cb = blockIdx.z * cbb + cb_l;
+  const bool active = cs < Cs && cb < Cb;
   float acc[TAPS];
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) acc[t] = 0.f;
   const int64_t nrows = (int64_t)B * Ds * Hs;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(nrows, r_begin + rows_per_cta);
   if (active) {
-    for (int64_t r = r_begin; r < r_end; ++r) {
+    for (int64_t r = r_begin + grp; r < r_end; r += groups) {
       const int oy = (int)(r % Hs), od = (int)((r / Hs) % Ds), b = (int)(r / ((int64_t)Hs * Ds));
       const float* srow = S + r * Ws * Cs + cs;
       const float* brow[KD * K];
@@ -602,17 +605,19 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
   RCMVS_REQUIRE(B > 0 && Ds > 0 && Hs > 0 && Ws > 0 && Cs > 0 && Cb > 0 && (stride == 1 || stride == 2), RCMVS_ERR_BAD_ARG,
                 "rcmvs_conv_wgrad: bad dims");
   const int cbb = Cb >= 32 ? 32 : (Cb >= 16 ? 16 : (Cb >= 8 ? 8 : (Cb >= 4 ? 4 : (Cb >= 2 ? 2 : 1))));
-  const int cs_per = 256 / cbb;
+  int csb = 1;
+  while (csb < Cs && csb * cbb < 256) csb *= 2;          // power of two >= min(Cs, 256 / cbb)
+  const int groups = 256 / (cbb * csb);
   const int64_t nrows = (int64_t)B * Ds * Hs;
-  const int gy = ceil_div(Cs, cs_per), gz = ceil_div(Cb, cbb);
-  // ~6 waves of CTAs over the row dimension, at least 2 rows per CTA so the atomics stay a small share
+  const int gy = ceil_div(Cs, csb), gz = ceil_div(Cb, cbb);
+  // ~6 waves of CTAs over the row dimension, at least 2 rows per thread group so the atomics stay a small share
   int64_t rpc64 = ceil_div<int64_t>(nrows * gy * gz, 148 * 6);
-  if (rpc64 < 2) rpc64 = 2;
+  if (rpc64 < 2 * groups) rpc64 = 2 * groups;
   if (rpc64 > nrows) rpc64 = nrows;
   const int rpc = (int)rpc64;
   dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc), gy, gz);
   cudaStream_t st = as_stream(stream);
-#define RCMVS_WG(KD, KK, SS) wgrad_kernel<KD, KK, SS><<<grid, 256, 0, st>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, rpc, cbb)
+#define RCMVS_WG(KD, KK, SS) wgrad_kernel<KD, KK, SS><<<grid, 256, 0, st>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, rpc, cbb, csb)
   if (dim3d) {
     RCMVS_REQUIRE(k == 3, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_wgrad: 3-D kernels are 3x3x3");
     if (stride == 1) RCMVS_WG(3, 3, 1); else RCMVS_WG(3, 3, 2);

@@ -224,6 +224,8 @@ class CostReg(nn.Module):
                     if name == "conv0" and w.shape[1] < cin_pad:      # 41 -> 48 input channels, zero weights
                         w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, cin_pad - w.shape[1]))
                     P[name] = (ops.pack_conv3d_weight(w.contiguous(), scale, False), shift)
+                    if name == "conv0" and (w.shape[1], w.shape[0]) in ops.SLAB_SUPPORTED:
+                        P["conv0.slab"] = (ops.conv3d_slab_pack(w.contiguous(), scale), shift)   # tcgen05 + TMA, bf16x3
                 for name in ("conv7", "conv9", "conv11"):
                     seq = getattr(self, name)
                     scale, shift = (t.contiguous() for t in fold_bn(seq[1]))
@@ -247,8 +249,11 @@ class CostReg(nn.Module):
 
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cpad] -> [B,D,h,w,8]; eval-mode BN folded, no ReLU anywhere."""
-        P = self.packed(x_cl.shape[-1])
-        c0 = ops.conv3d(x_cl, *P["conv0"], relu=False)
+        P = self.packed(x_cl.shape[-1])          # (the split form has its channel count last as well)
+        if x_cl.dtype == torch.bfloat16:                  # pre-split input from resize_depth_cl_split: tensor-core conv0
+            c0 = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False)
+        else:
+            c0 = ops.conv3d(x_cl, *P["conv0"], relu=False)
         c2 = ops.conv3d(ops.conv3d(c0, *P["conv1"], stride=2, relu=False), *P["conv2"], relu=False)
         c4 = ops.conv3d(ops.conv3d(c2, *P["conv3"], stride=2, relu=False), *P["conv4"], relu=False)
         y = ops.conv3d(ops.conv3d(c4, *P["conv5"], stride=2, relu=False), *P["conv6"], relu=False)
@@ -294,8 +299,11 @@ class Neural_Volume_Net(nn.Module):
     def forward_cl(self, volume_feature):
         """NCDHW in -> channels-last encoded volume [B,128,h,w,8] (what the point-feature kernel consumes)."""
         x = ops.to_channels_last(volume_feature.float().contiguous())
-        x = ops.resize_depth_cl(x, 128, (x.shape[-1] + 7) // 8 * 8)
-        return self.cost_reg_2.forward_cl(x)
+        cpad = (x.shape[-1] + 7) // 8 * 8
+        from .modules import conv_precision
+        if conv_precision() == "bf16x3" and (cpad, 8) in ops.SLAB_SUPPORTED and min(x.shape[2:4]) >= 2:
+            return self.cost_reg_2.forward_cl(ops.resize_depth_cl_split(x, 128, cpad))
+        return self.cost_reg_2.forward_cl(ops.resize_depth_cl(x, 128, cpad))
 
 
 def create_nerf_mvs(args, pts_embedder=True, use_mvs=False, dir_embedder=True, share_warp=False):

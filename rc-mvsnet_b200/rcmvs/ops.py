@@ -230,7 +230,7 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     return y
 
 
-SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16)}      # (Cin, Cout) of the TMA-fed split-bf16 slab kernel
+SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16), (48, 8)}      # (Cin, Cout) of the TMA-fed split-bf16 slab kernel
 
 
 def _chk_bf16(t, name):
@@ -364,6 +364,15 @@ def resize_depth_cl(x_cl, D1, Cpad):
     B, D0, h, w, C = x_cl.shape
     y = torch.empty((B, D1, h, w, Cpad), device=x_cl.device, dtype=torch.float32)
     _ffi.call("rcmvs_resize_depth_cl", _chk(x_cl, "x"), _chk(y, "y"), B, D0, D1, h * w, C, Cpad, _stream())
+    return y
+
+
+@_on_device
+def resize_depth_cl_split(x_cl, D1, Cpad):
+    """Like resize_depth_cl, written as split-bf16 planes [2,B,D1,h,w,Cpad] for the TMA-fed tensor-core conv0."""
+    B, D0, h, w, C = x_cl.shape
+    y = torch.empty((2, B, D1, h, w, Cpad), device=x_cl.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_resize_depth_cl_split", _chk(x_cl, "x"), y.data_ptr(), B, D0, D1, h * w, C, Cpad, _stream())
     return y
 
 
