@@ -483,12 +483,11 @@ def main():
         for _ in range(args.steps):
             step_resident()
         torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms_total, launches, reps_resident = timed(step_resident, args.steps, args.reps)
-    ms_e2e, _, reps_e2e = timed(step_e2e, args.steps, args.reps)
-    # the same loops with ONE reference view at a time (single stream): the per-view latency
+    # ONE reference view at a time first (single stream: the per-view latency), then the headline loops
     single = None
     if nfl > 1:
+        for _ in range(args.warmup):
+            step_single()
         ms1, _, _ = timed(step_single, args.steps, max(3, args.reps // 3))
         pipe_n, pipe = pipe, HostPipeline(model, dev, compute_streams=1)
         for _ in range(args.warmup):
@@ -498,6 +497,13 @@ def main():
         single = {"value": world * B * args.steps / (ms1 * 1e-3), "ms_per_step": ms1 / args.steps,
                   "e2e_value": world * B * args.steps / (ms1e * 1e-3), "e2e_ms_per_step": ms1e / args.steps,
                   "unit": "ref-views/s", "views_in_flight": 1}
+        for _ in range(args.warmup):
+            step_resident()
+            step_e2e()
+        barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches, reps_resident = timed(step_resident, args.steps, args.reps)
+    ms_e2e, _, reps_e2e = timed(step_e2e, args.steps, args.reps)
     clocks = sampler.stop() if sampler else None
 
     value = world * B * args.steps / (ms_total * 1e-3)

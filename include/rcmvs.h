@@ -337,6 +337,12 @@ int rcmvs_geo_consistency(const float* depth_ref, const float* conf, const float
                           float prob_thresh, int num_consistent, uint8_t* masks, float* depth_reproj, float* xy_src,
                           int32_t* geo_mask_sum, float* depth_avg, uint8_t* final_mask, rcmvs_stream_t stream);
 
+/* ---- f4 wire format: PFM depth / confidence maps (datasets/data_io.py:8-73; eval_rcmvsnet_dtu.py:199-253) — HOST functions,
+ * host pointers.  Rows in memory are top-down (what read_pfm returns / save_pfm takes); the file stores them bottom-up. ------ */
+int rcmvs_pfm_read_header(const char* path, int* width, int* height, int* channels, float* scale);
+int rcmvs_pfm_read(const char* path, float* out, int height, int width, int channels);
+int rcmvs_pfm_write(const char* path, const float* img, int height, int width, int channels, float scale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -200,30 +200,35 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
           brow[kd * K + kh] = (iz >= 0 && iz < Db && iy >= 0 && iy < Hb)
                                   ? Bg + (((int64_t)b * Db + iz) * Hb + iy) * Wb * Cb + cb : nullptr;
         }
+      // rotating register window: input column ix lives in slot (ix + PAD) mod K, so sliding by STRIDE only overwrites
+      // the STRIDE oldest slots (no register moves); the loop is unrolled over one period U of the slot pattern
+      constexpr int U = (K % STRIDE == 0) ? K / STRIDE : K;            // STRIDE·U ≡ 0 (mod K)
       float win[KD * K][K];
-      // window for ox = 0 covers ix = -PAD .. K-1-PAD
 #pragma unroll
       for (int q = 0; q < KD * K; ++q)
 #pragma unroll
-        for (int kw = 0; kw < K; ++kw) {
+        for (int kw = 0; kw < K; ++kw) {                              // window of ox = 0: ix = kw - PAD -> slot kw
           const int ix = kw - PAD;
           win[q][kw] = (brow[q] && ix >= 0 && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
         }
-      for (int ox = 0; ox < Ws; ++ox) {
-        const float sv = __ldg(srow + (int64_t)ox * Cs);
+      for (int ox0 = 0; ox0 < Ws; ox0 += U) {
 #pragma unroll
-        for (int q = 0; q < KD * K; ++q)
+        for (int u = 0; u < U; ++u) {
+          const int ox = ox0 + u;
+          if (ox < Ws) {
+            const float sv = __ldg(srow + (int64_t)ox * Cs);
 #pragma unroll
-          for (int kw = 0; kw < K; ++kw) acc[q * K + kw] = fmaf(sv, win[q][kw], acc[q * K + kw]);
-        // slide by STRIDE
+            for (int q = 0; q < KD * K; ++q)
 #pragma unroll
-        for (int q = 0; q < KD * K; ++q) {
+              for (int kw = 0; kw < K; ++kw) acc[q * K + kw] = fmaf(sv, win[q][(STRIDE * u + kw) % K], acc[q * K + kw]);
+            // the STRIDE columns entering the next window replace the STRIDE oldest slots
 #pragma unroll
-          for (int kw = 0; kw + STRIDE < K; ++kw) win[q][kw] = win[q][kw + STRIDE];
+            for (int q = 0; q < KD * K; ++q)
 #pragma unroll
-          for (int kw = (K > STRIDE ? K - STRIDE : 0); kw < K; ++kw) {
-            const int ix = STRIDE * (ox + 1) + kw - PAD;
-            win[q][kw] = (brow[q] && ix >= 0 && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
+              for (int j = 0; j < STRIDE && j < K; ++j) {
+                const int ix = STRIDE * ox - PAD + K + j;
+                win[q][(STRIDE * u + j) % K] = (brow[q] && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
+              }
           }
         }
       }

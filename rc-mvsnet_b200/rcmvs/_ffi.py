@@ -20,7 +20,7 @@ _CTYPES = {
     "int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
     "rcmvs_stream_t": ctypes.c_void_p, "uint64_t": ctypes.c_uint64, "const float* const*": ctypes.c_void_p,
     "uint8_t*": ctypes.c_void_p, "const uint8_t*": ctypes.c_void_p, "const int32_t*": ctypes.c_void_p,
-    "void*": ctypes.c_void_p, "double*": ctypes.c_void_p, "const double*": ctypes.c_void_p, "const void*": ctypes.c_void_p, "const int*": ctypes.c_void_p, "int*": ctypes.c_void_p,
+    "const char*": ctypes.c_char_p, "float *": ctypes.c_void_p, "void*": ctypes.c_void_p, "double*": ctypes.c_void_p, "const double*": ctypes.c_void_p, "const void*": ctypes.c_void_p, "const int*": ctypes.c_void_p, "int*": ctypes.c_void_p,
 }
 
 
