@@ -175,6 +175,18 @@ int rcmvs_pack_conv2d_weight(const float* w, const float* scale, float* packed, 
 int rcmvs_conv2d_fwd(const float* x, const float* packed_w, const float* bias, const float* up, float* y, int N, int H,
                      int W, int Cin, int Cout, int K, int stride, int relu, rcmvs_stream_t stream);
 
+/* Same layer, additionally (or only: y may be NULL) writing the result as split-bf16 planes y_split [2][N][Ho][Wo][Cout] for a
+ * tensor-core consumer (rcmvs_conv2d_slab_fwd). */
+int rcmvs_conv2d_fwd_split(const float* x, const float* packed_w, const float* bias, const float* up, float* y, void* y_split,
+                           int N, int H, int W, int Cin, int Cout, int K, int stride, int relu, rcmvs_stream_t stream);
+/* FeatureNet's 3x3 stride-1 convolutions on tcgen05 (kind::f16, bf16x3) fed by TMA, persistent over (image, tile) items:
+ * x_split [2][N][H][W][Cin] bf16 (hi, lo) -> y fp32 [N][H][W][Cout] and/or y_split; bias = folded BatchNorm shift or NULL.
+ * (Cin, Cout) in {(16,16), (32,32), (32,16), (32,8)}: conv1.1/1.2, conv2.1/2.2, out2, out3 (models/modules.py:394-417). */
+int64_t rcmvs_conv2d_slab_weight_elems(int Cin, int Cout);
+int rcmvs_conv2d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
+int rcmvs_conv2d_slab_fwd(const void* x_split, const void* wimg, const float* bias, float* y, void* y_split, int N, int H, int W,
+                          int Cin, int Cout, int relu, rcmvs_stream_t stream);
+
 /* ---- a7 Neural_Volume_Net resize: models/render_models.py:755-756 ------------------------------------------------ */
 /* x [B][D0][S][C] channels-last (S = h*w) -> y [B][D1][S][Cpad]: linear along D with align_corners=True, channels
  * C..Cpad-1 zero-filled (the 41-channel volume is padded to 48 for the convolution kernels). */

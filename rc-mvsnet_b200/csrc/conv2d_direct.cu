@@ -6,6 +6,8 @@
 // 4 output rows x 8 output channels, shared-memory halo tile of 8 input channels at a time stored [row][c4][col] as
 // float4 (a warp's LDS.128 for one tap is 32 consecutive 16-byte words), weight slice [K*K][8][Cout] in shared
 // memory read as warp-uniform broadcasts.  Kernel sizes 1, 3, 5; strides 1, 2; Cout 8, 16, 32.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace rcmvs {
@@ -33,8 +35,8 @@ struct Conv2Smem {
 template <int COUT, int STRIDE, int KS>
 __global__ void __launch_bounds__(Conv2Tile<COUT>::THREADS)
 conv2d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
-                     const float* __restrict__ up, float* __restrict__ y, int H, int W, int Cin, int Ho, int Wo,
-                     int relu) {
+                     const float* __restrict__ up, float* __restrict__ y, __nv_bfloat16* __restrict__ ys,
+                     int64_t ys_part_stride, int H, int W, int Cin, int Ho, int Wo, int relu) {
   using T = Conv2Tile<COUT>;
   using S = Conv2Smem<COUT, STRIDE, KS>;
   constexpr int TH = T::TH, IH = S::IH, IW = S::IW, PAD = KS / 2;
@@ -131,8 +133,20 @@ conv2d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wp, 
       v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
       v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
     }
-    st4(y + o, make_float4(v[0], v[1], v[2], v[3]));
-    st4(y + o + 4, make_float4(v[4], v[5], v[6], v[7]));
+    if (y) {
+      st4(y + o, make_float4(v[0], v[1], v[2], v[3]));
+      st4(y + o + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
+    if (ys) {   // pre-split copy (hi = bf16(v), lo = bf16(v - hi)) for a tensor-core consumer (conv2d_slab_bf16.cu)
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        h[c] = __float2bfloat16_rn(v[c]);
+        l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+      }
+      *reinterpret_cast<uint4*>(ys + o) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(ys + ys_part_stride + o) = *reinterpret_cast<const uint4*>(l);
+    }
   }
 }
 
@@ -167,8 +181,8 @@ __global__ void pack_conv2d_weight_kernel(const float* __restrict__ w, const flo
 }
 
 template <int COUT, int STRIDE, int KS>
-static int launch_conv2d(const float* x, const float* wp, const float* bias, const float* up, float* y, int N, int H,
-                         int W, int Cin, int relu, cudaStream_t st) {
+static int launch_conv2d(const float* x, const float* wp, const float* bias, const float* up, float* y, void* ys, int N,
+                         int H, int W, int Cin, int relu, cudaStream_t st) {
   using T = Conv2Tile<COUT>;
   using S = Conv2Smem<COUT, STRIDE, KS>;
   const int Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
@@ -180,7 +194,8 @@ static int launch_conv2d(const float* x, const float* wp, const float* bias, con
   }
   RCMVS_REQUIRE(N <= 65535 && ceil_div(Ho, T::TH) <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv2d_fwd: grid too large");
   dim3 grid(ceil_div(Wo, 32), ceil_div(Ho, T::TH), N);
-  kern<<<grid, T::THREADS, S::BYTES, st>>>(x, wp, bias, up, y, H, W, Cin, Ho, Wo, relu);
+  kern<<<grid, T::THREADS, S::BYTES, st>>>(x, wp, bias, up, y, reinterpret_cast<__nv_bfloat16*>(ys),
+                                           (int64_t)N * Ho * Wo * COUT, H, W, Cin, Ho, Wo, relu);
   RCMVS_CHECK_LAUNCH("rcmvs_conv2d_fwd");
   return RCMVS_OK;
 }
@@ -209,18 +224,29 @@ extern "C" int rcmvs_pack_conv2d_weight(const float* w, const float* scale, floa
   return RCMVS_OK;
 }
 
+extern "C" int rcmvs_conv2d_fwd_split(const float* x, const float* packed_w, const float* bias, const float* up, float* y,
+                                      void* y_split, int N, int H, int W, int Cin, int Cout, int K, int stride, int relu,
+                                      rcmvs_stream_t stream);
+
 extern "C" int rcmvs_conv2d_fwd(const float* x, const float* packed_w, const float* bias, const float* up, float* y,
                                 int N, int H, int W, int Cin, int Cout, int K, int stride, int relu,
                                 rcmvs_stream_t stream) {
+  return rcmvs_conv2d_fwd_split(x, packed_w, bias, up, y, nullptr, N, H, W, Cin, Cout, K, stride, relu, stream);
+}
+
+extern "C" int rcmvs_conv2d_fwd_split(const float* x, const float* packed_w, const float* bias, const float* up, float* y,
+                                      void* y_split, int N, int H, int W, int Cin, int Cout, int K, int stride, int relu,
+                                      rcmvs_stream_t stream) {
   using namespace rcmvs;
-  RCMVS_REQUIRE(x && packed_w && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv2d_fwd: null pointer");
+  void* ys = y_split;
+  RCMVS_REQUIRE(x && packed_w && (y || ys), RCMVS_ERR_BAD_ARG, "rcmvs_conv2d_fwd: null pointer");
   RCMVS_REQUIRE(N > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv2d_fwd: bad dims");
   RCMVS_REQUIRE(Cin % 8 == 0 && Cin > 0, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv2d_fwd: Cin=%d must be a multiple of 8", Cin);
   RCMVS_REQUIRE(!up || (stride == 1 && H % 2 == 0 && W % 2 == 0), RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv2d_fwd: the fused upsample-add needs stride 1 and even H, W");
   cudaStream_t st = as_stream(stream);
 #define RCMVS_C2(CO, S, KK) \
-  if (Cout == CO && stride == S && K == KK) return launch_conv2d<CO, S, KK>(x, packed_w, bias, up, y, N, H, W, Cin, relu, st)
+  if (Cout == CO && stride == S && K == KK) return launch_conv2d<CO, S, KK>(x, packed_w, bias, up, y, ys, N, H, W, Cin, relu, st)
   RCMVS_C2(8, 1, 3); RCMVS_C2(16, 1, 3); RCMVS_C2(32, 1, 3);
   RCMVS_C2(16, 2, 5); RCMVS_C2(32, 2, 5);
   RCMVS_C2(32, 1, 1);

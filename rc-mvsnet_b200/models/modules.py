@@ -151,13 +151,19 @@ class FeatureNet(nn.Module):
                         w = blk.conv.weight.detach().contiguous()
                         cin_pad = (w.shape[1] + 7) // 8 * 8
                         P["%s.%d" % (name, i)] = (ops.pack_conv2d_weight(w, scale, cin_pad), shift, blk.stride)
+                        if tc and blk.stride == 1 and w.shape[2] == 3 and (w.shape[1], w.shape[0]) in ops.SLAB2D_SUPPORTED:
+                            P["%s.%d.slab" % (name, i)] = (ops.conv2d_slab_pack(w, scale), shift)
                 for name in ("out1", "inner1", "inner2", "out2", "out3"):
                     conv = getattr(self, name, None)
                     if conv is not None:
                         b = conv.bias.detach().contiguous() if conv.bias is not None else None
-                        P[name] = (ops.pack_conv2d_weight(conv.weight.detach().contiguous(), None), b, 1)
+                        w = conv.weight.detach().contiguous()
+                        P[name] = (ops.pack_conv2d_weight(w, None), b, 1)
+                        if tc and w.shape[2] == 3 and (w.shape[1], w.shape[0]) in ops.SLAB2D_SUPPORTED:
+                            P[name + ".slab"] = (ops.conv2d_slab_pack(w, None), b)
             return P
-        return self._folded.get(_versions(self), build)
+        tc = conv_precision() == "bf16x3" and self.base_channels == 8
+        return self._folded.get((_versions(self), tc), build)
 
     def forward_cl(self, x, side_stream=None):
         """x [N,3,H,W] -> {"stageK": [N,h,w,C] channels-last contiguous}; every layer is one librcmvs launch
@@ -167,21 +173,39 @@ class FeatureNet(nn.Module):
         is enqueued on that stream and the result carries `"_ready"`, a CUDA event the consumer's stream must wait for
         before it touches `stage2` / `stage3`; the caller's stream goes straight on with stage 1."""
         P = self._packed()
+        tc = "conv1.1.slab" in P          # bf16x3 mode: the 3x3 stride-1 layers with 16 / 32 input channels run on tcgen05
 
-        def cbr(t, key):
+        def cbr(t, key, split_out=False):
+            """conv + folded BN + ReLU.  `t` fp32 [N,H,W,C] or split-bf16 [2,N,H,W,C]; returns fp32, or the split form when
+            the consumer is a tensor-core layer (`split_out`)."""
+            if t.dtype == torch.bfloat16:
+                img, shift = P[key + ".slab"]
+                return ops.conv2d_slab(t, img, img_cout[key], shift, True, want_y=not split_out, want_split=split_out)
             w, b, stride = P[key]
-            return ops.conv2d(t, w, b, None, stride=stride, relu=True)
+            return ops.conv2d(t, w, b, None, stride=stride, relu=True, want_y=not split_out, want_split=split_out)
+
+        img_cout = {"conv1.1": 16, "conv1.2": 16, "conv2.1": 32, "conv2.2": 32}
+
+        def head(t, key, cout):
+            """plain 3x3 convolution (out2 / out3)."""
+            if t.dtype == torch.bfloat16:
+                return ops.conv2d_slab(t, P[key + ".slab"][0], cout, None, False)
+            return ops.conv2d(t, P[key][0], None, None, relu=False)
 
         def tail(out):
-            intra = ops.conv2d(c1, P["inner1"][0], P["inner1"][1], c2, relu=False)      # up2(c2) + inner1(c1)
-            out["stage2"] = ops.conv2d(intra, P["out2"][0], None, None, relu=False)
+            # up2(c2) + inner1(c1): fp32 for the next lateral, split-bf16 for the tensor-core out2
+            if tc:
+                intra, intra_s = ops.conv2d(c1, P["inner1"][0], P["inner1"][1], c2, relu=False, want_split=True)
+            else:
+                intra = intra_s = ops.conv2d(c1, P["inner1"][0], P["inner1"][1], c2, relu=False)
+            out["stage2"] = head(intra_s, "out2", 16)
             if self.num_stage == 3:
-                intra = ops.conv2d(c0, P["inner2"][0], P["inner2"][1], intra, relu=False)
-                out["stage3"] = ops.conv2d(intra, P["out3"][0], None, None, relu=False)
+                intra2 = ops.conv2d(c0, P["inner2"][0], P["inner2"][1], intra, relu=False, want_y=not tc, want_split=tc)
+                out["stage3"] = head(intra2, "out3", 8)
 
         c0 = cbr(cbr(ops.images_to_nhwc8(x.float().contiguous()), "conv0.0"), "conv0.1")
-        c1 = cbr(cbr(cbr(c0, "conv1.0"), "conv1.1"), "conv1.2")
-        c2 = cbr(cbr(cbr(c1, "conv2.0"), "conv2.1"), "conv2.2")
+        c1 = cbr(cbr(cbr(c0, "conv1.0", tc), "conv1.1", tc), "conv1.2")
+        c2 = cbr(cbr(cbr(c1, "conv2.0", tc), "conv2.1", tc), "conv2.2")
         out = {}
         if side_stream is None:
             out["stage1"] = ops.conv2d(c2, P["out1"][0], None, None, relu=False)

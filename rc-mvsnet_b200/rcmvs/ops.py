@@ -471,16 +471,44 @@ def pack_conv2d_weight(w, scale=None, cin_pad=None):
 
 
 @_on_device
-def conv2d(x_cl, packed_w, bias=None, up=None, stride=1, relu=True):
-    """x_cl [N,H,W,Cin] -> [N,Ho,Wo,Cout]: conv(K, pad K/2) + bias, ReLU, then + nearest-2x-upsampled `up`."""
+def conv2d(x_cl, packed_w, bias=None, up=None, stride=1, relu=True, want_y=True, want_split=False):
+    """x_cl [N,H,W,Cin] -> [N,Ho,Wo,Cout]: conv(K, pad K/2) + bias, ReLU, then + nearest-2x-upsampled `up`.
+    want_split: also (or only) the split-bf16 form [2,N,Ho,Wo,Cout] for the tensor-core layers."""
     N, H, W, Cin = x_cl.shape
     KK, _, Cout = packed_w.shape
     K = {1: 1, 9: 3, 25: 5}[KK]
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
-    y = torch.empty((N, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32)
-    _ffi.call("rcmvs_conv2d_fwd", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"), _opt(up, "up"),
-              _chk(y, "y"), N, H, W, Cin, Cout, K, stride, 1 if relu else 0, _stream())
-    return y
+    y = torch.empty((N, Ho, Wo, Cout), device=x_cl.device, dtype=torch.float32) if want_y else None
+    ys = torch.empty((2, N, Ho, Wo, Cout), device=x_cl.device, dtype=torch.bfloat16) if want_split else None
+    _ffi.call("rcmvs_conv2d_fwd_split", _chk(x_cl, "x"), _chk(packed_w, "w"), _opt(bias, "bias"), _opt(up, "up"),
+              _opt(y, "y"), None if ys is None else ys.data_ptr(), N, H, W, Cin, Cout, K, stride, 1 if relu else 0, _stream())
+    if want_y and want_split:
+        return y, ys
+    return y if want_y else ys
+
+
+SLAB2D_SUPPORTED = {(16, 16), (32, 32), (32, 16), (32, 8)}      # (Cin, Cout) of the 2-D TMA slab kernel (3x3, stride 1)
+
+
+@_on_device
+def conv2d_slab_pack(w, scale=None):
+    Cout, Cin = w.shape[:2]
+    img = torch.empty((_ffi.lib().rcmvs_conv2d_slab_weight_elems(Cin, Cout),), device=w.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_conv2d_slab_pack", _chk(w, "w"), _opt(scale, "scale"), img.data_ptr(), Cout, Cin, _stream())
+    return img
+
+
+@_on_device
+def conv2d_slab(x_split, img, Cout, bias=None, relu=True, want_y=True, want_split=False):
+    """x_split [2,N,H,W,Cin] bf16 -> y [N,H,W,Cout] fp32 and/or y_split [2,N,H,W,Cout]: 3x3 stride-1 conv on tcgen05."""
+    _, N, H, W, Cin = x_split.shape
+    y = torch.empty((N, H, W, Cout), device=x_split.device, dtype=torch.float32) if want_y else None
+    ys = torch.empty((2, N, H, W, Cout), device=x_split.device, dtype=torch.bfloat16) if want_split else None
+    _ffi.call("rcmvs_conv2d_slab_fwd", _chk_bf16(x_split, "x_split"), _chk_bf16(img, "wimg"), _opt(bias, "bias"), _opt(y, "y"),
+              None if ys is None else ys.data_ptr(), N, H, W, Cin, Cout, 1 if relu else 0, _stream())
+    if want_y and want_split:
+        return y, ys
+    return y if want_y else ys
 
 
 # ---- f2 unsupervised loss stack ---------------------------------------------------------------------------------------

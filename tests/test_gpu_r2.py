@@ -697,3 +697,31 @@ def test_rendering_consistency_net_training_step_on_own_kernels(dev):
     gn = lambda m: sum(float(p.grad.abs().sum()) for p in m.parameters() if p.grad is not None)
     assert gn(nerf.network_fn) > 0 and gn(nerf.MVSNet) > 0 and gn(cas.feature) > 0
     assert all(torch.isfinite(p.grad).all() for p in list(nerf.parameters()) + list(cas.feature.parameters()) if p.grad is not None)
+
+
+# ---- f1 FeatureNet on tensor cores: 2-D TMA slab kernel ---------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,nhw", [(16, 16, (2, 9, 37)), (32, 32, (1, 20, 64)), (32, 16, (3, 7, 31)), (32, 8, (2, 33, 95)),
+                                          (16, 16, (5, 64, 80)), (32, 32, (1, 1, 1)), (32, 8, (1, 12, 30))])
+def test_conv2d_slab_bf16x3_vs_oracle(dev, cin, cout, nhw):
+    from oracle import ref_np as O
+    from rcmvs import ops
+    rng = np.random.default_rng(cin * 100 + cout + nhw[0])
+    N, H, W = nhw
+    xs = [rng.standard_normal((cin, H, W), dtype=np.float32) for _ in range(N)]
+    w = (rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(9 * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    lin = np.stack([O.conv2d(x, w * scale[:, None, None, None], None, pad=1) for x in xs])
+    want = np.maximum(lin + bias[None, :, None, None], 0)
+    x_cl = cu(np.stack(xs).transpose(0, 2, 3, 1), dev)
+    xs_split = ops.split_bf16(x_cl)
+    img = ops.conv2d_slab_pack(cu(w, dev), cu(scale, dev))
+    y, ys = ops.conv2d_slab(xs_split, img, cout, cu(bias, dev), True, True, True)
+    np.testing.assert_allclose(y.permute(0, 3, 1, 2).cpu().numpy(), want, atol=1e-4, rtol=1e-4)
+    assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
+    y2 = ops.conv2d_slab(xs_split, img, cout, None, False)
+    np.testing.assert_allclose(y2.permute(0, 3, 1, 2).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
+    # the FFMA producer's split output is the same split of its fp32 output
+    pw = ops.pack_conv2d_weight(cu(w, dev), cu(scale, dev))
+    yf, yfs = ops.conv2d(x_cl, pw, cu(bias, dev), None, relu=True, want_split=True)
+    assert torch.equal(yfs, ops.split_bf16(yf))

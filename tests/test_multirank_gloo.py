@@ -61,3 +61,40 @@ def test_shard_units_partition():
             parts = [shard.shard_units(n, r, world) for r in range(world)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def _train_worker(rank, world, port, out):
+    """Host logic of the data-parallel training step (rcmvs.train.FlatParams) on CPU/gloo: parameters and gradients are
+    views of two flat buffers, ONE all-reduce sums the gradients of all ranks, the 1/world factor goes to the optimiser."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "rc-mvsnet_b200")]
+    from rcmvs.train import FlatParams
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    flat = FlatParams([net])
+    n = sum(p.numel() for p in net.parameters())
+    assert flat.flat.numel() == n and all(p.data_ptr() >= flat.flat.data_ptr() for p in net.parameters())
+    flat.zero_grad()
+    x = torch.full((4, 5), float(rank + 1))
+    net(x).sum().backward()
+    local = flat.grad.clone()
+    assert torch.equal(torch.cat([p.grad.reshape(-1) for p in net.parameters()]), local)    # .grad are views
+    world_seen = flat.all_reduce()
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = torch.allclose(flat.grad, sum(gathered)) and world_seen == world
+    flat.zero_grad()
+    ok = ok and float(flat.grad.abs().sum()) == 0.0 and all(float(p.grad.abs().sum()) == 0.0 for p in net.parameters())
+    if rank == 0:
+        torch.save({"ok": bool(ok)}, out)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_two_ranks_gloo(tmp_path):
+    out = str(tmp_path / "t0.pt")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]
