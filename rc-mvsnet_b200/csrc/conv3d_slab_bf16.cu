@@ -61,6 +61,7 @@ struct Params {
   int B, D, H, W;
   int d_chunk, chunks;
   int relu;
+  int dbg;                     // experiment switches (tools/slab_experiments.py); 0 in the product path
 };
 
 template <int CIN, int COUT, int KM, int NS>
@@ -129,6 +130,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       for (int ii = 0; ii < nslabs; ++ii) {
         const int buf = ii % NS;
         mbar_wait(empty + buf, ((ii / NS) & 1) ^ 1);
+        if (p.dbg & 8) { mbar_arrive(full + buf); continue; }   // experiment: no TMA traffic
         mbar_arrive_expect_tx(full + buf, (uint32_t)C::STAGE_B);
         const int z = d0 - 1 + ii;
         const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * C::STAGE_B);
@@ -150,7 +152,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       const int qnew = i;                                                  // plane first touched by this slab (j=2)
       if (qnew < nplanes && qnew >= NG) mbar_wait(grp_free + (qnew % NG), ((qnew / NG) - 1) & 1);
       const int buf = i % NS;
-      mbar_wait(full + buf, (i / NS) & 1);
+      if (!(p.dbg & 2)) mbar_wait(full + buf, (i / NS) & 1);
       tc_fence_after();
       const uint32_t a_base = smem_u32(a_smem + (size_t)buf * C::STAGE_B);
       // split the valid block range into (at most two) ring-contiguous runs; per run: TMEM column, B row offset, N
@@ -158,7 +160,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       const int n_all = jhi - jlo + 1;
       const int n0 = min(n_all, NG - g0), n1 = n_all - n0;                 // second run wraps to group 0
       const uint32_t d0c = tmem_base + g0 * G, d1c = tmem_base;
-      const uint32_t idesc0 = make_idesc_bf16(128, n0 * G), idesc1 = make_idesc_bf16(128, (n1 > 0 ? n1 : 1) * G);
+      const uint32_t idesc0 = make_idesc_bf16(128, (p.dbg & 32) ? G : n0 * G), idesc1 = make_idesc_bf16(128, (n1 > 0 ? n1 : 1) * G);
       const uint32_t boff0 = (uint32_t)(jlo * G), boff1 = (uint32_t)((jlo + n0) * G);   // in 16-byte rows
       const uint32_t a_lo0 = desc_lo(a_base, C::PLANE_B);                  // hi-part slab
       const uint32_t b_lo0 = desc_lo(b_base, 3 * G * 16);
@@ -172,13 +174,17 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
             const uint32_t a_hi_d = a_lo0 + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + kw);
             const uint32_t b_blk_d = b_lo0 + (uint32_t)(((kw * C::KS + ks) * C::BBLK_B) >> 4);
             const uint32_t dm = (uint32_t)(mt * (NG * G));
-            if (leader) {
-              umma_bf16_lohi(d0c + dm, a_hi_d + kLoOff, b_blk_d + boff0, idesc0);            // x_lo · w_hi
-              umma_bf16_lohi(d0c + dm, a_hi_d, b_blk_d + boff0 + kBLoOff, idesc0);           // x_hi · w_lo
+            if (leader && !((p.dbg & 16) && kw > 0)) {
+              if (!(p.dbg & 1)) {
+                umma_bf16_lohi(d0c + dm, a_hi_d + kLoOff, b_blk_d + boff0, idesc0);          // x_lo · w_hi
+                umma_bf16_lohi(d0c + dm, a_hi_d, b_blk_d + boff0 + kBLoOff, idesc0);         // x_hi · w_lo
+              }
               umma_bf16_lohi(d0c + dm, a_hi_d, b_blk_d + boff0, idesc0);                     // x_hi · w_hi
               if (n1 > 0) {
-                umma_bf16_lohi(d1c + dm, a_hi_d + kLoOff, b_blk_d + boff1, idesc1);
-                umma_bf16_lohi(d1c + dm, a_hi_d, b_blk_d + boff1 + kBLoOff, idesc1);
+                if (!(p.dbg & 1)) {
+                  umma_bf16_lohi(d1c + dm, a_hi_d + kLoOff, b_blk_d + boff1, idesc1);
+                  umma_bf16_lohi(d1c + dm, a_hi_d, b_blk_d + boff1 + kBLoOff, idesc1);
+                }
                 umma_bf16_lohi(d1c + dm, a_hi_d, b_blk_d + boff1, idesc1);
               }
             }
@@ -222,6 +228,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(grp_free + g);
+      if (p.dbg & 4) continue;                                   // experiment: drain only
       // ---- sum over kh: input row ri = 4*mt + warp contributes its kh block to output row j = ri - kh.  Each kh
       //      writes its own exchange plane (no read-modify-write), one barrier, then the store phase adds the three.
 #pragma unroll
@@ -415,6 +422,9 @@ extern "C" int rcmvs_split_bf16(const float* x, void* xs, int64_t n, rcmvs_strea
   return RCMVS_OK;
 }
 
+// experiment switches for tools/slab_experiments.py (set through ctypes in_dll; not part of the ABI, 0 = product behaviour)
+extern "C" int rcmvs_slab_debug_flags = 0;
+
 extern "C" int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip,
                                      float* y, void* y_split, int B, int D, int H, int W, int Cin, int Cout, int relu,
                                      rcmvs_stream_t stream) {
@@ -429,7 +439,7 @@ extern "C" int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, cons
   Params p;
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.bias = bias; p.skip = skip; p.y = y; p.ys = reinterpret_cast<__nv_bfloat16*>(y_split);
-  p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu;
+  p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu; p.dbg = rcmvs_slab_debug_flags;
   int km = 2, chunks = 1;
   plan(B, D, H, W, Cin, Cout, km, chunks);
   p.d_chunk = ceil_div(D, chunks);
