@@ -171,20 +171,24 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ x, c
 // input values per (kd, kh) so a position costs STRIDE·KD·K loads (coalesced over cb, L1-resident: the CS warps of a CTA
 // read the same addresses) + 1 broadcast load for KD·K·K FMAs.  Partial sums are added to G with fp32 atomics.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KD, int K, int STRIDE>
+template <int KD, int K, int STRIDE, bool ROT, int CSR>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* __restrict__ G, int B, int Ds, int Hs,
              int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int cbb, int csb) {
   constexpr int TAPS = KD * K * K, PAD = K / 2, PADD = KD / 2;
   // 256 threads = `groups` x csb x cbb: few-channel layers (the full-resolution ones) do not fill a CTA with (cs, cb)
-  // pairs, so the remaining threads form further groups that take every groups-th row of the CTA's row range
+  // pairs, so the remaining threads form further groups that take every groups-th row of the CTA's row range.
+  // A thread owns CSR consecutive S channels (one 16-byte load when CSR = 4) x one Bg channel: the sliding window is
+  // loaded once for CSR·TAPS FMAs.
   const int cb_l = threadIdx.x % cbb, cs_l = (threadIdx.x / cbb) % csb, grp = threadIdx.x / (cbb * csb);
   const int groups = 256 / (cbb * csb);
-  const int cs = blockIdx.y * csb + cs_l, cb = blockIdx.z * cbb + cb_l;
+  const int cs = (blockIdx.y * csb + cs_l) * CSR, cb = blockIdx.z * cbb + cb_l;
   const bool active = cs < Cs && cb < Cb;
-  float acc[TAPS];
+  float acc[CSR][TAPS];
 #pragma unroll
-  for (int t = 0; t < TAPS; ++t) acc[t] = 0.f;
+  for (int c = 0; c < CSR; ++c)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[c][t] = 0.f;
   const int64_t nrows = (int64_t)B * Ds * Hs;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(nrows, r_begin + rows_per_cta);
   if (active) {
@@ -200,9 +204,6 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
           brow[kd * K + kh] = (iz >= 0 && iz < Db && iy >= 0 && iy < Hb)
                                   ? Bg + (((int64_t)b * Db + iz) * Hb + iy) * Wb * Cb + cb : nullptr;
         }
-      // rotating register window: input column ix lives in slot (ix + PAD) mod K, so sliding by STRIDE only overwrites
-      // the STRIDE oldest slots (no register moves); the loop is unrolled over one period U of the slot pattern
-      constexpr int U = (K % STRIDE == 0) ? K / STRIDE : K;            // STRIDE·U ≡ 0 (mod K)
       float win[KD * K][K];
 #pragma unroll
       for (int q = 0; q < KD * K; ++q)
@@ -211,30 +212,73 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
           const int ix = kw - PAD;
           win[q][kw] = (brow[q] && ix >= 0 && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
         }
-      for (int ox0 = 0; ox0 < Ws; ox0 += U) {
+      auto load_s = [&](int ox, float (&sv)[CSR]) {
+        if constexpr (CSR == 4) {
+          const float4 t = ldg4(srow + (int64_t)ox * Cs);
+          sv[0] = t.x; sv[1] = t.y; sv[2] = t.z; sv[3] = t.w;
+        } else {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int ox = ox0 + u;
-          if (ox < Ws) {
-            const float sv = __ldg(srow + (int64_t)ox * Cs);
+          for (int c = 0; c < CSR; ++c) sv[c] = __ldg(srow + (int64_t)ox * Cs + c);
+        }
+      };
+      if constexpr (ROT) {
+        // rotating register window: input column ix lives in slot (ix + PAD) mod K, so sliding by STRIDE only
+        // overwrites the STRIDE oldest slots (no register moves); unrolled over one period U of the slot pattern
+        constexpr int U = (K % STRIDE == 0) ? K / STRIDE : K;          // STRIDE·U ≡ 0 (mod K)
+        for (int ox0 = 0; ox0 < Ws; ox0 += U) {
 #pragma unroll
-            for (int q = 0; q < KD * K; ++q)
+          for (int u = 0; u < U; ++u) {
+            const int ox = ox0 + u;
+            if (ox < Ws) {
+              float sv[CSR];
+              load_s(ox, sv);
 #pragma unroll
-              for (int kw = 0; kw < K; ++kw) acc[q * K + kw] = fmaf(sv, win[q][(STRIDE * u + kw) % K], acc[q * K + kw]);
-            // the STRIDE columns entering the next window replace the STRIDE oldest slots
+              for (int q = 0; q < KD * K; ++q)
 #pragma unroll
-            for (int q = 0; q < KD * K; ++q)
+                for (int kw = 0; kw < K; ++kw) {
+                  const float wv = win[q][(STRIDE * u + kw) % K];
 #pragma unroll
-              for (int j = 0; j < STRIDE && j < K; ++j) {
-                const int ix = STRIDE * ox - PAD + K + j;
-                win[q][(STRIDE * u + j) % K] = (brow[q] && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
-              }
+                  for (int c = 0; c < CSR; ++c) acc[c][q * K + kw] = fmaf(sv[c], wv, acc[c][q * K + kw]);
+                }
+#pragma unroll
+              for (int q = 0; q < KD * K; ++q)
+#pragma unroll
+                for (int j = 0; j < STRIDE && j < K; ++j) {
+                  const int ix = STRIDE * ox - PAD + K + j;
+                  win[q][(STRIDE * u + j) % K] = (brow[q] && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
+                }
+            }
+          }
+        }
+      } else {
+        for (int ox = 0; ox < Ws; ++ox) {
+          float sv[CSR];
+          load_s(ox, sv);
+#pragma unroll
+          for (int q = 0; q < KD * K; ++q)
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) {
+              const float wv = win[q][kw];
+#pragma unroll
+              for (int c = 0; c < CSR; ++c) acc[c][q * K + kw] = fmaf(sv[c], wv, acc[c][q * K + kw]);
+            }
+#pragma unroll
+          for (int q = 0; q < KD * K; ++q) {                           // slide by STRIDE (register moves)
+#pragma unroll
+            for (int kw = 0; kw + STRIDE < K; ++kw) win[q][kw] = win[q][kw + STRIDE];
+#pragma unroll
+            for (int kw = (K > STRIDE ? K - STRIDE : 0); kw < K; ++kw) {
+              const int ix = STRIDE * (ox + 1) + kw - PAD;
+              win[q][kw] = (brow[q] && ix >= 0 && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) atomicAdd(G + ((int64_t)cs * Cb + cb) * TAPS + t, acc[t]);
+    for (int c = 0; c < CSR; ++c)
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) atomicAdd(G + ((int64_t)(cs + c) * Cb + cb) * TAPS + t, acc[c][t]);
   }
 }
 
@@ -603,6 +647,10 @@ extern "C" int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, 
   return RCMVS_OK;
 }
 
+// A/B switches for tools/train_experiments.py (ctypes in_dll; not part of the ABI): bit 0 = window slides by register
+// moves instead of rotating, bit 1 = one S channel per thread instead of four
+extern "C" int rcmvs_wgrad_variant = 0;
+
 // dims = {B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb}; dim3 = 1: 3-D (27 taps, k = 3), 0: 2-D (Ds = Db = 1, k in {1,3,5})
 extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B, int Ds, int Hs, int Ws, int Cs, int Db,
                                 int Hb, int Wb, int Cb, int k, int stride, int dim3d, rcmvs_stream_t stream) {
@@ -610,11 +658,13 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
   RCMVS_REQUIRE(B > 0 && Ds > 0 && Hs > 0 && Ws > 0 && Cs > 0 && Cb > 0 && (stride == 1 || stride == 2), RCMVS_ERR_BAD_ARG,
                 "rcmvs_conv_wgrad: bad dims");
   const int cbb = Cb >= 32 ? 32 : (Cb >= 16 ? 16 : (Cb >= 8 ? 8 : (Cb >= 4 ? 4 : (Cb >= 2 ? 2 : 1))));
+  const int csr = (Cs % 4 == 0 && !(rcmvs_wgrad_variant & 2)) ? 4 : 1;   // S channels per thread
+  const int csg = Cs / csr;                                             // channel groups along S
   int csb = 1;
-  while (csb < Cs && csb * cbb < 256) csb *= 2;          // power of two >= min(Cs, 256 / cbb)
+  while (csb < csg && csb * cbb < 256) csb *= 2;         // power of two >= min(csg, 256 / cbb)
   const int groups = 256 / (cbb * csb);
   const int64_t nrows = (int64_t)B * Ds * Hs;
-  const int gy = ceil_div(Cs, csb), gz = ceil_div(Cb, cbb);
+  const int gy = ceil_div(csg, csb), gz = ceil_div(Cb, cbb);
   // ~6 waves of CTAs over the row dimension, at least 2 rows per thread group so the atomics stay a small share
   int64_t rpc64 = ceil_div<int64_t>(nrows * gy * gz, 148 * 6);
   if (rpc64 < 2 * groups) rpc64 = 2 * groups;
@@ -622,7 +672,17 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
   const int rpc = (int)rpc64;
   dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc), gy, gz);
   cudaStream_t st = as_stream(stream);
-#define RCMVS_WG(KD, KK, SS) wgrad_kernel<KD, KK, SS><<<grid, 256, 0, st>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, rpc, cbb, csb)
+  const bool rot = !(rcmvs_wgrad_variant & 1);
+#define RCMVS_WG_(KD, KK, SS, RR, CC) \
+  wgrad_kernel<KD, KK, SS, RR, CC><<<grid, 256, 0, st>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, rpc, cbb, csb)
+#define RCMVS_WG(KD, KK, SS)                                   \
+  do {                                                         \
+    if (csr == 4) {                                            \
+      if (rot) RCMVS_WG_(KD, KK, SS, true, 4); else RCMVS_WG_(KD, KK, SS, false, 4); \
+    } else {                                                   \
+      if (rot) RCMVS_WG_(KD, KK, SS, true, 1); else RCMVS_WG_(KD, KK, SS, false, 1); \
+    }                                                          \
+  } while (0)
   if (dim3d) {
     RCMVS_REQUIRE(k == 3, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_wgrad: 3-D kernels are 3x3x3");
     if (stride == 1) RCMVS_WG(3, 3, 1); else RCMVS_WG(3, 3, 2);
@@ -636,6 +696,7 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
     else { set_error("rcmvs_conv_wgrad: unsupported 2-D k=%d stride=%d", k, stride); return RCMVS_ERR_UNSUPPORTED; }
   }
 #undef RCMVS_WG
+#undef RCMVS_WG_
   RCMVS_CHECK_LAUNCH("rcmvs_conv_wgrad");
   return RCMVS_OK;
 }

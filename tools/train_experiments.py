@@ -1,0 +1,14 @@
+"""A/B of the weight-gradient kernel variants inside the real training step (csrc/train.cu rcmvs_wgrad_variant):
+bit 0 = window slides by register moves (instead of the rotating window), bit 1 = one S channel per thread (instead of 4)."""
+import ctypes, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "rc-mvsnet_b200"))
+from rcmvs import _ffi, train
+dev = torch.device("cuda:0")
+flag = ctypes.c_int.in_dll(_ffi.lib(), "rcmvs_wgrad_variant")
+for v in (0, 1, 2, 3, 0):
+    flag.value = v
+    r = train.bench_train_step(dev, steps=5)
+    print("wgrad variant %d: %.3f ms/step  loss %.6f" % (v, r["ms_per_step"], r["loss"]), flush=True)
+flag.value = 0
