@@ -31,8 +31,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a barrier that never completes (a protocol bug, a TMA box whose byte count differs from expect_tx)
+// traps after ~2^28 polls (seconds) instead of hanging the GPU; legitimate waits are micro- to milliseconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++polls == (1u << 28)) __trap();
   }
 }
 

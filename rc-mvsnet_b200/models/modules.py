@@ -296,6 +296,8 @@ def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit, slab=Fa
         cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, transposed, nsplit), shift, cout, nsplit, gmode))
     if slab and not transposed and stride == 1 and (cin, cout) in ops.SLAB_SUPPORTED:
         cands.append(("slab", ops.conv3d_slab_pack(w, scale), shift, cout))
+    if slab and not transposed and stride == 2 and (cin, cout) == (8, 16):
+        cands.append(("slab2", ops.conv3d_s2_slab_pack(w, scale), shift, cout))
     return {"cands": cands, "tr": transposed, "stride": stride, "relu": relu, "choice": {}}
 
 
@@ -349,11 +351,17 @@ class CostRegNet(nn.Module):
         return self._packed.get((_versions(self), mode), build)
 
     @staticmethod
-    def _call(cand, layer, x, skip):
+    def _call(cand, layer, x, skip, out="y"):
+        """`out`: "y" fp32 result; "split" / "both": also / only the pre-split bf16 form (slab engines only)."""
         kind = cand[0]
-        if kind == "slab":      # TMA-fed split-bf16 tcgen05 kernel; the input is pre-split by its producer when possible
+        if kind in ("slab", "slab2"):   # TMA-fed split-bf16 tcgen05 kernels; the input is pre-split by its producer when possible
             xs = x if x.dtype == torch.bfloat16 else ops.split_bf16(x)
-            return ops.conv3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"])
+            wy, ws = out in ("y", "both"), out in ("split", "both")
+            if kind == "slab2":
+                return ops.conv3d_s2_slab(xs, cand[1], cand[2], layer["relu"], want_y=wy, want_split=ws)
+            return ops.conv3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"], want_y=wy, want_split=ws)
+        if out != "y":
+            raise RuntimeError("rcmvs: only the slab engines write split-bf16 activations")
         if x.dtype == torch.bfloat16:
             raise RuntimeError("rcmvs: split-bf16 activations can only feed the slab tensor-core engine")
         if kind == "gemm":
@@ -396,11 +404,16 @@ class CostRegNet(nn.Module):
         return layer["choice"][key]
 
     @classmethod
-    def _run(cls, layer, x, skip=None):
+    def _run(cls, layer, x, skip=None, out="y"):
         """Run a layer with the engine chosen for this input shape (static table, or timed once with CUDA events under
         RCMVS_AUTOTUNE=1, then cached)."""
         shape = x.shape[1:] if x.dtype == torch.bfloat16 else x.shape
-        return cls._call(layer["cands"][cls._choose(layer, shape, x, skip)], layer, x, skip)
+        return cls._call(layer["cands"][cls._choose(layer, shape, x, skip)], layer, x, skip, out)
+
+    @classmethod
+    def _kind(cls, layer, shape):
+        """Name of the engine the static table picks for `layer` at this input shape."""
+        return layer["cands"][cls._choose(layer, tuple(shape))][0]
 
     @staticmethod
     def _default_engine(layer, cands, shape):
@@ -413,6 +426,8 @@ class CostRegNet(nn.Module):
         cin = shape[-1]
         if "slab" in kinds:                                                # bf16x3 mode: conv0 (Cin 16/32), conv2
             return kinds.index("slab")
+        if "slab2" in kinds:                                               # bf16x3 mode: conv1 (8 -> 16, stride 2)
+            return kinds.index("slab2")
         if "tc" in kinds:
             cout = cands[kinds.index("tc")][3]
             return kinds.index("tc") if cout != 1 else 0
@@ -428,10 +443,16 @@ class CostRegNet(nn.Module):
             return {}
         return {n: {str(k): l["cands"][i][0] for k, i in l["choice"].items()} for n, l in self._packed.last.items()}
 
+    @staticmethod
+    def _static_engines():
+        """bf16x3 mode with the built-in engine table (no RCMVS_ENGINE pin, no RCMVS_AUTOTUNE)."""
+        return conv_precision() == "bf16x3" and not os.environ.get("RCMVS_ENGINE") and \
+            os.environ.get("RCMVS_AUTOTUNE", "0") != "1"
+
     def wants_split_input(self):
         """True when conv0 runs on the split-bf16 slab engine: the sweep kernel then writes the variance pre-split
         ([2,B,D,h,w,C] bf16: hi, lo) and no conversion pass sits between the two kernels."""
-        if conv_precision() != "bf16x3" or os.environ.get("RCMVS_ENGINE") or os.environ.get("RCMVS_AUTOTUNE", "0") == "1":
+        if not self._static_engines():
             return False
         return (self.conv0.conv.in_channels, self.conv0.conv.out_channels) in ops.SLAB_SUPPORTED
 
@@ -442,8 +463,19 @@ class CostRegNet(nn.Module):
             # three stride-2 levels: the reference fails at the first skip add (modules.py:497) for such shapes
             raise ValueError("CostRegNet needs D, H, W divisible by 8, got %s" % (tuple(dims),))
         P, run = self.packed(), self._run
-        c0 = run(P["conv0"], x_cl)
-        c2 = run(P["conv2"], run(P["conv1"], c0))
+        B = x_cl.shape[1] if x_cl.dtype == torch.bfloat16 else x_cl.shape[0]
+        D, H, W = (int(v) for v in dims)
+        c = self.conv0.conv.out_channels
+        chain = self._static_engines()                          # activations may flow pre-split between slab engines
+        k0 = self._kind(P["conv0"], (B, D, H, W, self.conv0.conv.in_channels)) if chain else ""
+        k1 = self._kind(P["conv1"], (B, D, H, W, c)) if chain else ""
+        k2 = self._kind(P["conv2"], (B, D // 2, H // 2, W // 2, 2 * c)) if chain else ""
+        if k0 == "slab" and k1 == "slab2":
+            c0, c0s = run(P["conv0"], x_cl, out="both")           # fp32 for the conv11 skip, split for conv1
+        else:
+            c0 = c0s = run(P["conv0"], x_cl)
+        c1 = run(P["conv1"], c0s, out="split" if (k1 == "slab2" and k2 == "slab") else "y")
+        c2 = run(P["conv2"], c1)
         c4 = run(P["conv4"], run(P["conv3"], c2))
         y = run(P["conv6"], run(P["conv5"], c4))
         y = run(P["conv7"], y, c4)                               # skip + relu(bn(convT(y)))  (modules.py:497-499)

@@ -290,6 +290,32 @@ def test_conv3d_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
     np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
 
 
+@pytest.mark.parametrize("dhw", [(2, 2, 2), (4, 8, 62), (6, 34, 64), (16, 24, 126), (10, 64, 80), (2, 26, 190)])
+def test_conv3d_s2_slab_bf16x3_vs_oracle(dev, dhw):
+    """conv1 (8 -> 16, stride 2) on tcgen05: strided TMA boxes (parity sub-planes), two taps per K = 16 step through the
+    descriptor's leading-dimension offset, kd through a TMEM ring.  Same accuracy class as the stride-1 slab kernel."""
+    from oracle import ref_np as O
+    from rcmvs import ops
+    rng = np.random.default_rng(sum(dhw))
+    D, H, W = dhw
+    xs = [rng.standard_normal((8, D, H, W), dtype=np.float32) for _ in range(2)]
+    w = (rng.standard_normal((16, 8, 3, 3, 3)) / np.sqrt(27 * 8)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 16).astype(np.float32)
+    bias = rng.standard_normal(16).astype(np.float32)
+    lin = np.stack([O.conv3d(x, w * scale[:, None, None, None, None], stride=2) for x in xs])
+    want = np.maximum(lin + bias[None, :, None, None, None], 0)
+    img = ops.conv3d_s2_slab_pack(cu(w, dev), cu(scale, dev))
+    x_split = ops.split_bf16(cu(np.stack(xs).transpose(0, 2, 3, 4, 1), dev))
+    y, ys = ops.conv3d_s2_slab(x_split, img, cu(bias, dev), True, True, True)
+    assert tuple(y.shape) == (2, D // 2, H // 2, W // 2, 16)
+    np.testing.assert_allclose(y.permute(0, 4, 1, 2, 3).cpu().numpy(), want, atol=1e-4, rtol=1e-4)
+    assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
+    y2 = ops.conv3d_s2_slab(x_split, img, None, False)
+    np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
+    ys_only = ops.conv3d_s2_slab(x_split, img, cu(bias, dev), True, want_y=False, want_split=True)
+    assert torch.equal(ys_only, ys)
+
+
 # ---- a1+a2 round-2 sweep kernel (v3) -------------------------------------------------------------------------------------
 def test_sweep_v3_bitwise_equals_v1_and_split_output(dev):
     """The plane-distributed v3 kernel (shifted in-bounds quad + folded weights, packed fp32x2 math, IEEE division) must
