@@ -62,6 +62,7 @@ struct Params {
   int d_chunk, chunks;
   int relu;
   int dbg;                     // experiment switches (tools/slab_experiments.py); 0 in the product path
+  long long* trace;            // experiment: clock64 timeline of two CTAs (null in the product path)
 };
 
 template <int CIN, int COUT, int KM, int NS>
@@ -87,6 +88,17 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   const int d1 = min(p.D, d0 + p.d_chunk);
   const int nplanes = d1 - d0;           // output planes d0..d1-1 ; input slabs z = d0-1 .. d1  (nplanes + 2)
   const int nslabs = nplanes + 2;
+  // experiment: timeline of the first CTA and of the middle one: [0] start, [1] prologue done, [2] end, [3] nslabs,
+  // [8+i] producer got the stage of slab i, [72+i] issuer saw slab i landed, [136+i] issuer finished issuing slab i,
+  // [200+q] epilogue saw plane q complete, [264+q] epilogue stored plane q
+  long long* tr = nullptr;
+  if (p.trace) {
+    const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    if (lin == 0) tr = p.trace;
+    else if (lin == total / 2) tr = p.trace + 512;
+  }
+  if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[3] = nslabs; }
 
   // ---- one-time setup -------------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -121,6 +133,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 4) {
     // =============================== TMA producer =================================================================
@@ -130,6 +143,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       for (int ii = 0; ii < nslabs; ++ii) {
         const int buf = ii % NS;
         mbar_wait(empty + buf, ((ii / NS) & 1) ^ 1);
+        if (tr && ii < 64) tr[8 + ii] = clock64();
         if (p.dbg & 8) { mbar_arrive(full + buf); continue; }   // experiment: no TMA traffic
         mbar_arrive_expect_tx(full + buf, (uint32_t)C::STAGE_B);
         const int z = d0 - 1 + ii;
@@ -152,8 +166,9 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       const int qnew = i;                                                  // plane first touched by this slab (j=2)
       if (qnew < nplanes && qnew >= NG) mbar_wait(grp_free + (qnew % NG), ((qnew / NG) - 1) & 1);
       const int buf = i % NS;
-      if (!(p.dbg & 2)) mbar_wait(full + buf, (i / NS) & 1);
+      mbar_wait(full + buf, (i / NS) & 1);
       tc_fence_after();
+      if (tr && leader && i < 64) tr[72 + i] = clock64();
       const uint32_t a_base = smem_u32(a_smem + (size_t)buf * C::STAGE_B);
       // split the valid block range into (at most two) ring-contiguous runs; per run: TMEM column, B row offset, N
       const int g0 = (i - 2 + jlo + NG) % NG;
@@ -194,6 +209,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       if (leader) {
         umma_commit(empty + buf);                                   // slab consumed once these MMAs retire
         if (i >= 2) umma_commit(grp_full + ((i - 2) % NG));         // output plane q = i-2 is complete
+        if (tr && i < 64) tr[136 + i] = clock64();
       }
       __syncwarp();
     }
@@ -206,6 +222,7 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       const int g = q % NG;
       mbar_wait(grp_full + g, (q / NG) & 1);
       tc_fence_after();
+      if (tr && threadIdx.x == 0 && q < 64) tr[200 + q] = clock64();
       uint32_t vr[KM][G];
 #pragma unroll
       for (int mt = 0; mt < KM; ++mt) {
@@ -297,12 +314,14 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
         }
       }
       epi_bar_sync();                              // exchange buffer is reused by the next plane
+      if (tr && threadIdx.x == 0 && q < 64) tr[264 + q] = clock64();
     }
   }
 
   // ---- teardown -------------------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -424,6 +443,7 @@ extern "C" int rcmvs_split_bf16(const float* x, void* xs, int64_t n, rcmvs_strea
 
 // experiment switches for tools/slab_experiments.py (set through ctypes in_dll; not part of the ABI, 0 = product behaviour)
 extern "C" int rcmvs_slab_debug_flags = 0;
+extern "C" long long* rcmvs_slab_trace = nullptr;      // device buffer of 1024 int64 (tools/slab_experiments.py)
 
 extern "C" int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip,
                                      float* y, void* y_split, int B, int D, int H, int W, int Cin, int Cout, int relu,
@@ -439,7 +459,7 @@ extern "C" int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, cons
   Params p;
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.bias = bias; p.skip = skip; p.y = y; p.ys = reinterpret_cast<__nv_bfloat16*>(y_split);
-  p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu; p.dbg = rcmvs_slab_debug_flags;
+  p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu; p.dbg = rcmvs_slab_debug_flags; p.trace = rcmvs_slab_trace;
   int km = 2, chunks = 1;
   plan(B, D, H, W, Cin, Cout, km, chunks);
   p.d_chunk = ceil_div(D, chunks);

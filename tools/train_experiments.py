@@ -1,5 +1,5 @@
 """A/B of the weight-gradient kernel variants inside the real training step (csrc/train.cu rcmvs_wgrad_variant):
-bit 0 = window slides by register moves (instead of the rotating window), bit 1 = one S channel per thread (instead of 4)."""
+bit 0 = rotating register window (instead of sliding by register moves), bit 1 = one S channel per thread (instead of 4)."""
 import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
