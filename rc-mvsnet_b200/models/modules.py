@@ -472,9 +472,13 @@ class CostRegNet(nn.Module):
         k2 = self._kind(P["conv2"], (B, D // 2, H // 2, W // 2, 2 * c)) if chain else ""
         if k0 == "slab" and k1 == "slab2":
             c0, c0s = run(P["conv0"], x_cl, out="both")           # fp32 for the conv11 skip, split for conv1
+            c1 = run(P["conv1"], c0s, out="split" if k2 == "slab" else "y")
         else:
-            c0 = c0s = run(P["conv0"], x_cl)
-        c1 = run(P["conv1"], c0s, out="split" if (k1 == "slab2" and k2 == "slab") else "y")
+            c0 = run(P["conv0"], x_cl)
+            if k1 == "slab2":      # fp32 input (stage 3: conv0 has 8 input channels and runs on the TF32 slab engine): a separate
+                c1 = self._call(P["conv1"]["cands"][0], P["conv1"], c0, None)   # split pass costs more than slab2 saves (measured)
+            else:
+                c1 = run(P["conv1"], c0)
         c2 = run(P["conv2"], c1)
         c4 = run(P["conv4"], run(P["conv3"], c2))
         y = run(P["conv6"], run(P["conv5"], c4))

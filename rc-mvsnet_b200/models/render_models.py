@@ -224,8 +224,10 @@ class CostReg(nn.Module):
                     if name == "conv0" and w.shape[1] < cin_pad:      # 41 -> 48 input channels, zero weights
                         w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, cin_pad - w.shape[1]))
                     P[name] = (ops.pack_conv3d_weight(w.contiguous(), scale, False), shift)
-                    if name == "conv0" and (w.shape[1], w.shape[0]) in ops.SLAB_SUPPORTED:
-                        P["conv0.slab"] = (ops.conv3d_slab_pack(w.contiguous(), scale), shift)   # tcgen05 + TMA, bf16x3
+                    if name in ("conv0", "conv2") and (w.shape[1], w.shape[0]) in ops.SLAB_SUPPORTED:
+                        P[name + ".slab"] = (ops.conv3d_slab_pack(w.contiguous(), scale), shift)   # tcgen05 + TMA, bf16x3
+                    if name == "conv1" and (w.shape[1], w.shape[0]) == (8, 16):
+                        P["conv1.slab2"] = (ops.conv3d_s2_slab_pack(w.contiguous(), scale), shift)  # stride-2 TMA kernel
                 for name in ("conv7", "conv9", "conv11"):
                     seq = getattr(self, name)
                     scale, shift = (t.contiguous() for t in fold_bn(seq[1]))
@@ -250,11 +252,18 @@ class CostReg(nn.Module):
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cpad] -> [B,D,h,w,8]; eval-mode BN folded, no ReLU anywhere."""
         P = self.packed(x_cl.shape[-1])          # (the split form has its channel count last as well)
-        if x_cl.dtype == torch.bfloat16:                  # pre-split input from resize_depth_cl_split: tensor-core conv0
-            c0 = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False)
+        if x_cl.dtype == torch.bfloat16 and "conv1.slab2" in P and "conv2.slab" in P:
+            # pre-split input from resize_depth_cl_split: conv0 -> conv1 (stride 2) -> conv2 on the tensor-core slab kernels,
+            # activations handed over in split-bf16 form
+            c0, c0s = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False, want_split=True)
+            c1s = ops.conv3d_s2_slab(c0s, P["conv1.slab2"][0], P["conv1.slab2"][1], relu=False, want_y=False, want_split=True)
+            c2 = ops.conv3d_slab(c1s, P["conv2.slab"][0], 16, P["conv2.slab"][1], None, relu=False)
         else:
-            c0 = ops.conv3d(x_cl, *P["conv0"], relu=False)
-        c2 = ops.conv3d(ops.conv3d(c0, *P["conv1"], stride=2, relu=False), *P["conv2"], relu=False)
+            if x_cl.dtype == torch.bfloat16:
+                c0 = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False)
+            else:
+                c0 = ops.conv3d(x_cl, *P["conv0"], relu=False)
+            c2 = ops.conv3d(ops.conv3d(c0, *P["conv1"], stride=2, relu=False), *P["conv2"], relu=False)
         c4 = ops.conv3d(ops.conv3d(c2, *P["conv3"], stride=2, relu=False), *P["conv4"], relu=False)
         y = ops.conv3d(ops.conv3d(c4, *P["conv5"], stride=2, relu=False), *P["conv6"], relu=False)
         y = ops.conv_transpose3d(y, *P["conv7"], skip=c4, relu=False)
