@@ -296,6 +296,8 @@ def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit, slab=Fa
         cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, transposed, nsplit), shift, cout, nsplit, gmode))
     if slab and not transposed and stride == 1 and (cin, cout) in ops.SLAB_SUPPORTED:
         cands.append(("slab", ops.conv3d_slab_pack(w, scale), shift, cout))
+    if slab and transposed and (cin, cout) == (16, 8):
+        cands.append(("slabt", ops.conv_transpose3d_slab_pack(w, scale), shift, cout))
     if slab and not transposed and stride == 2 and (cin, cout) == (8, 16):
         cands.append(("slab2", ops.conv3d_s2_slab_pack(w, scale), shift, cout))
     return {"cands": cands, "tr": transposed, "stride": stride, "relu": relu, "choice": {}}
@@ -354,9 +356,13 @@ class CostRegNet(nn.Module):
     def _call(cand, layer, x, skip, out="y"):
         """`out`: "y" fp32 result; "split" / "both": also / only the pre-split bf16 form (slab engines only)."""
         kind = cand[0]
-        if kind in ("slab", "slab2"):   # TMA-fed split-bf16 tcgen05 kernels; the input is pre-split by its producer when possible
+        if kind in ("slab", "slab2", "slabt"):   # TMA-fed split-bf16 tcgen05 kernels; the input is pre-split by its producer when possible
             xs = x if x.dtype == torch.bfloat16 else ops.split_bf16(x)
             wy, ws = out in ("y", "both"), out in ("split", "both")
+            if kind == "slabt":
+                if out != "y":
+                    raise RuntimeError("rcmvs: the transposed slab engine writes fp32 only")
+                return ops.conv_transpose3d_slab(xs, cand[1], cand[2], skip, layer["relu"])
             if kind == "slab2":
                 return ops.conv3d_s2_slab(xs, cand[1], cand[2], layer["relu"], want_y=wy, want_split=ws)
             return ops.conv3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"], want_y=wy, want_split=ws)
@@ -428,6 +434,8 @@ class CostRegNet(nn.Module):
             return kinds.index("slab")
         if "slab2" in kinds:                                               # bf16x3 mode: conv1 (8 -> 16, stride 2)
             return kinds.index("slab2")
+        if "slabt" in kinds:                                               # bf16x3 mode: conv11 (16 -> 8, transposed)
+            return kinds.index("slabt")
         if "tc" in kinds:
             cout = cands[kinds.index("tc")][3]
             return kinds.index("tc") if cout != 1 else 0
