@@ -33,21 +33,25 @@ template <int CIN, int COUT, int KM, int NS>
 struct Cfg {
   static constexpr int CP = COUT < 8 ? 8 : COUT;                  // channel slots per kh block
   static constexpr int G = ((3 * CP + 15) / 16) * 16;             // TMEM columns / B rows per plane block
-  static constexpr int KS = CIN / 16;                             // K steps (16 bf16 channels each)
+  static constexpr int KS = CIN / 16;                             // K steps (16 bf16 channels each) per kw tap, CIN >= 16
+  // CIN = 8: one K = 16 step covers TWO kw taps of the 8 channels — K-chunk 1 is the next position (LBO = 16 B); the
+  // second step is (kw = 2, zero): its chunk 1 reads a zero block (and has zero weights)
+  static constexpr int NSTEP = CIN == 8 ? 2 : 3 * KS;             // MMA steps per (slab, M-tile, term)
   static constexpr int NCH = CIN / 8;                             // 16-byte channel chunks
   static constexpr int ROWS = 4 * KM;
   static constexpr int OROWS = ROWS - 2;
   static constexpr int PLANE_B = ROWS * PW * 16;                  // one chunk plane = one TMA box
   static constexpr int SLAB_B = NCH * PLANE_B;                    // one part (hi or lo)
   static constexpr int STAGE_B = 2 * SLAB_B;
-  static constexpr int A_BYTES = NS * STAGE_B + 128;              // + the kw = 1, 2 overrun of the last M-tile
-  static constexpr int BBLK_B = 2 * 3 * G * 16;                   // one (kw, K-step): 2 chunks x 3G rows x 16 B
-  static constexpr int BTERM_B = 3 * KS * BBLK_B;
+  static constexpr int ZERO_OFF = NS * STAGE_B + 128;             // (CIN = 8) 2 KB of zeros: K-chunk 1 of the (kw = 2, zero) step
+  static constexpr int A_BYTES = NS * STAGE_B + 128 + (CIN == 8 ? 2048 + 128 : 0);   // + the kw overrun of the last M-tile
+  static constexpr int BBLK_B = 2 * 3 * G * 16;                   // one step: 2 chunks x 3G rows x 16 B
+  static constexpr int BTERM_B = NSTEP * BBLK_B;
   static constexpr int B_BYTES = 2 * BTERM_B;                     // hi, lo
   static constexpr int NG = 512 / (KM * G);
   static constexpr int EX_B = 3 * OROWS * PW * CP * 4;
   static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + EX_B + 512;
-  static_assert(CIN % 16 == 0, "K step = 16 bf16 channels");
+  static_assert(CIN == 8 || CIN % 16 == 0, "K step = 16 bf16 channels");
   static_assert(NG >= 4, "TMEM ring needs at least 4 plane groups");
   static_assert(PLANE_B % 128 == 0, "TMA destination alignment");
 };
@@ -118,7 +122,8 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
     float4* dst = reinterpret_cast<float4*>(b_smem);
     for (int i = threadIdx.x; i < C::B_BYTES / 16; i += kThreads) dst[i] = __ldg(src + i);
     // the overrun pad behind the last stage is read (into discarded accumulator rows) by the kw = 1, 2 taps
-    if (threadIdx.x < 8) reinterpret_cast<float4*>(a_smem + NS * C::STAGE_B)[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < (C::A_BYTES - NS * C::STAGE_B) / 16; i += kThreads)
+      reinterpret_cast<float4*>(a_smem + NS * C::STAGE_B)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -177,31 +182,43 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       const uint32_t d0c = tmem_base + g0 * G, d1c = tmem_base;
       const uint32_t idesc0 = make_idesc_bf16(128, (p.dbg & 32) ? G : n0 * G), idesc1 = make_idesc_bf16(128, (n1 > 0 ? n1 : 1) * G);
       const uint32_t boff0 = (uint32_t)(jlo * G), boff1 = (uint32_t)((jlo + n0) * G);   // in 16-byte rows
-      const uint32_t a_lo0 = desc_lo(a_base, C::PLANE_B);                  // hi-part slab
       const uint32_t b_lo0 = desc_lo(b_base, 3 * G * 16);
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
+      for (int st = 0; st < C::NSTEP; ++st) {
+        constexpr int KSD = C::KS > 0 ? C::KS : 1;
+        const int kw = CIN == 8 ? 2 * st : st / KSD, ks = CIN == 8 ? 0 : st % KSD;
 #pragma unroll
-        for (int ks = 0; ks < C::KS; ++ks) {
-#pragma unroll
-          for (int mt = 0; mt < KM; ++mt) {
-            constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
-            const uint32_t a_hi_d = a_lo0 + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + kw);
-            const uint32_t b_blk_d = b_lo0 + (uint32_t)(((kw * C::KS + ks) * C::BBLK_B) >> 4);
-            const uint32_t dm = (uint32_t)(mt * (NG * G));
-            if (leader && !((p.dbg & 16) && kw > 0)) {
+        for (int mt = 0; mt < KM; ++mt) {
+          constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
+          uint32_t a_hi_d, a_lo_d;
+          if constexpr (CIN == 8) {
+            const uint32_t a_off = (uint32_t)((mt * 128 + kw) * 16);               // bytes from the slab start
+            if (st == 0) {                                                        // (kw0, kw1): chunk 1 = next position
+              a_hi_d = desc_lo(a_base + a_off, 16);
+              a_lo_d = a_hi_d + kLoOff;
+            } else {                                                              // (kw2, zero): chunk 1 = zero block
+              const uint32_t zb = smem_u32(a_smem) + C::ZERO_OFF;
+              a_hi_d = desc_lo(a_base + a_off, zb - (a_base + a_off));
+              a_lo_d = desc_lo(a_base + C::SLAB_B + a_off, zb - (a_base + C::SLAB_B + a_off));
+            }
+          } else {
+            a_hi_d = desc_lo(a_base, C::PLANE_B) + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + kw);
+            a_lo_d = a_hi_d + kLoOff;
+          }
+          const uint32_t b_blk_d = b_lo0 + (uint32_t)((st * C::BBLK_B) >> 4);
+          const uint32_t dm = (uint32_t)(mt * (NG * G));
+          if (leader && !((p.dbg & 16) && kw > 0)) {
+            if (!(p.dbg & 1)) {
+              umma_bf16_lohi(d0c + dm, a_lo_d, b_blk_d + boff0, idesc0);                   // x_lo · w_hi
+              umma_bf16_lohi(d0c + dm, a_hi_d, b_blk_d + boff0 + kBLoOff, idesc0);         // x_hi · w_lo
+            }
+            umma_bf16_lohi(d0c + dm, a_hi_d, b_blk_d + boff0, idesc0);                     // x_hi · w_hi
+            if (n1 > 0) {
               if (!(p.dbg & 1)) {
-                umma_bf16_lohi(d0c + dm, a_hi_d + kLoOff, b_blk_d + boff0, idesc0);          // x_lo · w_hi
-                umma_bf16_lohi(d0c + dm, a_hi_d, b_blk_d + boff0 + kBLoOff, idesc0);         // x_hi · w_lo
+                umma_bf16_lohi(d1c + dm, a_lo_d, b_blk_d + boff1, idesc1);
+                umma_bf16_lohi(d1c + dm, a_hi_d, b_blk_d + boff1 + kBLoOff, idesc1);
               }
-              umma_bf16_lohi(d0c + dm, a_hi_d, b_blk_d + boff0, idesc0);                     // x_hi · w_hi
-              if (n1 > 0) {
-                if (!(p.dbg & 1)) {
-                  umma_bf16_lohi(d1c + dm, a_hi_d + kLoOff, b_blk_d + boff1, idesc1);
-                  umma_bf16_lohi(d1c + dm, a_hi_d, b_blk_d + boff1 + kBLoOff, idesc1);
-                }
-                umma_bf16_lohi(d1c + dm, a_hi_d, b_blk_d + boff1, idesc1);
-              }
+              umma_bf16_lohi(d1c + dm, a_hi_d, b_blk_d + boff1, idesc1);
             }
           }
         }
@@ -329,26 +346,29 @@ conv3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
 }
 
 // Weight image: torch Conv3d weight [Cout][Cin][27] x BN scale ->
-//   img[term][kw][ks][chunk][row = jblk*G + kh*CP + n][e],  kd = 2 - jblk, channel = ks*16 + chunk*8 + e
+//   img[term][step][chunk][row = jblk*G + kh*CP + n][e],  kd = 2 - jblk
+//     Cin >= 16: step = kw*KS + ks, channel = ks*16 + chunk*8 + e
+//     Cin == 8 : step s covers taps kw = 2s + chunk (kw = 3: zero), channel = e
 //   term 0 = bf16(w·scale), term 1 = bf16(w·scale - term 0); zero for padded rows
 __global__ void pack_slab_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                         __nv_bfloat16* __restrict__ img, int Cout, int Cin, int CP, int G) {
   const int KS = Cin / 16;
-  const int per_term = 3 * KS * 2 * 3 * G * 8;
+  const int nstep = Cin == 8 ? 2 : 3 * KS;
+  const int per_term = nstep * 2 * 3 * G * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_term) return;
   const int e = i & 7;
   int r = i >> 3;
   const int row = r % (3 * G); r /= (3 * G);
   const int chunk = r & 1; r >>= 1;
-  const int ks = r % KS;
-  const int kw = r / KS;
+  const int st = r;
+  const int kw = Cin == 8 ? 2 * st + chunk : st / KS;
+  const int ci = Cin == 8 ? e : (st % KS) * 16 + chunk * 8 + e;
   const int jblk = row / G, rr = row % G;
   const int kh = rr / CP, n = rr % CP;
   float v = 0.f;
-  if (kh < 3 && n < Cout) {
+  if (kh < 3 && n < Cout && kw < 3) {
     const int kd = 2 - jblk;
-    const int ci = ks * 16 + chunk * 8 + e;
     v = w[((int64_t)n * Cin + ci) * 27 + (kd * 9 + kh * 3 + kw)];
     if (scale) v *= scale[n];
   }
@@ -389,7 +409,7 @@ static int launch(const void* x, const Params& p, cudaStream_t st) {
 }
 
 static bool supported(int Cin, int Cout) {
-  return (Cout == 8 && (Cin == 16 || Cin == 32 || Cin == 48)) || (Cout == 16 && Cin == 16);
+  return (Cout == 8 && (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 48)) || (Cout == 16 && Cin == 16);
 }
 
 // depth chunks + M-tiles per CTA: one CTA per SM (shared memory), so minimise
@@ -414,7 +434,8 @@ static void plan(int B, int D, int H, int W, int Cin, int Cout, int& km, int& ch
 extern "C" int64_t rcmvs_conv3d_slab_weight_elems(int Cin, int Cout) {
   const int cp = Cout < 8 ? 8 : Cout;
   const int g = ((3 * cp + 15) / 16) * 16;
-  return (int64_t)2 * 3 * (Cin / 16) * 2 * 3 * g * 8;
+  const int nstep = Cin == 8 ? 2 : 3 * (Cin / 16);
+  return (int64_t)2 * nstep * 2 * 3 * g * 8;
 }
 
 extern "C" int rcmvs_conv3d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin,
@@ -425,7 +446,7 @@ extern "C" int rcmvs_conv3d_slab_pack(const float* w, const float* scale, void* 
                 Cout);
   const int cp = Cout < 8 ? 8 : Cout;
   const int g = ((3 * cp + 15) / 16) * 16;
-  const int per_term = 3 * (Cin / 16) * 2 * 3 * g * 8;
+  const int per_term = (Cin == 8 ? 2 : 3 * (Cin / 16)) * 2 * 3 * g * 8;
   slab::pack_slab_weight_kernel<<<ceil_div(per_term, 256), 256, 0, as_stream(stream)>>>(
       w, scale, reinterpret_cast<__nv_bfloat16*>(img), Cout, Cin, cp, g);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_slab_pack");
@@ -466,6 +487,7 @@ extern "C" int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, cons
   p.chunks = ceil_div(D, p.d_chunk);
   cudaStream_t st = as_stream(stream);
   if (Cin == 32 && Cout == 8) return km == 3 ? launch<32, 8, 3, 3>(x_split, p, st) : launch<32, 8, 2, 4>(x_split, p, st);
+  if (Cin == 8 && Cout == 8) return km == 3 ? launch<8, 8, 3, 8>(x_split, p, st) : launch<8, 8, 2, 8>(x_split, p, st);   // conv0, stage 3
   if (Cin == 16 && Cout == 8) return km == 3 ? launch<16, 8, 3, 5>(x_split, p, st) : launch<16, 8, 2, 6>(x_split, p, st);
   if (Cin == 16 && Cout == 16) return launch<16, 16, 2, 5>(x_split, p, st);
   if (Cin == 48 && Cout == 8) return launch<48, 8, 2, 3>(x_split, p, st);      // Neural_Volume_Net conv0 (41 -> 48 padded)

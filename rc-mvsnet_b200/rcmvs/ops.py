@@ -230,7 +230,7 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     return y
 
 
-SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16), (48, 8)}      # (Cin, Cout) of the TMA-fed split-bf16 slab kernel
+SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16), (48, 8), (8, 8)}      # (Cin, Cout) of the TMA-fed split-bf16 slab kernel
 
 
 def _chk_bf16(t, name):

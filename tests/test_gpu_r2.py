@@ -262,7 +262,7 @@ def test_model_on_second_device_while_first_is_current():
 # ---- a3 round-2 engine: TMA-fed split-bf16 slab convolution ---------------------------------------------------------------
 @pytest.mark.parametrize("cin,cout,dhw", [
     (32, 8, (4, 17, 61)), (16, 8, (2, 8, 30)), (16, 16, (9, 5, 64)), (32, 8, (1, 1, 1)), (32, 8, (20, 8, 31)),
-    (16, 8, (23, 21, 95)), (16, 16, (13, 14, 31)), (32, 8, (7, 40, 33)),
+    (16, 8, (23, 21, 95)), (16, 16, (13, 14, 31)), (32, 8, (7, 40, 33)), (8, 8, (8, 24, 61)), (8, 8, (3, 10, 30)), (8, 8, (1, 1, 1)),
 ])
 def test_conv3d_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
     """kind::f16 tcgen05 + TMA, split-bf16 operands: fp32-class accuracy (dropped terms <= 3·2^-17 relative per product)."""
