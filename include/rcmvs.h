@@ -150,14 +150,16 @@ int64_t rcmvs_conv3d_s2_slab_weight_elems(void);
 int rcmvs_conv3d_s2_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
 int rcmvs_conv3d_s2_slab_fwd(const void* x_split, const void* wimg, const float* bias, float* y, void* y_split, int B,
                              int D, int H, int W, int Cin, int Cout, int relu, rcmvs_stream_t stream);
-/* Transposed member of the family: conv11 of CostRegNet (ConvTranspose3d 16 -> 8, k3, stride 2, pad 1, output_padding 1
- * + folded BN + ReLU + skip add; reference models/modules.py:166-210, :488, :499).  x_split [2][B][D][H][W][16] ->
- * y [B][2D][2H][2W][8] fp32; skip (same shape as y) may be NULL.  Only (Cin, Cout) = (16, 8). */
-int64_t rcmvs_conv_transpose3d_slab_weight_elems(void);
+/* Transposed members of the family: conv11 (ConvTranspose3d 16 -> 8) and conv9 (32 -> 16) of CostRegNet, k3, stride 2,
+ * pad 1, output_padding 1 + folded BN + ReLU + skip add (reference models/modules.py:166-210, :486-488, :498-499).
+ * x_split [2][B][D][H][W][Cin] -> y [B][2D][2H][2W][Cout] fp32 and / or y_split [2][B][2D][2H][2W][Cout] (either may be
+ * NULL); skip (fp32, same shape as y) may be NULL.  (Cin, Cout) in {(16,8), (32,16)}. */
+int64_t rcmvs_conv_transpose3d_slab_weight_elems(int Cin, int Cout);
 int rcmvs_conv_transpose3d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin,
                                      rcmvs_stream_t stream);
 int rcmvs_conv_transpose3d_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip, float* y,
-                                    int B, int D, int H, int W, int Cin, int Cout, int relu, rcmvs_stream_t stream);
+                                    void* y_split, int B, int D, int H, int W, int Cin, int Cout, int relu,
+                                    rcmvs_stream_t stream);
 /* x [n] fp32 -> xs [2][n] bf16 (hi plane, lo plane). */
 int rcmvs_split_bf16(const float* x, void* xs, int64_t n, rcmvs_stream_t stream);
 

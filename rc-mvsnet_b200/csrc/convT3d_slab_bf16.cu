@@ -12,6 +12,10 @@
 // (each input voxel scatters 8 x 32 B of output and reads 8 x 32 B of skip tensor), so it is sized for TWO CTAs per SM
 // (107 KB of shared memory, 256 TMEM columns each): eight epilogue warps per SM keep twice the loads in flight.
 //
+// conv9 (32 -> 16, quarter -> half resolution) runs on the same kernel: two K steps, N = 128, the shifts with dz = 1 only
+// address the 64 columns of the classes that use them, the epilogue walks the classes in two passes, and the result is
+// written pre-split for conv11 (one CTA per SM: its weight image alone is 96 KB).
+//
 // Warp roles: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer.
 #include "slab_common.cuh"
 
@@ -20,7 +24,6 @@ namespace slabt {
 
 using namespace rcmvs::slab;
 
-constexpr int CIN = 16, COUT = 8, N = 8 * COUT;
 constexpr int TWI = 31;                                            // input columns per tile (column 31 = halo for dx = 1)
 
 __device__ __forceinline__ void umma_bf16_lohi_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
@@ -35,36 +38,44 @@ __device__ __forceinline__ void umma_bf16_lohi_acc(uint32_t tmem_d, uint32_t a_l
       : "memory");
 }
 
-template <int KM, int NS>
+template <int CIN, int COUT, int KM, int NS>
 struct Cfg {
+  static constexpr int N = 8 * COUT;                               // 8 output parity classes x COUT
+  static constexpr int KS = CIN / 16, NCH = CIN / 8;
   static constexpr int ROWS = 4 * KM;                              // input rows per CTA tile (all produce outputs)
   static constexpr int PLANE_B = (ROWS + 1) * PW * 16;             // one 8-channel chunk plane (+1 halo row for dy = 1)
-  static constexpr int SLAB_B = 2 * PLANE_B;                       // one part (hi or lo): 2 chunks
+  static constexpr int SLAB_B = NCH * PLANE_B;                     // one part (hi or lo)
   static constexpr int STAGE_B = 2 * SLAB_B;
   static constexpr int A_BYTES = NS * STAGE_B + 128;               // + overrun of the (dy, dx) = (1, 1) shift
-  static constexpr int BBLK_B = 2 * N * 16;                        // one shift: 2 chunks x 64 rows x 16 B
-  static constexpr int BTERM_B = 8 * BBLK_B;
+  // B blocks: the four dz = 0 shifts carry all 8 classes (N rows), the four dz = 1 shifts only the classes with a = 1
+  // (the upper N/2 rows / TMEM columns)
+  static constexpr int BBLK0_B = 2 * N * 16, BBLK1_B = N * 16;     // per (shift, K step): 2 chunks x rows x 16 B
+  static constexpr int BTERM_B = 4 * KS * (BBLK0_B + BBLK1_B);
   static constexpr int B_BYTES = 2 * BTERM_B;                      // hi, lo
   static constexpr int TCOLS = 2 * KM * N;                         // double-buffered accumulators
+  static constexpr int CPP = 64 / COUT;                            // classes per epilogue pass (64 accumulator columns)
   static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + 256;
   static_assert(PLANE_B % 128 == 0, "TMA destination alignment");
   static_assert(TCOLS == 256 || TCOLS == 512, "TMEM allocation is a power of two");
+  static_assert(CIN % 16 == 0 && (COUT == 8 || COUT == 16), "configuration");
 };
 
 struct Params {
   const __nv_bfloat16* wimg;
-  const float* bias;           // [8] or null
-  const float* skip;           // [B][2D][2H][2W][8] or null
-  float* y;                    // [B][2D][2H][2W][8]
+  const float* bias;           // [COUT] or null
+  const float* skip;           // [B][2D][2H][2W][COUT] or null
+  float* y;                    // [B][2D][2H][2W][COUT] fp32 or null
+  __nv_bfloat16* ys;           // [2][B][2D][2H][2W][COUT] split-bf16 or null
   int B, D, H, W;              // input dims
   int d_chunk, chunks;
   int relu;
 };
 
-template <int KM, int NS>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int CIN, int COUT, int KM, int NS, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 convT3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  using C = Cfg<KM, NS>;
+  using C = Cfg<CIN, COUT, KM, NS>;
+  constexpr int N = C::N;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* a_smem = smem;
   unsigned char* b_smem = smem + C::A_BYTES;
@@ -120,15 +131,15 @@ convT3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
 #pragma unroll
         for (int part = 0; part < 2; ++part)
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch)
+          for (int ch = 0; ch < C::NCH; ++ch)
             tma_load_5d(dst0 + part * C::SLAB_B + ch * C::PLANE_B, &tmap, full + buf, ch * 8, x0, y0, z0 + ii, part * p.B + b);
       }
     }
   } else if (warp == 5) {
     // =============================== MMA issuer ==================================================================
     const bool leader = elect_one();
-    const uint32_t b_lo0 = desc_lo(smem_u32(b_smem), N * 16);
-    const uint32_t idesc = make_idesc_bf16(128, N);
+    const uint32_t b_base = smem_u32(b_smem);
+    constexpr uint32_t idesc_full = make_idesc_bf16(128, N), idesc_half = make_idesc_bf16(128, N / 2);
     for (int s = 0; s < nsteps; ++s) {
       const int stage = s & 1;
       mbar_wait(acc_empty + stage, ((s >> 1) & 1) ^ 1);
@@ -140,19 +151,27 @@ convT3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
         mbar_wait(full + buf, (i / NS) & 1);       // (slab s + 1 is waited for again as slab (s+1) + 0: already complete)
         tc_fence_after();
         const uint32_t a_lo0 = desc_lo(smem_u32(a_smem + (size_t)buf * C::STAGE_B), C::PLANE_B);
+        // dz = 0: all 8 classes (N columns); dz = 1: only the classes with a = 1 = the upper N/2 columns / rows
+        const uint32_t idesc = dz == 0 ? idesc_full : idesc_half;
+        const uint32_t col_off = dz == 0 ? 0u : (uint32_t)(N / 2);
+        const uint32_t blk_b = dz == 0 ? (uint32_t)C::BBLK0_B : (uint32_t)C::BBLK1_B;
+        const uint32_t b_lo0 = desc_lo(b_base + (dz == 0 ? 0 : 4 * C::KS * C::BBLK0_B), blk_b / 2);
 #pragma unroll
         for (int dyx = 0; dyx < 4; ++dyx) {
-          const int sh = dz * 4 + dyx;                                   // shift index (dz, dy, dx)
 #pragma unroll
-          for (int mt = 0; mt < KM; ++mt) {
-            constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
-            const uint32_t a_d = a_lo0 + (uint32_t)(mt * 128 + (dyx >> 1) * PW + (dyx & 1));
-            const uint32_t b_d = b_lo0 + (uint32_t)((sh * C::BBLK_B) >> 4);
-            const uint32_t d = tmem_base + (uint32_t)(stage * KM * N + mt * N);
-            if (leader) {
-              umma_bf16_lohi_acc(d, a_d + kLoOff, b_d, idesc, sh == 0 ? 0u : 1u);   // x_lo · w_hi (first MMA overwrites)
-              umma_bf16_lohi_acc(d, a_d, b_d + kBLoOff, idesc, 1u);                 // x_hi · w_lo
-              umma_bf16_lohi_acc(d, a_d, b_d, idesc, 1u);                           // x_hi · w_hi
+          for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+            for (int mt = 0; mt < KM; ++mt) {
+              constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
+              const uint32_t a_d = a_lo0 + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + (dyx >> 1) * PW + (dyx & 1));
+              const uint32_t b_d = b_lo0 + (uint32_t)(((dyx * C::KS + ks) * blk_b) >> 4);
+              const uint32_t d = tmem_base + (uint32_t)(stage * KM * N + mt * N) + col_off;
+              const bool first = dz == 0 && dyx == 0 && ks == 0;
+              if (leader) {
+                umma_bf16_lohi_acc(d, a_d + kLoOff, b_d, idesc, first ? 0u : 1u);     // x_lo · w_hi (first MMA overwrites)
+                umma_bf16_lohi_acc(d, a_d, b_d + kBLoOff, idesc, 1u);                 // x_hi · w_lo
+                umma_bf16_lohi_acc(d, a_d, b_d, idesc, 1u);                           // x_hi · w_hi
+              }
             }
           }
         }
@@ -171,55 +190,63 @@ convT3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
     // after the previous M-tile's stores, not one load per class in front of its add (latency-bound otherwise)
     float4 sk[16];
     const bool use_skip = p.skip != nullptr;
-    float4 bs0 = make_float4(0.f, 0.f, 0.f, 0.f), bs1 = bs0;
-    if (p.bias) { bs0 = ldg4(p.bias); bs1 = ldg4(p.bias + 4); }
-    auto load_skip = [&](int iz, int mt) {
+    const int64_t part_stride = (int64_t)p.B * Do * Ho * Wo * COUT;
+    constexpr int CPP = C::CPP, NPASS = 8 / CPP, Q = COUT / 4;      // float4 groups per class
+    // one pass = CPP classes = 64 accumulator columns = 16 float4 of skip tensor
+    auto load_skip = [&](int iz, int mt, int pass) {
       const int gy = y0 + mt * 4 + warp;
       const bool ok = use_skip && col_ok && gy < p.H;
 #pragma unroll
-      for (int cls = 0; cls < 8; ++cls) {
+      for (int cc = 0; cc < CPP; ++cc) {
+        const int cls = pass * CPP + cc;
         const int oz = 2 * iz + (cls >> 2), oy = 2 * gy + ((cls >> 1) & 1), ox = 2 * gx + (cls & 1);
         const int64_t o = ((((int64_t)b * Do + oz) * Ho + oy) * Wo + ox) * COUT;
-        sk[cls * 2] = ok ? ldg4(p.skip + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-        sk[cls * 2 + 1] = ok ? ldg4(p.skip + o + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < Q; ++h) sk[cc * Q + h] = ok ? ldg4(p.skip + o + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     for (int s = 0; s < nsteps; ++s) {
       const int stage = s & 1;
       const int iz = z0 + s;
-      load_skip(iz, 0);
+      load_skip(iz, 0, 0);
       mbar_wait(acc_full + stage, (s >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int mt = 0; mt < KM; ++mt) {
-        uint32_t vr[N];
-        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * KM * N + mt * N;
+      for (int it = 0; it < KM * NPASS; ++it) {
+        const int mt = it / NPASS, pass = it % NPASS;
+        uint32_t vr[64];
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * KM * N + mt * N + pass * 64;
 #pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16_nowait(ta + c0, &vr[c0]);
+        for (int c0 = 0; c0 < 64; c0 += 16) tmem_ld16_nowait(ta + c0, &vr[c0]);
         tmem_ld_wait();
-        if (mt == KM - 1) {
+        if (it == KM * NPASS - 1) {
           tc_fence_before();
           mbar_arrive(acc_empty + stage);
         }
         const int gy = y0 + mt * 4 + warp;
         if (col_ok && gy < p.H) {
 #pragma unroll
-          for (int cls = 0; cls < 8; ++cls) {
+          for (int cc = 0; cc < CPP; ++cc) {
+            const int cls = pass * CPP + cc;
             const int oz = 2 * iz + (cls >> 2), oy = 2 * gy + ((cls >> 1) & 1), ox = 2 * gx + (cls & 1);
             const int64_t o = ((((int64_t)b * Do + oz) * Ho + oy) * Wo + ox) * COUT;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 bb = h ? bs1 : bs0;
-              float4 r = make_float4(__uint_as_float(vr[cls * COUT + 4 * h]) + bb.x, __uint_as_float(vr[cls * COUT + 4 * h + 1]) + bb.y,
-                                     __uint_as_float(vr[cls * COUT + 4 * h + 2]) + bb.z, __uint_as_float(vr[cls * COUT + 4 * h + 3]) + bb.w);
+            for (int h = 0; h < Q; ++h) {
+              float4 r = make_float4(__uint_as_float(vr[cc * COUT + 4 * h]), __uint_as_float(vr[cc * COUT + 4 * h + 1]),
+                                     __uint_as_float(vr[cc * COUT + 4 * h + 2]), __uint_as_float(vr[cc * COUT + 4 * h + 3]));
+              if (p.bias) {
+                const float4 bb = ldg4(p.bias + 4 * h);
+                r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+              }
               if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-              const float4 q = sk[cls * 2 + h];
+              const float4 q = sk[cc * Q + h];
               r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
-              st4(p.y + o + 4 * h, r);
+              if (p.y) st4(p.y + o + 4 * h, r);
+              if (p.ys) store_split4(p.ys, part_stride, o + 4 * h, r);
             }
           }
         }
-        if (mt + 1 < KM) load_skip(iz, mt + 1);
+        if (it + 1 < KM * NPASS) load_skip(iz, (it + 1) / NPASS, (it + 1) % NPASS);
       }
     }
   }
@@ -233,22 +260,27 @@ convT3d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
   }
 }
 
-// Weight image: torch ConvTranspose3d weight [16][8][27] x BN scale ->
-//   img[term][shift = dz*4+dy*2+dx][chunk][row = cls*8 + n][e], channel = chunk*8 + e; per dimension the tap used by output
-//   parity a with input shift d is k = (a == 0 ? (d == 0 ? 1 : none) : (d == 0 ? 2 : 0)); unused (class, shift) rows are zero
+// Weight image: torch ConvTranspose3d weight [Cin][Cout][27] x BN scale ->
+//   img[term][ dz=0: shift(4: dy*2+dx) x ks x chunk x row(N: cls*COUT + n) x e | dz=1: shift(4) x ks x chunk x row(N/2: classes 4..7) x e ]
+//   channel = ks*16 + chunk*8 + e; per dimension the tap used by output parity a with input shift d is
+//   k = (a == 0 ? (d == 0 ? 1 : none) : (d == 0 ? 2 : 0)); unused (class, shift) rows are zero
 __global__ void pack_convT_slab_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                              __nv_bfloat16* __restrict__ img) {
-  constexpr int PER_TERM = 8 * 2 * N * 8;
+                                              __nv_bfloat16* __restrict__ img, int Cin, int Cout) {
+  const int KS = Cin / 16, N = 8 * Cout;
+  const int e0 = 4 * KS * 2 * N * 8, e1 = 4 * KS * 2 * (N / 2) * 8, per_term = e0 + e1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= PER_TERM) return;
-  const int e = i & 7;
-  int r = i >> 3;
-  const int row = r % N; r /= N;
-  const int chunk = r & 1;
-  const int sh = r >> 1;
-  const int cls = row / COUT, n = row % COUT;
+  if (i >= per_term) return;
+  const int dz = i >= e0;
+  const int rows = dz ? N / 2 : N;
+  int r = dz ? i - e0 : i;
+  const int e = r & 7; r >>= 3;
+  const int row = r % rows; r /= rows;
+  const int chunk = r & 1; r >>= 1;
+  const int ks = r % KS;
+  const int dyx = r / KS;
+  const int cls = (dz ? 4 : 0) + row / Cout, n = row % Cout;
   const int par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
-  const int dsh[3] = {sh >> 2, (sh >> 1) & 1, sh & 1};
+  const int dsh[3] = {dz, dyx >> 1, dyx & 1};
   int k[3] = {0, 0, 0};
   bool used = true;
   for (int a = 0; a < 3; ++a) {
@@ -257,20 +289,20 @@ __global__ void pack_convT_slab_weight_kernel(const float* __restrict__ w, const
   }
   float v = 0.f;
   if (used) {
-    const int ci = chunk * 8 + e;
-    v = w[((int64_t)ci * COUT + n) * 27 + (k[0] * 9 + k[1] * 3 + k[2])];
+    const int ci = ks * 16 + chunk * 8 + e;
+    v = w[((int64_t)ci * Cout + n) * 27 + (k[0] * 9 + k[1] * 3 + k[2])];
     if (scale) v *= scale[n];
   }
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   img[i] = hi;
-  img[PER_TERM + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  img[per_term + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-template <int KM, int NS>
+template <int CIN, int COUT, int KM, int NS, int MINB>
 static int launch(const void* x, const Params& p, cudaStream_t st) {
-  using C = Cfg<KM, NS>;
-  static_assert(C::SMEM <= 113 * 1024, "two CTAs per SM");
-  auto kern = convT3d_slab_bf16_kernel<KM, NS>;
+  using C = Cfg<CIN, COUT, KM, NS>;
+  static_assert(C::SMEM <= (MINB == 2 ? 113 * 1024 : 232448), "shared memory budget");
+  auto kern = convT3d_slab_bf16_kernel<CIN, COUT, KM, NS, MINB>;
   static SmemAttrOnce smem_attr;
   {
     cudaError_t e = smem_attr.ensure(kern, (int)C::SMEM);
@@ -287,40 +319,47 @@ static int launch(const void* x, const Params& p, cudaStream_t st) {
   return RCMVS_OK;
 }
 
+static bool supported(int Cin, int Cout) { return (Cin == 16 && Cout == 8) || (Cin == 32 && Cout == 16); }
+
 }  // namespace slabt
 }  // namespace rcmvs
 
-extern "C" int64_t rcmvs_conv_transpose3d_slab_weight_elems(void) { return (int64_t)2 * 8 * 2 * 64 * 8; }
+extern "C" int64_t rcmvs_conv_transpose3d_slab_weight_elems(int Cin, int Cout) {
+  const int KS = Cin / 16, N = 8 * Cout;
+  return (int64_t)2 * (4 * KS * 2 * N * 8 + 4 * KS * 2 * (N / 2) * 8);
+}
 
 extern "C" int rcmvs_conv_transpose3d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin,
                                                 rcmvs_stream_t stream) {
   using namespace rcmvs;
   RCMVS_REQUIRE(w && img, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_slab_pack: null pointer");
-  RCMVS_REQUIRE(Cin == slabt::CIN && Cout == slabt::COUT, RCMVS_ERR_UNSUPPORTED,
-                "rcmvs_conv_transpose3d_slab_pack: only Cin=16, Cout=8 (got %d, %d)", Cin, Cout);
-  const int per_term = 8 * 2 * 64 * 8;
+  RCMVS_REQUIRE(slabt::supported(Cin, Cout), RCMVS_ERR_UNSUPPORTED,
+                "rcmvs_conv_transpose3d_slab_pack: unsupported Cin=%d Cout=%d", Cin, Cout);
+  const int per_term = (int)(rcmvs_conv_transpose3d_slab_weight_elems(Cin, Cout) / 2);
   slabt::pack_convT_slab_weight_kernel<<<ceil_div(per_term, 256), 256, 0, as_stream(stream)>>>(
-      w, scale, reinterpret_cast<__nv_bfloat16*>(img));
+      w, scale, reinterpret_cast<__nv_bfloat16*>(img), Cin, Cout);
   RCMVS_CHECK_LAUNCH("rcmvs_conv_transpose3d_slab_pack");
   return RCMVS_OK;
 }
 
 extern "C" int rcmvs_conv_transpose3d_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip,
-                                               float* y, int B, int D, int H, int W, int Cin, int Cout, int relu,
-                                               rcmvs_stream_t stream) {
+                                               float* y, void* y_split, int B, int D, int H, int W, int Cin, int Cout,
+                                               int relu, rcmvs_stream_t stream) {
   using namespace rcmvs;
   using namespace rcmvs::slabt;
-  RCMVS_REQUIRE(x_split && wimg && y, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_slab_fwd: null pointer");
-  RCMVS_REQUIRE(Cin == CIN && Cout == COUT, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_transpose3d_slab_fwd: only Cin=16, Cout=8");
+  RCMVS_REQUIRE(x_split && wimg && (y || y_split), RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_slab_fwd: null pointer");
+  RCMVS_REQUIRE(supported(Cin, Cout), RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_transpose3d_slab_fwd: unsupported Cin=%d Cout=%d", Cin,
+                Cout);
   RCMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, RCMVS_ERR_BAD_ARG, "rcmvs_conv_transpose3d_slab_fwd: bad dims");
   RCMVS_REQUIRE((reinterpret_cast<uintptr_t>(x_split) & 15) == 0, RCMVS_ERR_BAD_ARG,
                 "rcmvs_conv_transpose3d_slab_fwd: x_split must be 16-byte aligned (TMA)");
   Params p;
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
-  p.bias = bias; p.skip = skip; p.y = y;
+  p.bias = bias; p.skip = skip; p.y = y; p.ys = reinterpret_cast<__nv_bfloat16*>(y_split);
   p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu;
-  // depth chunks: two CTAs per SM; minimise waves(tiles x chunks / 296) x slabs per CTA (planes + 1 halo slab)
+  // depth chunks: minimise waves(tiles x chunks / resident CTAs) x slabs per CTA (planes + 1 halo slab)
   constexpr int KM = 2;
+  const int resident = Cout == 8 ? 296 : 148;
   const int tiles = ceil_div(W, TWI) * ceil_div(H, 4 * KM) * B;
   int chunks = 1;
   {
@@ -328,11 +367,13 @@ extern "C" int rcmvs_conv_transpose3d_slab_fwd(const void* x_split, const void* 
     for (int c = 1; c <= D; ++c) {
       const int dc = ceil_div(D, c);
       const int cc = ceil_div(D, dc);
-      const long cost = (long)ceil_div(tiles * cc, 296) * (dc + 1);
+      const long cost = (long)ceil_div(tiles * cc, resident) * (dc + 1);
       if (best < 0 || cost < best) { best = cost; chunks = cc; }
     }
   }
   p.d_chunk = ceil_div(D, chunks);
   p.chunks = ceil_div(D, p.d_chunk);
-  return launch<KM, 4>(x_split, p, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (Cout == 8) return launch<16, 8, KM, 4, 2>(x_split, p, st);       // conv11: two CTAs per SM
+  return launch<32, 16, KM, 2, 1>(x_split, p, st);                       // conv9: 96 KB weight image, one CTA per SM
 }

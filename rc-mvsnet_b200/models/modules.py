@@ -296,7 +296,7 @@ def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit, slab=Fa
         cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, transposed, nsplit), shift, cout, nsplit, gmode))
     if slab and not transposed and stride == 1 and (cin, cout) in ops.SLAB_SUPPORTED:
         cands.append(("slab", ops.conv3d_slab_pack(w, scale), shift, cout))
-    if slab and transposed and (cin, cout) == (16, 8):
+    if slab and transposed and (cin, cout) in ops.SLABT_SUPPORTED:
         cands.append(("slabt", ops.conv_transpose3d_slab_pack(w, scale), shift, cout))
     if slab and not transposed and stride == 2 and (cin, cout) == (8, 16):
         cands.append(("slab2", ops.conv3d_s2_slab_pack(w, scale), shift, cout))
@@ -360,9 +360,7 @@ class CostRegNet(nn.Module):
             xs = x if x.dtype == torch.bfloat16 else ops.split_bf16(x)
             wy, ws = out in ("y", "both"), out in ("split", "both")
             if kind == "slabt":
-                if out != "y":
-                    raise RuntimeError("rcmvs: the transposed slab engine writes fp32 only")
-                return ops.conv_transpose3d_slab(xs, cand[1], cand[2], skip, layer["relu"])
+                return ops.conv_transpose3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"], want_y=wy, want_split=ws)
             if kind == "slab2":
                 return ops.conv3d_s2_slab(xs, cand[1], cand[2], layer["relu"], want_y=wy, want_split=ws)
             return ops.conv3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"], want_y=wy, want_split=ws)
@@ -434,7 +432,7 @@ class CostRegNet(nn.Module):
             return kinds.index("slab")
         if "slab2" in kinds:                                               # bf16x3 mode: conv1 (8 -> 16, stride 2)
             return kinds.index("slab2")
-        if "slabt" in kinds:                                               # bf16x3 mode: conv11 (16 -> 8, transposed)
+        if "slabt" in kinds:                                               # bf16x3 mode: conv9 / conv11 (transposed)
             return kinds.index("slabt")
         if "tc" in kinds:
             cout = cands[kinds.index("tc")][3]
@@ -491,7 +489,11 @@ class CostRegNet(nn.Module):
         c4 = run(P["conv4"], run(P["conv3"], c2))
         y = run(P["conv6"], run(P["conv5"], c4))
         y = run(P["conv7"], y, c4)                               # skip + relu(bn(convT(y)))  (modules.py:497-499)
-        y = run(P["conv9"], y, c2)
+        if chain and self._kind(P["conv9"], (B, D // 4, H // 4, W // 4, 4 * c)) == "slabt" and \
+                self._kind(P["conv11"], (B, D // 2, H // 2, W // 2, 2 * c)) == "slabt":
+            y = run(P["conv9"], y, c2, out="split")             # only conv11 reads it: handed over pre-split
+        else:
+            y = run(P["conv9"], y, c2)
         y = run(P["conv11"], y, c0)
         return run(P["prob"], y).squeeze(-1)
 

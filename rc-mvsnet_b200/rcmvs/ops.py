@@ -296,24 +296,33 @@ def conv3d_s2_slab(x_split, img, bias=None, relu=True, want_y=True, want_split=F
     return y if want_y else ys
 
 
+SLABT_SUPPORTED = {(16, 8), (32, 16)}     # (Cin, Cout) of the TMA transposed-conv kernel (conv11, conv9)
+
+
 @_on_device
 def conv_transpose3d_slab_pack(w, scale=None):
-    """torch ConvTranspose3d weight [16,8,3,3,3] (x BN scale) -> operand image of the TMA transposed-conv kernel."""
+    """torch ConvTranspose3d weight [Cin,Cout,3,3,3] (x BN scale) -> operand image of the TMA transposed-conv kernel."""
     Cin, Cout = w.shape[:2]
-    n = _ffi.lib().rcmvs_conv_transpose3d_slab_weight_elems()
+    n = _ffi.lib().rcmvs_conv_transpose3d_slab_weight_elems(Cin, Cout)
     img = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
     _ffi.call("rcmvs_conv_transpose3d_slab_pack", _chk(w, "w"), _opt(scale, "scale"), img.data_ptr(), Cout, Cin, _stream())
     return img
 
 
 @_on_device
-def conv_transpose3d_slab(x_split, img, bias=None, skip=None, relu=True):
-    """x_split [2,B,D,H,W,16] bf16 -> [B,2D,2H,2W,8] fp32 (k3, s2, p1, output_padding 1; + bias, ReLU, skip)."""
+def conv_transpose3d_slab(x_split, img, Cout, bias=None, skip=None, relu=True, want_y=True, want_split=False):
+    """x_split [2,B,D,H,W,Cin] bf16 -> [B,2D,2H,2W,Cout] (k3, s2, p1, output_padding 1; + bias, ReLU, skip) as fp32 and/or
+    split-bf16."""
     _, B, D, H, W, Cin = x_split.shape
-    y = torch.empty((B, 2 * D, 2 * H, 2 * W, 8), device=x_split.device, dtype=torch.float32)
+    shp = (B, 2 * D, 2 * H, 2 * W, Cout)
+    y = torch.empty(shp, device=x_split.device, dtype=torch.float32) if want_y else None
+    ys = torch.empty((2,) + shp, device=x_split.device, dtype=torch.bfloat16) if want_split else None
     _ffi.call("rcmvs_conv_transpose3d_slab_fwd", _chk_bf16(x_split, "x_split"), _chk_bf16(img, "wimg"), _opt(bias, "bias"),
-              _opt(skip, "skip"), _chk(y, "y"), B, D, H, W, Cin, 8, 1 if relu else 0, _stream())
-    return y
+              _opt(skip, "skip"), _opt(y, "y"), None if ys is None else ys.data_ptr(), B, D, H, W, Cin, Cout,
+              1 if relu else 0, _stream())
+    if want_y and want_split:
+        return y, ys
+    return y if want_y else ys
 
 
 def gemm_tc_supported(Cin, Cout):

@@ -316,26 +316,29 @@ def test_conv3d_s2_slab_bf16x3_vs_oracle(dev, dhw):
     assert torch.equal(ys_only, ys)
 
 
-@pytest.mark.parametrize("dhw", [(1, 1, 1), (2, 8, 31), (3, 9, 33), (5, 16, 62), (4, 20, 80), (12, 7, 40)])
-def test_conv_transpose3d_slab_bf16x3_vs_oracle(dev, dhw):
-    """conv11 (ConvTranspose3d 16 -> 8, stride 2, output_padding 1) + bias + ReLU + skip on the TMA-fed tcgen05 kernel."""
+@pytest.mark.parametrize("cin,cout,dhw", [(16, 8, (1, 1, 1)), (16, 8, (2, 8, 31)), (16, 8, (3, 9, 33)), (16, 8, (5, 16, 62)),
+                                          (16, 8, (4, 20, 80)), (16, 8, (12, 7, 40)), (32, 16, (1, 1, 1)), (32, 16, (3, 9, 33)),
+                                          (32, 16, (6, 16, 40)), (32, 16, (2, 5, 64))])
+def test_conv_transpose3d_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
+    """conv11 / conv9 (ConvTranspose3d, stride 2, output_padding 1) + bias + ReLU + skip on the TMA-fed tcgen05 kernel."""
     from oracle import ref_np as O
     from rcmvs import ops
-    rng = np.random.default_rng(sum(dhw) + 5)
+    rng = np.random.default_rng(sum(dhw) + cin)
     D, H, W = dhw
-    xs = [rng.standard_normal((16, D, H, W), dtype=np.float32) for _ in range(2)]
-    w = (rng.standard_normal((16, 8, 3, 3, 3)) / np.sqrt(27 * 16 / 8)).astype(np.float32)
-    scale = rng.uniform(0.5, 1.5, 8).astype(np.float32)
-    bias = rng.standard_normal(8).astype(np.float32)
+    xs = [rng.standard_normal((cin, D, H, W), dtype=np.float32) for _ in range(2)]
+    w = (rng.standard_normal((cin, cout, 3, 3, 3)) / np.sqrt(27 * cin / 8)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
     lin = np.stack([O.conv_transpose3d(x, w * scale[None, :, None, None, None]) for x in xs])
-    assert lin.shape == (2, 8, 2 * D, 2 * H, 2 * W)
+    assert lin.shape == (2, cout, 2 * D, 2 * H, 2 * W)
     skip = rng.standard_normal(lin.shape, dtype=np.float32)
     want = np.maximum(lin + bias[None, :, None, None, None], 0) + skip
     img = ops.conv_transpose3d_slab_pack(cu(w, dev), cu(scale, dev))
     x_split = ops.split_bf16(cu(np.stack(xs).transpose(0, 2, 3, 4, 1), dev))
-    y = ops.conv_transpose3d_slab(x_split, img, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), True)
+    y, ys = ops.conv_transpose3d_slab(x_split, img, cout, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), True, True, True)
     np.testing.assert_allclose(y.permute(0, 4, 1, 2, 3).cpu().numpy(), want, atol=1e-4, rtol=1e-4)
-    y2 = ops.conv_transpose3d_slab(x_split, img, None, None, False)
+    assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
+    y2 = ops.conv_transpose3d_slab(x_split, img, cout, None, None, False)
     np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
 
 
