@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
-mkdir -p gpuruo_out
-timeout -k 10 300 python -m pytest tests/test_gpu_r2.py -m gpu -q -x -k "transpose3d_slab" > gpuruo_out/o_slab8.log 2>&1; echo "rc=$?" >> gpuruo_out/o_slab8.log
-timeout -k 10 900 python -m pytest tests -m gpu -q > gpuruo_out/o_tests.log 2>&1; echo "tests rc=$?" >> gpuruo_out/o_tests.log
-timeout -k 10 900 python bench.py --no-cpu-baseline --no-stock-torch > gpuruo_out/o_bench.json 2> gpuruo_out/o_bench.err; echo "bench rc=$?" >> gpuruo_out/o_bench.err
+mkdir -p gpurun_out
+timeout -k 10 300 python -m pytest tests/test_gpu_r2.py -m gpu -q -x -k "transpose3d_slab" > gpurun_out/o_slab8.log 2>&1; echo "rc=$?" >> gpurun_out/o_slab8.log
+timeout -k 10 900 python -m pytest tests -m gpu -q > gpurun_out/o_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/o_tests.log
+timeout -k 10 900 python bench.py --no-cpu-baseline --no-stock-torch > gpurun_out/o_bench.json 2> gpurun_out/o_bench.err; echo "bench rc=$?" >> gpurun_out/o_bench.err
 echo done
