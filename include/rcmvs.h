@@ -207,6 +207,15 @@ int rcmvs_conv2d_slab_pack(const float* w, const float* scale, void* img, int Co
 int rcmvs_conv2d_slab_fwd(const void* x_split, const void* wimg, const float* bias, float* y, void* y_split, int N, int H, int W,
                           int Cin, int Cout, int relu, rcmvs_stream_t stream);
 
+/* FeatureNet's two down-sampling convolutions on the same tensor-core family: conv1.0 = Conv2d(8, 16, 5, stride 2, pad 2)
+ * and conv2.0 = Conv2d(16, 32, 5, stride 2, pad 2) + folded BN + ReLU (reference models/modules.py:394-395, 399-400).
+ * Parity sub-planes by strided TMA boxes, all 25 taps as descriptor offsets (two taps per K = 16 step for 8 channels).
+ * x_split [2][N][H][W][Cin] (H, W even) -> y [N][H/2][W/2][Cout] fp32 and / or y_split.  (Cin, Cout) in {(8,16), (16,32)}. */
+int64_t rcmvs_conv2d_s2k5_slab_weight_elems(int Cin, int Cout);
+int rcmvs_conv2d_s2k5_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
+int rcmvs_conv2d_s2k5_slab_fwd(const void* x_split, const void* wimg, const float* bias, float* y, void* y_split, int N,
+                               int H, int W, int Cin, int Cout, int relu, rcmvs_stream_t stream);
+
 /* ---- a7 Neural_Volume_Net resize: models/render_models.py:755-756 ------------------------------------------------ */
 /* x [B][D0][S][C] channels-last (S = h*w) -> y [B][D1][S][Cpad]: linear along D with align_corners=True, channels
  * C..Cpad-1 zero-filled (the 41-channel volume is padded to 48 for the convolution kernels). */

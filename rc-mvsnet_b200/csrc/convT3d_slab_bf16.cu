@@ -26,18 +26,6 @@ using namespace rcmvs::slab;
 
 constexpr int TWI = 31;                                            // input columns per tile (column 31 = halo for dx = 1)
 
-__device__ __forceinline__ void umma_bf16_lohi_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                                   uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
-      : "memory");
-}
-
 template <int CIN, int COUT, int KM, int NS>
 struct Cfg {
   static constexpr int N = 8 * COUT;                               // 8 output parity classes x COUT

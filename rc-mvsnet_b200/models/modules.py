@@ -153,6 +153,8 @@ class FeatureNet(nn.Module):
                         P["%s.%d" % (name, i)] = (ops.pack_conv2d_weight(w, scale, cin_pad), shift, blk.stride)
                         if tc and blk.stride == 1 and w.shape[2] == 3 and (w.shape[1], w.shape[0]) in ops.SLAB2D_SUPPORTED:
                             P["%s.%d.slab" % (name, i)] = (ops.conv2d_slab_pack(w, scale), shift)
+                        if tc and blk.stride == 2 and w.shape[2] == 5 and (w.shape[1], w.shape[0]) in ops.S2K5_SUPPORTED:
+                            P["%s.%d.s2slab" % (name, i)] = (ops.conv2d_s2k5_slab_pack(w, scale), shift)
                 for name in ("out1", "inner1", "inner2", "out2", "out3"):
                     conv = getattr(self, name, None)
                     if conv is not None:
@@ -203,9 +205,26 @@ class FeatureNet(nn.Module):
                 intra2 = ops.conv2d(c0, P["inner2"][0], P["inner2"][1], intra, relu=False, want_y=not tc, want_split=tc)
                 out["stage3"] = head(intra2, "out3", 8)
 
-        c0 = cbr(cbr(ops.images_to_nhwc8(x.float().contiguous()), "conv0.0"), "conv0.1")
-        c1 = cbr(cbr(cbr(c0, "conv1.0", tc), "conv1.1", tc), "conv1.2")
-        c2 = cbr(cbr(cbr(c1, "conv2.0", tc), "conv2.1", tc), "conv2.2")
+        # the 5x5 stride-2 layers run on the tensor cores too when their input has even height and width: their producers
+        # then hand over the activation in both forms (fp32 for the FPN lateral, split-bf16 for the tensor-core consumer)
+        s2 = tc and "conv1.0.s2slab" in P and "conv2.0.s2slab" in P and x.shape[-2] % 4 == 0 and x.shape[-1] % 4 == 0
+
+        def down(ts, key, cout):
+            img, shift = P[key + ".s2slab"]
+            return ops.conv2d_s2k5_slab(ts, img, cout, shift, True, want_y=False, want_split=True)
+
+        c0 = cbr(ops.images_to_nhwc8(x.float().contiguous()), "conv0.0")
+        if s2:
+            w, b, stride = P["conv0.1"]
+            c0, c0s = ops.conv2d(c0, w, b, None, stride=stride, relu=True, want_y=True, want_split=True)
+            img, shift = P["conv1.2.slab"]
+            c1, c1s = ops.conv2d_slab(cbr(down(c0s, "conv1.0", 16), "conv1.1", True), img, 16, shift, True, want_y=True,
+                                      want_split=True)
+            c2 = cbr(cbr(down(c1s, "conv2.0", 32), "conv2.1", True), "conv2.2")
+        else:
+            c0 = cbr(c0, "conv0.1")
+            c1 = cbr(cbr(cbr(c0, "conv1.0", tc), "conv1.1", tc), "conv1.2")
+            c2 = cbr(cbr(cbr(c1, "conv2.0", tc), "conv2.1", tc), "conv2.2")
         out = {}
         if side_stream is None:
             out["stage1"] = ops.conv2d(c2, P["out1"][0], None, None, relu=False)

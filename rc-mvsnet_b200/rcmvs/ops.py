@@ -565,6 +565,30 @@ def conv2d_slab(x_split, img, Cout, bias=None, relu=True, want_y=True, want_spli
     return y if want_y else ys
 
 
+S2K5_SUPPORTED = {(8, 16), (16, 32)}      # (Cin, Cout) of the 5x5 stride-2 tensor-core kernel (FeatureNet conv1.0 / conv2.0)
+
+
+@_on_device
+def conv2d_s2k5_slab_pack(w, scale=None):
+    Cout, Cin = w.shape[:2]
+    img = torch.empty((_ffi.lib().rcmvs_conv2d_s2k5_slab_weight_elems(Cin, Cout),), device=w.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_conv2d_s2k5_slab_pack", _chk(w, "w"), _opt(scale, "scale"), img.data_ptr(), Cout, Cin, _stream())
+    return img
+
+
+@_on_device
+def conv2d_s2k5_slab(x_split, img, Cout, bias=None, relu=True, want_y=True, want_split=False):
+    """x_split [2,N,H,W,Cin] bf16 (H, W even) -> 5x5 stride-2 pad-2 conv: y [N,H/2,W/2,Cout] fp32 and/or y_split."""
+    _, N, H, W, Cin = x_split.shape
+    y = torch.empty((N, H // 2, W // 2, Cout), device=x_split.device, dtype=torch.float32) if want_y else None
+    ys = torch.empty((2, N, H // 2, W // 2, Cout), device=x_split.device, dtype=torch.bfloat16) if want_split else None
+    _ffi.call("rcmvs_conv2d_s2k5_slab_fwd", _chk_bf16(x_split, "x_split"), _chk_bf16(img, "wimg"), _opt(bias, "bias"),
+              _opt(y, "y"), None if ys is None else ys.data_ptr(), N, H, W, Cin, Cout, 1 if relu else 0, _stream())
+    if want_y and want_split:
+        return y, ys
+    return y if want_y else ys
+
+
 # ---- f2 unsupervised loss stack ---------------------------------------------------------------------------------------
 @_on_device
 def images_subsample_nhwc(imgs, step):

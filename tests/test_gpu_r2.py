@@ -777,3 +777,28 @@ def test_conv2d_slab_bf16x3_vs_oracle(dev, cin, cout, nhw):
     pw = ops.pack_conv2d_weight(cu(w, dev), cu(scale, dev))
     yf, yfs = ops.conv2d(x_cl, pw, cu(bias, dev), None, relu=True, want_split=True)
     assert torch.equal(yfs, ops.split_bf16(yf))
+
+
+@pytest.mark.parametrize("cin,cout,nhw", [(8, 16, (2, 2, 2)), (8, 16, (1, 24, 62)), (8, 16, (3, 50, 124)), (8, 16, (2, 64, 80)),
+                                          (16, 32, (1, 2, 2)), (16, 32, (2, 18, 60)), (16, 32, (1, 36, 126)), (16, 32, (5, 32, 40))])
+def test_conv2d_s2k5_slab_bf16x3_vs_oracle(dev, cin, cout, nhw):
+    """FeatureNet conv1.0 / conv2.0 (5x5, stride 2, pad 2) on tcgen05: parity sub-planes by strided TMA, 25 taps as
+    descriptor offsets (8 channels: two taps per K step through the leading-dimension offset)."""
+    from oracle import ref_np as O
+    from rcmvs import ops
+    rng = np.random.default_rng(cin + cout + sum(nhw))
+    N, H, W = nhw
+    xs = [rng.standard_normal((cin, H, W), dtype=np.float32) for _ in range(N)]
+    w = (rng.standard_normal((cout, cin, 5, 5)) / np.sqrt(25 * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    lin = np.stack([O.conv2d(x, w * scale[:, None, None, None], None, stride=2, pad=2) for x in xs])
+    assert lin.shape == (N, cout, H // 2, W // 2)
+    want = np.maximum(lin + bias[None, :, None, None], 0)
+    xs_split = ops.split_bf16(cu(np.stack(xs).transpose(0, 2, 3, 1), dev))
+    img = ops.conv2d_s2k5_slab_pack(cu(w, dev), cu(scale, dev))
+    y, ys = ops.conv2d_s2k5_slab(xs_split, img, cout, cu(bias, dev), True, True, True)
+    np.testing.assert_allclose(y.permute(0, 3, 1, 2).cpu().numpy(), want, atol=1e-4, rtol=1e-4)
+    assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
+    y2 = ops.conv2d_s2k5_slab(xs_split, img, cout, None, False)
+    np.testing.assert_allclose(y2.permute(0, 3, 1, 2).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
