@@ -180,6 +180,81 @@ __global__ void pack_conv2d_weight_kernel(const float* __restrict__ w, const flo
   packed[i] = v;
 }
 
+// FPN laterals (modules.py:451, 455: intra = up2(coarser) + inner(c)): 1x1 convolution to 32 channels + bias + the
+// nearest-2x-upsampled coarser map, as a streaming kernel — the generic tile kernel above spends its time staging halo
+// tiles a 1x1 tap does not need.  Thread = one pixel x 8 output channels (4 threads per pixel: a warp writes 8 pixels =
+// 1 KB contiguous), weights [CIN][32] in shared memory (4 distinct 32-byte rows per warp: broadcast reads).
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv1x1_c32_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                   const float* __restrict__ up, float* __restrict__ y, __nv_bfloat16* __restrict__ ys,
+                   int64_t ys_part_stride, int64_t npix, int H, int W, int relu) {
+  __shared__ __align__(16) float ws[CIN * 32];
+  for (int i = threadIdx.x; i < CIN * 32; i += 256) ws[i] = __ldg(wp + i);
+  __syncthreads();
+  const int cg = threadIdx.x & 3;
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (bias) { b0 = ldg4(bias + cg * 8); b1 = ldg4(bias + cg * 8 + 4); }
+  for (int64_t pix = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2); pix < npix; pix += (int64_t)gridDim.x * 64) {
+    float4 xv[CIN / 4];
+#pragma unroll
+    for (int i = 0; i < CIN / 4; ++i) xv[i] = ldg4(x + pix * CIN + 4 * i);
+    float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+    if (up) {
+      const int px = (int)(pix % W), py = (int)((pix / W) % H);
+      const int64_t n = pix / ((int64_t)W * H);
+      const int64_t uo = ((n * (H / 2) + (py >> 1)) * (W / 2) + (px >> 1)) * 32 + cg * 8;
+      u0 = ldg4(up + uo); u1 = ldg4(up + uo + 4);
+    }
+    float4 a0 = b0, a1 = b1;
+#pragma unroll
+    for (int i = 0; i < CIN / 4; ++i) {
+      const float xs4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (4 * i + k) * 32 + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (4 * i + k) * 32 + cg * 8 + 4);
+        a0.x = fmaf(xs4[k], w0.x, a0.x); a0.y = fmaf(xs4[k], w0.y, a0.y); a0.z = fmaf(xs4[k], w0.z, a0.z); a0.w = fmaf(xs4[k], w0.w, a0.w);
+        a1.x = fmaf(xs4[k], w1.x, a1.x); a1.y = fmaf(xs4[k], w1.y, a1.y); a1.z = fmaf(xs4[k], w1.z, a1.z); a1.w = fmaf(xs4[k], w1.w, a1.w);
+      }
+    }
+    if (relu) {
+      a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a0.z = fmaxf(a0.z, 0.f); a0.w = fmaxf(a0.w, 0.f);
+      a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f); a1.z = fmaxf(a1.z, 0.f); a1.w = fmaxf(a1.w, 0.f);
+    }
+    a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+    a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
+    const int64_t o = pix * 32 + cg * 8;
+    if (y) { st4(y + o, a0); st4(y + o + 4, a1); }
+    if (ys) {
+      const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+        const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * k] - __bfloat162float(h0), v[2 * k + 1] - __bfloat162float(h1));
+        hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[k] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      *reinterpret_cast<uint4*>(ys + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(ys + ys_part_stride + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+template <int CIN>
+static int launch_conv1x1_c32(const float* x, const float* wp, const float* bias, const float* up, float* y, void* ys, int N,
+                              int H, int W, int relu, cudaStream_t st) {
+  const int64_t npix = (int64_t)N * H * W;
+  const int64_t want = ceil_div<int64_t>(npix, 64);
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  conv1x1_c32_kernel<CIN><<<grid, 256, 0, st>>>(x, wp, bias, up, y, reinterpret_cast<__nv_bfloat16*>(ys), npix * 32, npix, H, W,
+                                                relu);
+  RCMVS_CHECK_LAUNCH("rcmvs_conv2d_fwd");
+  return RCMVS_OK;
+}
+
 template <int COUT, int STRIDE, int KS>
 static int launch_conv2d(const float* x, const float* wp, const float* bias, const float* up, float* y, void* ys, int N,
                          int H, int W, int Cin, int relu, cudaStream_t st) {
@@ -245,6 +320,11 @@ extern "C" int rcmvs_conv2d_fwd_split(const float* x, const float* packed_w, con
   RCMVS_REQUIRE(!up || (stride == 1 && H % 2 == 0 && W % 2 == 0), RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv2d_fwd: the fused upsample-add needs stride 1 and even H, W");
   cudaStream_t st = as_stream(stream);
+  if (K == 1 && stride == 1 && Cout == 32) {            // FPN laterals / out1: streaming 1x1 kernel
+    if (Cin == 8) return launch_conv1x1_c32<8>(x, packed_w, bias, up, y, ys, N, H, W, relu, st);
+    if (Cin == 16) return launch_conv1x1_c32<16>(x, packed_w, bias, up, y, ys, N, H, W, relu, st);
+    if (Cin == 32) return launch_conv1x1_c32<32>(x, packed_w, bias, up, y, ys, N, H, W, relu, st);
+  }
 #define RCMVS_C2(CO, S, KK) \
   if (Cout == CO && stride == S && K == KK) return launch_conv2d<CO, S, KK>(x, packed_w, bias, up, y, ys, N, H, W, Cin, relu, st)
   RCMVS_C2(8, 1, 3); RCMVS_C2(16, 1, 3); RCMVS_C2(32, 1, 3);
