@@ -141,12 +141,20 @@ int64_t rcmvs_conv3d_slab_weight_elems(int Cin, int Cout);
 int rcmvs_conv3d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
 int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip, float* y,
                           void* y_split, int B, int D, int H, int W, int Cin, int Cout, int relu, rcmvs_stream_t stream);
-/* Stride-2 member of the same family: conv1 of CostRegNet (8 -> 16 channels, 3x3x3, stride 2, pad 1; reference
- * models/modules.py:472, and conv1 of the renderer's CostReg, models/render_models.py:696).  The input plane is fetched
- * as four parity sub-planes by TMA boxes with traversal stride 2 (elementStrides), one K = 16 MMA step covers two taps
- * of the 8 input channels, all 27 taps are summed in TMEM.  x_split [2][B][D][H][W][8] (D, H, W even) ->
- * y [B][D/2][H/2][W/2][16] fp32 and / or y_split (either may be NULL).  Only (Cin, Cout) = (8, 16). */
-int64_t rcmvs_conv3d_s2_slab_weight_elems(void);
+/* 32-output-channel member: conv4 of CostRegNet (32 -> 32, quarter resolution, reference models/modules.py:478).  Only kd
+ * is folded into N (TMEM ring of output planes); the nine (kh, kw) taps are descriptor start offsets, no epilogue
+ * exchange.  Same operand formats as rcmvs_conv3d_slab_fwd.  (Cin, Cout) = (32, 32). */
+int64_t rcmvs_conv3d_o_slab_weight_elems(int Cin, int Cout);
+int rcmvs_conv3d_o_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
+int rcmvs_conv3d_o_slab_fwd(const void* x_split, const void* wimg, const float* bias, const float* skip, float* y,
+                            void* y_split, int B, int D, int H, int W, int Cin, int Cout, int relu, rcmvs_stream_t stream);
+
+/* Stride-2 members of the same family: conv1 (8 -> 16 channels) and conv3 (16 -> 32) of CostRegNet, 3x3x3, stride 2, pad 1
+ * (reference models/modules.py:472, :476; conv1 of the renderer's CostReg, models/render_models.py:696).  The input plane
+ * is fetched as four parity sub-planes by TMA boxes with traversal stride 2 (elementStrides); all 27 taps are summed in
+ * TMEM (8 channels: one K = 16 MMA step covers two taps).  x_split [2][B][D][H][W][Cin] (D, H, W even) ->
+ * y [B][D/2][H/2][W/2][Cout] fp32 and / or y_split (either may be NULL).  (Cin, Cout) in {(8,16), (16,32)}. */
+int64_t rcmvs_conv3d_s2_slab_weight_elems(int Cin, int Cout);
 int rcmvs_conv3d_s2_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
 int rcmvs_conv3d_s2_slab_fwd(const void* x_split, const void* wimg, const float* bias, float* y, void* y_split, int B,
                              int D, int H, int W, int Cin, int Cout, int relu, rcmvs_stream_t stream);

@@ -27,34 +27,39 @@ namespace slab2 {
 
 using namespace rcmvs::slab;
 
-constexpr int CIN = 8, COUT = 16;
 constexpr int TWO = 31;                                            // real output columns per tile (column 0 = halo)
 constexpr int NG = 4;                                              // TMEM ring: output planes in flight
 
-template <int KM, int NS>
+// (CIN, COUT) = (8, 16): conv1 — 5 steps of two taps each (see above).  (16, 32): conv3 (half -> quarter resolution,
+// modules.py:476) — 16 channels fill a K = 16 step, so the 9 (kh, kw) taps are 9 steps and K-chunk 1 is the second chunk
+// plane of the same sub-plane.
+template <int CIN, int COUT, int KM, int NS>
 struct Cfg {
+  static constexpr int NCH = CIN / 8;
+  static constexpr int NSTEP = CIN == 8 ? 5 : 9;
   static constexpr int ROWS_S = 4 * KM + 1;                        // sub-plane rows (1 halo row above)
   static constexpr int OROWS = 4 * KM;
-  static constexpr int SUB_B = ROWS_S * PW * 16;                   // one parity sub-plane of one part
+  static constexpr int PLANE_B = ROWS_S * PW * 16;                 // one 8-channel chunk plane of a sub-plane
+  static constexpr int SUB_B = NCH * PLANE_B;                      // one parity sub-plane of one part
   static constexpr int PART_B = 4 * SUB_B;
   static constexpr int STAGE_B = 2 * PART_B;                       // hi, lo
-  static constexpr int A_BYTES = NS * STAGE_B;
-  static constexpr int ODD_B = 5 * 2 * 32 * 16;                    // 5 tap pairs x 2 K-chunks x 32 rows (kd=2 | kd=0) x 16 B
-  static constexpr int EVEN_B = 5 * 2 * 16 * 16;                   // 5 tap pairs x 2 K-chunks x 16 rows (kd=1)
+  static constexpr int A_BYTES = NS * STAGE_B + 128;
+  static constexpr int ODD_B = NSTEP * 2 * (2 * COUT) * 16;        // steps x 2 K-chunks x 2·COUT rows (kd=2 | kd=0) x 16 B
+  static constexpr int EVEN_B = NSTEP * 2 * COUT * 16;             // steps x 2 K-chunks x COUT rows (kd=1)
   static constexpr int BTERM_B = ODD_B + EVEN_B;
   static constexpr int B_BYTES = 2 * BTERM_B;                      // hi, lo
   static constexpr int TCOLS = NG * KM * COUT;                     // accumulator columns in use
   static constexpr int TALLOC = TCOLS <= 128 ? 128 : 256;
   static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + 512;
-  static_assert(SUB_B % 128 == 0, "TMA destination alignment");
-  static_assert(TCOLS <= 256, "TMEM budget");
+  static_assert(PLANE_B % 128 == 0, "TMA destination alignment");
+  static_assert(TCOLS <= 256 && (CIN == 8 || CIN == 16), "configuration");
 };
 
 struct Params {
   const __nv_bfloat16* wimg;
-  const float* bias;           // [16] or null
-  float* y;                    // [B][Do][Ho][Wo][16] fp32 or null
-  __nv_bfloat16* ys;           // [2][B][Do][Ho][Wo][16] split-bf16 or null
+  const float* bias;           // [COUT] or null
+  float* y;                    // [B][Do][Ho][Wo][COUT] fp32 or null
+  __nv_bfloat16* ys;           // [2][B][Do][Ho][Wo][COUT] split-bf16 or null
   int B, D, H, W;              // input dims (even)
   int Do, Ho, Wo;
   int d_chunk, chunks;         // output planes per CTA
@@ -66,11 +71,14 @@ struct Params {
 __device__ __forceinline__ constexpr int pair_sp(int p) { return p == 0 ? 2 : p == 1 ? 0 : p == 2 ? 2 : p == 3 ? 3 : 1; }
 __device__ __forceinline__ constexpr int pair_off(int p) { return p == 0 ? -PW : p == 1 ? 0 : p == 2 ? 0 : p == 3 ? -PW - 1 : -1; }
 __device__ __forceinline__ constexpr int pair_lbo_sub(int p) { return p == 3 ? 0 : p == 4 ? 2 : 1; }
+// 16 input channels: step t = tap (kh, kw) = (t / 3, t % 3): parity sub-plane and offset of that tap
+__device__ __forceinline__ constexpr int tap_sp(int t) { return ((t / 3) == 1 ? 0 : 2) + ((t % 3) == 1 ? 0 : 1); }
+__device__ __forceinline__ constexpr int tap_off(int t) { return ((t / 3) == 0 ? -PW : 0) + ((t % 3) == 0 ? -1 : 0); }
 
-template <int KM, int NS>
+template <int CIN, int COUT, int KM, int NS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_s2_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  using C = Cfg<KM, NS>;
+  using C = Cfg<CIN, COUT, KM, NS>;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* a_smem = smem;
   unsigned char* b_smem = smem + C::A_BYTES;
@@ -106,6 +114,7 @@ conv3d_s2_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Param
     const float4* src = reinterpret_cast<const float4*>(p.wimg);
     float4* dst = reinterpret_cast<float4*>(b_smem);
     for (int i = threadIdx.x; i < C::B_BYTES / 16; i += kThreads) dst[i] = __ldg(src + i);
+    if (threadIdx.x < 8) reinterpret_cast<float4*>(a_smem + NS * C::STAGE_B)[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -133,15 +142,17 @@ conv3d_s2_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Param
         for (int part = 0; part < 2; ++part)
 #pragma unroll
           for (int sp = 0; sp < 4; ++sp)
-            tma_load_5d(dst0 + part * C::PART_B + sp * C::SUB_B, &tmap, full + buf, 0, 2 * (ox0 - 1) + (sp & 1),
-                        2 * (oy0 - 1) + (sp >> 1), z, part * p.B + b);
+#pragma unroll
+            for (int ch = 0; ch < C::NCH; ++ch)
+              tma_load_5d(dst0 + part * C::PART_B + sp * C::SUB_B + ch * C::PLANE_B, &tmap, full + buf, ch * 8,
+                          2 * (ox0 - 1) + (sp & 1), 2 * (oy0 - 1) + (sp >> 1), z, part * p.B + b);
       }
     }
   } else if (warp == 5) {
     // =============================== MMA issuer ==================================================================
     const bool leader = elect_one();
     const uint32_t b_base = smem_u32(b_smem);
-    const uint32_t idesc16 = make_idesc_bf16(128, 16), idesc32 = make_idesc_bf16(128, 32);
+    constexpr uint32_t idesc16 = make_idesc_bf16(128, COUT), idesc32 = make_idesc_bf16(128, 2 * COUT);   // one / two kd blocks
     for (int i = 0; i < nslabs; ++i) {
       const bool odd = (i & 1) == 0;                         // z = z0 + i with z0 odd
       const int q_lo = odd ? i / 2 - 1 : (i - 1) / 2;        // odd z: kd = 2 -> plane (z-1)/2 ; even z: kd = 1 -> plane z/2
@@ -156,12 +167,13 @@ conv3d_s2_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Param
       const int g_lo = (q_lo + NG) % NG, g_hi = q_hi % NG;
       const bool fused = odd && lo_ok && hi_ok && g_hi == g_lo + 1;       // two neighbouring groups: one N = 32 MMA
 #pragma unroll
-      for (int pr = 0; pr < 5; ++pr) {
-        const int sp = pair_sp(pr), off = pair_off(pr), lbs = pair_lbo_sub(pr);
-        const uint32_t lbo = lbs == 0 ? 512u : (uint32_t)(lbs * C::SUB_B);
+      for (int pr = 0; pr < C::NSTEP; ++pr) {
+        const int sp = CIN == 8 ? pair_sp(pr) : tap_sp(pr), off = CIN == 8 ? pair_off(pr) : tap_off(pr);
+        const int lbs = pair_lbo_sub(pr % 5);
+        const uint32_t lbo = CIN == 8 ? (lbs == 0 ? 512u : (uint32_t)(lbs * C::SUB_B)) : (uint32_t)C::PLANE_B;
         const uint32_t a0 = desc_lo(a_base + sp * C::SUB_B, lbo);
-        const uint32_t b_odd = desc_lo(b_base + pr * (2 * 32 * 16), 32 * 16);
-        const uint32_t b_even = desc_lo(b_base + C::ODD_B + pr * (2 * 16 * 16), 16 * 16);
+        const uint32_t b_odd = desc_lo(b_base + pr * (2 * 2 * COUT * 16), 2 * COUT * 16);
+        const uint32_t b_even = desc_lo(b_base + C::ODD_B + pr * (2 * COUT * 16), COUT * 16);
         constexpr uint32_t kLoOff = C::PART_B >> 4, kBLoOff = C::BTERM_B >> 4;
 #pragma unroll
         for (int mt = 0; mt < KM; ++mt) {
@@ -179,17 +191,17 @@ conv3d_s2_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Param
               umma_bf16_lohi(d, a_hi_d, b_odd + kBLoOff, idesc32);
               umma_bf16_lohi(d, a_hi_d, b_odd, idesc32);
             } else {
-              if (lo_ok) {                                                          // kd = 2 rows 0..15
+              if (lo_ok) {                                                          // kd = 2 rows 0..COUT-1
                 const uint32_t d = dm + g_lo * COUT;
                 umma_bf16_lohi(d, a_hi_d + kLoOff, b_odd, idesc16);
                 umma_bf16_lohi(d, a_hi_d, b_odd + kBLoOff, idesc16);
                 umma_bf16_lohi(d, a_hi_d, b_odd, idesc16);
               }
-              if (hi_ok) {                                                          // kd = 0 rows 16..31
+              if (hi_ok) {                                                          // kd = 0 rows COUT..2·COUT-1
                 const uint32_t d = dm + g_hi * COUT;
-                umma_bf16_lohi(d, a_hi_d + kLoOff, b_odd + 16, idesc16);
-                umma_bf16_lohi(d, a_hi_d, b_odd + 16 + kBLoOff, idesc16);
-                umma_bf16_lohi(d, a_hi_d, b_odd + 16, idesc16);
+                umma_bf16_lohi(d, a_hi_d + kLoOff, b_odd + COUT, idesc16);
+                umma_bf16_lohi(d, a_hi_d, b_odd + COUT + kBLoOff, idesc16);
+                umma_bf16_lohi(d, a_hi_d, b_odd + COUT, idesc16);
               }
             }
           }
@@ -217,11 +229,15 @@ conv3d_s2_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Param
       uint32_t vr[KM][COUT];
 #pragma unroll
       for (int mt = 0; mt < KM; ++mt)
-        tmem_ld16_nowait(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * (NG * COUT) + g * COUT, &vr[mt][0]);
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16)
+          tmem_ld16_nowait(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * (NG * COUT) + g * COUT + c0, &vr[mt][c0]);
       tmem_ld_wait();
 #pragma unroll
       for (int mt = 0; mt < KM; ++mt)
-        tmem_st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * (NG * COUT) + g * COUT);
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16)
+          tmem_st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * (NG * COUT) + g * COUT + c0);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(grp_free + g);
@@ -252,39 +268,42 @@ conv3d_s2_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Param
   }
 }
 
-// Weight image: torch Conv3d weight [16][8][3][3][3] x BN scale ->
-//   img[term][ odd: pair(5) x chunk(2) x row(32: kd=2 couts | kd=0 couts) x e(8) | even: pair(5) x chunk(2) x row(16: kd=1) x e(8) ]
+// Weight image: torch Conv3d weight [Cout][Cin][3][3][3] x BN scale ->
+//   img[term][ odd: step x chunk(2) x row(2·Cout: kd=2 couts | kd=0 couts) x e(8) | even: step x chunk(2) x row(Cout: kd=1) x e(8) ]
+//   Cin = 8: step = tap pair, chunk = tap within the pair, channel = e;  Cin = 16: step = tap, channel = chunk*8 + e
 //   term 0 = bf16(w·scale), term 1 = bf16(w·scale - term 0)
 __global__ void pack_s2_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                      __nv_bfloat16* __restrict__ img) {
-  constexpr int ODD_E = 5 * 2 * 32 * 8, EVEN_E = 5 * 2 * 16 * 8, PER_TERM = ODD_E + EVEN_E;
+                                      __nv_bfloat16* __restrict__ img, int Cout, int Cin) {
+  const int nstep = Cin == 8 ? 5 : 9;
+  const int odd_e = nstep * 2 * 2 * Cout * 8, even_e = nstep * 2 * Cout * 8, per_term = odd_e + even_e;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= PER_TERM) return;
-  // taps (kh, kw) of the two K-chunks of each pair; kh = -1: zero weights
+  if (i >= per_term) return;
+  // Cin = 8: taps (kh, kw) of the two K-chunks of each pair; kh = -1: zero weights
   const int KH[5][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 2}, {1, -1}};
   const int KW[5][2] = {{1, 2}, {1, 2}, {1, 2}, {0, 0}, {0, 0}};
-  int pr, chunk, row, e, kd, n;
-  if (i < ODD_E) {
-    e = i & 7; row = (i >> 3) % 32; chunk = (i >> 8) & 1; pr = i >> 9;
-    kd = row < 16 ? 2 : 0; n = row & 15;
-  } else {
-    const int j = i - ODD_E;
-    e = j & 7; row = (j >> 3) % 16; chunk = (j >> 7) & 1; pr = j >> 8;
-    kd = 1; n = row;
-  }
+  const bool odd = i < odd_e;
+  const int rows = odd ? 2 * Cout : Cout;
+  int r = odd ? i : i - odd_e;
+  const int e = r & 7; r >>= 3;
+  const int row = r % rows; r /= rows;
+  const int chunk = r & 1;
+  const int st = r >> 1;
+  const int kd = odd ? (row < Cout ? 2 : 0) : 1, n = row % Cout;
+  int kh, kw, ci;
+  if (Cin == 8) { kh = KH[st][chunk]; kw = KW[st][chunk]; ci = e; }
+  else { kh = st / 3; kw = st % 3; ci = chunk * 8 + e; }
   float v = 0.f;
-  const int kh = KH[pr][chunk], kw = KW[pr][chunk];
   if (kh >= 0) {
-    v = w[((int64_t)n * CIN + e) * 27 + (kd * 9 + kh * 3 + kw)];
+    v = w[((int64_t)n * Cin + ci) * 27 + (kd * 9 + kh * 3 + kw)];
     if (scale) v *= scale[n];
   }
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   img[i] = hi;
-  img[PER_TERM + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  img[per_term + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// 5-D map over split-bf16 activations [2·B][D][H][W][8], traversal stride 2 along W and H: box {8, 2·32, 2·rows, 1, 1}
-static int make_tmap_s2(CUtensorMap* map, const void* x, int B, int D, int H, int W, int rows) {
+// 5-D map over split-bf16 activations [2·B][D][H][W][C], traversal stride 2 along W and H: box {8, 2·32, 2·rows, 1, 1}
+static int make_tmap_s2(CUtensorMap* map, const void* x, int B, int D, int H, int W, int CIN, int rows) {
   EncodeTiledFn fn = encode_fn();
   RCMVS_REQUIRE(fn != nullptr, RCMVS_ERR_CUDA, "rcmvs_conv3d_s2_slab_fwd: cuTensorMapEncodeTiled not available");
   const cuuint64_t gdim[5] = {(cuuint64_t)CIN, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)2 * B};
@@ -299,18 +318,18 @@ static int make_tmap_s2(CUtensorMap* map, const void* x, int B, int D, int H, in
   return RCMVS_OK;
 }
 
-template <int KM, int NS>
+template <int CIN, int COUT, int KM, int NS>
 static int launch(const void* x, const Params& p, cudaStream_t st) {
-  using C = Cfg<KM, NS>;
+  using C = Cfg<CIN, COUT, KM, NS>;
   static_assert(C::SMEM <= 232448, "shared memory budget exceeded");
-  auto kern = conv3d_s2_slab_bf16_kernel<KM, NS>;
+  auto kern = conv3d_s2_slab_bf16_kernel<CIN, COUT, KM, NS>;
   static SmemAttrOnce smem_attr;
   {
     cudaError_t e = smem_attr.ensure(kern, (int)C::SMEM);
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv3d_s2_slab_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   CUtensorMap map;
-  const int rc = make_tmap_s2(&map, x, p.B, p.D, p.H, p.W, C::ROWS_S);
+  const int rc = make_tmap_s2(&map, x, p.B, p.D, p.H, p.W, CIN, C::ROWS_S);
   if (rc != RCMVS_OK) return rc;
   dim3 grid(ceil_div(p.Wo, TWO), ceil_div(p.Ho, C::OROWS), p.B * p.chunks);
   RCMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_s2_slab_fwd: grid too large");
@@ -320,9 +339,9 @@ static int launch(const void* x, const Params& p, cudaStream_t st) {
 }
 
 // M-tiles per CTA and output-plane chunks: one CTA per SM, minimise waves x (input planes per CTA) x KM
-static void plan(int B, int Do, int Ho, int Wo, int& km, int& chunks) {
+static void plan(int B, int Do, int Ho, int Wo, int km_lo, int km_hi, int& km, int& chunks) {
   long best = -1;
-  for (int k = 3; k <= 4; ++k) {
+  for (int k = km_lo; k <= km_hi; ++k) {
     const int tiles = ceil_div(Wo, TWO) * ceil_div(Ho, 4 * k) * B;
     for (int c = 1; c <= Do; ++c) {
       const int dc = ceil_div(Do, c);
@@ -333,20 +352,25 @@ static void plan(int B, int Do, int Ho, int Wo, int& km, int& chunks) {
   }
 }
 
+static bool supported(int Cin, int Cout) { return (Cin == 8 && Cout == 16) || (Cin == 16 && Cout == 32); }
+
 }  // namespace slab2
 }  // namespace rcmvs
 
-extern "C" int64_t rcmvs_conv3d_s2_slab_weight_elems(void) { return (int64_t)2 * (5 * 2 * 32 * 8 + 5 * 2 * 16 * 8); }
+extern "C" int64_t rcmvs_conv3d_s2_slab_weight_elems(int Cin, int Cout) {
+  const int nstep = Cin == 8 ? 5 : 9;
+  return (int64_t)2 * (nstep * 2 * 2 * Cout * 8 + nstep * 2 * Cout * 8);
+}
 
 extern "C" int rcmvs_conv3d_s2_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin,
                                          rcmvs_stream_t stream) {
   using namespace rcmvs;
   RCMVS_REQUIRE(w && img, RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_s2_slab_pack: null pointer");
-  RCMVS_REQUIRE(Cin == slab2::CIN && Cout == slab2::COUT, RCMVS_ERR_UNSUPPORTED,
-                "rcmvs_conv3d_s2_slab_pack: only Cin=8, Cout=16 (got %d, %d)", Cin, Cout);
-  const int per_term = 5 * 2 * 32 * 8 + 5 * 2 * 16 * 8;
+  RCMVS_REQUIRE(slab2::supported(Cin, Cout), RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_s2_slab_pack: unsupported Cin=%d Cout=%d", Cin,
+                Cout);
+  const int per_term = (int)(rcmvs_conv3d_s2_slab_weight_elems(Cin, Cout) / 2);
   slab2::pack_s2_weight_kernel<<<ceil_div(per_term, 256), 256, 0, as_stream(stream)>>>(
-      w, scale, reinterpret_cast<__nv_bfloat16*>(img));
+      w, scale, reinterpret_cast<__nv_bfloat16*>(img), Cout, Cin);
   RCMVS_CHECK_LAUNCH("rcmvs_conv3d_s2_slab_pack");
   return RCMVS_OK;
 }
@@ -356,7 +380,8 @@ extern "C" int rcmvs_conv3d_s2_slab_fwd(const void* x_split, const void* wimg, c
   using namespace rcmvs;
   using namespace rcmvs::slab2;
   RCMVS_REQUIRE(x_split && wimg && (y || y_split), RCMVS_ERR_BAD_ARG, "rcmvs_conv3d_s2_slab_fwd: null pointer");
-  RCMVS_REQUIRE(Cin == CIN && Cout == COUT, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_s2_slab_fwd: only Cin=8, Cout=16");
+  RCMVS_REQUIRE(slab2::supported(Cin, Cout), RCMVS_ERR_UNSUPPORTED, "rcmvs_conv3d_s2_slab_fwd: unsupported Cin=%d Cout=%d", Cin,
+                Cout);
   RCMVS_REQUIRE(B > 0 && D >= 2 && H >= 2 && W >= 2 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, RCMVS_ERR_UNSUPPORTED,
                 "rcmvs_conv3d_s2_slab_fwd: D, H, W must be even (got %d, %d, %d)", D, H, W);
   RCMVS_REQUIRE((reinterpret_cast<uintptr_t>(x_split) & 15) == 0, RCMVS_ERR_BAD_ARG,
@@ -366,9 +391,15 @@ extern "C" int rcmvs_conv3d_s2_slab_fwd(const void* x_split, const void* wimg, c
   p.bias = bias; p.y = y; p.ys = reinterpret_cast<__nv_bfloat16*>(y_split);
   p.B = B; p.D = D; p.H = H; p.W = W; p.Do = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.relu = relu;
   int km = 3, chunks = 1;
-  plan(B, p.Do, p.Ho, p.Wo, km, chunks);
+  cudaStream_t st = as_stream(stream);
+  if (Cin == 8) {
+    plan(B, p.Do, p.Ho, p.Wo, 3, 4, km, chunks);
+    p.d_chunk = ceil_div(p.Do, chunks);
+    p.chunks = ceil_div(p.Do, p.d_chunk);
+    return km == 4 ? launch<8, 16, 4, 3>(x_split, p, st) : launch<8, 16, 3, 4>(x_split, p, st);
+  }
+  plan(B, p.Do, p.Ho, p.Wo, 2, 2, km, chunks);
   p.d_chunk = ceil_div(p.Do, chunks);
   p.chunks = ceil_div(p.Do, p.d_chunk);
-  cudaStream_t st = as_stream(stream);
-  return km == 4 ? launch<4, 3>(x_split, p, st) : launch<3, 4>(x_split, p, st);
+  return launch<16, 32, 2, 2>(x_split, p, st);
 }

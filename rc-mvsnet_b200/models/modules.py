@@ -315,9 +315,11 @@ def pack_conv3d_layer(w, scale, shift, transposed, stride, relu, nsplit, slab=Fa
         cands.append(("gemm", ops.conv3d_gemm_tc_pack(w, scale, transposed, nsplit), shift, cout, nsplit, gmode))
     if slab and not transposed and stride == 1 and (cin, cout) in ops.SLAB_SUPPORTED:
         cands.append(("slab", ops.conv3d_slab_pack(w, scale), shift, cout))
+    if slab and not transposed and stride == 1 and (cin, cout) in ops.SLABO_SUPPORTED:
+        cands.append(("slabo", ops.conv3d_o_slab_pack(w, scale), shift, cout))
     if slab and transposed and (cin, cout) in ops.SLABT_SUPPORTED:
         cands.append(("slabt", ops.conv_transpose3d_slab_pack(w, scale), shift, cout))
-    if slab and not transposed and stride == 2 and (cin, cout) == (8, 16):
+    if slab and not transposed and stride == 2 and (cin, cout) in ops.SLAB2_SUPPORTED:
         cands.append(("slab2", ops.conv3d_s2_slab_pack(w, scale), shift, cout))
     return {"cands": cands, "tr": transposed, "stride": stride, "relu": relu, "choice": {}}
 
@@ -375,13 +377,15 @@ class CostRegNet(nn.Module):
     def _call(cand, layer, x, skip, out="y"):
         """`out`: "y" fp32 result; "split" / "both": also / only the pre-split bf16 form (slab engines only)."""
         kind = cand[0]
-        if kind in ("slab", "slab2", "slabt"):   # TMA-fed split-bf16 tcgen05 kernels; the input is pre-split by its producer when possible
+        if kind in ("slab", "slab2", "slabt", "slabo"):   # TMA-fed split-bf16 tcgen05 kernels; the input is pre-split by its producer when possible
             xs = x if x.dtype == torch.bfloat16 else ops.split_bf16(x)
             wy, ws = out in ("y", "both"), out in ("split", "both")
+            if kind == "slabo":
+                return ops.conv3d_o_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"], want_y=wy, want_split=ws)
             if kind == "slabt":
                 return ops.conv_transpose3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"], want_y=wy, want_split=ws)
             if kind == "slab2":
-                return ops.conv3d_s2_slab(xs, cand[1], cand[2], layer["relu"], want_y=wy, want_split=ws)
+                return ops.conv3d_s2_slab(xs, cand[1], cand[3], cand[2], layer["relu"], want_y=wy, want_split=ws)
             return ops.conv3d_slab(xs, cand[1], cand[3], cand[2], skip, layer["relu"], want_y=wy, want_split=ws)
         if out != "y":
             raise RuntimeError("rcmvs: only the slab engines write split-bf16 activations")
@@ -451,6 +455,8 @@ class CostRegNet(nn.Module):
             return kinds.index("slab")
         if "slab2" in kinds:                                               # bf16x3 mode: conv1 (8 -> 16, stride 2)
             return kinds.index("slab2")
+        if "slabo" in kinds:                                               # bf16x3 mode: conv4 (32 -> 32)
+            return kinds.index("slabo")
         if "slabt" in kinds:                                               # bf16x3 mode: conv9 / conv11 (transposed)
             return kinds.index("slabt")
         if "tc" in kinds:
@@ -504,8 +510,15 @@ class CostRegNet(nn.Module):
                 c1 = self._call(P["conv1"]["cands"][0], P["conv1"], c0, None)   # split pass costs more than slab2 saves (measured)
             else:
                 c1 = run(P["conv1"], c0)
-        c2 = run(P["conv2"], c1)
-        c4 = run(P["conv4"], run(P["conv3"], c2))
+        k3 = self._kind(P["conv3"], (B, D // 2, H // 2, W // 2, 2 * c)) if chain else ""
+        k4 = self._kind(P["conv4"], (B, D // 4, H // 4, W // 4, 4 * c)) if chain else ""
+        if k2 == "slab" and k3 == "slab2":
+            c2, c2s = run(P["conv2"], c1, out="both")            # fp32 for the conv9 skip, split for conv3
+            c3 = run(P["conv3"], c2s, out="split" if k4 == "slabo" else "y")
+        else:
+            c2 = run(P["conv2"], c1)
+            c3 = run(P["conv3"], c2)
+        c4 = run(P["conv4"], c3)
         y = run(P["conv6"], run(P["conv5"], c4))
         y = run(P["conv7"], y, c4)                               # skip + relu(bn(convT(y)))  (modules.py:497-499)
         if chain and self._kind(P["conv9"], (B, D // 4, H // 4, W // 4, 4 * c)) == "slabt" and \

@@ -256,7 +256,7 @@ class CostReg(nn.Module):
             # pre-split input from resize_depth_cl_split: conv0 -> conv1 (stride 2) -> conv2 on the tensor-core slab kernels,
             # activations handed over in split-bf16 form
             c0, c0s = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False, want_split=True)
-            c1s = ops.conv3d_s2_slab(c0s, P["conv1.slab2"][0], P["conv1.slab2"][1], relu=False, want_y=False, want_split=True)
+            c1s = ops.conv3d_s2_slab(c0s, P["conv1.slab2"][0], 16, P["conv1.slab2"][1], relu=False, want_y=False, want_split=True)
             c2 = ops.conv3d_slab(c1s, P["conv2.slab"][0], 16, P["conv2.slab"][1], None, relu=False)
         else:
             if x_cl.dtype == torch.bfloat16:

@@ -271,26 +271,53 @@ def conv3d_slab(x_split, img, Cout, bias=None, skip=None, relu=True, want_y=True
     return y if want_y else ys
 
 
+SLABO_SUPPORTED = {(32, 32)}      # (Cin, Cout) of the all-taps-as-offsets slab kernel (conv4)
+
+
+@_on_device
+def conv3d_o_slab_pack(w, scale=None):
+    Cout, Cin = w.shape[:2]
+    img = torch.empty((_ffi.lib().rcmvs_conv3d_o_slab_weight_elems(Cin, Cout),), device=w.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_conv3d_o_slab_pack", _chk(w, "w"), _opt(scale, "scale"), img.data_ptr(), Cout, Cin, _stream())
+    return img
+
+
+@_on_device
+def conv3d_o_slab(x_split, img, Cout, bias=None, skip=None, relu=True, want_y=True, want_split=False):
+    """x_split [2,B,D,H,W,Cin] bf16 -> 3x3x3 stride-1 conv: y [B,D,H,W,Cout] fp32 and/or y_split (conv4: 32 -> 32)."""
+    _, B, D, H, W, Cin = x_split.shape
+    y = torch.empty((B, D, H, W, Cout), device=x_split.device, dtype=torch.float32) if want_y else None
+    ys = torch.empty((2, B, D, H, W, Cout), device=x_split.device, dtype=torch.bfloat16) if want_split else None
+    _ffi.call("rcmvs_conv3d_o_slab_fwd", _chk_bf16(x_split, "x_split"), _chk_bf16(img, "wimg"), _opt(bias, "bias"),
+              _opt(skip, "skip"), _opt(y, "y"), None if ys is None else ys.data_ptr(), B, D, H, W, Cin, Cout,
+              1 if relu else 0, _stream())
+    if want_y and want_split:
+        return y, ys
+    return y if want_y else ys
+
+
+SLAB2_SUPPORTED = {(8, 16), (16, 32)}      # (Cin, Cout) of the stride-2 TMA slab kernel (conv1, conv3)
+
+
 @_on_device
 def conv3d_s2_slab_pack(w, scale=None):
-    """torch Conv3d weight [16,8,3,3,3] (x BN scale) -> operand image of the stride-2 TMA slab kernel."""
+    """torch Conv3d weight [Cout,Cin,3,3,3] (x BN scale) -> operand image of the stride-2 TMA slab kernel."""
     Cout, Cin = w.shape[:2]
-    n = _ffi.lib().rcmvs_conv3d_s2_slab_weight_elems()
+    n = _ffi.lib().rcmvs_conv3d_s2_slab_weight_elems(Cin, Cout)
     img = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
     _ffi.call("rcmvs_conv3d_s2_slab_pack", _chk(w, "w"), _opt(scale, "scale"), img.data_ptr(), Cout, Cin, _stream())
     return img
 
 
 @_on_device
-def conv3d_s2_slab(x_split, img, bias=None, relu=True, want_y=True, want_split=False):
-    """x_split [2,B,D,H,W,8] bf16 (D, H, W even) -> 3x3x3 stride-2 conv to 16 channels: y [B,D/2,H/2,W/2,16] fp32 and/or
-    y_split [2,B,D/2,H/2,W/2,16] bf16."""
+def conv3d_s2_slab(x_split, img, Cout, bias=None, relu=True, want_y=True, want_split=False):
+    """x_split [2,B,D,H,W,Cin] bf16 (D, H, W even) -> 3x3x3 stride-2 conv: y [B,D/2,H/2,W/2,Cout] fp32 and/or y_split."""
     _, B, D, H, W, Cin = x_split.shape
-    shp = (B, D // 2, H // 2, W // 2, 16)
+    shp = (B, D // 2, H // 2, W // 2, Cout)
     y = torch.empty(shp, device=x_split.device, dtype=torch.float32) if want_y else None
     ys = torch.empty((2,) + shp, device=x_split.device, dtype=torch.bfloat16) if want_split else None
     _ffi.call("rcmvs_conv3d_s2_slab_fwd", _chk_bf16(x_split, "x_split"), _chk_bf16(img, "wimg"), _opt(bias, "bias"),
-              _opt(y, "y"), None if ys is None else ys.data_ptr(), B, D, H, W, Cin, 16, 1 if relu else 0, _stream())
+              _opt(y, "y"), None if ys is None else ys.data_ptr(), B, D, H, W, Cin, Cout, 1 if relu else 0, _stream())
     if want_y and want_split:
         return y, ys
     return y if want_y else ys

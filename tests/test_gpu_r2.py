@@ -290,29 +290,31 @@ def test_conv3d_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
     np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
 
 
-@pytest.mark.parametrize("dhw", [(2, 2, 2), (4, 8, 62), (6, 34, 64), (16, 24, 126), (10, 64, 80), (2, 26, 190)])
-def test_conv3d_s2_slab_bf16x3_vs_oracle(dev, dhw):
-    """conv1 (8 -> 16, stride 2) on tcgen05: strided TMA boxes (parity sub-planes), two taps per K = 16 step through the
-    descriptor's leading-dimension offset, kd through a TMEM ring.  Same accuracy class as the stride-1 slab kernel."""
+@pytest.mark.parametrize("cin,cout,dhw", [(8, 16, (2, 2, 2)), (8, 16, (4, 8, 62)), (8, 16, (6, 34, 64)), (8, 16, (16, 24, 126)),
+                                          (8, 16, (10, 64, 80)), (8, 16, (2, 26, 190)), (16, 32, (2, 2, 2)), (16, 32, (4, 8, 62)),
+                                          (16, 32, (12, 32, 40)), (16, 32, (6, 18, 66))])
+def test_conv3d_s2_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
+    """conv1 (8 -> 16) / conv3 (16 -> 32), stride 2, on tcgen05: strided TMA boxes (parity sub-planes), taps as descriptor
+    offsets (8 channels: two taps per K = 16 step through the leading-dimension offset), kd through a TMEM ring."""
     from oracle import ref_np as O
     from rcmvs import ops
-    rng = np.random.default_rng(sum(dhw))
+    rng = np.random.default_rng(sum(dhw) + cin)
     D, H, W = dhw
-    xs = [rng.standard_normal((8, D, H, W), dtype=np.float32) for _ in range(2)]
-    w = (rng.standard_normal((16, 8, 3, 3, 3)) / np.sqrt(27 * 8)).astype(np.float32)
-    scale = rng.uniform(0.5, 1.5, 16).astype(np.float32)
-    bias = rng.standard_normal(16).astype(np.float32)
+    xs = [rng.standard_normal((cin, D, H, W), dtype=np.float32) for _ in range(2)]
+    w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(27 * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
     lin = np.stack([O.conv3d(x, w * scale[:, None, None, None, None], stride=2) for x in xs])
     want = np.maximum(lin + bias[None, :, None, None, None], 0)
     img = ops.conv3d_s2_slab_pack(cu(w, dev), cu(scale, dev))
     x_split = ops.split_bf16(cu(np.stack(xs).transpose(0, 2, 3, 4, 1), dev))
-    y, ys = ops.conv3d_s2_slab(x_split, img, cu(bias, dev), True, True, True)
-    assert tuple(y.shape) == (2, D // 2, H // 2, W // 2, 16)
+    y, ys = ops.conv3d_s2_slab(x_split, img, cout, cu(bias, dev), True, True, True)
+    assert tuple(y.shape) == (2, D // 2, H // 2, W // 2, cout)
     np.testing.assert_allclose(y.permute(0, 4, 1, 2, 3).cpu().numpy(), want, atol=1e-4, rtol=1e-4)
     assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
-    y2 = ops.conv3d_s2_slab(x_split, img, None, False)
+    y2 = ops.conv3d_s2_slab(x_split, img, cout, None, False)
     np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
-    ys_only = ops.conv3d_s2_slab(x_split, img, cu(bias, dev), True, want_y=False, want_split=True)
+    ys_only = ops.conv3d_s2_slab(x_split, img, cout, cu(bias, dev), True, want_y=False, want_split=True)
     assert torch.equal(ys_only, ys)
 
 
@@ -802,3 +804,26 @@ def test_conv2d_s2k5_slab_bf16x3_vs_oracle(dev, cin, cout, nhw):
     assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
     y2 = ops.conv2d_s2k5_slab(xs_split, img, cout, None, False)
     np.testing.assert_allclose(y2.permute(0, 3, 1, 2).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("dhw", [(1, 1, 1), (3, 8, 30), (4, 9, 31), (6, 16, 40), (12, 32, 40), (2, 20, 61)])
+def test_conv3d_o_slab_bf16x3_vs_oracle(dev, dhw):
+    """conv4 (32 -> 32, stride 1) on tcgen05: kd folded into N (TMEM plane ring), the nine (kh, kw) taps as descriptor offsets."""
+    from oracle import ref_np as O
+    from rcmvs import ops
+    rng = np.random.default_rng(sum(dhw) + 77)
+    D, H, W = dhw
+    xs = [rng.standard_normal((32, D, H, W), dtype=np.float32) for _ in range(2)]
+    w = (rng.standard_normal((32, 32, 3, 3, 3)) / np.sqrt(27 * 32)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 32).astype(np.float32)
+    bias = rng.standard_normal(32).astype(np.float32)
+    lin = np.stack([O.conv3d(x, w * scale[:, None, None, None, None]) for x in xs])
+    skip = rng.standard_normal(lin.shape, dtype=np.float32)
+    want = np.maximum(lin + bias[None, :, None, None, None], 0) + skip
+    img = ops.conv3d_o_slab_pack(cu(w, dev), cu(scale, dev))
+    x_split = ops.split_bf16(cu(np.stack(xs).transpose(0, 2, 3, 4, 1), dev))
+    y, ys = ops.conv3d_o_slab(x_split, img, 32, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), True, True, True)
+    np.testing.assert_allclose(y.permute(0, 4, 1, 2, 3).cpu().numpy(), want, atol=1e-4, rtol=1e-4)
+    assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
+    y2 = ops.conv3d_o_slab(x_split, img, 32, None, None, False)
+    np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
