@@ -195,6 +195,8 @@ int rcmvs_softargmin_conf_fwd(const float* cost, const float* depth_planes, int 
 /* ---- f1 FeatureNet building blocks: models/modules.py:28-62, 363-464 ------------------------------------------------ */
 /* img [N][C<=8][H][W] -> out [N][H][W][8] (zero-padded channels-last input of the first convolution). */
 int rcmvs_images_to_nhwc8(const float* img, float* out, int N, int C, int H, int W, rcmvs_stream_t stream);
+/* same, written as split-bf16 planes out_split [2][N][H][W][8] for the tensor-core first layer (rcmvs_conv2d_slab_fwd, Cin = 8) */
+int rcmvs_images_to_nhwc8_split(const float* img, void* out_split, int N, int C, int H, int W, rcmvs_stream_t stream);
 /* torch Conv2d weight [Cout][Cin][K][K] x folded BatchNorm scale[Cout] (NULL = 1) -> packed [K*K][Cin_pad][Cout]. */
 int rcmvs_pack_conv2d_weight(const float* w, const float* scale, float* packed, int Cout, int Cin, int Cin_pad, int K,
                              rcmvs_stream_t stream);
@@ -209,7 +211,8 @@ int rcmvs_conv2d_fwd_split(const float* x, const float* packed_w, const float* b
                            int N, int H, int W, int Cin, int Cout, int K, int stride, int relu, rcmvs_stream_t stream);
 /* FeatureNet's 3x3 stride-1 convolutions on tcgen05 (kind::f16, bf16x3) fed by TMA, persistent over (image, tile) items:
  * x_split [2][N][H][W][Cin] bf16 (hi, lo) -> y fp32 [N][H][W][Cout] and/or y_split; bias = folded BatchNorm shift or NULL.
- * (Cin, Cout) in {(16,16), (32,32), (32,16), (32,8)}: conv1.1/1.2, conv2.1/2.2, out2, out3 (models/modules.py:394-417). */
+ * (Cin, Cout) in {(8,8), (16,16), (32,32), (32,16), (32,8)}: conv0.0/0.1 (the 3 image channels padded to 8; two kw taps per
+ * K = 16 step), conv1.1/1.2, conv2.1/2.2, out2, out3 (models/modules.py:391-417). */
 int64_t rcmvs_conv2d_slab_weight_elems(int Cin, int Cout);
 int rcmvs_conv2d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);
 int rcmvs_conv2d_slab_fwd(const void* x_split, const void* wimg, const float* bias, float* y, void* y_split, int N, int H, int W,

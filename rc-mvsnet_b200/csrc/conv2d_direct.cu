@@ -164,6 +164,28 @@ __global__ void images_to_nhwc8_kernel(const float* __restrict__ img, float* __r
   st4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
 }
 
+// same, written as split-bf16 planes [2][N][H][W][8] for the tensor-core first layer
+__global__ void images_to_nhwc8_split_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int64_t HW,
+                                             int C, int64_t part_stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (i >= HW) return;
+  const float* p = img + (int64_t)n * C * HW + i;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v0 = 2 * k < C ? __ldg(p + (int64_t)(2 * k) * HW) : 0.f, v1 = 2 * k + 1 < C ? __ldg(p + (int64_t)(2 * k + 1) * HW) : 0.f;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+    const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+    hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    lo[k] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  const int64_t o = ((int64_t)n * HW + i) * 8;
+  *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(out + part_stride + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 // torch [Cout][Cin][K][K] x scale[Cout] -> [K*K][Cin_pad][Cout] (rows Cin..Cin_pad-1 zero)
 __global__ void pack_conv2d_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                           float* __restrict__ packed, int Cout, int Cin, int Cin_pad, int taps) {
@@ -285,6 +307,20 @@ extern "C" int rcmvs_images_to_nhwc8(const float* img, float* out, int N, int C,
   dim3 grid((unsigned)ceil_div<int64_t>(HW, 256), N);
   images_to_nhwc8_kernel<<<grid, 256, 0, as_stream(stream)>>>(img, out, HW, C);
   RCMVS_CHECK_LAUNCH("rcmvs_images_to_nhwc8");
+  return RCMVS_OK;
+}
+
+extern "C" int rcmvs_images_to_nhwc8_split(const float* img, void* out_split, int N, int C, int H, int W,
+                                           rcmvs_stream_t stream) {
+  using namespace rcmvs;
+  RCMVS_REQUIRE(img && out_split, RCMVS_ERR_BAD_ARG, "rcmvs_images_to_nhwc8_split: null pointer");
+  RCMVS_REQUIRE(N > 0 && C > 0 && C <= 8 && H > 0 && W > 0 && N <= 65535, RCMVS_ERR_BAD_ARG,
+                "rcmvs_images_to_nhwc8_split: bad dims");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)ceil_div<int64_t>(HW, 256), N);
+  images_to_nhwc8_split_kernel<<<grid, 256, 0, as_stream(stream)>>>(img, reinterpret_cast<__nv_bfloat16*>(out_split), HW, C,
+                                                                    (int64_t)N * HW * 8);
+  RCMVS_CHECK_LAUNCH("rcmvs_images_to_nhwc8_split");
   return RCMVS_OK;
 }
 

@@ -22,20 +22,24 @@ struct Cfg {
   static constexpr int CP = COUT < 8 ? 8 : COUT;
   static constexpr int G = ((3 * CP + 15) / 16) * 16;             // TMEM columns / B rows: 3 kh blocks of CP channels
   static constexpr int KS = CIN / 16;
+  // CIN = 8 (conv0.0 / conv0.1): one K = 16 step covers TWO kw taps — K-chunk 1 is the next position (LBO = 16 B); the
+  // second step is (kw = 2, zero block)
+  static constexpr int NSTEP = CIN == 8 ? 2 : 3 * KS;
   static constexpr int NCH = CIN / 8;
   static constexpr int ROWS = 4 * KM;
   static constexpr int OROWS = ROWS - 2;
   static constexpr int PLANE_B = ROWS * PW * 16;
   static constexpr int SLAB_B = NCH * PLANE_B;
   static constexpr int STAGE_B = 2 * SLAB_B;
-  static constexpr int A_BYTES = NS * STAGE_B + 128;
-  static constexpr int BBLK_B = 2 * G * 16;                       // one (kw, K-step): 2 chunks x G rows x 16 B
-  static constexpr int BTERM_B = 3 * KS * BBLK_B;
+  static constexpr int ZERO_OFF = NS * STAGE_B + 128;             // (CIN = 8) 2 KB of zeros
+  static constexpr int A_BYTES = NS * STAGE_B + 128 + (CIN == 8 ? 2048 + 128 : 0);
+  static constexpr int BBLK_B = 2 * G * 16;                       // one step: 2 chunks x G rows x 16 B
+  static constexpr int BTERM_B = NSTEP * BBLK_B;
   static constexpr int B_BYTES = 2 * BTERM_B;
   static constexpr int NG = 512 / (KM * G) >= 4 ? 4 : 512 / (KM * G);   // accumulator groups in flight (2..4)
   static constexpr int EX_B = 3 * OROWS * PW * CP * 4;
   static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + EX_B + 512;
-  static_assert(CIN % 16 == 0 && NG >= 2 && PLANE_B % 128 == 0, "configuration");
+  static_assert((CIN == 8 || CIN % 16 == 0) && NG >= 2 && PLANE_B % 128 == 0, "configuration");
 };
 
 struct Params {
@@ -90,7 +94,8 @@ conv2d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
     const float4* src = reinterpret_cast<const float4*>(p.wimg);
     float4* dst = reinterpret_cast<float4*>(b_smem);
     for (int i = threadIdx.x; i < C::B_BYTES / 16; i += kThreads) dst[i] = __ldg(src + i);
-    if (threadIdx.x < 8) reinterpret_cast<float4*>(a_smem + NS * C::STAGE_B)[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < (C::A_BYTES - NS * C::STAGE_B) / 16; i += kThreads)       // overrun pad (+ zero block)
+      reinterpret_cast<float4*>(a_smem + NS * C::STAGE_B)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -132,22 +137,35 @@ conv2d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       if (i >= NG) mbar_wait(grp_free + g, ((i / NG) - 1) & 1);
       mbar_wait(full + buf, (i / NS) & 1);
       tc_fence_after();
-      const uint32_t a_lo0 = desc_lo(smem_u32(a_smem + (size_t)buf * C::STAGE_B), C::PLANE_B);
+      const uint32_t a_base = smem_u32(a_smem + (size_t)buf * C::STAGE_B);
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
+      for (int st = 0; st < C::NSTEP; ++st) {
+        constexpr int KSD = C::KS > 0 ? C::KS : 1;
+        const int kw = CIN == 8 ? 2 * st : st / KSD, ks = CIN == 8 ? 0 : st % KSD;
 #pragma unroll
-        for (int ks = 0; ks < C::KS; ++ks) {
-#pragma unroll
-          for (int mt = 0; mt < KM; ++mt) {
-            constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
-            const uint32_t a_d = a_lo0 + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + kw);
-            const uint32_t b_d = b_lo0 + (uint32_t)(((kw * C::KS + ks) * C::BBLK_B) >> 4);
-            const uint32_t d = tmem_base + (uint32_t)(mt * (NG * G) + g * G);
-            if (leader) {
-              umma_bf16_lohi(d, a_d + kLoOff, b_d, idesc);            // x_lo · w_hi
-              umma_bf16_lohi(d, a_d, b_d + kBLoOff, idesc);           // x_hi · w_lo
-              umma_bf16_lohi(d, a_d, b_d, idesc);                     // x_hi · w_hi
+        for (int mt = 0; mt < KM; ++mt) {
+          constexpr uint32_t kLoOff = C::SLAB_B >> 4, kBLoOff = C::BTERM_B >> 4;
+          uint32_t a_d, a_lo_d;
+          if constexpr (CIN == 8) {
+            const uint32_t a_addr = a_base + (uint32_t)((mt * 128 + kw) * 16);
+            if (st == 0) {
+              a_d = desc_lo(a_addr, 16);
+              a_lo_d = a_d + kLoOff;
+            } else {
+              const uint32_t zb = smem_u32(a_smem) + C::ZERO_OFF;
+              a_d = desc_lo(a_addr, zb - a_addr);
+              a_lo_d = desc_lo(a_addr + C::SLAB_B, zb - (a_addr + C::SLAB_B));
             }
+          } else {
+            a_d = desc_lo(a_base, C::PLANE_B) + (uint32_t)((ks * 2 * C::PLANE_B) >> 4) + (uint32_t)(mt * 128 + kw);
+            a_lo_d = a_d + kLoOff;
+          }
+          const uint32_t b_d = b_lo0 + (uint32_t)((st * C::BBLK_B) >> 4);
+          const uint32_t d = tmem_base + (uint32_t)(mt * (NG * G) + g * G);
+          if (leader) {
+            umma_bf16_lohi(d, a_lo_d, b_d, idesc);                  // x_lo · w_hi
+            umma_bf16_lohi(d, a_d, b_d + kBLoOff, idesc);           // x_hi · w_lo
+            umma_bf16_lohi(d, a_d, b_d, idesc);                     // x_hi · w_hi
           }
         }
       }
@@ -228,24 +246,26 @@ conv2d_slab_bf16_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   }
 }
 
-// Weight image: torch Conv2d weight [Cout][Cin][3][3] x BN scale ->
-//   img[term][kw][ks][chunk][row = kh*CP + n][e], channel = ks*16 + chunk*8 + e; term 0 = bf16(w·s), term 1 = bf16(rest)
+// Weight image: torch Conv2d weight [Cout][Cin][3][3] x BN scale -> img[term][step][chunk][row = kh*CP + n][e]
+//   Cin >= 16: step = kw*KS + ks, channel = ks*16 + chunk*8 + e;  Cin == 8: step s covers taps kw = 2s + chunk (kw = 3: zero)
+//   term 0 = bf16(w·s), term 1 = bf16(rest)
 __global__ void pack_slab2d_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                           __nv_bfloat16* __restrict__ img, int Cout, int Cin, int CP, int G) {
   const int KS = Cin / 16;
-  const int per_term = 3 * KS * 2 * G * 8;
+  const int nstep = Cin == 8 ? 2 : 3 * KS;
+  const int per_term = nstep * 2 * G * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_term) return;
   const int e = i & 7;
   int r = i >> 3;
   const int row = r % G; r /= G;
   const int chunk = r & 1; r >>= 1;
-  const int ks = r % KS;
-  const int kw = r / KS;
+  const int st = r;
+  const int kw = Cin == 8 ? 2 * st + chunk : st / KS;
+  const int ci = Cin == 8 ? e : (st % KS) * 16 + chunk * 8 + e;
   const int kh = row / CP, n = row % CP;
   float v = 0.f;
-  if (kh < 3 && n < Cout) {
-    const int ci = ks * 16 + chunk * 8 + e;
+  if (kh < 3 && n < Cout && kw < 3) {
     v = w[((int64_t)n * Cin + ci) * 9 + kh * 3 + kw];
     if (scale) v *= scale[n];
   }
@@ -279,7 +299,7 @@ static int launch(const void* x, Params p, cudaStream_t st) {
 }
 
 static bool supported(int Cin, int Cout) {
-  return (Cin == 16 && Cout == 16) || (Cin == 32 && (Cout == 32 || Cout == 16 || Cout == 8));
+  return (Cin == 8 && Cout == 8) || (Cin == 16 && Cout == 16) || (Cin == 32 && (Cout == 32 || Cout == 16 || Cout == 8));
 }
 
 }  // namespace slab2d
@@ -288,7 +308,7 @@ static bool supported(int Cin, int Cout) {
 extern "C" int64_t rcmvs_conv2d_slab_weight_elems(int Cin, int Cout) {
   const int cp = Cout < 8 ? 8 : Cout;
   const int g = ((3 * cp + 15) / 16) * 16;
-  return (int64_t)2 * 3 * (Cin / 16) * 2 * g * 8;
+  return (int64_t)2 * (Cin == 8 ? 2 : 3 * (Cin / 16)) * 2 * g * 8;
 }
 
 extern "C" int rcmvs_conv2d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin,
@@ -299,7 +319,7 @@ extern "C" int rcmvs_conv2d_slab_pack(const float* w, const float* scale, void* 
                 Cout);
   const int cp = Cout < 8 ? 8 : Cout;
   const int g = ((3 * cp + 15) / 16) * 16;
-  const int per_term = 3 * (Cin / 16) * 2 * g * 8;
+  const int per_term = (Cin == 8 ? 2 : 3 * (Cin / 16)) * 2 * g * 8;
   slab2d::pack_slab2d_weight_kernel<<<ceil_div(per_term, 256), 256, 0, as_stream(stream)>>>(
       w, scale, reinterpret_cast<__nv_bfloat16*>(img), Cout, Cin, cp, g);
   RCMVS_CHECK_LAUNCH("rcmvs_conv2d_slab_pack");
@@ -322,6 +342,7 @@ extern "C" int rcmvs_conv2d_slab_fwd(const void* x_split, const void* wimg, cons
   p.N = N; p.H = H; p.W = W; p.relu = relu;
   p.tiles_x = p.tiles_y = p.items = p.items_per_cta = 0;
   cudaStream_t st = as_stream(stream);
+  if (Cin == 8 && Cout == 8) return launch<8, 8, 3, 8>(x_split, p, st);         // conv0.0 (3 -> 8, input padded to 8), conv0.1
   if (Cin == 16 && Cout == 16) return launch<16, 16, 3, 6>(x_split, p, st);
   if (Cin == 32 && Cout == 32) return launch<32, 32, 2, 3>(x_split, p, st);
   if (Cin == 32 && Cout == 16) return launch<32, 16, 3, 3>(x_split, p, st);

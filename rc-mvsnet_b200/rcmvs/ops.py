@@ -542,6 +542,15 @@ def images_to_nhwc8(img):
 
 
 @_on_device
+def images_to_nhwc8_split(img):
+    """[N,C<=8,H,W] fp32 -> split-bf16 [2,N,H,W,8] (channels C..7 zero)."""
+    N, C, H, W = img.shape
+    out = torch.empty((2, N, H, W, 8), device=img.device, dtype=torch.bfloat16)
+    _ffi.call("rcmvs_images_to_nhwc8_split", _chk(img, "img"), out.data_ptr(), N, C, H, W, _stream())
+    return out
+
+
+@_on_device
 def pack_conv2d_weight(w, scale=None, cin_pad=None):
     Cout, Cin, K, _ = w.shape
     cin_pad = cin_pad or Cin
@@ -568,7 +577,7 @@ def conv2d(x_cl, packed_w, bias=None, up=None, stride=1, relu=True, want_y=True,
     return y if want_y else ys
 
 
-SLAB2D_SUPPORTED = {(16, 16), (32, 32), (32, 16), (32, 8)}      # (Cin, Cout) of the 2-D TMA slab kernel (3x3, stride 1)
+SLAB2D_SUPPORTED = {(8, 8), (16, 16), (32, 32), (32, 16), (32, 8)}      # (Cin, Cout) of the 2-D TMA slab kernel (3x3, stride 1)
 
 
 @_on_device

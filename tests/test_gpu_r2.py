@@ -755,7 +755,8 @@ def test_rendering_consistency_net_training_step_on_own_kernels(dev):
 
 # ---- f1 FeatureNet on tensor cores: 2-D TMA slab kernel ---------------------------------------------------------------------
 @pytest.mark.parametrize("cin,cout,nhw", [(16, 16, (2, 9, 37)), (32, 32, (1, 20, 64)), (32, 16, (3, 7, 31)), (32, 8, (2, 33, 95)),
-                                          (16, 16, (5, 64, 80)), (32, 32, (1, 1, 1)), (32, 8, (1, 12, 30))])
+                                          (16, 16, (5, 64, 80)), (32, 32, (1, 1, 1)), (32, 8, (1, 12, 30)), (8, 8, (2, 21, 61)),
+                                          (8, 8, (1, 64, 80)), (8, 8, (1, 1, 1))])
 def test_conv2d_slab_bf16x3_vs_oracle(dev, cin, cout, nhw):
     from oracle import ref_np as O
     from rcmvs import ops
