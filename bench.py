@@ -356,6 +356,7 @@ def main():
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the configs[2]/[3]/[4] side timings")
     ap.add_argument("--no-stock-torch", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launch sequence instead of CUDA-graph replay")
     ap.add_argument("--in-flight", type=int, default=2, dest="in_flight",
                     help="reference views in flight per GPU (alternating CUDA streams) in the headline loops; the "
                          "one-view-at-a-time numbers are reported under `single_stream`")
@@ -410,21 +411,40 @@ def main():
     nfl = max(1, args.in_flight)
     lanes = [torch.cuda.Stream(dev) for _ in range(nfl)] if nfl > 1 else None
 
+    # CUDA graphs (rcmvs.graph): the ~60 launches of one forward are captured once per lane and replayed — the host then
+    # issues one launch per reference view; the inputs of every step are copied into the graph's static buffers first
+    # (device-to-device, inside the timed region).  --no-graphs times the eager launch sequence instead.
+    use_graphs = not args.no_graphs
+    graphs = {}
+
+    def lane_graph(i):
+        if i not in graphs:
+            from rcmvs.graph import GraphedForward
+            graphs[i] = GraphedForward(model, *sets_d[0])
+        return graphs[i]
+
     def step_resident():
         counter[0] += 1
+        lane = counter[0] % nfl
         with torch.no_grad():
             if lanes is None:
+                if use_graphs:
+                    return lane_graph(0)(*sets_d[counter[0] % NSETS])
                 return model(*sets_d[counter[0] % NSETS])
-            with torch.cuda.stream(lanes[counter[0] % nfl]):
+            with torch.cuda.stream(lanes[lane]):
+                if use_graphs:
+                    return lane_graph(lane)(*sets_d[counter[0] % NSETS])
                 return model(*sets_d[counter[0] % NSETS])
 
     def step_single():
         counter[0] += 1
         with torch.no_grad():
+            if use_graphs:
+                return lane_graph(-1)(*sets_d[counter[0] % NSETS])
             return model(*sets_d[counter[0] % NSETS])
 
     from rcmvs.pipeline import HostPipeline
-    pipe = HostPipeline(model, dev, compute_streams=nfl)
+    pipe = HostPipeline(model, dev, compute_streams=nfl, graphs=use_graphs)
 
     def step_e2e():
         # host buffers in, host buffers out, every step: the H2D copy of this step's inputs and the D2H copy of its
@@ -488,11 +508,11 @@ def main():
     if nfl > 1:
         for _ in range(args.warmup):
             step_single()
-        ms1, _, _ = timed(step_single, args.steps, max(3, args.reps // 3))
-        pipe_n, pipe = pipe, HostPipeline(model, dev, compute_streams=1)
+        ms1, _, _ = timed(step_single, args.steps, max(5, args.reps // 2))
+        pipe_n, pipe = pipe, HostPipeline(model, dev, compute_streams=1, graphs=use_graphs)
         for _ in range(args.warmup):
             step_e2e()
-        ms1e, _, _ = timed(step_e2e, args.steps, max(3, args.reps // 3))
+        ms1e, _, _ = timed(step_e2e, args.steps, max(5, args.reps // 2))
         pipe = pipe_n
         single = {"value": world * B * args.steps / (ms1 * 1e-3), "ms_per_step": ms1 / args.steps,
                   "e2e_value": world * B * args.steps / (ms1e * 1e-3), "e2e_ms_per_step": ms1e / args.steps,
@@ -585,7 +605,9 @@ def main():
                    "parallelism": "view-sharded replicas x%d" % world,
                    "cache": "per-step working set %.0f MB of volumes >> 126 MB L2 (no explicit flush needed); %d input "
                             "sets alternate" % (4 * (32 * 192 * 128 * 160 + 16 * 64 * 256 * 320 + 8 * 8 * 512 * 640) / 1e6, NSETS),
-                   "conv_precision": os.environ.get("RCMVS_CONV", "bf16x3")},
+                   "conv_precision": os.environ.get("RCMVS_CONV", "bf16x3"),
+                   "launch": ("CUDA-graph replay: one graph launch per reference view, inputs copied into the graph's static "
+                              "buffers inside the timed region") if use_graphs else "eager: one launch per kernel"},
         "timing": {"stat": "median of %d repetitions of the %d-step loop after >= 1 s spin-up" % (args.reps, args.steps),
                    "ms_per_rep_resident": reps_resident, "ms_per_rep_e2e": reps_e2e},
         "e2e": {"value": e2e_value, "unit": "ref-views/s", "ms_per_step": ms_e2e / args.steps,

@@ -145,7 +145,10 @@ class _CascadeBase(nn.Module):
         flat = imgs.reshape(B * V, *imgs.shape[2:])
         if flat.is_cuda and not torch.is_grad_enabled() and self.feature.base_channels == 8:
             # stage-2/3 feature maps are produced on a side stream while stage 1 runs (joined in _run)
-            out = self.feature.forward_cl(flat, side_stream=self._side_stream(flat.device))
+            # (not while a CUDA graph is being captured: blocks freed inside a capture are reused in capture order, which the
+            # cross-stream record_stream bookkeeping of the side-stream path cannot protect)
+            side = None if torch.cuda.is_current_stream_capturing() else self._side_stream(flat.device)
+            out = self.feature.forward_cl(flat, side_stream=side)
             stacked = {k: (v if k == "_ready" else v.view(B, V, *v.shape[1:])) for k, v in out.items()}
             return None, stacked
         out = self.feature(flat)

@@ -41,7 +41,9 @@ class PackedCache:
                     self._entries.popitem(last=False)
         else:
             value, event, stream = hit
-            if event is not None:
+            if event is not None and not torch.cuda.is_current_stream_capturing():
+                # (while a CUDA graph is being captured the packing finished long ago: rcmvs.graph warms up first, and an
+                # event query is not allowed inside a capture)
                 s = torch.cuda.current_stream()
                 if (s.device_index, s.cuda_stream) != stream and not event.query():
                     s.wait_event(event)

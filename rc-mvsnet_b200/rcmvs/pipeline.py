@@ -11,10 +11,12 @@ __all__ = ["HostPipeline"]
 
 
 class HostPipeline:
-    def __init__(self, model, device, slots=2, compute_streams=1):
+    def __init__(self, model, device, slots=2, compute_streams=1, graphs=False):
         """`compute_streams` > 1 runs consecutive submits on alternating CUDA streams: two reference views in flight
         fill the SMs during the small 1/4- and 1/8-resolution layers and overlap one view's FFMA-bound FeatureNet with
-        the other's tensor-core-bound regularisation.  Results are identical; memory use doubles."""
+        the other's tensor-core-bound regularisation.  Results are identical; memory use doubles.
+        `graphs`: capture the forward of every slot into a CUDA graph (rcmvs.graph) on first use and replay it — one launch
+        per reference view instead of ~60; the slot's device input buffers are the graph's static inputs."""
         slots = max(slots, compute_streams + 1)
         self.model, self.device, self.slots = model, torch.device(device), slots
         self.h2d, self.d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
@@ -23,6 +25,8 @@ class HostPipeline:
         self._dev_in = [None] * slots            # per slot: (imgs, {stage: proj}, depth_values) on the device
         self._consumed = [None] * slots          # event: the forward that read slot s has been enqueued and finished
         self._n = 0
+        self._graphs = [None] * slots if graphs else None
+        self._copied = [None] * slots           # event: the outputs of slot s have been copied to the host
 
     def _slot_buffers(self, s, imgs_h, proj_h, dv_h):
         cur = self._dev_in[s]
@@ -33,6 +37,8 @@ class HostPipeline:
             mk = lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device)
             cur = (mk(imgs_h), {k: mk(v) for k, v in proj_h.items()}, mk(dv_h))
             self._dev_in[s] = cur
+            if self._graphs is not None:
+                self._graphs[s] = None              # captured for the old buffers
         return cur
 
     def submit(self, imgs_h, proj_h, dv_h, depth_out_h, conf_out_h):
@@ -53,10 +59,20 @@ class HostPipeline:
             ready = torch.cuda.Event()
             ready.record(self.h2d)
         main.wait_event(ready)
-        with torch.no_grad(), torch.cuda.stream(main):
-            out = self.model(imgs_d, proj_d, dv_d)
-        if isinstance(out, tuple):
-            out = out[0]
+        if self._graphs is not None:
+            if self._graphs[s] is None:
+                from .graph import GraphedForward
+                ready.synchronize()                                 # capture needs real inputs for its warm-up runs
+                self._graphs[s] = GraphedForward(self.model, imgs_d, proj_d, dv_d, in_place=True)
+            if self._copied[s] is not None:
+                main.wait_event(self._copied[s])                    # the static outputs of this slot have been read
+            with torch.cuda.stream(main):
+                out = self._graphs[s].replay()
+        else:
+            with torch.no_grad(), torch.cuda.stream(main):
+                out = self.model(imgs_d, proj_d, dv_d)
+            if isinstance(out, tuple):
+                out = out[0]
         done = torch.cuda.Event()
         done.record(main)
         self._consumed[s] = done
@@ -65,10 +81,12 @@ class HostPipeline:
             self.d2h.wait_event(done)
             depth_out_h.copy_(depth, non_blocking=True)
             conf_out_h.copy_(conf, non_blocking=True)
-            depth.record_stream(self.d2h)
-            conf.record_stream(self.d2h)
+            if self._graphs is None:
+                depth.record_stream(self.d2h)
+                conf.record_stream(self.d2h)
             copied = torch.cuda.Event()
             copied.record(self.d2h)
+        self._copied[s] = copied
         self._pending.append(copied)
         if len(self._pending) > self.slots:
             self._pending.pop(0)

@@ -828,3 +828,38 @@ def test_conv3d_o_slab_bf16x3_vs_oracle(dev, dhw):
     assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * max(1e-6, float(y.abs().max()))
     y2 = ops.conv3d_o_slab(x_split, img, 32, None, None, False)
     np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
+
+
+def test_cuda_graph_replay_is_bitwise_the_eager_forward(dev):
+    """rcmvs.graph.GraphedForward / HostPipeline(graphs=True): the captured forward replays the eager launch sequence
+    (same kernels, same arithmetic): outputs are bit-identical, also for new inputs loaded into the static buffers."""
+    import models
+    from rcmvs import synth, weights
+    from rcmvs.graph import GraphedForward
+    from rcmvs.pipeline import HostPipeline
+    m = models.CascadeMVSNet_eval(ndepths=[16, 8, 8])
+    weights.load_model(m, os.path.join(G, "cas_model_000014.npz"))
+    m.to(dev).eval()
+    sets = []
+    for seed in (3, 4, 5):
+        imgs, proj, dv = synth.mvs_inputs(3, 64, 96, kind="textured", seed=seed)
+        sets.append((cu(imgs, dev), {k: cu(v, dev) for k, v in proj.items()}, cu(dv, dev)))
+    with torch.no_grad():
+        eager = [{k: m(*s)[k].clone() for k in ("depth", "photometric_confidence")} for s in sets]
+    g = GraphedForward(m, *sets[0])
+    assert g.kernels > 20
+    for s, e in zip(sets, eager):
+        out = g(*s)
+        torch.cuda.synchronize()
+        assert torch.equal(out["depth"], e["depth"]) and torch.equal(out["photometric_confidence"], e["photometric_confidence"])
+    pipe = HostPipeline(m, dev, compute_streams=2, graphs=True)
+    outs = []
+    for i in range(7):
+        s = sets[i % 3]
+        d_h = torch.empty(s[0].shape[0], 64, 96).pin_memory()
+        c_h = torch.empty(s[0].shape[0], 64, 96).pin_memory()
+        pipe.submit(s[0].cpu().pin_memory(), {k: v.cpu().pin_memory() for k, v in s[1].items()}, s[2].cpu().pin_memory(), d_h, c_h)
+        outs.append((i % 3, d_h, c_h))
+    pipe.synchronize()
+    for i, d_h, c_h in outs:
+        assert torch.equal(d_h, eager[i]["depth"].cpu()) and torch.equal(c_h, eager[i]["photometric_confidence"].cpu())
