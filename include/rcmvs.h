@@ -135,7 +135,8 @@ int rcmvs_conv_transpose3d_tc_fwd(const float* x, const float* wimg, const float
  * arrives PRE-SPLIT as two bf16 planes x_split [2][B][D][H][W][Cin] (hi plane, lo plane; 16-byte aligned), written by the
  * producing kernel (rcmvs_costvolume_var_fwd_split, y_split of this function, rcmvs_conv3d_fwd_split) or, at an API
  * boundary, by rcmvs_split_bf16.  Output: fp32 y and/or split-bf16 y_split (either may be NULL).
- * (Cin, Cout) in {(32,8), (16,8), (16,16), (48,8), (8,8)}; with 8 input channels one K = 16 step covers two kw taps.
+ * (Cin, Cout) in {(32,8), (16,8), (16,16), (48,8), (8,8), (8,1)} ((8,1) = `prob`, fp32 output only); with 8 input channels
+ * one K = 16 step covers two kw taps.
  * Weight image: rcmvs_conv3d_slab_weight_elems() bf16 elements. */
 int64_t rcmvs_conv3d_slab_weight_elems(int Cin, int Cout);
 int rcmvs_conv3d_slab_pack(const float* w, const float* scale, void* img, int Cout, int Cin, rcmvs_stream_t stream);

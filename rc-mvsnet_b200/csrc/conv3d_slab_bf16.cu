@@ -409,7 +409,7 @@ static int launch(const void* x, const Params& p, cudaStream_t st) {
 }
 
 static bool supported(int Cin, int Cout) {
-  return (Cout == 8 && (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 48)) || (Cout == 16 && Cin == 16);
+  return (Cout == 8 && (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 48)) || (Cout == 16 && Cin == 16) || (Cout == 1 && Cin == 8);
 }
 
 // depth chunks + M-tiles per CTA: one CTA per SM (shared memory), so minimise
@@ -487,6 +487,7 @@ extern "C" int rcmvs_conv3d_slab_fwd(const void* x_split, const void* wimg, cons
   p.chunks = ceil_div(D, p.d_chunk);
   cudaStream_t st = as_stream(stream);
   if (Cin == 32 && Cout == 8) return km == 3 ? launch<32, 8, 3, 3>(x_split, p, st) : launch<32, 8, 2, 4>(x_split, p, st);
+  if (Cin == 8 && Cout == 1) return km == 3 ? launch<8, 1, 3, 8>(x_split, p, st) : launch<8, 1, 2, 8>(x_split, p, st);   // `prob`
   if (Cin == 8 && Cout == 8) return km == 3 ? launch<8, 8, 3, 8>(x_split, p, st) : launch<8, 8, 2, 8>(x_split, p, st);   // conv0, stage 3
   if (Cin == 16 && Cout == 8) return km == 3 ? launch<16, 8, 3, 5>(x_split, p, st) : launch<16, 8, 2, 6>(x_split, p, st);
   if (Cin == 16 && Cout == 16) return launch<16, 16, 2, 5>(x_split, p, st);

@@ -531,7 +531,8 @@ class CostRegNet(nn.Module):
             y = run(P["conv9"], y, c2, out="split")             # only conv11 reads it: handed over pre-split
         else:
             y = run(P["conv9"], y, c2)
-        y = run(P["conv11"], y, c0)
+        kp = self._kind(P["prob"], (B, D, H, W, c)) if chain else ""
+        y = run(P["conv11"], y, c0, out="split" if (kp == "slab" and self._kind(P["conv11"], (B, D // 2, H // 2, W // 2, 2 * c)) == "slabt") else "y")
         return run(P["prob"], y).squeeze(-1)
 
     def needs_autograd(self, x=None):

@@ -230,7 +230,7 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
     return y
 
 
-SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16), (48, 8), (8, 8)}      # (Cin, Cout) of the TMA-fed split-bf16 slab kernel
+SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16), (48, 8), (8, 8), (8, 1)}      # (Cin, Cout) of the TMA-fed split-bf16 slab kernel
 
 
 def _chk_bf16(t, name):
@@ -261,6 +261,8 @@ def conv3d_slab_pack(w, scale=None):
 def conv3d_slab(x_split, img, Cout, bias=None, skip=None, relu=True, want_y=True, want_split=False):
     """x_split [2,B,D,H,W,Cin] bf16 (hi, lo) -> y [B,D,H,W,Cout] fp32 and/or y_split [2,B,D,H,W,Cout] bf16."""
     _, B, D, H, W, Cin = x_split.shape
+    if Cout == 1 and want_split:
+        raise RuntimeError("rcmvs: the single-channel slab layer (`prob`) writes fp32 only")
     y = torch.empty((B, D, H, W, Cout), device=x_split.device, dtype=torch.float32) if want_y else None
     ys = torch.empty((2, B, D, H, W, Cout), device=x_split.device, dtype=torch.bfloat16) if want_split else None
     _ffi.call("rcmvs_conv3d_slab_fwd", _chk_bf16(x_split, "x_split"), _chk_bf16(img, "wimg"), _opt(bias, "bias"),

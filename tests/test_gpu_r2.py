@@ -262,7 +262,7 @@ def test_model_on_second_device_while_first_is_current():
 # ---- a3 round-2 engine: TMA-fed split-bf16 slab convolution ---------------------------------------------------------------
 @pytest.mark.parametrize("cin,cout,dhw", [
     (32, 8, (4, 17, 61)), (16, 8, (2, 8, 30)), (16, 16, (9, 5, 64)), (32, 8, (1, 1, 1)), (32, 8, (20, 8, 31)),
-    (16, 8, (23, 21, 95)), (16, 16, (13, 14, 31)), (32, 8, (7, 40, 33)), (8, 8, (8, 24, 61)), (8, 8, (3, 10, 30)), (8, 8, (1, 1, 1)),
+    (16, 8, (23, 21, 95)), (16, 16, (13, 14, 31)), (32, 8, (7, 40, 33)), (8, 8, (8, 24, 61)), (8, 8, (3, 10, 30)), (8, 8, (1, 1, 1)), (8, 1, (6, 21, 62)), (8, 1, (9, 8, 30)),
 ])
 def test_conv3d_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
     """kind::f16 tcgen05 + TMA, split-bf16 operands: fp32-class accuracy (dropped terms <= 3·2^-17 relative per product)."""
@@ -282,10 +282,13 @@ def test_conv3d_slab_bf16x3_vs_oracle(dev, cin, cout, dhw):
     x_split = ops.split_bf16(x_cl)
     assert torch.equal(x_split[0].float() + x_split[1].float(), x_split[0].float() + x_split[1].float())
     assert (x_split[0].float() + x_split[1].float() - x_cl).abs().max() <= 2.0 ** -16 * x_cl.abs().max()
-    y, ys = ops.conv3d_slab(x_split, img, cout, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), True, True, True)
+    if cout == 1:                             # `prob`: fp32 output only
+        y = ops.conv3d_slab(x_split, img, cout, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), True)
+    else:
+        y, ys = ops.conv3d_slab(x_split, img, cout, cu(bias, dev), cu(skip.transpose(0, 2, 3, 4, 1), dev), True, True, True)
+        assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * y.abs().max()
     got = y.permute(0, 4, 1, 2, 3).cpu().numpy()
     np.testing.assert_allclose(got, want + skip, atol=1e-4, rtol=1e-4)
-    assert (ys[0].float() + ys[1].float() - y).abs().max() <= 2.0 ** -16 * y.abs().max()
     y2 = ops.conv3d_slab(x_split, img, cout, None, None, False)
     np.testing.assert_allclose(y2.permute(0, 4, 1, 2, 3).cpu().numpy(), lin, atol=1e-4, rtol=1e-4)
 
