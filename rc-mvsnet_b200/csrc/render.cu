@@ -42,28 +42,44 @@ __global__ void resize_depth_cl_kernel(const float* __restrict__ x, float* __res
 
 // Same resize, written as split-bf16 planes [2][B][D1][S][Cpad] (hi, lo): the operand format of the TMA-fed tensor-core
 // convolution (csrc/conv3d_slab_bf16.cu) that runs Neural_Volume_Net's conv0, the largest layer of the renderer.
-__global__ void resize_depth_cl_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int D0,
-                                             int D1, int64_t S, int C, int Cpad) {
+// Thread = one (plane, position, 8-channel chunk): 16 scalar loads (C = 41 is not a multiple of 4), two 16-byte stores.
+__global__ void __launch_bounds__(256)
+resize_depth_cl_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int D0, int D1, int64_t S,
+                             int C, int Cpad) {
+  const int nch = Cpad / 8;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)D1 * S * Cpad;
-  if (i >= total) return;
-  const int c = (int)(i % Cpad);
-  const int64_t s = (i / Cpad) % S;
-  const int d = (int)(i / ((int64_t)Cpad * S));
+  const int64_t total8 = (int64_t)D1 * S * nch;
+  if (i >= total8) return;
+  const int ch = (int)(i % nch);
+  const int64_t s = (i / nch) % S;
+  const int d = (int)(i / ((int64_t)nch * S));
   const int b = blockIdx.y;
-  float v = 0.f;
-  if (c < C) {
-    const float scale = D1 > 1 ? (float)(D0 - 1) / (float)(D1 - 1) : 0.f;
-    const float src = scale * (float)d;
-    const int i0 = min((int)src, D0 - 1);
-    const int i1 = min(i0 + 1, D0 - 1);
-    const float l1 = src - (float)i0, l0 = 1.f - l1;
-    const float* xb = x + (int64_t)b * D0 * S * C;
-    v = l0 * __ldg(xb + ((int64_t)i0 * S + s) * C + c) + l1 * __ldg(xb + ((int64_t)i1 * S + s) * C + c);
+  const float scale = D1 > 1 ? (float)(D0 - 1) / (float)(D1 - 1) : 0.f;
+  const float src = scale * (float)d;
+  const int i0 = min((int)src, D0 - 1);
+  const int i1 = min(i0 + 1, D0 - 1);
+  const float l1 = src - (float)i0, l0 = 1.f - l1;
+  const float* x0 = x + (((int64_t)b * D0 + i0) * S + s) * C + ch * 8;
+  const float* x1 = x + (((int64_t)b * D0 + i1) * S + s) * C + ch * 8;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = ch * 8 + 2 * k + e;
+      v[e] = c < C ? l0 * __ldg(x0 + 2 * k + e) + l1 * __ldg(x1 + 2 * k + e) : 0.f;
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+    const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[0] - __bfloat162float(h0), v[1] - __bfloat162float(h1));
+    hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    lo[k] = *reinterpret_cast<const uint32_t*>(&ll);
   }
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  y[(int64_t)b * total + i] = h;
-  y[((int64_t)B + b) * total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  const int64_t total = (int64_t)D1 * S * Cpad;
+  const int64_t o = (int64_t)b * total + i * 8;
+  *reinterpret_cast<uint4*>(y + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(y + (int64_t)B * total + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -470,8 +486,9 @@ extern "C" int rcmvs_resize_depth_cl_split(const float* x, void* y_split, int B,
   using namespace rcmvs;
   RCMVS_REQUIRE(x && y_split && B > 0 && D0 > 0 && D1 > 0 && S > 0 && C > 0 && Cpad >= C && B <= 65535, RCMVS_ERR_BAD_ARG,
                 "rcmvs_resize_depth_cl_split: bad arguments");
-  const int64_t total = (int64_t)D1 * S * Cpad;
-  dim3 grid((unsigned)ceil_div<int64_t>(total, 256), B);
+  RCMVS_REQUIRE(Cpad % 8 == 0, RCMVS_ERR_BAD_ARG, "rcmvs_resize_depth_cl_split: Cpad must be a multiple of 8");
+  const int64_t total8 = (int64_t)D1 * S * (Cpad / 8);
+  dim3 grid((unsigned)ceil_div<int64_t>(total8, 256), B);
   resize_depth_cl_split_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y_split), B, D0, D1, S,
                                                                     C, Cpad);
   RCMVS_CHECK_LAUNCH("rcmvs_resize_depth_cl_split");

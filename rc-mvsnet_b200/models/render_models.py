@@ -226,12 +226,17 @@ class CostReg(nn.Module):
                     P[name] = (ops.pack_conv3d_weight(w.contiguous(), scale, False), shift)
                     if name in ("conv0", "conv2") and (w.shape[1], w.shape[0]) in ops.SLAB_SUPPORTED:
                         P[name + ".slab"] = (ops.conv3d_slab_pack(w.contiguous(), scale), shift)   # tcgen05 + TMA, bf16x3
-                    if name == "conv1" and (w.shape[1], w.shape[0]) == (8, 16):
-                        P["conv1.slab2"] = (ops.conv3d_s2_slab_pack(w.contiguous(), scale), shift)  # stride-2 TMA kernel
+                    if name in ("conv1", "conv3") and (w.shape[1], w.shape[0]) in ops.SLAB2_SUPPORTED:
+                        P[name + ".slab2"] = (ops.conv3d_s2_slab_pack(w.contiguous(), scale), shift)  # stride-2 TMA kernel
+                    if name == "conv4" and (w.shape[1], w.shape[0]) in ops.SLABO_SUPPORTED:
+                        P["conv4.slabo"] = (ops.conv3d_o_slab_pack(w.contiguous(), scale), shift)
                 for name in ("conv7", "conv9", "conv11"):
                     seq = getattr(self, name)
                     scale, shift = (t.contiguous() for t in fold_bn(seq[1]))
                     P[name] = (ops.pack_conv3d_weight(seq[0].weight.detach().contiguous(), scale, True), shift)
+                    wt = seq[0].weight.detach().contiguous()
+                    if (wt.shape[0], wt.shape[1]) in ops.SLABT_SUPPORTED:
+                        P[name + ".slabt"] = (ops.conv_transpose3d_slab_pack(wt, scale), shift)      # transposed TMA kernel
             return P
         return self._packed.get((_versions(self), cin_pad), build)
 
@@ -252,9 +257,22 @@ class CostReg(nn.Module):
     def forward_cl(self, x_cl):
         """x_cl [B,D,h,w,Cpad] -> [B,D,h,w,8]; eval-mode BN folded, no ReLU anywhere."""
         P = self.packed(x_cl.shape[-1])          # (the split form has its channel count last as well)
+        tma = x_cl.dtype == torch.bfloat16 and all(k in P for k in ("conv1.slab2", "conv2.slab", "conv3.slab2", "conv4.slabo",
+                                                                     "conv9.slabt", "conv11.slabt"))
+        if tma:
+            # pre-split input from resize_depth_cl_split: every layer down to quarter resolution and the two upper transposed
+            # convolutions on the TMA-fed tensor-core kernels, activations handed over in split-bf16 form (no ReLU anywhere)
+            c0, c0s = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False, want_split=True)
+            c1s = ops.conv3d_s2_slab(c0s, P["conv1.slab2"][0], 16, P["conv1.slab2"][1], relu=False, want_y=False, want_split=True)
+            c2, c2s = ops.conv3d_slab(c1s, P["conv2.slab"][0], 16, P["conv2.slab"][1], None, relu=False, want_split=True)
+            c3s = ops.conv3d_s2_slab(c2s, P["conv3.slab2"][0], 32, P["conv3.slab2"][1], relu=False, want_y=False, want_split=True)
+            c4 = ops.conv3d_o_slab(c3s, P["conv4.slabo"][0], 32, P["conv4.slabo"][1], None, relu=False)
+            y = ops.conv3d(ops.conv3d(c4, *P["conv5"], stride=2, relu=False), *P["conv6"], relu=False)
+            y = ops.conv_transpose3d(y, *P["conv7"], skip=c4, relu=False)
+            y9s = ops.conv_transpose3d_slab(ops.split_bf16(y), P["conv9.slabt"][0], 16, P["conv9.slabt"][1], c2, relu=False,
+                                            want_y=False, want_split=True)
+            return ops.conv_transpose3d_slab(y9s, P["conv11.slabt"][0], 8, P["conv11.slabt"][1], c0, relu=False)
         if x_cl.dtype == torch.bfloat16 and "conv1.slab2" in P and "conv2.slab" in P:
-            # pre-split input from resize_depth_cl_split: conv0 -> conv1 (stride 2) -> conv2 on the tensor-core slab kernels,
-            # activations handed over in split-bf16 form
             c0, c0s = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False, want_split=True)
             c1s = ops.conv3d_s2_slab(c0s, P["conv1.slab2"][0], 16, P["conv1.slab2"][1], relu=False, want_y=False, want_split=True)
             c2 = ops.conv3d_slab(c1s, P["conv2.slab"][0], 16, P["conv2.slab"][1], None, relu=False)
