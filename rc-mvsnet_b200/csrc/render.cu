@@ -290,6 +290,9 @@ constexpr int MLP_PE = 64;       // embedding row pitch
 template <int N_T>   // outputs per thread along n: 8 (N=128) or 4 (N=64)
 __device__ __forceinline__ void mlp_gemm(float (&acc)[8][N_T], const float* __restrict__ A, int lda, int K,
                                          const float* __restrict__ Wt, int N, int p0, int n0) {
+  // unrolled: the weight rows of four k steps are requested before the first FMA block needs them (ncu: the loop was
+  // latency-bound on these L1 / L2 loads at 8 warps per SM, profiles/r02_render_branch_ncu.md)
+#pragma unroll 4
   for (int k = 0; k < K; ++k) {
     float a[8];
 #pragma unroll

@@ -6,6 +6,8 @@ train_rcmvsnet.py keeps working until the fused backward kernels land (DESIGN.md
 Unlike the reference this module does NOT switch on torch.autograd.set_detect_anomaly at import (render_models.py:2)."""
 import ctypes
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -269,9 +271,13 @@ class CostReg(nn.Module):
             c4 = ops.conv3d_o_slab(c3s, P["conv4.slabo"][0], 32, P["conv4.slabo"][1], None, relu=False)
             y = ops.conv3d(ops.conv3d(c4, *P["conv5"], stride=2, relu=False), *P["conv6"], relu=False)
             y = ops.conv_transpose3d(y, *P["conv7"], skip=c4, relu=False)
-            y9s = ops.conv_transpose3d_slab(ops.split_bf16(y), P["conv9.slabt"][0], 16, P["conv9.slabt"][1], c2, relu=False,
-                                            want_y=False, want_split=True)
-            return ops.conv_transpose3d_slab(y9s, P["conv11.slabt"][0], 8, P["conv11.slabt"][1], c0, relu=False)
+            if os.environ.get("RCMVS_NVN_TCT", "0") == "1":     # measured: with the two upper transposed convs on bf16x3 as well,
+                # 4 of 163 840 sampled point features of the full-size golden miss the 5e-3 absolute bar (6.8e-3): off by default
+                y9s = ops.conv_transpose3d_slab(ops.split_bf16(y), P["conv9.slabt"][0], 16, P["conv9.slabt"][1], c2, relu=False,
+                                                want_y=False, want_split=True)
+                return ops.conv_transpose3d_slab(y9s, P["conv11.slabt"][0], 8, P["conv11.slabt"][1], c0, relu=False)
+            y = ops.conv_transpose3d(y, *P["conv9"], skip=c2, relu=False)
+            return ops.conv_transpose3d(y, *P["conv11"], skip=c0, relu=False)
         if x_cl.dtype == torch.bfloat16 and "conv1.slab2" in P and "conv2.slab" in P:
             c0, c0s = ops.conv3d_slab(x_cl, P["conv0.slab"][0], 8, P["conv0.slab"][1], None, relu=False, want_split=True)
             c1s = ops.conv3d_s2_slab(c0s, P["conv1.slab2"][0], 16, P["conv1.slab2"][1], relu=False, want_y=False, want_split=True)
