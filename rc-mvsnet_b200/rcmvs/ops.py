@@ -231,8 +231,8 @@ def conv3d_tc(x_cl, img, Cout, bias=None, skip=None, nsplit=3, relu=True):
 
 
 # (Cin, Cout) the models route to the TMA-fed split-bf16 slab kernel.  The kernel also takes (8, 1) = `prob`, measured SLOWER
-# there than on the FFMA plane-march kernel (190 vs 87 us at stage 1: one useful accumulator column per operand tile), so the
-# models do not use it.
+# there than on the FFMA plane-march kernel (CostRegNet of stage 1: 1.03 ms with it, 0.93 ms with the march kernel: one useful
+# accumulator column per operand tile), so the models do not use it.
 SLAB_SUPPORTED = {(32, 8), (16, 8), (16, 16), (48, 8), (8, 8)}
 
 
