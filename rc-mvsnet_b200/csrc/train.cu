@@ -171,7 +171,9 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ x, c
 // input values per (kd, kh) so a position costs STRIDE·KD·K loads (coalesced over cb, L1-resident: the CS warps of a CTA
 // read the same addresses) + 1 broadcast load for KD·K·K FMAs.  Partial sums are added to G with fp32 atomics.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KD, int K, int STRIDE, bool ROT, int CSR>
+// MODE 0: window slides by register moves; 1: rotating window; 2: moves + software prefetch (the S values and the entering
+// window columns of position ox + 1 are requested before the FMA block of position ox)
+template <int KD, int K, int STRIDE, int MODE, int CSR>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* __restrict__ G, int B, int Ds, int Hs,
              int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int cbb, int csb) {
@@ -221,7 +223,7 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
           for (int c = 0; c < CSR; ++c) sv[c] = __ldg(srow + (int64_t)ox * Cs + c);
         }
       };
-      if constexpr (ROT) {
+      if constexpr (MODE == 1) {
         // rotating register window: input column ix lives in slot (ix + PAD) mod K, so sliding by STRIDE only
         // overwrites the STRIDE oldest slots (no register moves); unrolled over one period U of the slot pattern
         constexpr int U = (K % STRIDE == 0) ? K / STRIDE : K;          // STRIDE·U ≡ 0 (mod K)
@@ -249,6 +251,39 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
                 }
             }
           }
+        }
+      } else if constexpr (MODE == 2) {
+        constexpr int NEWC = STRIDE < K ? STRIDE : K;                  // columns entering the window per step
+        float sv[CSR];
+        load_s(0, sv);
+        for (int ox = 0; ox < Ws; ++ox) {
+          float svn[CSR], wn[KD * K][NEWC];
+          const int oxn = min(ox + 1, Ws - 1);                          // (the last prefetch re-reads valid data, unused)
+          load_s(oxn, svn);
+#pragma unroll
+          for (int q = 0; q < KD * K; ++q)
+#pragma unroll
+            for (int j = 0; j < NEWC; ++j) {
+              const int ix = STRIDE * (ox + 1) + (K - NEWC + j) - PAD;
+              wn[q][j] = (brow[q] && ix >= 0 && ix < Wb) ? __ldg(brow[q] + (int64_t)ix * Cb) : 0.f;
+            }
+#pragma unroll
+          for (int q = 0; q < KD * K; ++q)
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) {
+              const float wv = win[q][kw];
+#pragma unroll
+              for (int c = 0; c < CSR; ++c) acc[c][q * K + kw] = fmaf(sv[c], wv, acc[c][q * K + kw]);
+            }
+#pragma unroll
+          for (int q = 0; q < KD * K; ++q) {
+#pragma unroll
+            for (int kw = 0; kw + STRIDE < K; ++kw) win[q][kw] = win[q][kw + STRIDE];
+#pragma unroll
+            for (int j = 0; j < NEWC; ++j) win[q][K - NEWC + j] = wn[q][j];
+          }
+#pragma unroll
+          for (int c = 0; c < CSR; ++c) sv[c] = svn[c];
         }
       } else {
         for (int ox = 0; ox < Ws; ++ox) {
@@ -648,7 +683,7 @@ extern "C" int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, 
 }
 
 // A/B switches for tools/train_experiments.py (ctypes in_dll; not part of the ABI): bit 0 = rotating register window
-// instead of sliding by register moves, bit 1 = one S channel per thread instead of four.  Measured per training step
+// instead of sliding by register moves, bit 1 = one S channel per thread instead of four, bit 2 = no software prefetch.  Measured per training step
 // (B200, 4 views 512x640): 0 -> 94.7 ms, 1 -> 106.1 ms, 2 -> 96.9 ms, 3 -> 109.5 ms.
 extern "C" int rcmvs_wgrad_variant = 0;
 
@@ -673,16 +708,20 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
   const int rpc = (int)rpc64;
   dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc), gy, gz);
   cudaStream_t st = as_stream(stream);
-  const bool rot = (rcmvs_wgrad_variant & 1) != 0;     // measured: the rotating window is 12 % slower per training step
-#define RCMVS_WG_(KD, KK, SS, RR, CC) \
-  wgrad_kernel<KD, KK, SS, RR, CC><<<grid, 256, 0, st>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, rpc, cbb, csb)
-#define RCMVS_WG(KD, KK, SS)                                   \
-  do {                                                         \
-    if (csr == 4) {                                            \
-      if (rot) RCMVS_WG_(KD, KK, SS, true, 4); else RCMVS_WG_(KD, KK, SS, false, 4); \
-    } else {                                                   \
-      if (rot) RCMVS_WG_(KD, KK, SS, true, 1); else RCMVS_WG_(KD, KK, SS, false, 1); \
-    }                                                          \
+  const int mode = (rcmvs_wgrad_variant & 1) ? 1 : ((rcmvs_wgrad_variant & 4) ? 0 : 2);
+#define RCMVS_WG_(KD, KK, SS, MM, CC) \
+  wgrad_kernel<KD, KK, SS, MM, CC><<<grid, 256, 0, st>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, rpc, cbb, csb)
+#define RCMVS_WG(KD, KK, SS)                                                          \
+  do {                                                                                \
+    if (csr == 4) {                                                                   \
+      if (mode == 2) RCMVS_WG_(KD, KK, SS, 2, 4);                                     \
+      else if (mode == 1) RCMVS_WG_(KD, KK, SS, 1, 4);                                \
+      else RCMVS_WG_(KD, KK, SS, 0, 4);                                               \
+    } else {                                                                          \
+      if (mode == 2) RCMVS_WG_(KD, KK, SS, 2, 1);                                     \
+      else if (mode == 1) RCMVS_WG_(KD, KK, SS, 1, 1);                                \
+      else RCMVS_WG_(KD, KK, SS, 0, 1);                                               \
+    }                                                                                 \
   } while (0)
   if (dim3d) {
     RCMVS_REQUIRE(k == 3, RCMVS_ERR_UNSUPPORTED, "rcmvs_conv_wgrad: 3-D kernels are 3x3x3");
