@@ -683,7 +683,7 @@ extern "C" int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, 
 }
 
 // A/B switches for tools/train_experiments.py (ctypes in_dll; not part of the ABI): bit 0 = rotating register window
-// instead of sliding by register moves, bit 1 = one S channel per thread instead of four, bit 2 = no software prefetch.  Measured per training step
+// instead of sliding by register moves, bit 1 = one S channel per thread instead of four, bit 2 = software prefetch of the next position's operands.  Measured per training step
 // (B200, 4 views 512x640): 0 -> 94.7 ms, 1 -> 106.1 ms, 2 -> 96.9 ms, 3 -> 109.5 ms.
 extern "C" int rcmvs_wgrad_variant = 0;
 
@@ -708,7 +708,8 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
   const int rpc = (int)rpc64;
   dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc), gy, gz);
   cudaStream_t st = as_stream(stream);
-  const int mode = (rcmvs_wgrad_variant & 1) ? 1 : ((rcmvs_wgrad_variant & 4) ? 0 : 2);
+  // measured per training step (B200, 4 views 512x640): moves 98.0 ms, moves + prefetch 101-103 ms (197 registers), rotating 106 ms
+  const int mode = (rcmvs_wgrad_variant & 1) ? 1 : ((rcmvs_wgrad_variant & 4) ? 2 : 0);
 #define RCMVS_WG_(KD, KK, SS, MM, CC) \
   wgrad_kernel<KD, KK, SS, MM, CC><<<grid, 256, 0, st>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, rpc, cbb, csb)
 #define RCMVS_WG(KD, KK, SS)                                                          \

@@ -1,6 +1,6 @@
 """A/B of the weight-gradient kernel variants inside the real training step (csrc/train.cu rcmvs_wgrad_variant):
 bit 0 = rotating register window (instead of sliding by register moves), bit 1 = one S channel per thread (instead of 4),
-bit 2 = no software prefetch of the next position's operands."""
+bit 2 = software prefetch of the next position's operands."""
 import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
