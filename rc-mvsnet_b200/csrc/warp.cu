@@ -389,15 +389,155 @@ costvolume_var_v3_kernel(const float* __restrict__ feats, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v4: the v3 kernel with TWO channel quads per lane (quads q and q + LPP, LPP = C/8 lanes per pixel): the per-plane
+// bookkeeping of a lane group (5 shuffles, the quad-reuse test, address formation) is shared by twice the channels, and
+// with 8 channels (stage 3) a pixel is a single lane — no shuffles at all.  Each of a lane's two 16-byte loads per tap
+// still falls into a fully used 64-byte run of the lane group (quads q and q + LPP are LPP·16 bytes apart), so the
+// sector efficiency of v3 is kept.  Per channel the arithmetic is that of v3 / v1 (bitwise, tested).
+// ------------------------------------------------------------------------------------------------------------------
+template <int C, bool PER_PIXEL, bool OUT_SPLIT>
+__global__ void __launch_bounds__(128)
+costvolume_var_v4_kernel(const float* __restrict__ feats, const float* __restrict__ rt_g,
+                         const float* __restrict__ depth, float* __restrict__ var, __nv_bfloat16* __restrict__ var_split,
+                         int B, int V, int D, int h, int w, int d_chunk, int chunks_per_batch) {
+  constexpr int LPP = C / 8;                    // lanes per pixel
+  constexpr int PXB = 128 / LPP;
+  constexpr int QB = LPP * 4;                   // channel offset of a lane's second quad
+  const int q = threadIdx.x % LPP;
+  const int xr = blockIdx.x * PXB + threadIdx.x / LPP;
+  const int x = min(xr, w - 1);                 // out-of-range lanes still take part in the shuffles
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / chunks_per_batch;
+  const int d_begin = (blockIdx.z % chunks_per_batch) * d_chunk;
+  const int d_end = min(D, d_begin + d_chunk);
+  __shared__ float rt_s[kMaxSrc * 12];
+  for (int i = threadIdx.x; i < (V - 1) * 12; i += 128) rt_s[i] = __ldg(rt_g + (int64_t)b * (V - 1) * 12 + i);
+  __syncthreads();
+
+  const int64_t hw = (int64_t)h * w;
+  feats += (int64_t)b * V * hw * C + q * 4;
+  depth += PER_PIXEL ? (int64_t)b * D * hw + (int64_t)y * w + x : (int64_t)b * D;
+  const float4 refa = ldg4(feats + ((int64_t)y * w + x) * C), refb = ldg4(feats + ((int64_t)y * w + x) * C + QB);
+  const float inv_v = 1.f / (float)V;
+  const float xf = (float)x, yf = (float)y;
+  const float* feats1 = feats + w * C;          // the quad's second row
+
+  for (int dg = d_begin; dg < d_end; dg += LPP) {
+    // [plane][0,1: quad a (xy, zw)  2,3: quad b]
+    float2 s[LPP][4], s2[LPP][4];
+#pragma unroll
+    for (int j = 0; j < LPP; ++j) {
+      s[j][0] = make_float2(refa.x, refa.y); s[j][1] = make_float2(refa.z, refa.w);
+      s[j][2] = make_float2(refb.x, refb.y); s[j][3] = make_float2(refb.z, refb.w);
+      s2[j][0] = make_float2(refa.x * refa.x, refa.y * refa.y); s2[j][1] = make_float2(refa.z * refa.z, refa.w * refa.w);
+      s2[j][2] = make_float2(refb.x * refb.x, refb.y * refb.y); s2[j][3] = make_float2(refb.z * refb.z, refb.w * refb.w);
+    }
+    const int my_d = min(dg + q, D - 1);
+    const float dep = PER_PIXEL ? __ldg(depth + (int64_t)my_d * hw) : __ldg(depth + my_d);
+    for (int v = 0; v < V - 1; ++v) {
+      const float* m = rt_s + v * 12;
+      // this lane's plane: p = rot·(x,y,1)·depth + trans ; (px,py) = p.xy / p.z   (modules.py:325-329)
+      const float rx = fmaf(m[0], xf, fmaf(m[1], yf, m[2]));
+      const float ry = fmaf(m[4], xf, fmaf(m[5], yf, m[6]));
+      const float rz = fmaf(m[8], xf, fmaf(m[9], yf, m[10]));
+      const float Z = fmaf(rz, dep, m[11]);
+      const float px = __fdiv_rn(fmaf(rx, dep, m[3]), Z), py = __fdiv_rn(fmaf(ry, dep, m[7]), Z);
+      const bool finite = (fabsf(px) < 1e8f) && (fabsf(py) < 1e8f);     // false for NaN
+      const float fx = floorf(px), fy = floorf(py);
+      const float ax = px - fx, ay = py - fy;
+      const int x0 = finite ? (int)fx : -4, y0 = finite ? (int)fy : -4;
+      const int bx = min(max(x0, 0), w - 2), by = min(max(y0, 0), h - 2);
+      const float wx0 = (x0 == bx) ? 1.f - ax : ((x0 == -1) ? ax : 0.f);
+      const float wx1 = (x0 == bx) ? ax : ((x0 == w - 1) ? 1.f - ax : 0.f);
+      const float wy0 = (y0 == by) ? 1.f - ay : ((y0 == -1) ? ay : 0.f);
+      const float wy1 = (y0 == by) ? ay : ((y0 == h - 1) ? 1.f - ay : 0.f);
+      const float my_w00 = wy0 * wx0, my_w01 = wy0 * wx1, my_w10 = wy1 * wx0, my_w11 = wy1 * wx1;
+      const unsigned my_base = (unsigned)(v + 1) * (unsigned)hw * C + (unsigned)(by * w + bx) * C;
+      unsigned prev = 0xffffffffu;
+      float2 t00[4], t01[4], t10[4], t11[4];    // the four texels: [0,1] quad a, [2,3] quad b
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t00[k] = t01[k] = t10[k] = t11[k] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < LPP; ++j) {
+        const unsigned base = LPP == 1 ? my_base : __shfl_sync(0xffffffffu, my_base, j, LPP);
+        const float w00 = LPP == 1 ? my_w00 : __shfl_sync(0xffffffffu, my_w00, j, LPP);
+        const float w01 = LPP == 1 ? my_w01 : __shfl_sync(0xffffffffu, my_w01, j, LPP);
+        const float w10 = LPP == 1 ? my_w10 : __shfl_sync(0xffffffffu, my_w10, j, LPP);
+        const float w11 = LPP == 1 ? my_w11 : __shfl_sync(0xffffffffu, my_w11, j, LPP);
+        if (base != prev) {                      // neighbouring planes mostly sample the same texel quad
+          const float* t = feats + base;
+          const float* t1 = feats1 + base;
+          const float4 a = ldg4(t), bb = ldg4(t + C), c = ldg4(t1), e = ldg4(t1 + C);
+          const float4 a2 = ldg4(t + QB), bb2 = ldg4(t + C + QB), c2 = ldg4(t1 + QB), e2 = ldg4(t1 + C + QB);
+          t00[0] = make_float2(a.x, a.y); t00[1] = make_float2(a.z, a.w); t00[2] = make_float2(a2.x, a2.y); t00[3] = make_float2(a2.z, a2.w);
+          t01[0] = make_float2(bb.x, bb.y); t01[1] = make_float2(bb.z, bb.w); t01[2] = make_float2(bb2.x, bb2.y); t01[3] = make_float2(bb2.z, bb2.w);
+          t10[0] = make_float2(c.x, c.y); t10[1] = make_float2(c.z, c.w); t10[2] = make_float2(c2.x, c2.y); t10[3] = make_float2(c2.z, c2.w);
+          t11[0] = make_float2(e.x, e.y); t11[1] = make_float2(e.z, e.w); t11[2] = make_float2(e2.x, e2.y); t11[3] = make_float2(e2.z, e2.w);
+          prev = base;
+        }
+        const float2 q00 = make_float2(w00, w00), q01 = make_float2(w01, w01), q10 = make_float2(w10, w10),
+                     q11 = make_float2(w11, w11);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __ffma2_rn(t11[k], q11, __ffma2_rn(t10[k], q10, __ffma2_rn(t01[k], q01, __fmul2_rn(t00[k], q00))));
+          s[j][k] = __fadd2_rn(s[j][k], f);
+          s2[j][k] = __ffma2_rn(f, f, s2[j][k]);
+        }
+      }
+    }
+    if (xr < w) {
+#pragma unroll
+      for (int j = 0; j < LPP; ++j) {
+        const int d = dg + j;
+        if (d < d_end) {
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            float4 o;
+            const float mx = s[j][2 * hq].x * inv_v, my = s[j][2 * hq].y * inv_v, mz = s[j][2 * hq + 1].x * inv_v,
+                        mw = s[j][2 * hq + 1].y * inv_v;
+            o.x = fmaf(-mx, mx, s2[j][2 * hq].x * inv_v);
+            o.y = fmaf(-my, my, s2[j][2 * hq].y * inv_v);
+            o.z = fmaf(-mz, mz, s2[j][2 * hq + 1].x * inv_v);
+            o.w = fmaf(-mw, mw, s2[j][2 * hq + 1].y * inv_v);
+            const int64_t oidx = ((((int64_t)b * D + d) * h + y) * w + x) * C + q * 4 + hq * QB;
+            if (OUT_SPLIT) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y);
+              const __nv_bfloat16 h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+              const __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
+              const __nv_bfloat162 lo01 = __floats2bfloat162_rn(o.x - __bfloat162float(h0), o.y - __bfloat162float(h1));
+              const __nv_bfloat162 lo23 = __floats2bfloat162_rn(o.z - __bfloat162float(h2), o.w - __bfloat162float(h3));
+              uint2 hv, lv;
+              hv.x = *reinterpret_cast<const uint32_t*>(&hi01); hv.y = *reinterpret_cast<const uint32_t*>(&hi23);
+              lv.x = *reinterpret_cast<const uint32_t*>(&lo01); lv.y = *reinterpret_cast<const uint32_t*>(&lo23);
+              __stcs(reinterpret_cast<uint2*>(var_split + oidx), hv);
+              __stcs(reinterpret_cast<uint2*>(var_split + (int64_t)B * D * hw * C + oidx), lv);
+            } else {
+              st4_stream(var + oidx, o);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // A/B switch for profiling sessions: RCMVS_SWEEP=v2 runs the round-1 kernel on the fp32-output eval path
-static bool sweep_use_v2() {
+// default kernel per channel count (measured): see kSweepDefault
+static int kSweepDefault(int C) { return 3; }
+// 0 = policy below; 2 / 3 / 4 force a kernel (tests and tools set it through ctypes in_dll; not part of the ABI)
+extern "C" int rcmvs_sweep_variant = 0;
+static int sweep_variant_for(int C) {        // RCMVS_SWEEP=v2|v3|v4 forces one kernel for every stage
+  if (rcmvs_sweep_variant) return rcmvs_sweep_variant;
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RCMVS_SWEEP");
-    v = (e && e[0] == 'v' && e[1] == '2') ? 1 : 0;
+    v = (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') ? e[1] - '0' : 0;
   }
-  return v == 1;
+  if (v) return v;
+  return kSweepDefault(C);
 }
+
 
 template <int C>
 static int launch_costvolume(const float* feats, const float* rt, const float* depth, int per_pixel, float* var,
@@ -413,7 +553,7 @@ static int launch_costvolume(const float* feats, const float* rt, const float* d
 #define RCMVS_CV_LAUNCH(PP, NR)                                                                              \
   costvolume_var_kernel<C, PP, NR><<<grid, 256, 0, st>>>(feats, rt, depth, var, var_noref, V, D, h, w, d_chunk, \
                                                          chunks)
-  if (!var_noref && h >= 2 && w >= 2 && (int64_t)h * w * C < (1ll << 31) && (var_split || !sweep_use_v2())) {
+  if (!var_noref && h >= 2 && w >= 2 && (int64_t)h * w * C < (1ll << 31) && (var_split || sweep_variant_for(C) != 2)) {
     // eval path: plane-distributed v3 kernel; planes per CTA rounded to the group size
     constexpr int LPP = C / 4;
     const int dch = ceil_div(d_chunk, LPP) * LPP;
@@ -421,7 +561,17 @@ static int launch_costvolume(const float* feats, const float* rt, const float* d
     dim3 grid2(ceil_div(w, PXB), h, B * nch);
     __nv_bfloat16* vs = reinterpret_cast<__nv_bfloat16*>(var_split);
 #define RCMVS_V3(PP, SP) costvolume_var_v3_kernel<C, PP, SP><<<grid2, 256, 0, st>>>(feats, rt, depth, var, vs, B, V, D, h, w, dch, nch)
-    if (per_pixel) { if (vs) RCMVS_V3(true, true); else RCMVS_V3(true, false); }
+    if (sweep_variant_for(C) == 4) {
+      // two channel quads per lane: C/8 lanes per pixel, C/8 planes per iteration, 128 threads = the same pixels per CTA
+      constexpr int LPP4 = C / 8;
+      const int dch4 = ceil_div(d_chunk, LPP4) * LPP4;
+      const int nch4 = ceil_div(D, dch4);
+      dim3 grid4(ceil_div(w, 128 / LPP4), h, B * nch4);
+#define RCMVS_V4(PP, SP) costvolume_var_v4_kernel<C, PP, SP><<<grid4, 128, 0, st>>>(feats, rt, depth, var, vs, B, V, D, h, w, dch4, nch4)
+      if (per_pixel) { if (vs) RCMVS_V4(true, true); else RCMVS_V4(true, false); }
+      else { if (vs) RCMVS_V4(false, true); else RCMVS_V4(false, false); }
+#undef RCMVS_V4
+    } else if (per_pixel) { if (vs) RCMVS_V3(true, true); else RCMVS_V3(true, false); }
     else { if (vs) RCMVS_V3(false, true); else RCMVS_V3(false, false); }
 #undef RCMVS_V3
   } else if (var_split) {

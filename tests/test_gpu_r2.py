@@ -368,6 +368,17 @@ def test_sweep_v3_bitwise_equals_v1_and_split_output(dev):
             assert vs.shape == (2,) + tuple(v3.shape) and vs.dtype == torch.bfloat16
             assert (vs[0].float() + vs[1].float() - v3).abs().max() <= 2.0 ** -16 * v3.abs().max()
             assert torch.equal(vs[0], v3.bfloat16())
+            # v4 (two channel quads per lane): the same numbers, bit for bit, in both output forms
+            import ctypes
+            from rcmvs import _ffi
+            flag = ctypes.c_int.in_dll(_ffi.lib(), "rcmvs_sweep_variant")
+            try:
+                flag.value = 4
+                v4 = ops.costvolume_variance(feats, rt, dt)
+                v4s = ops.costvolume_variance_split(feats, rt, dt)
+            finally:
+                flag.value = 0
+            assert torch.equal(v4, v3) and torch.equal(v4s, vs)
 
 
 # ---- training path: every backward kernel against torch autograd (library ops are the CHECKER here) -------------------------
