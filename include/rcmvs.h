@@ -264,6 +264,17 @@ int rcmvs_point_features(const float* vol_cl, const float* ndc, const float* pts
 int rcmvs_render_mlp(const float* ndc, const float* feat, const float* dirs, const float* const* weights, float* out,
                      int64_t P, int S, rcmvs_stream_t stream);
 
+/* Tensor-core variant of the same MLP (same inputs, outputs and the same 22 fp32 weight pointers): every 128 / 64-wide Linear
+ * layer runs as a TMA-fed tcgen05 GEMM on split-bf16 operands (3 products per operand pair, fp32 accumulation), the
+ * embedding / modulation / alpha / rgb heads are fused into a prep kernel and the GEMM epilogues.
+ * wimg: rcmvs_render_mlp_tc_weight_elems() bf16 elements filled by rcmvs_render_mlp_tc_pack (once per checkpoint);
+ * workspace: rcmvs_render_mlp_tc_workspace_bytes(P) bytes of device memory, 256-byte aligned (activations between layers). */
+int64_t rcmvs_render_mlp_tc_weight_elems(void);
+int64_t rcmvs_render_mlp_tc_workspace_bytes(int64_t P);
+int rcmvs_render_mlp_tc_pack(const float* const* weights, void* wimg, rcmvs_stream_t stream);
+int rcmvs_render_mlp_tc(const float* ndc, const float* feat, const float* dirs, const float* const* weights, const void* wimg,
+                        void* workspace, float* out, int64_t P, int S, rcmvs_stream_t stream);
+
 /* ---- a11 compositing: models/renderer.py:18-26, 65-93 ------------------------------------------------------------------ */
 /* raw [N][S][4], z [N][S] -> rgb [N][3], depth [N], weights [N][S], alpha [N][S]. */
 int rcmvs_composite(const float* raw, const float* z, float* rgb, float* depth, float* weights, float* alpha, int N,

@@ -144,12 +144,19 @@ class Renderer_ours(nn.Module):
                        self.views_linears[0].weight.t().contiguous(), self.views_linears[0].bias.contiguous(),
                        self.rgb_linear.weight.t().contiguous(), self.rgb_linear.bias.contiguous()]
                 arr = (ctypes.c_void_p * 22)(*[t.data_ptr() for t in ts])
-            return arr, ts                         # keep the tensors alive
-        return self._packed.get(_versions(self), build)[0]
+                # split-bf16 images of the eight wide Linear layers for the tensor-core path (rcmvs_render_mlp_tc)
+                wimg = ops.render_mlp_tc_pack(arr, ts[0].device) if ts[0].is_cuda else None
+            return arr, ts, wimg                   # keep the tensors alive
+        return self._packed.get(_versions(self), build)
 
     def forward_cuda(self, ndc, feat, dirs):
-        """ndc [N,S,3], feat [N,S,20], dirs [N,3] -> raw [N,S,4] (embedding fused in the kernel)."""
-        return ops.render_mlp(ndc.contiguous(), feat.contiguous(), dirs.contiguous(), self.packed())
+        """ndc [N,S,3], feat [N,S,20], dirs [N,3] -> raw [N,S,4] (embedding fused in the kernel).  RCMVS_CONV=bf16x3
+        (default): Linear layers on tcgen05 (csrc/mlp_tc.cu); other modes: the fused fp32 FFMA kernel (csrc/render.cu)."""
+        from .modules import conv_precision
+        arr, _, wimg = self.packed()
+        if conv_precision() == "bf16x3" and wimg is not None:
+            return ops.render_mlp_tc(ndc.contiguous(), feat.contiguous(), dirs.contiguous(), arr, wimg)
+        return ops.render_mlp(ndc.contiguous(), feat.contiguous(), dirs.contiguous(), arr)
 
 
 class RenderNet(nn.Module):

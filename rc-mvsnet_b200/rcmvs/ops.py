@@ -505,6 +505,25 @@ def render_mlp(ndc, feat, dirs, weight_ptrs):
     return out
 
 
+def render_mlp_tc_pack(weight_ptrs, device):
+    """Split-bf16 weight images of the tensor-core MLP from the 22 fp32 weight pointers of render_mlp (on `device`)."""
+    with torch.cuda.device(device):
+        img = torch.empty((_ffi.lib().rcmvs_render_mlp_tc_weight_elems(),), device=device, dtype=torch.bfloat16)
+        _ffi.call("rcmvs_render_mlp_tc_pack", weight_ptrs, img.data_ptr(), _stream())
+    return img
+
+
+@_on_device
+def render_mlp_tc(ndc, feat, dirs, weight_ptrs, wimg):
+    """Same contract as render_mlp, Linear layers on tcgen05 (split-bf16, fp32-equivalent)."""
+    N, S = ndc.shape[:2]
+    out = torch.empty((N, S, 4), device=ndc.device, dtype=torch.float32)
+    ws = torch.empty((_ffi.lib().rcmvs_render_mlp_tc_workspace_bytes(N * S),), device=ndc.device, dtype=torch.uint8)
+    _ffi.call("rcmvs_render_mlp_tc", _chk(ndc, "ndc"), _chk(feat, "feat"), _chk(dirs, "dirs"), weight_ptrs, _chk_bf16(wimg, "wimg"),
+              ws.data_ptr(), _chk(out, "out"), N * S, S, _stream())
+    return out
+
+
 @_on_device
 def composite(raw, z):
     N, S = z.shape

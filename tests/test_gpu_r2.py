@@ -877,3 +877,30 @@ def test_cuda_graph_replay_is_bitwise_the_eager_forward(dev):
     pipe.synchronize()
     for i, d_h, c_h in outs:
         assert torch.equal(d_h, eager[i]["depth"].cpu()) and torch.equal(c_h, eager[i]["photometric_confidence"].cpu())
+
+
+@pytest.mark.parametrize("n_rays,n_samples", [(7, 128), (64, 128), (3, 33)])
+def test_render_mlp_tensor_core_path_matches_fp32_kernel(dev, n_rays, n_samples, monkeypatch):
+    """a10 on tcgen05 (csrc/mlp_tc.cu: 8 split-bf16 GEMMs + prep / head fusions) against the fused fp32 FFMA kernel of the
+    same MLP, with weights scaled to a sane range (sigma ~ O(1), not the shipped checkpoint's 1e7) so that the comparison is
+    tight; row counts that are not multiples of the 128-row tile included."""
+    import models
+    from rcmvs import ops, synth
+    torch.manual_seed(5)
+    net = models.Rendering_Consistency_Net(synth.RenderArgs()).to(dev).eval()
+    mlp = net.network_fn.nerf
+    with torch.no_grad():
+        for prm in mlp.parameters():
+            prm.copy_(torch.randn_like(prm) * (0.5 / max(1, prm.shape[-1]) ** 0.5))
+        mlp.pts_bias.bias.add_(1.0)                      # modulation around 1
+    ndc = torch.rand(n_rays, n_samples, 3, device=dev)
+    feat = torch.randn(n_rays, n_samples, 20, device=dev)
+    dirs = torch.randn(n_rays, 3, device=dev)
+    monkeypatch.setenv("RCMVS_CONV", "fp32")
+    ref = mlp.forward_cuda(ndc, feat, dirs)
+    monkeypatch.setenv("RCMVS_CONV", "bf16x3")
+    got = mlp.forward_cuda(ndc, feat, dirs)
+    assert got.shape == ref.shape == (n_rays, n_samples, 4)
+    scale = float(ref[..., 3].abs().max()) + 1e-6
+    assert (got[..., 3] - ref[..., 3]).abs().max() <= 2e-4 * scale, ((got[..., 3] - ref[..., 3]).abs().max(), scale)
+    assert (got[..., :3] - ref[..., :3]).abs().max() <= 2e-4
