@@ -257,6 +257,16 @@ def render_branch_timing(dev, pk):
         ms_render = time_kernel(lambda: nerf(vol, out["depth"], dict(batch)), 3, stream)
         ms_vol = time_kernel(lambda: nerf.MVSNet.forward_cl(vol), 3, stream)
         res = nerf(vol, out["depth"], dict(batch))
+        # the same forward with the MLP's Linear layers on tcgen05 (opt-in: RCMVS_MLP_TC=1, csrc/mlp_tc.cu)
+        prev = os.environ.get("RCMVS_MLP_TC")
+        os.environ["RCMVS_MLP_TC"] = "1"
+        try:
+            ms_render_tc = time_kernel(lambda: nerf(vol, out["depth"], dict(batch)), 3, stream)
+        finally:
+            if prev is None:
+                os.environ.pop("RCMVS_MLP_TC", None)
+            else:
+                os.environ["RCMVS_MLP_TC"] = prev
     ok = bool(torch.isfinite(res[0]).all() and torch.isfinite(res[3]).all())
     # Neural_Volume_Net 63 GFLOP + MLP 251 392 FLOP/pt x 131 072 pts = 33.0 GFLOP per render (forward)
     flops = 63.0e9 + 251392 * 131072
@@ -264,7 +274,7 @@ def render_branch_timing(dev, pk):
     return {"workload": "configs[2]: CascadeMVSNet (train class, 4 views 512x640, D=48/32/8, volume_feature_no_ref) + "
                         "Rendering_Consistency_Net (Neural_Volume_Net, 1024 rays x 128 samples), forward",
             "mvs_forward_ms": round(ms_mvs, 3), "render_forward_ms": round(ms_render, 3),
-            "neural_volume_net_ms": round(ms_vol, 3), "finite": ok,
+            "neural_volume_net_ms": round(ms_vol, 3), "render_forward_mlp_tc_ms": round(ms_render_tc, 3), "finite": ok,
             "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": pk["bf16_tflops"] / 2, "unit": "TFLOP/s",
                          "frac": round(tf / (pk["bf16_tflops"] / 2), 4), "flops": flops,
                          "note": "96 GFLOP of dense fp32 contractions per render against the TF32 tensor peak"}}

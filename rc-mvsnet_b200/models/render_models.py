@@ -150,11 +150,12 @@ class Renderer_ours(nn.Module):
         return self._packed.get(_versions(self), build)
 
     def forward_cuda(self, ndc, feat, dirs):
-        """ndc [N,S,3], feat [N,S,20], dirs [N,3] -> raw [N,S,4] (embedding fused in the kernel).  RCMVS_CONV=bf16x3
-        (default): Linear layers on tcgen05 (csrc/mlp_tc.cu); other modes: the fused fp32 FFMA kernel (csrc/render.cu)."""
-        from .modules import conv_precision
+        """ndc [N,S,3], feat [N,S,20], dirs [N,3] -> raw [N,S,4] (embedding fused in the kernel).  Default: the fused fp32
+        FFMA kernel (csrc/render.cu).  RCMVS_MLP_TC=1: Linear layers on tcgen05 (csrc/mlp_tc.cu, split-bf16: 2.6x faster,
+        equal to 2e-4 on well-conditioned weights; with the shipped checkpoint on synthetic input — sigma up to 1e7 — 4 of
+        12 288 golden densities differ by up to 8e-3 relative instead of <= 2e-3, hence opt-in)."""
         arr, _, wimg = self.packed()
-        if conv_precision() == "bf16x3" and wimg is not None:
+        if os.environ.get("RCMVS_MLP_TC", "0") == "1" and wimg is not None:
             return ops.render_mlp_tc(ndc.contiguous(), feat.contiguous(), dirs.contiguous(), arr, wimg)
         return ops.render_mlp(ndc.contiguous(), feat.contiguous(), dirs.contiguous(), arr)
 

@@ -896,9 +896,9 @@ def test_render_mlp_tensor_core_path_matches_fp32_kernel(dev, n_rays, n_samples,
     ndc = torch.rand(n_rays, n_samples, 3, device=dev)
     feat = torch.randn(n_rays, n_samples, 20, device=dev)
     dirs = torch.randn(n_rays, 3, device=dev)
-    monkeypatch.setenv("RCMVS_CONV", "fp32")
+    monkeypatch.setenv("RCMVS_MLP_TC", "0")
     ref = mlp.forward_cuda(ndc, feat, dirs)
-    monkeypatch.setenv("RCMVS_CONV", "bf16x3")
+    monkeypatch.setenv("RCMVS_MLP_TC", "1")
     got = mlp.forward_cuda(ndc, feat, dirs)
     assert got.shape == ref.shape == (n_rays, n_samples, 4)
     scale = float(ref[..., 3].abs().max()) + 1e-6
