@@ -318,6 +318,99 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient, shared-memory variant (the default where it applies: Cs % 4 == 0, Cb % 4 == 0).  The register-window
+// kernel above streams its operands from L1 / L2 with one or two loads in flight per warp: ncu showed it latency-bound
+// (FMA pipe 12-24 %, 2-4 warps stalled on long-scoreboard per issue, L1 hit rate 13-43 %).  Here a CTA walks a range of
+// output rows; for each row the S row [Ws][CSB] and the KD·K input rows [Wb + 2·PAD][CBB] (zero halo columns, zero rows
+// outside the volume: no bounds checks in the inner loop) are staged in shared memory with coalesced 16-byte loads, and
+// all 256 threads work on that row: thread = (4 S channels, 1 Bg channel, x slice), x positions ox = slice, slice + NSL, …
+// so that the lanes of a warp (Bg channel fastest, then slice) read consecutive shared-memory words.  Every position costs
+// one LDS.128 + KD·K·K LDS.32 for 4·KD·K·K FMAs.  Partial sums are combined through shared-memory atomics at the end
+// of the row range, then added to G with one global atomic per weight and CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KD, int K, int STRIDE>
+__global__ void __launch_bounds__(256)
+wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* __restrict__ G, int B, int Ds, int Hs,
+                  int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int CSB, int CBB) {
+  constexpr int TAPS = KD * K * K, PAD = K / 2, PADD = KD / 2;
+  extern __shared__ __align__(16) unsigned char wg_smem_raw[];
+  float* sm = reinterpret_cast<float*>(wg_smem_raw);
+  const int Wbp = Wb + 2 * PAD;
+  float* s_row = sm;                                  // [Ws][CSB]
+  float* b_rows = sm + (size_t)Ws * CSB;              // [KD*K][Wbp][CBB]
+  const int csg_n = CSB / 4;                          // S channel groups in this CTA
+  const int NSL = 256 / (csg_n * CBB);                // x slices
+  const int cb_l = threadIdx.x % CBB, slice = (threadIdx.x / CBB) % NSL, cs_g = threadIdx.x / (CBB * NSL);
+  const bool active = cs_g < csg_n;
+  const int cs0 = blockIdx.y * CSB, cb0 = blockIdx.z * CBB;
+  float acc[4][TAPS];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[c][t] = 0.f;
+  const int64_t nrows = (int64_t)B * Ds * Hs;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(nrows, r_begin + rows_per_cta);
+  const int cs4 = CSB / 4, cb4 = CBB / 4;
+  for (int64_t r = r_begin; r < r_end; ++r) {
+    const int oy = (int)(r % Hs), od = (int)((r / Hs) % Ds), b = (int)(r / ((int64_t)Hs * Ds));
+    __syncthreads();                                   // the previous row has been consumed
+    {
+      const float* src = S + r * Ws * Cs + cs0;
+      for (int e = threadIdx.x; e < Ws * cs4; e += 256) {
+        const int ox = e / cs4, c4 = e % cs4;
+        *reinterpret_cast<float4*>(s_row + ox * CSB + 4 * c4) = ldg4(src + (int64_t)ox * Cs + 4 * c4);
+      }
+#pragma unroll
+      for (int q = 0; q < KD * K; ++q) {
+        const int iz = STRIDE * od + q / K - PADD, iy = STRIDE * oy + q % K - PAD;
+        const bool ok = iz >= 0 && iz < Db && iy >= 0 && iy < Hb;
+        const float* brow = Bg + (((int64_t)b * Db + iz) * Hb + iy) * Wb * Cb + cb0;
+        float* dst = b_rows + (size_t)q * Wbp * CBB;
+        for (int e = threadIdx.x; e < Wbp * cb4; e += 256) {
+          const int ixp = e / cb4, c4 = e % cb4, ix = ixp - PAD;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && ix >= 0 && ix < Wb) v = ldg4(brow + (int64_t)ix * Cb + 4 * c4);
+          *reinterpret_cast<float4*>(dst + ixp * CBB + 4 * c4) = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (active) {
+      for (int ox = slice; ox < Ws; ox += NSL) {
+        const float4 sv4 = *reinterpret_cast<const float4*>(s_row + ox * CSB + 4 * cs_g);
+        const float sv[4] = {sv4.x, sv4.y, sv4.z, sv4.w};
+        const float* bp = b_rows + (size_t)(ox * STRIDE) * CBB + cb_l;
+#pragma unroll
+        for (int q = 0; q < KD * K; ++q)
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) {
+            const float wv = bp[((size_t)q * Wbp + kw) * CBB];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c][q * K + kw] = fmaf(sv[c], wv, acc[c][q * K + kw]);
+          }
+      }
+    }
+  }
+  // ---- combine the x slices: shared-memory atomics on red[cs][cb][tap], then one global atomic per weight ------------
+  __syncthreads();
+  float* red = sm;
+  const int nred = CSB * CBB * TAPS;
+  for (int e = threadIdx.x; e < nred; e += 256) red[e] = 0.f;
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) atomicAdd(red + ((4 * cs_g + c) * CBB + cb_l) * TAPS + t, acc[c][t]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nred; e += 256) {
+    const int t = e % TAPS, cb = (e / TAPS) % CBB, cs = e / (TAPS * CBB);
+    if (cs0 + cs < Cs && cb0 + cb < Cb) atomicAdd(G + ((int64_t)(cs0 + cs) * Cb + cb0 + cb) * TAPS + t, red[e]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // 2-D data gradient (FeatureNet): dx[n,y,x,ci] = Σ_{kh,kw,co} dy[n,(y+P−kh)/s,(x+P−kw)/s,co]·w[co][ci][kh][kw]
 // (terms with non-integer or out-of-range output coordinates vanish).  Thread = one input pixel x 4 input channels;
 // the re-laid-out weights [tap][co][ci] sit in shared memory.  Optional `up2_add`: dx += the gradient arriving through a
@@ -683,7 +776,8 @@ extern "C" int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, 
 }
 
 // A/B switches for tools/train_experiments.py (ctypes in_dll; not part of the ABI): bit 0 = rotating register window
-// instead of sliding by register moves, bit 1 = one S channel per thread instead of four, bit 2 = software prefetch of the next position's operands.  Measured per training step
+// instead of sliding by register moves, bit 1 = one S channel per thread instead of four, bit 2 = software prefetch of the next position's operands,
+// bit 3 = register-window kernel instead of the shared-memory kernel.  Measured per training step
 // (B200, 4 views 512x640): 0 -> 94.7 ms, 1 -> 106.1 ms, 2 -> 96.9 ms, 3 -> 109.5 ms.
 extern "C" int rcmvs_wgrad_variant = 0;
 
@@ -693,6 +787,51 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
   RCMVS_REQUIRE(S && Bg && G, RCMVS_ERR_BAD_ARG, "rcmvs_conv_wgrad: null pointer");
   RCMVS_REQUIRE(B > 0 && Ds > 0 && Hs > 0 && Ws > 0 && Cs > 0 && Cb > 0 && (stride == 1 || stride == 2), RCMVS_ERR_BAD_ARG,
                 "rcmvs_conv_wgrad: bad dims");
+  cudaStream_t st0 = as_stream(stream);
+  if (!(rcmvs_wgrad_variant & 8) && Cs % 4 == 0 && Cb % 4 == 0 && (dim3d ? k == 3 : (Ds == 1 && Db == 1))) {
+    // shared-memory variant: channel blocks so that pairs (Cs-block/4 x Cb-block) <= 256 and the rows fit ~100 KB
+    const int KD = dim3d ? 3 : 1, pad = k / 2, taps = KD * k * k;
+    int CSB = Cs < 32 ? Cs : 32;
+    int CBB = Cb < 32 ? Cb : 32;
+    while ((CSB / 4) * CBB > 256) CBB /= 2;
+    auto smem_of = [&](int csb_, int cbb_) {
+      const size_t rows = ((size_t)Ws * csb_ + (size_t)KD * k * (Wb + 2 * pad) * cbb_) * 4;
+      const size_t red = (size_t)csb_ * cbb_ * taps * 4;
+      return rows > red ? rows : red;
+    };
+    while (smem_of(CSB, CBB) > 100 * 1024 && CBB > 4) CBB /= 2;
+    while (smem_of(CSB, CBB) > 100 * 1024 && CSB > 4) CSB /= 2;
+    const bool pow2 = (CBB & (CBB - 1)) == 0 && ((CSB / 4) & (CSB / 4 - 1)) == 0;
+    if (smem_of(CSB, CBB) <= 100 * 1024 && Cs % CSB == 0 && Cb % CBB == 0 && pow2 && CSB % 4 == 0 && CBB % 4 == 0) {
+      const size_t smem = smem_of(CSB, CBB);
+      const int64_t nrows = (int64_t)B * Ds * Hs;
+      const int gy = Cs / CSB, gz = Cb / CBB;
+      int64_t rpc64 = ceil_div<int64_t>(nrows * gy * gz, 148 * 4);      // ~2 waves of 2 CTAs per SM
+      if (rpc64 < 1) rpc64 = 1;
+      if (rpc64 > nrows) rpc64 = nrows;
+      dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc64), gy, gz);
+#define RCMVS_WS(KD_, KK, SS)                                                                                              \
+  do {                                                                                                                     \
+    static SmemAttrOnce attr;                                                                                              \
+    cudaError_t e = attr.ensure(wgrad_smem_kernel<KD_, KK, SS>, 100 * 1024);                                               \
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
+    wgrad_smem_kernel<KD_, KK, SS><<<grid, 256, smem, st0>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, (int)rpc64, CSB, CBB); \
+  } while (0)
+      bool launched = true;
+      if (dim3d) { if (stride == 1) RCMVS_WS(3, 3, 1); else RCMVS_WS(3, 3, 2); }
+      else if (k == 1 && stride == 1) RCMVS_WS(1, 1, 1);
+      else if (k == 3 && stride == 1) RCMVS_WS(1, 3, 1);
+      else if (k == 3 && stride == 2) RCMVS_WS(1, 3, 2);
+      else if (k == 5 && stride == 1) RCMVS_WS(1, 5, 1);
+      else if (k == 5 && stride == 2) RCMVS_WS(1, 5, 2);
+      else launched = false;
+#undef RCMVS_WS
+      if (launched) {
+        RCMVS_CHECK_LAUNCH("rcmvs_conv_wgrad");
+        return RCMVS_OK;
+      }
+    }
+  }
   const int cbb = Cb >= 32 ? 32 : (Cb >= 16 ? 16 : (Cb >= 8 ? 8 : (Cb >= 4 ? 4 : (Cb >= 2 ? 2 : 1))));
   const int csr = (Cs % 4 == 0 && !(rcmvs_wgrad_variant & 2)) ? 4 : 1;   // S channels per thread
   const int csg = Cs / csr;                                             // channel groups along S
