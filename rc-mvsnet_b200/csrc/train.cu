@@ -329,7 +329,7 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
 // of the row range, then added to G with one global atomic per weight and CTA.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int KD, int K, int STRIDE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (KD * K * K > 9 ? 2 : 3))       // 2 CTAs / SM for the 25- and 27-tap kernels (small spill)
 wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* __restrict__ G, int B, int Ds, int Hs,
                   int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int CSB, int CBB) {
   constexpr int TAPS = KD * K * K, PAD = K / 2, PADD = KD / 2;
