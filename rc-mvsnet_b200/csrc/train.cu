@@ -328,8 +328,8 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
 // one LDS.128 + KD·K·K LDS.32 for 4·KD·K·K FMAs.  Partial sums are combined through shared-memory atomics at the end
 // of the row range, then added to G with one global atomic per weight and CTA.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KD, int K, int STRIDE>
-__global__ void __launch_bounds__(256, (KD * K * K > 9 ? 2 : 3))       // 2 CTAs / SM for the 25- and 27-tap kernels (small spill)
+template <int KD, int K, int STRIDE, int CSR>    // CSR = S channels per thread: 4, or 1 when Cs is not a multiple of 4 (`prob`: Cs = 1)
+__global__ void __launch_bounds__(256, (CSR * KD * K * K > 36 ? 2 : 3))       // 2 CTAs / SM for the 25- and 27-tap kernels (small spill)
 wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* __restrict__ G, int B, int Ds, int Hs,
                   int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int CSB, int CBB) {
   constexpr int TAPS = KD * K * K, PAD = K / 2, PADD = KD / 2;
@@ -338,14 +338,14 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
   const int Wbp = Wb + 2 * PAD;
   float* s_row = sm;                                  // [Ws][CSB]
   float* b_rows = sm + (size_t)Ws * CSB;              // [KD*K][Wbp][CBB]
-  const int csg_n = CSB / 4;                          // S channel groups in this CTA
+  const int csg_n = CSB / CSR;                        // S channel groups in this CTA
   const int NSL = 256 / (csg_n * CBB);                // x slices
   const int cb_l = threadIdx.x % CBB, slice = (threadIdx.x / CBB) % NSL, cs_g = threadIdx.x / (CBB * NSL);
   const bool active = cs_g < csg_n;
   const int cs0 = blockIdx.y * CSB, cb0 = blockIdx.z * CBB;
-  float acc[4][TAPS];
+  float acc[CSR][TAPS];
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < CSR; ++c)
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) acc[c][t] = 0.f;
   const int64_t nrows = (int64_t)B * Ds * Hs;
@@ -356,9 +356,13 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
     __syncthreads();                                   // the previous row has been consumed
     {
       const float* src = S + r * Ws * Cs + cs0;
-      for (int e = threadIdx.x; e < Ws * cs4; e += 256) {
-        const int ox = e / cs4, c4 = e % cs4;
-        *reinterpret_cast<float4*>(s_row + ox * CSB + 4 * c4) = ldg4(src + (int64_t)ox * Cs + 4 * c4);
+      if constexpr (CSR == 4) {
+        for (int e = threadIdx.x; e < Ws * cs4; e += 256) {
+          const int ox = e / cs4, c4 = e % cs4;
+          *reinterpret_cast<float4*>(s_row + ox * CSB + 4 * c4) = ldg4(src + (int64_t)ox * Cs + 4 * c4);
+        }
+      } else {
+        for (int e = threadIdx.x; e < Ws * CSB; e += 256) s_row[e] = __ldg(src + (int64_t)(e / CSB) * Cs + e % CSB);
       }
 #pragma unroll
       for (int q = 0; q < KD * K; ++q) {
@@ -377,8 +381,13 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
     __syncthreads();
     if (active) {
       for (int ox = slice; ox < Ws; ox += NSL) {
-        const float4 sv4 = *reinterpret_cast<const float4*>(s_row + ox * CSB + 4 * cs_g);
-        const float sv[4] = {sv4.x, sv4.y, sv4.z, sv4.w};
+        float sv[CSR];
+        if constexpr (CSR == 4) {
+          const float4 sv4 = *reinterpret_cast<const float4*>(s_row + ox * CSB + 4 * cs_g);
+          sv[0] = sv4.x; sv[1] = sv4.y; sv[2] = sv4.z; sv[3] = sv4.w;
+        } else {
+          sv[0] = s_row[ox * CSB + cs_g];
+        }
         const float* bp = b_rows + (size_t)(ox * STRIDE) * CBB + cb_l;
 #pragma unroll
         for (int q = 0; q < KD * K; ++q)
@@ -386,7 +395,7 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
           for (int kw = 0; kw < K; ++kw) {
             const float wv = bp[((size_t)q * Wbp + kw) * CBB];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c][q * K + kw] = fmaf(sv[c], wv, acc[c][q * K + kw]);
+            for (int c = 0; c < CSR; ++c) acc[c][q * K + kw] = fmaf(sv[c], wv, acc[c][q * K + kw]);
           }
       }
     }
@@ -399,9 +408,9 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
   __syncthreads();
   if (active) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < CSR; ++c)
 #pragma unroll
-      for (int t = 0; t < TAPS; ++t) atomicAdd(red + ((4 * cs_g + c) * CBB + cb_l) * TAPS + t, acc[c][t]);
+      for (int t = 0; t < TAPS; ++t) atomicAdd(red + ((CSR * cs_g + c) * CBB + cb_l) * TAPS + t, acc[c][t]);
   }
   __syncthreads();
   for (int e = threadIdx.x; e < nred; e += 256) {
@@ -788,21 +797,27 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
   RCMVS_REQUIRE(B > 0 && Ds > 0 && Hs > 0 && Ws > 0 && Cs > 0 && Cb > 0 && (stride == 1 || stride == 2), RCMVS_ERR_BAD_ARG,
                 "rcmvs_conv_wgrad: bad dims");
   cudaStream_t st0 = as_stream(stream);
-  if (!(rcmvs_wgrad_variant & 8) && Cs % 4 == 0 && Cb % 4 == 0 && (dim3d ? k == 3 : (Ds == 1 && Db == 1))) {
-    // shared-memory variant: channel blocks so that pairs (Cs-block/4 x Cb-block) <= 256 and the rows fit ~100 KB
+  if (!(rcmvs_wgrad_variant & 8) && Cb % 4 == 0 && (dim3d ? k == 3 : (Ds == 1 && Db == 1))) {
+    // shared-memory variant: channel blocks so that pairs (Cs-block / CSR x Cb-block) <= 256 and the rows fit 100 KB (two
+    // CTAs per SM) or, failing that, 200 KB (one)
     const int KD = dim3d ? 3 : 1, pad = k / 2, taps = KD * k * k;
-    int CSB = Cs < 32 ? Cs : 32;
+    const int csr = Cs % 4 == 0 ? 4 : 1;
+    int CSB = csr == 4 ? (Cs < 32 ? Cs : 32) : 1;
     int CBB = Cb < 32 ? Cb : 32;
-    while ((CSB / 4) * CBB > 256) CBB /= 2;
+    while ((CSB / csr) * CBB > 256) CBB /= 2;
     auto smem_of = [&](int csb_, int cbb_) {
       const size_t rows = ((size_t)Ws * csb_ + (size_t)KD * k * (Wb + 2 * pad) * cbb_) * 4;
       const size_t red = (size_t)csb_ * cbb_ * taps * 4;
       return rows > red ? rows : red;
     };
-    while (smem_of(CSB, CBB) > 100 * 1024 && CBB > 4) CBB /= 2;
-    while (smem_of(CSB, CBB) > 100 * 1024 && CSB > 4) CSB /= 2;
-    const bool pow2 = (CBB & (CBB - 1)) == 0 && ((CSB / 4) & (CSB / 4 - 1)) == 0;
-    if (smem_of(CSB, CBB) <= 100 * 1024 && Cs % CSB == 0 && Cb % CBB == 0 && pow2 && CSB % 4 == 0 && CBB % 4 == 0) {
+    const size_t kTwo = 100 * 1024, kOne = 200 * 1024;
+    int csb2 = CSB, cbb2 = CBB;
+    while (smem_of(csb2, cbb2) > kTwo && cbb2 > 4) cbb2 /= 2;
+    while (smem_of(csb2, cbb2) > kTwo && csb2 > csr && csr == 4 && csb2 > 4) csb2 /= 2;
+    if (smem_of(csb2, cbb2) <= kTwo) { CSB = csb2; CBB = cbb2; }
+    else { while (smem_of(CSB, CBB) > kOne && CBB > 4) CBB /= 2; }
+    const bool pow2 = (CBB & (CBB - 1)) == 0 && ((CSB / csr) & (CSB / csr - 1)) == 0;
+    if (smem_of(CSB, CBB) <= kOne && Cs % CSB == 0 && Cb % CBB == 0 && pow2 && CBB % 4 == 0) {
       const size_t smem = smem_of(CSB, CBB);
       const int64_t nrows = (int64_t)B * Ds * Hs;
       const int gy = Cs / CSB, gz = Cb / CBB;
@@ -810,13 +825,15 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
       if (rpc64 < 1) rpc64 = 1;
       if (rpc64 > nrows) rpc64 = nrows;
       dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc64), gy, gz);
-#define RCMVS_WS(KD_, KK, SS)                                                                                              \
+#define RCMVS_WS_(KD_, KK, SS, CC)                                                                                         \
   do {                                                                                                                     \
     static SmemAttrOnce attr;                                                                                              \
-    cudaError_t e = attr.ensure(wgrad_smem_kernel<KD_, KK, SS>, 100 * 1024);                                               \
+    cudaError_t e = attr.ensure(wgrad_smem_kernel<KD_, KK, SS, CC>, (int)kOne);                                            \
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
-    wgrad_smem_kernel<KD_, KK, SS><<<grid, 256, smem, st0>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, (int)rpc64, CSB, CBB); \
+    wgrad_smem_kernel<KD_, KK, SS, CC><<<grid, 256, smem, st0>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, (int)rpc64, CSB, \
+                                                                 CBB);                                                     \
   } while (0)
+#define RCMVS_WS(KD_, KK, SS) do { if (csr == 4) RCMVS_WS_(KD_, KK, SS, 4); else RCMVS_WS_(KD_, KK, SS, 1); } while (0)
       bool launched = true;
       if (dim3d) { if (stride == 1) RCMVS_WS(3, 3, 1); else RCMVS_WS(3, 3, 2); }
       else if (k == 1 && stride == 1) RCMVS_WS(1, 1, 1);
@@ -826,6 +843,7 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
       else if (k == 5 && stride == 2) RCMVS_WS(1, 5, 2);
       else launched = false;
 #undef RCMVS_WS
+#undef RCMVS_WS_
       if (launched) {
         RCMVS_CHECK_LAUNCH("rcmvs_conv_wgrad");
         return RCMVS_OK;

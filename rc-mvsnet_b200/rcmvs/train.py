@@ -12,6 +12,12 @@ SyncBatchNorm sharing batch statistics (:524-525).
   * forward and backward run on librcmvs kernels through rcmvs.autograd (RCMVS_STRICT=1 raises on any library fallback);
   * SyncBatchNorm semantics = `rcmvs.autograd.SYNC_BN` (2·C doubles per BatchNorm layer over NCCL).
 The rendering-consistency branch joins the step when `nerf` is given (its differentiable path is selected by the module).
+
+`graph=True` (the default on one GPU without the render branch) captures "zero the gradients -> both forwards -> losses ->
+backward" — about 2000 kernel launches of 5-400 us — into ONE CUDA graph after three eager steps, and replays it per step:
+the sample, the masked image and its filter mask are copied into the graph's static inputs first (the mask rectangle is
+drawn on the host per step exactly as before), the gradient all-reduce and the Adam launch (whose step count is a host
+scalar) follow the replay eagerly.
 """
 import torch
 import torch.distributed as dist
@@ -63,7 +69,9 @@ class FlatParams:
 
 
 class TrainStep:
-    def __init__(self, model, nerf=None, lr=1e-4, w_aug=0.01, dlossw=(0.5, 1.0, 2.0), sync_bn=None):
+    GRAPH_WARMUP = 3                                 # eager steps before the capture (packing, kernel attributes, caches)
+
+    def __init__(self, model, nerf=None, lr=1e-4, w_aug=0.01, dlossw=(0.5, 1.0, 2.0), sync_bn=None, graph=None):
         from losses import AugLossMultiStage, UnsupLossMultiStage, random_image_mask
         self.model, self.nerf = model, nerf
         self.unsup, self.aug, self.mask_fn = UnsupLossMultiStage(), AugLossMultiStage(), random_image_mask
@@ -72,28 +80,74 @@ class TrainStep:
         if sync_bn is None:
             sync_bn = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         A.SYNC_BN = bool(sync_bn)
+        if graph is None:
+            graph = nerf is None and not A.SYNC_BN
+        self.use_graph, self._graph, self._static, self._eager_steps = bool(graph), None, None, 0
 
     def __call__(self, sample):
         """sample: imgs [B,V,3,H,W] (normalised), center_imgs (the loss's images), imgs_aug, proj_matrices {stageK},
         depth_values [B,Dv] — the keys the reference's loader produces (datasets/dtu_train.py:344-364)."""
+        self.model.train()
+        imgs_aug = sample["imgs_aug"].clone()
+        ref, fmask = self.mask_fn(imgs_aug[:, 0], (imgs_aug.shape[3] // 3, imgs_aug.shape[4] // 3))
+        imgs_aug[:, 0] = ref
+        if self.use_graph and self._eager_steps >= self.GRAPH_WARMUP:
+            loss, scal = self._replay(sample, imgs_aug, fmask)
+        else:
+            loss, scal = self._forward_backward(sample, imgs_aug, fmask)
+            self._eager_steps += 1
+        world = self.flat.all_reduce()
+        self.flat.adam(self.lr, world=world)
+        return loss, scal
+
+    def _forward_backward(self, sample, imgs_aug, fmask):
+        """Zero the gradients, both forwards, the losses and ONE backward — device work only (no host synchronisation), so
+        it can run eagerly or inside a CUDA-graph capture."""
         m = self.model
-        m.train()
         self.flat.zero_grad()
         out, vol = m(sample["imgs"], sample["proj_matrices"], sample["depth_values"])
         loss_base, scal = self.unsup(out, sample["center_imgs"], sample["proj_matrices"], dlossw=self.dlossw)
         pseudo = out["depth"].detach()
-        imgs_aug = sample["imgs_aug"].clone()
-        ref, fmask = self.mask_fn(imgs_aug[:, 0], (imgs_aug.shape[3] // 3, imgs_aug.shape[4] // 3))
-        imgs_aug[:, 0] = ref
         out_aug, _ = m(imgs_aug, sample["proj_matrices"], sample["depth_values"])
         loss_aug, _ = self.aug(out_aug, pseudo, None, fmask, dlossw=self.dlossw)
         loss = loss_base + self.w_aug * loss_aug
         if self.nerf is not None:
             loss = loss + self._render_losses(vol, pseudo, sample)
         loss.backward()
-        world = self.flat.all_reduce()
-        self.flat.adam(self.lr, world=world)
         return loss.detach(), {"loss_base": loss_base.detach(), "loss_aug": loss_aug.detach(), **{k: v.detach() for k, v in scal.items()}}
+
+    _KEYS = ("imgs", "center_imgs", "depth_values")
+
+    def _replay(self, sample, imgs_aug, fmask):
+        if fmask is None:                                # (filter = whole image: the reference passes no mask)
+            fmask = torch.ones_like(imgs_aug[:, 0])
+        if self._graph is None:
+            dev = imgs_aug.device
+            st = {k: sample[k].clone() for k in self._KEYS}
+            st["proj_matrices"] = {k: v.clone() for k, v in sample["proj_matrices"].items()}
+            self._static, self._s_aug, self._s_mask = st, imgs_aug.clone(), fmask.clone()
+            own = torch.cuda.Stream(dev)
+            own.wait_stream(torch.cuda.current_stream(dev))
+            own.synchronize()
+            from . import _ffi
+            n0 = _ffi.launches
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, stream=own):
+                self._out = self._forward_backward(st, self._s_aug, self._s_mask)
+            self.graph_kernels = _ffi.launches - n0
+            torch.cuda.current_stream(dev).wait_stream(own)
+            self.flat.zero_grad()                        # (re-attach .grad views should the capture have replaced any)
+        st = self._static
+        for k in self._KEYS:
+            st[k].copy_(sample[k], non_blocking=True)
+        for k, v in sample["proj_matrices"].items():
+            st["proj_matrices"][k].copy_(v, non_blocking=True)
+        self._s_aug.copy_(imgs_aug, non_blocking=True)
+        self._s_mask.copy_(fmask, non_blocking=True)
+        self._graph.replay()
+        from . import _ffi
+        _ffi.launches += self.graph_kernels
+        return self._out
 
     def _render_losses(self, vol, pseudo, sample):
         from losses import SL1Loss, masked_loss
@@ -114,7 +168,7 @@ def synthetic_sample(dev, views=4, H=512, W=640, seed=0):
             "proj_matrices": {k: t(v) for k, v in proj.items()}}
 
 
-def bench_train_step(dev, steps=5, views=4, H=512, W=640, ndepths=(48, 32, 8)):
+def bench_train_step(dev, steps=5, views=4, H=512, W=640, ndepths=(48, 32, 8), graph=None):
     """ms per optimiser step (2 forwards + losses + backward + gradient all-reduce + fused Adam) of the MVS part of the
     reference step at the default training shape (4 views 512x640, D=48/32/8, batch 1 per GPU), CUDA-event timed."""
     import os
@@ -125,11 +179,11 @@ def bench_train_step(dev, steps=5, views=4, H=512, W=640, ndepths=(48, 32, 8)):
     model = models.CascadeMVSNet(ndepths=list(ndepths))
     weights.load_model(model, os.path.join(root, "tests", "golden", "cas_model_000014.npz"))
     model.to(dev)
-    step = TrainStep(model)
+    step = TrainStep(model, graph=graph)
     rank = dist.get_rank() if dist.is_initialized() else 0
     sample = synthetic_sample(dev, views, H, W, seed=rank)
     np.random.seed(0)
-    for _ in range(2):
+    for _ in range(TrainStep.GRAPH_WARMUP + 2):      # (eager steps, the capture, one replay)
         loss, _ = step(sample)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -150,4 +204,6 @@ def bench_train_step(dev, steps=5, views=4, H=512, W=640, ndepths=(48, 32, 8)):
                         "AugLossMultiStage + backward + flat-gradient all-reduce (%.2f MB) + fused Adam, batch 1 per GPU"
                         % (views, H, W, "/".join(map(str, ndepths)), step.flat.grad.numel() * 4 / 1e6),
             "ms_per_step": round(ms, 3), "value": round(world * 1e3 / ms, 2), "unit": "ref-views/s (training)",
-            "n_gpus": world, "sync_bn": bool(A.SYNC_BN), "loss": float(loss), "finite": bool(torch.isfinite(loss))}
+            "n_gpus": world, "sync_bn": bool(A.SYNC_BN),
+            "launch": "cuda-graph replay of forward+backward, eager all-reduce + Adam" if step._graph is not None else "eager",
+            "loss": float(loss), "finite": bool(torch.isfinite(loss))}

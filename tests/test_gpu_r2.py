@@ -392,7 +392,7 @@ def _tconv_ref(x_cl, w, transposed, stride):
 @pytest.mark.parametrize("cin,cout,stride,transposed,dhw", [
     (32, 8, 1, False, (4, 8, 12)), (8, 16, 2, False, (4, 8, 12)), (16, 16, 1, False, (2, 6, 10)), (16, 32, 2, False, (4, 8, 8)),
     (64, 64, 1, False, (2, 2, 4)), (64, 32, 2, True, (2, 3, 4)), (32, 16, 2, True, (2, 4, 6)), (16, 8, 2, True, (3, 4, 10)),
-    (8, 8, 1, False, (3, 5, 33)),
+    (8, 8, 1, False, (3, 5, 33)), (8, 8, 1, False, (2, 3, 640)), (32, 8, 1, False, (2, 3, 320)),
 ])
 def test_conv3d_bn_relu_block_forward_backward_vs_torch(dev, cin, cout, stride, transposed, dhw):
     """conv -> BatchNorm3d (batch statistics) -> ReLU (+ skip): output, running statistics and all four gradients
@@ -765,6 +765,42 @@ def test_rendering_consistency_net_training_step_on_own_kernels(dev):
     gn = lambda m: sum(float(p.grad.abs().sum()) for p in m.parameters() if p.grad is not None)
     assert gn(nerf.network_fn) > 0 and gn(nerf.MVSNet) > 0 and gn(cas.feature) > 0
     assert all(torch.isfinite(p.grad).all() for p in list(nerf.parameters()) + list(cas.feature.parameters()) if p.grad is not None)
+
+
+def test_train_step_cuda_graph_replay_matches_eager_step(dev):
+    """rcmvs.train.TrainStep(graph=True): the captured zero-grad + two forwards + losses + backward, replayed, yields the
+    loss and the flat gradient of the eager step on the same sample and the same mask rectangle (lr = 0 keeps the weights
+    where they are; float atomics in the weight-gradient kernels bound the agreement), and a replay with another rectangle
+    follows the eager step with that rectangle — i.e. the static inputs are refreshed per step."""
+    import copy
+    import numpy as np
+    import models
+    from rcmvs import train, weights
+    base = models.CascadeMVSNet(ndepths=[16, 8, 8])
+    weights.load_model(base, os.path.join(G, "cas_model_000014.npz"))
+    base.to(dev)
+    sample = train.synthetic_sample(dev, 3, 64, 80, seed=2)
+    eager = train.TrainStep(copy.deepcopy(base), lr=0.0, graph=False)
+    graphed = train.TrainStep(copy.deepcopy(base), lr=0.0, graph=True)
+    for _ in range(train.TrainStep.GRAPH_WARMUP):
+        graphed(sample)
+    assert graphed._graph is None
+    for seed in (5, 11):
+        np.random.seed(seed)
+        le, _ = eager(sample)
+        ge = eager.flat.grad.clone()
+        np.random.seed(seed)
+        lg, sc = graphed(sample)
+        gg = graphed.flat.grad.clone()
+        assert graphed._graph is not None and graphed.graph_kernels > 100
+        assert torch.isfinite(lg) and abs(float(lg) - float(le)) <= 1e-5 * abs(float(le))
+        assert (gg - ge).abs().max() <= 2e-4 * float(ge.abs().max())
+        assert float(ge.abs().max()) > 0
+    np.random.seed(5)
+    l5, _ = eager(sample)
+    np.random.seed(11)
+    l11, _ = eager(sample)
+    assert float(l5) != float(l11)                       # (the two rectangles do give different steps)
 
 
 # ---- f1 FeatureNet on tensor cores: 2-D TMA slab kernel ---------------------------------------------------------------------

@@ -8,8 +8,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "rc-mvsnet_b200"
 from rcmvs import _ffi, train
 dev = torch.device("cuda:0")
 flag = ctypes.c_int.in_dll(_ffi.lib(), "rcmvs_wgrad_variant")
-for v in (0, 8, 0):
+for v, g in ((0, False), (0, True), (8, False), (0, True)):
     flag.value = v
-    r = train.bench_train_step(dev, steps=5)
-    print("wgrad variant %d: %.3f ms/step  loss %.6f" % (v, r["ms_per_step"], r["loss"]), flush=True)
+    r = train.bench_train_step(dev, steps=5, graph=g)
+    print("wgrad variant %d %s: %.3f ms/step  loss %.6f" % (v, r["launch"][:10], r["ms_per_step"], r["loss"]), flush=True)
 flag.value = 0
