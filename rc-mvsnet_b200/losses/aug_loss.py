@@ -47,7 +47,7 @@ def masked_loss(pred, target, mask=None, mask_kind=0, mode=0, scale=1.0, step=1)
 class AugLossMultiStage(nn.Module):
     def forward(self, inputs, pseudo_depth, mask_ms, filter_mask, **kwargs):
         weights = kwargs.get("dlossw", None)
-        total = torch.tensor(0.0, dtype=torch.float32, device=pseudo_depth.device)
+        total = torch.zeros((), dtype=torch.float32, device=pseudo_depth.device)
         scalars = {}
         for key in [k for k in inputs.keys() if "stage" in k]:
             idx = int(key.replace("stage", "")) - 1

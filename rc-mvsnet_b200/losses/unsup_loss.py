@@ -69,7 +69,7 @@ class UnsupLossMultiStage(nn.Module):
 
     def forward(self, inputs, imgs, cams, **kwargs):
         weights = kwargs.get("dlossw", None)
-        total = torch.tensor(0.0, dtype=torch.float32, device=imgs.device)
+        total = torch.zeros((), dtype=torch.float32, device=imgs.device)
         scalars = {}
         for key in [k for k in inputs.keys() if "stage" in k]:
             idx = int(key.replace("stage", "")) - 1

@@ -611,7 +611,7 @@ def get_depth_range_samples(cur_depth, ndepth, depth_inteval_pixel, device, dtyp
 def cas_mvsnet_loss(inputs, depth_gt_ms, mask_ms, **kwargs):
     """Supervised multi-stage smooth-L1 (reference :527-546); host glue, unchanged semantics."""
     weights = kwargs.get("dlossw", None)
-    total = torch.tensor(0.0, dtype=torch.float32, device=mask_ms["stage1"].device)
+    total = torch.zeros((), dtype=torch.float32, device=mask_ms["stage1"].device)
     depth_loss = None
     for key in [k for k in inputs.keys() if "stage" in k]:
         mask = mask_ms[key] > 0.5

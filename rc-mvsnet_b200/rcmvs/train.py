@@ -82,7 +82,7 @@ class TrainStep:
         A.SYNC_BN = bool(sync_bn)
         if graph is None:
             graph = nerf is None and not A.SYNC_BN
-        self.use_graph, self._graph, self._static, self._eager_steps = bool(graph), None, None, 0
+        self.use_graph, self._graph, self._static, self._eager_steps, self._stream = bool(graph), None, None, 0, None
 
     def __call__(self, sample):
         """sample: imgs [B,V,3,H,W] (normalised), center_imgs (the loss's images), imgs_aug, proj_matrices {stageK},
@@ -93,9 +93,19 @@ class TrainStep:
         imgs_aug[:, 0] = ref
         if self.use_graph and self._eager_steps >= self.GRAPH_WARMUP:
             loss, scal = self._replay(sample, imgs_aug, fmask)
+        elif self.use_graph:
+            # the eager steps before the capture run on the capture's own (non-default) stream: autograd's AccumulateGrad
+            # nodes remember the stream they were made on, and the legacy default stream cannot join a capture
+            cur = torch.cuda.current_stream(imgs_aug.device)
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(imgs_aug.device)
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                loss, scal = self._forward_backward(sample, imgs_aug, fmask)
+            cur.wait_stream(self._stream)
+            self._eager_steps += 1
         else:
             loss, scal = self._forward_backward(sample, imgs_aug, fmask)
-            self._eager_steps += 1
         world = self.flat.all_reduce()
         self.flat.adam(self.lr, world=world)
         return loss, scal
@@ -126,7 +136,7 @@ class TrainStep:
             st = {k: sample[k].clone() for k in self._KEYS}
             st["proj_matrices"] = {k: v.clone() for k, v in sample["proj_matrices"].items()}
             self._static, self._s_aug, self._s_mask = st, imgs_aug.clone(), fmask.clone()
-            own = torch.cuda.Stream(dev)
+            own = self._stream or torch.cuda.Stream(dev)
             own.wait_stream(torch.cuda.current_stream(dev))
             own.synchronize()
             from . import _ffi

@@ -772,16 +772,17 @@ def test_train_step_cuda_graph_replay_matches_eager_step(dev):
     loss and the flat gradient of the eager step on the same sample and the same mask rectangle (lr = 0 keeps the weights
     where they are; float atomics in the weight-gradient kernels bound the agreement), and a replay with another rectangle
     follows the eager step with that rectangle — i.e. the static inputs are refreshed per step."""
-    import copy
     import numpy as np
     import models
     from rcmvs import train, weights
-    base = models.CascadeMVSNet(ndepths=[16, 8, 8])
-    weights.load_model(base, os.path.join(G, "cas_model_000014.npz"))
-    base.to(dev)
-    sample = train.synthetic_sample(dev, 3, 64, 80, seed=2)
-    eager = train.TrainStep(copy.deepcopy(base), lr=0.0, graph=False)
-    graphed = train.TrainStep(copy.deepcopy(base), lr=0.0, graph=True)
+
+    def make():
+        m = models.CascadeMVSNet(ndepths=[16, 8, 8])
+        weights.load_model(m, os.path.join(G, "cas_model_000014.npz"))
+        return m.to(dev)
+    sample = train.synthetic_sample(dev, 3, 64, 96, seed=2)
+    eager = train.TrainStep(make(), lr=0.0, graph=False)
+    graphed = train.TrainStep(make(), lr=0.0, graph=True)
     for _ in range(train.TrainStep.GRAPH_WARMUP):
         graphed(sample)
     assert graphed._graph is None
