@@ -24,6 +24,26 @@ namespace train {
 // ---------------------------------------------------------------------------------------------------------------------
 // BatchNorm (training): x [M][C] channels-last
 // ---------------------------------------------------------------------------------------------------------------------
+// Block-level reduction of per-thread channel partials (thread = channel quad g = threadIdx.x % cq, C = 4·cq): lanes that hold
+// the same quad are summed by shuffles first (cq a power of two <= 32), so that 8 warps, not 256 threads, meet at each
+// shared-memory double — a contended shared fp64 atomicAdd is a compare-and-swap loop.
+__device__ __forceinline__ void reduce_channel_partials(double (&a)[4], double (&b)[4], double* sm, int C, int cq, int g) {
+  const bool by_warp = (cq & (cq - 1)) == 0 && cq <= 32;
+  if (by_warp) {
+    for (int off = 16; off >= cq; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+        b[k] += __shfl_xor_sync(0xffffffffu, b[k], off);
+      }
+    }
+  }
+  if (by_warp ? (int)(threadIdx.x & 31) < cq : (int)threadIdx.x < (256 / cq) * cq) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { atomicAdd(&sm[g * 4 + k], a[k]); atomicAdd(&sm[C + g * 4 + k], b[k]); }
+  }
+}
+
 // partial sums: stats[0..C) += Σ x, stats[C..2C) += Σ x²  (double atomics; caller zero-fills)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int64_t M,
                                                         int C, int rows_per_cta) {
@@ -34,23 +54,20 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   const int g = threadIdx.x % cq, r0 = threadIdx.x / cq, rstep = 256 / cq;
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_end = min(M, row_begin + rows_per_cta);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  int n = 0;
   double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
-  for (int64_t r = row_begin + r0; r < row_end; r += rstep) {
-    const float4 v = ldg4(x + r * C + g * 4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
-    if (++n == 64) {                             // flush fp32 partials into doubles every 64 rows
-      ds[0] += s.x; ds[1] += s.y; ds[2] += s.z; ds[3] += s.w; dq[0] += q.x; dq[1] += q.y; dq[2] += q.z; dq[3] += q.w;
-      s = make_float4(0.f, 0.f, 0.f, 0.f); q = s; n = 0;
+  for (int64_t rb = row_begin + r0; rb < row_end; rb += (int64_t)rstep * 64) {   // fp32 partials over <= 64 rows, then doubles
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    const int cnt = (int)min((int64_t)64, (row_end - rb + rstep - 1) / rstep);
+    const float* xp = x + rb * C + g * 4;
+#pragma unroll 8
+    for (int j = 0; j < cnt; ++j) {
+      const float4 v = ldg4(xp + (int64_t)j * rstep * C);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
     }
+    ds[0] += s.x; ds[1] += s.y; ds[2] += s.z; ds[3] += s.w; dq[0] += q.x; dq[1] += q.y; dq[2] += q.z; dq[3] += q.w;
   }
-  ds[0] += s.x; ds[1] += s.y; ds[2] += s.z; ds[3] += s.w; dq[0] += q.x; dq[1] += q.y; dq[2] += q.z; dq[3] += q.w;
-  if (threadIdx.x < (256 / cq) * cq) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { atomicAdd(&sm[g * 4 + k], ds[k]); atomicAdd(&sm[C + g * 4 + k], dq[k]); }
-  }
+  reduce_channel_partials(ds, dq, sm, C, cq, g);
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(stats + i, sm[i]);
 }
@@ -103,31 +120,29 @@ bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ x, 
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_end = min(M, row_begin + rows_per_cta);
   const float4 mu = ldg4(mean + g * 4), is = ldg4(invstd + g * 4), ga = ldg4(gamma + g * 4), be = ldg4(beta + g * 4);
-  float a[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};
+  const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w};
   double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
-  int n = 0;
-  for (int64_t r = row_begin + r0; r < row_end; r += rstep) {
-    const float4 v = ldg4(x + r * C + g * 4), d = ldg4(dz + r * C + g * 4);
-    const float xh[4] = {(v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w};
-    const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w}, dd[4] = {d.x, d.y, d.z, d.w};
+  for (int64_t rb = row_begin + r0; rb < row_end; rb += (int64_t)rstep * 64) {
+    float a[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};
+    const int cnt = (int)min((int64_t)64, (row_end - rb + rstep - 1) / rstep);
+    const int64_t o0 = rb * C + g * 4;
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const int64_t o = o0 + (int64_t)j * rstep * C;
+      const float4 v = ldg4(x + o), d = ldg4(dz + o);
+      const float xh[4] = {(v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w};
+      const float dd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float dv = (relu && !(fmaf(xh[k], gg[k], bb[k]) > 0.f)) ? 0.f : dd[k];
-      a[k] += dv;
-      bq[k] = fmaf(dv, xh[k], bq[k]);
+      for (int k = 0; k < 4; ++k) {
+        const float dv = (relu && !(fmaf(xh[k], gg[k], bb[k]) > 0.f)) ? 0.f : dd[k];
+        a[k] += dv;
+        bq[k] = fmaf(dv, xh[k], bq[k]);
+      }
     }
-    if (++n == 64) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { da[k] += a[k]; db[k] += bq[k]; a[k] = 0.f; bq[k] = 0.f; }
-      n = 0;
-    }
+    for (int k = 0; k < 4; ++k) { da[k] += a[k]; db[k] += bq[k]; }
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { da[k] += a[k]; db[k] += bq[k]; }
-  if (threadIdx.x < (256 / cq) * cq) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { atomicAdd(&sm[g * 4 + k], da[k]); atomicAdd(&sm[C + g * 4 + k], db[k]); }
-  }
+  reduce_channel_partials(da, db, sm, C, cq, g);
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(sums + i, sm[i]);
 }
@@ -328,16 +343,29 @@ wgrad_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* _
 // one LDS.128 + KD·K·K LDS.32 for 4·KD·K·K FMAs.  Partial sums are combined through shared-memory atomics at the end
 // of the row range, then added to G with one global atomic per weight and CTA.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KD, int K, int STRIDE, int CSR>    // CSR = S channels per thread: 4, or 1 when Cs is not a multiple of 4 (`prob`: Cs = 1)
-__global__ void __launch_bounds__(256, (CSR * KD * K * K > 36 ? 2 : 3))       // 2 CTAs / SM for the 25- and 27-tap kernels (small spill)
+// 16-byte asynchronous global -> shared copy; `valid` false writes zeros (src-size 0) and reads nothing
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+// CSR = S channels per thread: 4, or 1 when Cs is not a multiple of 4 (`prob`: Cs = 1).
+// RING: the Bg rows of one (batch, od) run live in K + STRIDE slots per kd plane, slot = (STRIDE·oy + kh) mod (K + STRIDE):
+// going from output row oy to oy + 1 only STRIDE new rows per plane are fetched (3 instead of 9 for the 3x3x3 stride-1
+// layers), into slots the current row does not read, WHILE the current row is being accumulated (the S row is double
+// buffered) — staging costs a third and hides behind the FMAs.  A new (batch, od) run restarts with a full, synchronous fill.
+template <int KD, int K, int STRIDE, int CSR, bool RING>
+__global__ void __launch_bounds__(256, (CSR * KD * K * K > 36 ? (RING ? 1 : 2) : 3))   // 25/27 taps x 4 channels: 100-108 accumulators
 wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, float* __restrict__ G, int B, int Ds, int Hs,
                   int Ws, int Cs, int Db, int Hb, int Wb, int Cb, int rows_per_cta, int CSB, int CBB) {
   constexpr int TAPS = KD * K * K, PAD = K / 2, PADD = KD / 2;
+  constexpr int NSLOT = RING ? K + STRIDE : K, NSB = RING ? 2 : 1;
   extern __shared__ __align__(16) unsigned char wg_smem_raw[];
   float* sm = reinterpret_cast<float*>(wg_smem_raw);
   const int Wbp = Wb + 2 * PAD;
-  float* s_row = sm;                                  // [Ws][CSB]
-  float* b_rows = sm + (size_t)Ws * CSB;              // [KD*K][Wbp][CBB]
+  float* s_rows = sm;                                 // [NSB][Ws][CSB]
+  float* b_rows = sm + (size_t)NSB * Ws * CSB;        // [KD][NSLOT][Wbp][CBB]
   const int csg_n = CSB / CSR;                        // S channel groups in this CTA
   const int NSL = 256 / (csg_n * CBB);                // x slices
   const int cb_l = threadIdx.x % CBB, slice = (threadIdx.x / CBB) % NSL, cs_g = threadIdx.x / (CBB * NSL);
@@ -351,35 +379,56 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
   const int64_t nrows = (int64_t)B * Ds * Hs;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(nrows, r_begin + rows_per_cta);
   const int cs4 = CSB / 4, cb4 = CBB / 4;
-  for (int64_t r = r_begin; r < r_end; ++r) {
+  const int row_elems = Wbp * CBB, plane_elems = NSLOT * row_elems;
+
+  // global -> shared with 16-byte cp.async (no register staging, every thread keeps all its copies in flight; src-size 0
+  // zero-fills the halo).  `full`: all K rows of every plane; otherwise only the STRIDE rows that are new against row r - 1.
+  auto stage = [&](int64_t r, int buf, bool full) {
     const int oy = (int)(r % Hs), od = (int)((r / Hs) % Ds), b = (int)(r / ((int64_t)Hs * Ds));
-    __syncthreads();                                   // the previous row has been consumed
-    {
-      const float* src = S + r * Ws * Cs + cs0;
-      if constexpr (CSR == 4) {
-        for (int e = threadIdx.x; e < Ws * cs4; e += 256) {
-          const int ox = e / cs4, c4 = e % cs4;
-          *reinterpret_cast<float4*>(s_row + ox * CSB + 4 * c4) = ldg4(src + (int64_t)ox * Cs + 4 * c4);
-        }
-      } else {
-        for (int e = threadIdx.x; e < Ws * CSB; e += 256) s_row[e] = __ldg(src + (int64_t)(e / CSB) * Cs + e % CSB);
+    float* s_row = s_rows + (size_t)buf * Ws * CSB;
+    const float* src = S + r * Ws * Cs + cs0;
+    if constexpr (CSR == 4) {
+      for (int e = threadIdx.x; e < Ws * cs4; e += 256) {
+        const int ox = e / cs4, c4 = e % cs4;
+        cp_async16(s_row + ox * CSB + 4 * c4, src + (int64_t)ox * Cs + 4 * c4, true);
       }
+    } else {
+      for (int e = threadIdx.x; e < Ws * CSB; e += 256) s_row[e] = __ldg(src + (int64_t)(e / CSB) * Cs + e % CSB);
+    }
 #pragma unroll
-      for (int q = 0; q < KD * K; ++q) {
-        const int iz = STRIDE * od + q / K - PADD, iy = STRIDE * oy + q % K - PAD;
-        const bool ok = iz >= 0 && iz < Db && iy >= 0 && iy < Hb;
-        const float* brow = Bg + (((int64_t)b * Db + iz) * Hb + iy) * Wb * Cb + cb0;
-        float* dst = b_rows + (size_t)q * Wbp * CBB;
-        for (int e = threadIdx.x; e < Wbp * cb4; e += 256) {
-          const int ixp = e / cb4, c4 = e % cb4, ix = ixp - PAD;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && ix >= 0 && ix < Wb) v = ldg4(brow + (int64_t)ix * Cb + 4 * c4);
-          *reinterpret_cast<float4*>(dst + ixp * CBB + 4 * c4) = v;
-        }
+    for (int q = 0; q < KD * K; ++q) {
+      const int kdi = q / K, kh = q % K;
+      if (!full && kh < K - STRIDE) continue;
+      const int iz = STRIDE * od + kdi - PADD, iy = STRIDE * oy + kh - PAD;
+      const int slot = RING ? (STRIDE * oy + kh) % NSLOT : kh;
+      const bool ok = iz >= 0 && iz < Db && iy >= 0 && iy < Hb;
+      const float* brow = ok ? Bg + (((int64_t)b * Db + iz) * Hb + iy) * Wb * Cb + cb0 : Bg;
+      float* dst = b_rows + (size_t)kdi * plane_elems + (size_t)slot * row_elems;
+      for (int e = threadIdx.x; e < Wbp * cb4; e += 256) {
+        const int ixp = e / cb4, c4 = e % cb4, ix = ixp - PAD;
+        const bool in = ok && ix >= 0 && ix < Wb;
+        cp_async16(dst + ixp * CBB + 4 * c4, in ? brow + (int64_t)ix * Cb + 4 * c4 : Bg, in);
       }
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (r_begin < r_end) {
+    stage(r_begin, 0, true);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  for (int64_t r = r_begin; r < r_end; ++r) {
+    const bool next = r + 1 < r_end;
+    const bool same = RING && next && (r + 1) % Hs != 0;       // the next row continues this (batch, od) run
+    if (same) stage(r + 1, buf ^ 1, false);                    // lands in the other S buffer and in slots row r does not read
     if (active) {
+      const int sbase = STRIDE * (int)(r % Hs);
+      int roff[KD * K];                                        // (plane, slot) offsets of this row's KD·K Bg rows
+#pragma unroll
+      for (int q = 0; q < KD * K; ++q) roff[q] = (q / K) * plane_elems + (RING ? (sbase + q % K) % NSLOT : q % K) * row_elems;
+      const float* s_row = s_rows + (size_t)(RING ? buf : 0) * Ws * CSB;
       for (int ox = slice; ox < Ws; ox += NSL) {
         float sv[CSR];
         if constexpr (CSR == 4) {
@@ -390,15 +439,27 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
         }
         const float* bp = b_rows + (size_t)(ox * STRIDE) * CBB + cb_l;
 #pragma unroll
-        for (int q = 0; q < KD * K; ++q)
+        for (int kw = 0; kw < K; ++kw) {
+          const float* bpk = bp + kw * CBB;
 #pragma unroll
-          for (int kw = 0; kw < K; ++kw) {
-            const float wv = bp[((size_t)q * Wbp + kw) * CBB];
+          for (int q = 0; q < KD * K; ++q) {
+            const float wv = bpk[roff[q]];
 #pragma unroll
             for (int c = 0; c < CSR; ++c) acc[c][q * K + kw] = fmaf(sv[c], wv, acc[c][q * K + kw]);
           }
+        }
       }
     }
+    if (same) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                         // row r consumed by all, row r + 1 complete for all
+    } else if (next) {
+      __syncthreads();
+      stage(r + 1, buf ^ 1, true);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    buf ^= 1;
   }
   // ---- combine the x slices: shared-memory atomics on red[cs][cb][tap], then one global atomic per weight ------------
   __syncthreads();
@@ -786,7 +847,7 @@ extern "C" int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, 
 
 // A/B switches for tools/train_experiments.py (ctypes in_dll; not part of the ABI): bit 0 = rotating register window
 // instead of sliding by register moves, bit 1 = one S channel per thread instead of four, bit 2 = software prefetch of the next position's operands,
-// bit 3 = register-window kernel instead of the shared-memory kernel.  Measured per training step
+// bit 3 = register-window kernel instead of the shared-memory kernel, bit 4 = shared-memory kernel without the row ring.  Measured per training step
 // (B200, 4 views 512x640): 0 -> 94.7 ms, 1 -> 106.1 ms, 2 -> 96.9 ms, 3 -> 109.5 ms.
 extern "C" int rcmvs_wgrad_variant = 0;
 
@@ -805,35 +866,42 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
     int CSB = csr == 4 ? (Cs < 32 ? Cs : 32) : 1;
     int CBB = Cb < 32 ? Cb : 32;
     while ((CSB / csr) * CBB > 256) CBB /= 2;
+    const bool ring = !(rcmvs_wgrad_variant & 16);
+    const int nslot = ring ? k + stride : k, nsb = ring ? 2 : 1;
     auto smem_of = [&](int csb_, int cbb_) {
-      const size_t rows = ((size_t)Ws * csb_ + (size_t)KD * k * (Wb + 2 * pad) * cbb_) * 4;
+      const size_t rows = ((size_t)nsb * Ws * csb_ + (size_t)KD * nslot * (Wb + 2 * pad) * cbb_) * 4;
       const size_t red = (size_t)csb_ * cbb_ * taps * 4;
       return rows > red ? rows : red;
     };
     const size_t kTwo = 100 * 1024, kOne = 200 * 1024;
+    const bool one_cta = ring && csr * taps > 36;               // (those variants hold > 128 registers: one CTA per SM anyway)
     int csb2 = CSB, cbb2 = CBB;
     while (smem_of(csb2, cbb2) > kTwo && cbb2 > 4) cbb2 /= 2;
     while (smem_of(csb2, cbb2) > kTwo && csb2 > csr && csr == 4 && csb2 > 4) csb2 /= 2;
-    if (smem_of(csb2, cbb2) <= kTwo) { CSB = csb2; CBB = cbb2; }
+    if (!one_cta && smem_of(csb2, cbb2) <= kTwo) { CSB = csb2; CBB = cbb2; }
     else { while (smem_of(CSB, CBB) > kOne && CBB > 4) CBB /= 2; }
     const bool pow2 = (CBB & (CBB - 1)) == 0 && ((CSB / csr) & (CSB / csr - 1)) == 0;
     if (smem_of(CSB, CBB) <= kOne && Cs % CSB == 0 && Cb % CBB == 0 && pow2 && CBB % 4 == 0) {
       const size_t smem = smem_of(CSB, CBB);
       const int64_t nrows = (int64_t)B * Ds * Hs;
       const int gy = Cs / CSB, gz = Cb / CBB;
-      int64_t rpc64 = ceil_div<int64_t>(nrows * gy * gz, 148 * 4);      // ~2 waves of 2 CTAs per SM
+      int64_t rpc64 = ceil_div<int64_t>(nrows * gy * gz, one_cta ? 148 * 2 : 148 * 4);      // ~2 waves of 1 or 2 CTAs per SM
       if (rpc64 < 1) rpc64 = 1;
       if (rpc64 > nrows) rpc64 = nrows;
       dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc64), gy, gz);
-#define RCMVS_WS_(KD_, KK, SS, CC)                                                                                         \
+#define RCMVS_WS_(KD_, KK, SS, CC, RR)                                                                                     \
   do {                                                                                                                     \
     static SmemAttrOnce attr;                                                                                              \
-    cudaError_t e = attr.ensure(wgrad_smem_kernel<KD_, KK, SS, CC>, (int)kOne);                                            \
+    cudaError_t e = attr.ensure(wgrad_smem_kernel<KD_, KK, SS, CC, RR>, (int)kOne);                                        \
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
-    wgrad_smem_kernel<KD_, KK, SS, CC><<<grid, 256, smem, st0>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, (int)rpc64, CSB, \
-                                                                 CBB);                                                     \
+    wgrad_smem_kernel<KD_, KK, SS, CC, RR><<<grid, 256, smem, st0>>>(S, Bg, G, B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, (int)rpc64, \
+                                                                     CSB, CBB);                                            \
   } while (0)
-#define RCMVS_WS(KD_, KK, SS) do { if (csr == 4) RCMVS_WS_(KD_, KK, SS, 4); else RCMVS_WS_(KD_, KK, SS, 1); } while (0)
+#define RCMVS_WS(KD_, KK, SS)                                                                                              \
+  do {                                                                                                                     \
+    if (csr == 4) { if (ring) RCMVS_WS_(KD_, KK, SS, 4, true); else RCMVS_WS_(KD_, KK, SS, 4, false); }                    \
+    else { if (ring) RCMVS_WS_(KD_, KK, SS, 1, true); else RCMVS_WS_(KD_, KK, SS, 1, false); }                             \
+  } while (0)
       bool launched = true;
       if (dim3d) { if (stride == 1) RCMVS_WS(3, 3, 1); else RCMVS_WS(3, 3, 2); }
       else if (k == 1 && stride == 1) RCMVS_WS(1, 1, 1);
