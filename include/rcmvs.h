@@ -323,7 +323,8 @@ int rcmvs_bn_apply(const float* x, const float* mean, const float* invstd, const
                    const float* skip, float* z, int64_t M, int C, int relu, rcmvs_stream_t stream);
 /* BatchNorm(+ReLU) backward: dz, x (the convolution output the forward normalised) -> dx (gradient w.r.t. x), dgamma,
  * dbeta [C]; sums = 2·C doubles of zero-filled workspace.  frozen = 1: mean / invstd were running statistics (eval-mode
- * BatchNorm under autograd), so the batch-statistic correction terms are dropped. */
+ * BatchNorm under autograd), so the batch-statistic correction terms are dropped; frozen bit 1 (value 2): dgamma / dbeta
+ * are accumulated into (+=) instead of overwritten (gradient buffers of an optimiser, cf. rcmvs_conv_wgrad's G). */
 int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, const float* invstd, const float* gamma,
                  const float* beta, double* sums, float* dx, float* dgamma, float* dbeta, int64_t M, int C, int relu,
                  int frozen, rcmvs_stream_t stream);

@@ -154,9 +154,11 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ x, c
                     const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int64_t n4, double M, int C, int relu, int frozen) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool accumulate = (frozen & 2) != 0;       // flags: bit 0 = frozen statistics, bit 1 = dgamma / dbeta are += targets
+  frozen &= 1;
   if (blockIdx.x == 0 && threadIdx.x < C) {
-    if (dbeta) dbeta[threadIdx.x] = (float)sums[threadIdx.x];
-    if (dgamma) dgamma[threadIdx.x] = (float)sums[C + threadIdx.x];
+    if (dbeta) dbeta[threadIdx.x] = (accumulate ? dbeta[threadIdx.x] : 0.f) + (float)sums[threadIdx.x];
+    if (dgamma) dgamma[threadIdx.x] = (accumulate ? dgamma[threadIdx.x] : 0.f) + (float)sums[C + threadIdx.x];
   }
   if (i >= n4) return;
   const int c = (int)((i * 4) % C);
@@ -385,7 +387,7 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
   // zero-fills the halo).  `full`: all K rows of every plane; otherwise only the STRIDE rows that are new against row r - 1.
   auto stage = [&](int64_t r, int buf, bool full) {
     const int oy = (int)(r % Hs), od = (int)((r / Hs) % Ds), b = (int)(r / ((int64_t)Hs * Ds));
-    float* s_row = s_rows + (size_t)buf * Ws * CSB;
+    float* s_row = s_rows + (size_t)(RING ? buf : 0) * Ws * CSB;
     const float* src = S + r * Ws * Cs + cs0;
     if constexpr (CSR == 4) {
       for (int e = threadIdx.x; e < Ws * cs4; e += 256) {
@@ -467,7 +469,18 @@ wgrad_smem_kernel(const float* __restrict__ S, const float* __restrict__ Bg, flo
   const int nred = CSB * CBB * TAPS;
   for (int e = threadIdx.x; e < nred; e += 256) red[e] = 0.f;
   __syncthreads();
-  if (active) {
+  // lanes of a warp = CBB channels x 32 / CBB slices of ONE S channel group (CBB, csg_n, NSL are powers of two on this
+  // path): the slices meet by shuffles, so 32 / CBB times fewer threads contend for each shared-memory sum
+  const bool by_warp = CBB < 32 && (CBB & (CBB - 1)) == 0 && NSL * CBB >= 32 && (NSL & (NSL - 1)) == 0;
+  if (by_warp) {
+    for (int off = 16; off >= CBB; off >>= 1) {
+#pragma unroll
+      for (int c = 0; c < CSR; ++c)
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], off);
+    }
+  }
+  if (active && (!by_warp || (int)(threadIdx.x & 31) < CBB)) {
 #pragma unroll
     for (int c = 0; c < CSR; ++c)
 #pragma unroll
@@ -885,7 +898,9 @@ extern "C" int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B
       const size_t smem = smem_of(CSB, CBB);
       const int64_t nrows = (int64_t)B * Ds * Hs;
       const int gy = Cs / CSB, gz = Cb / CBB;
-      int64_t rpc64 = ceil_div<int64_t>(nrows * gy * gz, one_cta ? 148 * 2 : 148 * 4);      // ~2 waves of 1 or 2 CTAs per SM
+      int64_t target = one_cta ? 148 * 2 : 148 * 4;                     // ~2 waves of 1 or 2 CTAs per SM ...
+      if (nrows * gy * gz <= 2 * target) target = 148;                  // ... or, for the small 2-D layers, one wave of long CTAs:
+      int64_t rpc64 = ceil_div<int64_t>(nrows * gy * gz, target);       // the ring and the epilogue amortise over the rows
       if (rpc64 < 1) rpc64 = 1;
       if (rpc64 > nrows) rpc64 = nrows;
       dim3 grid((unsigned)ceil_div<int64_t>(nrows, rpc64), gy, gz);

@@ -16,6 +16,11 @@ from . import _ffi, ops
 from .ops import _chk, _opt, _stream, _on_device
 
 
+GRAD_IN_PLACE = False  # True (rcmvs.train.TrainStep): weight / gamma / beta gradients of conv_block are accumulated by the
+                       # kernels straight into the parameters' existing .grad buffers (autograd receives None for them) — no
+                       # zero-fill + AccumulateGrad add per parameter use, ~1200 tiny launches per training step
+STATS_ARENA = None     # [buffer of zeroed doubles, cursor] while rcmvs.train.TrainStep runs a step: the 2·C-double workspaces of
+                       # the BatchNorm kernels are slices of ONE buffer zeroed once per step instead of ~300 torch.zeros launches
 SYNC_BN = False      # True: batch statistics (forward) and their gradient sums (backward) are all-reduced over the ranks
                      # of the default process group = nn.SyncBatchNorm semantics (train_rcmvsnet.py:524-525)
 
@@ -36,7 +41,7 @@ def _sync_world():
 def bn_batch_stats(x2d, running_mean, running_var, momentum, eps):
     """x2d [M,C] -> (mean, invstd); running statistics updated in place like nn.BatchNorm in train mode."""
     M, C = x2d.shape
-    stats = torch.zeros((2 * C,), device=x2d.device, dtype=torch.float64)
+    stats = _zeros64(2 * C, x2d.device)
     _ffi.call("rcmvs_bn_stats", _chk(x2d, "x"), stats.data_ptr(), M, C, _stream())
     dist, world = _sync_world()
     if dist is not None:                                  # SyncBatchNorm: 2·C doubles over NCCL, equal rows per rank
@@ -58,20 +63,52 @@ def bn_apply(x2d, mean, invstd, gamma, beta, skip, relu):
     return z
 
 
+def stats_arena_begin(dev, n=1 << 17):
+    """Zero the step's workspace arena (allocated once per device) and make _zeros64 hand out slices of it."""
+    global STATS_ARENA
+    buf = _ARENAS.get(dev)
+    if buf is None or buf.numel() < n:
+        buf = _ARENAS[dev] = torch.empty((n,), device=dev, dtype=torch.float64)
+    buf.zero_()
+    STATS_ARENA = [buf, 0]
+
+
+def stats_arena_end():
+    global STATS_ARENA
+    STATS_ARENA = None
+
+
+_ARENAS = {}
+
+
+def _zeros64(n, dev):
+    a = STATS_ARENA
+    if a is not None and a[0].device == dev and a[1] + n <= a[0].numel():
+        out = a[0][a[1]:a[1] + n]
+        a[1] += n
+        return out
+    return torch.zeros((n,), device=dev, dtype=torch.float64)
+
+
 @_on_device
-def bn_backward(dz2d, x2d, mean, invstd, gamma, beta, relu, frozen):
+def bn_backward(dz2d, x2d, mean, invstd, gamma, beta, relu, frozen, grad_into=None):
+    """-> dx, dgamma, dbeta.  grad_into = (gamma.grad, beta.grad): the kernel adds into these and (None, None) comes back."""
     M, C = x2d.shape
-    sums = torch.zeros((2 * C,), device=x2d.device, dtype=torch.float64)
+    sums = _zeros64(2 * C, x2d.device)
     dx = torch.empty_like(x2d)
-    dgamma = torch.empty((C,), device=x2d.device, dtype=torch.float32)
-    dbeta = torch.empty_like(dgamma)
     dist, world = _sync_world()
     if dist is None or frozen:
+        if grad_into is not None:
+            dgamma, dbeta = grad_into
+        else:
+            dgamma = torch.empty((C,), device=x2d.device, dtype=torch.float32)
+            dbeta = torch.empty_like(dgamma)
         _ffi.call("rcmvs_bn_bwd", _chk(dz2d, "dz"), _chk(x2d, "x"), _chk(mean, "mean"), _chk(invstd, "invstd"),
                   _chk(gamma, "gamma"), _chk(beta, "beta"), sums.data_ptr(), _chk(dx, "dx"), _chk(dgamma, "dgamma"),
-                  _chk(dbeta, "dbeta"), M, C, 1 if relu else 0, 1 if frozen else 0, _stream())
+                  _chk(dbeta, "dbeta"), M, C, 1 if relu else 0, (1 if frozen else 0) | (2 if grad_into is not None else 0),
+                  _stream())
         _ffi.launches += 1
-        return dx, dgamma, dbeta
+        return (dx, None, None) if grad_into is not None else (dx, dgamma, dbeta)
     # SyncBatchNorm backward: the correction terms use the sums over ALL ranks; dgamma / dbeta stay local (DDP's gradient
     # all-reduce averages them like every other parameter gradient)
     _ffi.call("rcmvs_bn_bwd_reduce", _chk(dz2d, "dz"), _chk(x2d, "x"), _chk(mean, "mean"), _chk(invstd, "invstd"),
@@ -81,6 +118,10 @@ def bn_backward(dz2d, x2d, mean, invstd, gamma, beta, relu, frozen):
     _ffi.call("rcmvs_bn_bwd_apply", _chk(dz2d, "dz"), _chk(x2d, "x"), _chk(mean, "mean"), _chk(invstd, "invstd"),
               _chk(gamma, "gamma"), _chk(beta, "beta"), sums.data_ptr(), _chk(dx, "dx"), None, None, M, M * world, C,
               1 if relu else 0, 0, _stream())
+    if grad_into is not None:
+        grad_into[0].add_(local[C:].float())
+        grad_into[1].add_(local[:C].float())
+        return dx, None, None
     return dx, local[C:].float(), local[:C].float()
 
 
@@ -88,14 +129,15 @@ def bn_backward(dz2d, x2d, mean, invstd, gamma, beta, relu, frozen):
 def channel_sums(x2d):
     """Σ over rows of x2d [M,C] (bias gradients)."""
     M, C = x2d.shape
-    stats = torch.zeros((2 * C,), device=x2d.device, dtype=torch.float64)
+    stats = _zeros64(2 * C, x2d.device)
     _ffi.call("rcmvs_bn_stats", _chk(x2d, "x"), stats.data_ptr(), M, C, _stream())
     return stats[:C].float()
 
 
 @_on_device
-def conv_wgrad(S, Bg, k, stride, dim3d):
-    """S [B,(Ds,)Hs,Ws,Cs], Bg [B,(Db,)Hb,Wb,Cb] -> G [Cs,Cb,taps] (see include/rcmvs.h)."""
+def conv_wgrad(S, Bg, k, stride, dim3d, out=None):
+    """S [B,(Ds,)Hs,Ws,Cs], Bg [B,(Db,)Hb,Wb,Cb] -> G [Cs,Cb,taps] (see include/rcmvs.h).  `out`: a contiguous fp32 buffer of
+    Cs·Cb·taps elements the kernel ADDS into (its partial sums are atomics on G either way)."""
     if dim3d:
         B, Ds, Hs, Ws, Cs = S.shape
         _, Db, Hb, Wb, Cb = Bg.shape
@@ -104,7 +146,12 @@ def conv_wgrad(S, Bg, k, stride, dim3d):
         _, Hb, Wb, Cb = Bg.shape
         Ds = Db = 1
     taps = k ** 3 if dim3d else k * k
-    G = torch.zeros((Cs, Cb, taps), device=S.device, dtype=torch.float32)
+    if out is not None:
+        if out.numel() != Cs * Cb * taps or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("rcmvs: conv_wgrad out= must be %d contiguous fp32 elements" % (Cs * Cb * taps))
+        G = out
+    else:
+        G = torch.zeros((Cs, Cb, taps), device=S.device, dtype=torch.float32)
     _ffi.call("rcmvs_conv_wgrad", _chk(S, "S"), _chk(Bg, "Bg"), _chk(G, "G"), B, Ds, Hs, Ws, Cs, Db, Hb, Wb, Cb, k, stride,
               1 if dim3d else 0, _stream())
     return G
@@ -190,9 +237,14 @@ class _ConvBNAct(torch.autograd.Function):
         dz = dz.contiguous()
         C = dz.shape[-1]
         dgamma = dbeta = dbias = None
+        inplace = lambda p: GRAD_IN_PLACE and p is not None and p.grad is not None and p.grad.is_contiguous() and \
+            p.grad.dtype == torch.float32
         if ctx.has_bn:
             xc, w, y, mean, invstd, g, b = ctx.saved_tensors
-            dy2, dgamma, dbeta = bn_backward(dz.view(-1, C), y.view(-1, C), mean, invstd, g, b, relu, not cfg["batch_stats"])
+            gp, bp = cfg.get("gamma_param"), cfg.get("beta_param")
+            into = (gp.grad, bp.grad) if inplace(gp) and inplace(bp) else None
+            dy2, dgamma, dbeta = bn_backward(dz.view(-1, C), y.view(-1, C), mean, invstd, g, b, relu, not cfg["batch_stats"],
+                                             grad_into=into)
             dy = dy2.view(dz.shape)
         else:
             xc, w = ctx.saved_tensors
@@ -208,13 +260,21 @@ class _ConvBNAct(torch.autograd.Function):
                 if dx.shape[-1] != xc.shape[-1]:          # zero-padded input channels (never differentiated: the image)
                     dx = torch.nn.functional.pad(dx, (0, xc.shape[-1] - dx.shape[-1]))
         k = w.shape[2]
+        wp = cfg.get("weight_param")
+        # (2-D with zero-padded input channels: G is wider than the weight, autograd takes the slice as before)
+        out = wp.grad if inplace(wp) and (dim3d or xc.shape[-1] == w.shape[1]) and wp.grad.numel() == w.numel() else None
         if dim3d and transposed:
-            G = conv_wgrad(xc, dy, 3, 2, True)                      # [Cin_t, Cout_t, 27]
+            G = conv_wgrad(xc, dy, 3, 2, True, out=out)                      # [Cin_t, Cout_t, 27]
         elif dim3d:
-            G = conv_wgrad(dy, xc, 3, stride, True)                 # [Cout, Cin, 27]
+            G = conv_wgrad(dy, xc, 3, stride, True, out=out)                 # [Cout, Cin, 27]
         else:
-            G = conv_wgrad(dy, xc, k, stride, False)[:, :w.shape[1]]  # [Cout, Cin(_pad -> Cin), k*k]
-        dw = G.reshape(w.shape) if G.is_contiguous() else G.contiguous().view(w.shape)
+            G = conv_wgrad(dy, xc, k, stride, False, out=out)
+            if out is None:
+                G = G[:, :w.shape[1]]                                        # [Cout, Cin(_pad -> Cin), k*k]
+        if out is not None:
+            dw = None
+        else:
+            dw = G.reshape(w.shape) if G.is_contiguous() else G.contiguous().view(w.shape)
         return dx, dw, dbias, dgamma, dbeta, (dz if ctx.has_skip else None), None
 
 
@@ -231,9 +291,11 @@ def conv_block(x_cl, conv, bn=None, skip=None, relu=True, training=True):
         cfg["eps"] = bn.eps
         cfg["running_mean"], cfg["running_var"] = bn.running_mean, bn.running_var
         gamma, beta = bn.weight, bn.bias
+        cfg["gamma_param"], cfg["beta_param"] = bn.weight, bn.bias
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
     weight = conv.weight
+    cfg["weight_param"] = conv.weight
     if dim3d and not transposed and x_cl.shape[-1] > weight.shape[1]:
         # zero-padded input channels (Neural_Volume_Net: 41 -> 48): pad the weight alike; autograd slices dW back
         weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, 0, 0, x_cl.shape[-1] - weight.shape[1]))

@@ -10,7 +10,9 @@ SyncBatchNorm sharing batch statistics (:524-525).
   * parameters and gradients live in two FLAT fp32 buffers (the modules' .data / .grad are views), so the data-parallel
     exchange is ONE NCCL all-reduce of 5.4 MB over NVLink and the optimiser is ONE fused Adam launch (csrc/train.cu);
   * forward and backward run on librcmvs kernels through rcmvs.autograd (RCMVS_STRICT=1 raises on any library fallback);
-  * SyncBatchNorm semantics = `rcmvs.autograd.SYNC_BN` (2·C doubles per BatchNorm layer over NCCL).
+  * SyncBatchNorm semantics = `rcmvs.autograd.SYNC_BN` (2·C doubles per BatchNorm layer over NCCL);
+  * the weight-gradient and BatchNorm-backward kernels add into the flat gradient buffer directly
+    (`rcmvs.autograd.GRAD_IN_PLACE`): no zero-filled temporary and no AccumulateGrad add per parameter use.
 The rendering-consistency branch joins the step when `nerf` is given (its differentiable path is selected by the module).
 
 `graph=True` (the default on one GPU without the render branch) captures "zero the gradients -> both forwards -> losses ->
@@ -71,11 +73,13 @@ class FlatParams:
 class TrainStep:
     GRAPH_WARMUP = 3                                 # eager steps before the capture (packing, kernel attributes, caches)
 
-    def __init__(self, model, nerf=None, lr=1e-4, w_aug=0.01, dlossw=(0.5, 1.0, 2.0), sync_bn=None, graph=None):
+    def __init__(self, model, nerf=None, lr=1e-4, w_aug=0.01, dlossw=(0.5, 1.0, 2.0), sync_bn=None, graph=None,
+                 grad_in_place=True):
         from losses import AugLossMultiStage, UnsupLossMultiStage, random_image_mask
         self.model, self.nerf = model, nerf
         self.unsup, self.aug, self.mask_fn = UnsupLossMultiStage(), AugLossMultiStage(), random_image_mask
         self.lr, self.w_aug, self.dlossw = lr, w_aug, list(dlossw)
+        self.grad_in_place = bool(grad_in_place)    # conv / BatchNorm parameter gradients go straight into the flat buffer
         self.flat = FlatParams([model] + ([nerf] if nerf is not None else []))
         if sync_bn is None:
             sync_bn = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -115,6 +119,15 @@ class TrainStep:
         it can run eagerly or inside a CUDA-graph capture."""
         m = self.model
         self.flat.zero_grad()
+        prev, A.GRAD_IN_PLACE = A.GRAD_IN_PLACE, self.grad_in_place
+        A.stats_arena_begin(imgs_aug.device)
+        try:
+            return self._forward_backward_body(m, sample, imgs_aug, fmask)
+        finally:
+            A.GRAD_IN_PLACE = prev
+            A.stats_arena_end()
+
+    def _forward_backward_body(self, m, sample, imgs_aug, fmask):
         out, vol = m(sample["imgs"], sample["proj_matrices"], sample["depth_values"])
         loss_base, scal = self.unsup(out, sample["center_imgs"], sample["proj_matrices"], dlossw=self.dlossw)
         pseudo = out["depth"].detach()

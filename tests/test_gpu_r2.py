@@ -771,7 +771,8 @@ def test_train_step_cuda_graph_replay_matches_eager_step(dev):
     """rcmvs.train.TrainStep(graph=True): the captured zero-grad + two forwards + losses + backward, replayed, yields the
     loss and the flat gradient of the eager step on the same sample and the same mask rectangle (lr = 0 keeps the weights
     where they are; float atomics in the weight-gradient kernels bound the agreement), and a replay with another rectangle
-    follows the eager step with that rectangle — i.e. the static inputs are refreshed per step."""
+    follows the eager step with that rectangle — i.e. the static inputs are refreshed per step.  The eager step lets
+    autograd accumulate the parameter gradients, the graphed one has the kernels add into the flat buffer (GRAD_IN_PLACE)."""
     import numpy as np
     import models
     from rcmvs import train, weights
@@ -781,7 +782,7 @@ def test_train_step_cuda_graph_replay_matches_eager_step(dev):
         weights.load_model(m, os.path.join(G, "cas_model_000014.npz"))
         return m.to(dev)
     sample = train.synthetic_sample(dev, 3, 64, 96, seed=2)
-    eager = train.TrainStep(make(), lr=0.0, graph=False)
+    eager = train.TrainStep(make(), lr=0.0, graph=False, grad_in_place=False)     # (autograd accumulates the gradients)
     graphed = train.TrainStep(make(), lr=0.0, graph=True)
     for _ in range(train.TrainStep.GRAPH_WARMUP):
         graphed(sample)
