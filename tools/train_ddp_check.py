@@ -49,4 +49,5 @@ dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     print("OK: %d ranks, sync_bn=%s, graph=%s, flat gradient buffer %.2f MB, %.2f ms per step (max over ranks, %dx%d)"
           % (world, train.A.SYNC_BN, step._graph is not None, step.flat.grad.numel() * 4 / 1e6, float(ms), H, W))
+step.close()
 dist.destroy_process_group()
