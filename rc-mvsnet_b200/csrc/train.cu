@@ -545,6 +545,65 @@ conv2d_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ wd /
   st4(dx + pix * Cin + g * 4, acc);
 }
 
+// Stride-1 variant, register-blocked: thread = 4 consecutive input pixels x 4 input channels.  Per (kh, 4 output channels)
+// it loads the K + 3 dy columns its four pixels touch once (float4 each) and the K x 4 weight rows once, for K·4·16 FMAs —
+// 10.7 FMAs per load at K = 3 against 3.2 for one pixel per thread — and a CTA walks over many tiles, so the weights are
+// staged in shared memory once per CTA instead of once per 32-64 pixels.
+template <int K>
+__global__ void __launch_bounds__(256)
+conv2d_dgrad_s1_kernel(const float* __restrict__ dy, const float* __restrict__ wd /* [K*K][Cout][Cin] */,
+                       float* __restrict__ dx, int N, int H, int W, int Cin, int Cout) {
+  extern __shared__ __align__(16) float wsm[];
+  const int nw = K * K * Cout * Cin;
+  for (int i = threadIdx.x; i < nw / 4; i += 256) reinterpret_cast<float4*>(wsm)[i] = ldg4(wd + 4 * i);
+  __syncthreads();
+  constexpr int P = K / 2, NC = K + 3;
+  const int cq = Cin / 4, Wt = (W + 3) / 4;
+  const int64_t total = (int64_t)N * H * Wt * cq;
+  for (int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x; gid < total; gid += (int64_t)gridDim.x * 256) {
+    const int g = (int)(gid % cq);
+    const int64_t tile = gid / cq;
+    const int x0 = (int)(tile % Wt) * 4, y = (int)((tile / Wt) % H), n = (int)(tile / ((int64_t)Wt * H));
+    float4 acc[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh) {
+      const int oy = y + P - kh;
+      if (oy < 0 || oy >= H) continue;
+      const float* drow = dy + ((int64_t)n * H + oy) * W * Cout;
+      for (int co = 0; co < Cout; co += 4) {
+        float4 d[NC];                                  // dy columns x0 - P .. x0 + 3 + P
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int ox = x0 - P + c;
+          d[c] = (ox >= 0 && ox < W) ? ldg4(drow + (int64_t)ox * Cout + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const float* wp = wsm + ((kh * K + kw) * Cout + co) * Cin + g * 4;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + Cin);
+          const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * Cin);
+          const float4 w3 = *reinterpret_cast<const float4*>(wp + 3 * Cin);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float4 dv = d[p + 2 * P - kw];       // pixel x0 + p reads dy column x0 + p + P - kw
+            acc[p].x = fmaf(dv.x, w0.x, fmaf(dv.y, w1.x, fmaf(dv.z, w2.x, fmaf(dv.w, w3.x, acc[p].x))));
+            acc[p].y = fmaf(dv.x, w0.y, fmaf(dv.y, w1.y, fmaf(dv.z, w2.y, fmaf(dv.w, w3.y, acc[p].y))));
+            acc[p].z = fmaf(dv.x, w0.z, fmaf(dv.y, w1.z, fmaf(dv.z, w2.z, fmaf(dv.w, w3.z, acc[p].z))));
+            acc[p].w = fmaf(dv.x, w0.w, fmaf(dv.y, w1.w, fmaf(dv.z, w2.w, fmaf(dv.w, w3.w, acc[p].w))));
+          }
+        }
+      }
+    }
+    float* out = dx + (((int64_t)n * H + y) * W + x0) * Cin + g * 4;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (x0 + p < W) st4(out + (int64_t)p * Cin, acc[p]);
+  }
+}
+
 // torch Conv2d weight [Cout][Cin][K][K] -> [K*K][Cout][Cin_pad] (input channels contiguous, zero-padded)
 __global__ void pack_dgrad2d_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin, int Cin_pad,
                                     int KK) {
@@ -860,7 +919,8 @@ extern "C" int rcmvs_bn_bwd(const float* dz, const float* x, const float* mean, 
 
 // A/B switches for tools/train_experiments.py (ctypes in_dll; not part of the ABI): bit 0 = rotating register window
 // instead of sliding by register moves, bit 1 = one S channel per thread instead of four, bit 2 = software prefetch of the next position's operands,
-// bit 3 = register-window kernel instead of the shared-memory kernel, bit 4 = shared-memory kernel without the row ring.  Measured per training step
+// bit 3 = register-window kernel instead of the shared-memory kernel, bit 4 = shared-memory kernel without the row ring,
+// bit 5 = one-pixel-per-thread 2-D data-gradient kernel for the stride-1 layers.  Measured per training step
 // (B200, 4 views 512x640): 0 -> 94.7 ms, 1 -> 106.1 ms, 2 -> 96.9 ms, 3 -> 109.5 ms.
 extern "C" int rcmvs_wgrad_variant = 0;
 
@@ -1004,13 +1064,26 @@ extern "C" int rcmvs_conv2d_dgrad(const float* dy, const float* w, float* wd_ws,
     RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv2d_dgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
     conv2d_dgrad_kernel<KK, SS><<<grid, 256, smem, st>>>(dy, wd_ws, dx, N, H, W, cin_pad, Ho, Wo, Cout);        \
   }
+#define RCMVS_DG1(KK)                                                                                           \
+  {                                                                                                             \
+    static SmemAttrOnce attr;                                                                                   \
+    cudaError_t e = attr.ensure(conv2d_dgrad_s1_kernel<KK>, 200 * 1024);                                        \
+    RCMVS_REQUIRE(e == cudaSuccess, RCMVS_ERR_CUDA, "rcmvs_conv2d_dgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
+    const int64_t thr4 = (int64_t)N * H * ((W + 3) / 4) * (cin_pad / 4);                                        \
+    const int per_sm = smem > 64 * 1024 ? 2 : (smem > 32 * 1024 ? 4 : 6);                                       \
+    const unsigned g4 = (unsigned)std::min<int64_t>(ceil_div<int64_t>(thr4, 256), (int64_t)148 * per_sm);       \
+    conv2d_dgrad_s1_kernel<KK><<<g4, 256, smem, st>>>(dy, wd_ws, dx, N, H, W, cin_pad, Cout);                   \
+  }
   if (k == 1 && stride == 1) RCMVS_DG(1, 1)
+  else if (k == 3 && stride == 1 && !(rcmvs_wgrad_variant & 32)) RCMVS_DG1(3)
+  else if (k == 5 && stride == 1 && !(rcmvs_wgrad_variant & 32)) RCMVS_DG1(5)
   else if (k == 3 && stride == 1) RCMVS_DG(3, 1)
   else if (k == 3 && stride == 2) RCMVS_DG(3, 2)
   else if (k == 5 && stride == 1) RCMVS_DG(5, 1)
   else if (k == 5 && stride == 2) RCMVS_DG(5, 2)
   else { set_error("rcmvs_conv2d_dgrad: unsupported k=%d stride=%d", k, stride); return RCMVS_ERR_UNSUPPORTED; }
 #undef RCMVS_DG
+#undef RCMVS_DG1
   RCMVS_CHECK_LAUNCH("rcmvs_conv2d_dgrad");
   return RCMVS_OK;
 }

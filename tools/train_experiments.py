@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "rc-mvsnet_b200"
 from rcmvs import _ffi, train
 dev = torch.device("cuda:0")
 flag = ctypes.c_int.in_dll(_ffi.lib(), "rcmvs_wgrad_variant")
-for v, g in ((0, True), (16, True), (0, True)):
+for v, g in ((0, True), (32, True), (0, True)):
     flag.value = v
     r = train.bench_train_step(dev, steps=5, graph=g)
     print("wgrad variant %d %s: %.3f ms/step  loss %.6f" % (v, r["launch"][:10], r["ms_per_step"], r["loss"]), flush=True)
