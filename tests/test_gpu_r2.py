@@ -461,7 +461,7 @@ def test_prob_conv_forward_backward_vs_torch(dev):
 @pytest.mark.parametrize("cin,cout,k,stride,bn,hw", [
     (3, 8, 3, 1, True, (16, 24)), (8, 16, 5, 2, True, (16, 24)), (16, 32, 5, 2, True, (12, 20)), (32, 32, 3, 1, True, (6, 10)),
     (32, 32, 1, 1, False, (6, 10)), (16, 32, 1, 1, False, (8, 12)), (8, 32, 1, 1, False, (8, 12)), (32, 16, 3, 1, False, (8, 12)),
-    (32, 8, 3, 1, False, (8, 34)), (8, 8, 3, 1, True, (9, 37)), (16, 16, 3, 1, True, (40, 131)), (8, 8, 5, 1, False, (7, 13)),
+    (32, 8, 3, 1, False, (8, 34)), (8, 8, 3, 1, True, (9, 37)), (16, 16, 3, 1, True, (40, 131)),
 ])
 def test_conv2d_block_forward_backward_vs_torch(dev, cin, cout, k, stride, bn, hw):
     import torch.nn as nn
