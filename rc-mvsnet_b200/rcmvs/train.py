@@ -167,6 +167,7 @@ class TrainStep:
             with torch.cuda.graph(self._graph, stream=own):
                 self._out = self._forward_backward(st, self._s_aug, self._s_mask)
             self.graph_kernels = _ffi.launches - n0
+            _ffi.launches = n0                           # (captured, not executed: the replay below counts them)
             torch.cuda.current_stream(dev).wait_stream(own)
             self.flat.zero_grad()                        # (re-attach .grad views should the capture have replaced any)
         st = self._static
