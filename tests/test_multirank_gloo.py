@@ -98,3 +98,30 @@ def test_flat_gradient_allreduce_two_ranks_gloo(tmp_path):
     out = str(tmp_path / "t0.pt")
     mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert torch.load(out)["ok"]
+
+
+def test_step_workspace_arena_hands_out_zeroed_slices():
+    """rcmvs.autograd's per-step arena (the BatchNorm kernels' 2·C-double workspaces in a training step): slices are zero,
+    disjoint, come from ONE buffer that is re-zeroed by the next begin, and the plain torch.zeros path takes over when the
+    arena is inactive or exhausted."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "rc-mvsnet_b200")]
+    from rcmvs import autograd as A
+    dev = torch.device("cpu")
+    assert A.STATS_ARENA is None
+    plain = A._zeros64(16, dev)
+    assert plain.dtype == torch.float64 and float(plain.abs().sum()) == 0.0
+    A.stats_arena_begin(dev, n=64)
+    try:
+        a, b = A._zeros64(16, dev), A._zeros64(32, dev)
+        assert a.data_ptr() + 16 * 8 == b.data_ptr() and float(a.abs().sum() + b.abs().sum()) == 0.0
+        a.fill_(3.0); b.fill_(5.0)
+        big = A._zeros64(32, dev)                      # 16 + 32 + 32 > 64: falls back to its own allocation
+        assert big.data_ptr() != b.data_ptr() + 32 * 8 and float(big.abs().sum()) == 0.0
+        A.stats_arena_begin(dev, n=64)                 # next step: same buffer, zeroed again, cursor at 0
+        c = A._zeros64(16, dev)
+        assert c.data_ptr() == a.data_ptr() and float(c.abs().sum()) == 0.0
+    finally:
+        A.stats_arena_end()
+    assert A.STATS_ARENA is None
