@@ -22,6 +22,8 @@ drawn on the host per step exactly as before), the gradient all-reduce and the A
 scalar) follow the replay eagerly.  With SyncBatchNorm the ~300 NCCL all-reduces of 2·C doubles are captured too (measured on
 2 GPUs: 51.1 ms per step replayed, 68.4 ms eager); `close()` drops the graph before the process group goes away.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -85,6 +87,8 @@ class TrainStep:
         if sync_bn is None:
             sync_bn = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         A.SYNC_BN = bool(sync_bn)
+        if os.environ.get("RCMVS_TRAIN_GRAPH") == "0":
+            graph = False
         if graph is None:
             graph = nerf is None        # (SyncBatchNorm's all-reduces of the statistics are captured with the kernels)
         self.use_graph, self._graph, self._static, self._eager_steps, self._stream = bool(graph), None, None, 0, None
@@ -164,8 +168,16 @@ class TrainStep:
             from . import _ffi
             n0 = _ffi.launches
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph, stream=own):
-                self._out = self._forward_backward(st, self._s_aug, self._s_mask)
+            try:
+                with torch.cuda.graph(self._graph, stream=own):
+                    self._out = self._forward_backward(st, self._s_aug, self._s_mask)
+            except Exception as e:                       # e.g. a collective that cannot be captured on this NCCL build
+                import warnings
+                warnings.warn("rcmvs.train: CUDA-graph capture of the training step failed (%s: %s); the steps stay eager "
+                              "(same kernels, launched one by one)" % (type(e).__name__, e))
+                self._graph, self._static, self.use_graph = None, None, False
+                _ffi.launches = n0
+                return self._forward_backward(sample, imgs_aug, fmask)
             self.graph_kernels = _ffi.launches - n0
             _ffi.launches = n0                           # (captured, not executed: the replay below counts them)
             torch.cuda.current_stream(dev).wait_stream(own)
