@@ -334,8 +334,8 @@ int rcmvs_bn_bwd_reduce(const float* dz, const float* x, const float* mean, cons
 int rcmvs_bn_bwd_apply(const float* dz, const float* x, const float* mean, const float* invstd, const float* gamma,
                        const float* beta, const double* sums, float* dx, float* dgamma, float* dbeta, int64_t M,
                        int64_t M_total, int C, int relu, int frozen, rcmvs_stream_t stream);
-/* Weight gradient G[cs][cb][taps] += Σ_o S[o][cs]·Bg[stride·o + tap - pad][cb] (G zero-filled by the caller, torch weight
- * layout): Conv: S = dy [B][Ds][Hs][Ws][Cs=Cout], Bg = x [B][Db][Hb][Wb][Cb=Cin] -> dW [Cout][Cin][taps];
+/* Weight gradient G[cs][cb][taps] += Σ_o S[o][cs]·Bg[stride·o + tap - pad][cb] (fp32 atomics: G holds zeros for a plain
+ * gradient, or an optimiser's gradient buffer to accumulate into; torch weight layout): Conv: S = dy [B][Ds][Hs][Ws][Cs=Cout], Bg = x [B][Db][Hb][Wb][Cb=Cin] -> dW [Cout][Cin][taps];
  * ConvTranspose(k3,s2,p1,op1): S = x (Cs = Cin), Bg = dy (Cb = Cout), stride 2 -> dW [Cin][Cout][27].
  * dim3d = 1: 3x3x3; dim3d = 0: 2-D (Ds = Db = 1), k in {1,3,5}. */
 int rcmvs_conv_wgrad(const float* S, const float* Bg, float* G, int B, int Ds, int Hs, int Ws, int Cs, int Db, int Hb,
