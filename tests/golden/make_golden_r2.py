@@ -1,6 +1,6 @@
 """Round-2 golden vectors, produced by RUNNING THE UNMODIFIED REFERENCE on CPU (authoring container only).
 
-    PYTHONPATH=/root/reference python tests/golden/make_golden_r2.py [idx] [tanks] [render_full] [geo] [loss]
+    PYTHONPATH=/root/reference python tests/golden/make_golden_r2.py [idx] [tanks] [render_full] [geo] [loss] [train_grad]
 
   idx          depth_index of the three stages of mvs_small.npz, computed with the reference's own op sequence
                (models/casmvsnet.py:111-121: softmax -> depth_regression with arange -> .long() -> clamp)
@@ -9,6 +9,9 @@
                48/32/8, 1024 rays x 128 samples; the sampled pixels / depth candidates are stored for injection
   geo          eval_rcmvsnet_dtu.py:281-338 reproject_with_depth / check_geometric_consistency on synthetic depth maps
   loss         losses/unsup_loss.py UnSupLoss (+ gradient w.r.t. depth) on a small synthetic case
+  train_grad   the reference's FeatureNet and CostRegNet (stage 1, 32 input channels) in train() mode on CPU: outputs, the
+               gradients of every parameter and of the input for fixed random cotangents, BatchNorm running statistics
+               after the step — what pins the torch checker of the GPU gradient tests (tests/test_gpu_r2.py) to the reference
   tanks_sensitivity  (prints only) the reference re-run on ~1-ulp-perturbed images: its own conditioning at cfg 5
 
 Inputs always come from rcmvs.synth with the seeds written next to each case, so the GPU tests regenerate them.
@@ -229,3 +232,40 @@ if "tanks_sensitivity" in what:
         err = np.abs(g["depth_" + k] - d) / np.abs(d).max()
         print(k, "reference(x) vs reference(x·(1 + 1e-7·n)): rel L-inf %.3e, p99.9 %.3e" % (err.max(), np.percentile(err, 99.9)))
     # measured in the authoring container: stage1 1.111e-06 / 7.1e-07, stage2 1.497e-05 / 6.9e-06, stage3 1.641e-04 / 2.2e-05
+
+
+# ---- train_grad ----------------------------------------------------------------------------------------------------
+if "train_grad" in what:
+    from models.casmvsnet import CascadeMVSNet  # reference (train class)
+    torch.manual_seed(0)
+    cas = CascadeMVSNet(ndepths=[16, 8, 8])
+    cas.load_state_dict(ck_cas, strict=True)
+    cas.train()
+    rng = np.random.default_rng(11)
+    out = {}
+    # FeatureNet (reference models/modules.py:363-464), one "view" batch of 2 images
+    x = t(rng.standard_normal((2, 3, 32, 40), dtype=np.float32)).requires_grad_(True)
+    f = cas.feature(x)
+    cot = {k: t(rng.standard_normal(tuple(v.shape), dtype=np.float32)) for k, v in f.items()}
+    sum((f[k] * cot[k]).sum() for k in f).backward()
+    out["feat_x"], out["feat_dx"] = x.detach().numpy(), x.grad.numpy()
+    for k in f:
+        out["feat_out_" + k], out["feat_cot_" + k] = f[k].detach().numpy(), cot[k].numpy()
+    for n, p_ in cas.feature.named_parameters():
+        out["feat_grad/" + n] = p_.grad.numpy().copy()
+    for n, b in cas.feature.named_buffers():
+        if n.endswith("running_mean") or n.endswith("running_var"):
+            out["feat_buf/" + n] = b.numpy().copy()
+    # CostRegNet of stage 1 (reference models/modules.py:470-501): 32 input channels
+    reg = cas.cost_regularization[0]
+    v = t(rng.standard_normal((1, 32, 8, 16, 24), dtype=np.float32)).requires_grad_(True)
+    y = reg(v)
+    cy = t(rng.standard_normal(tuple(y.shape), dtype=np.float32))
+    (y * cy).sum().backward()
+    out["reg_x"], out["reg_dx"], out["reg_out"], out["reg_cot"] = v.detach().numpy(), v.grad.numpy(), y.detach().numpy(), cy.numpy()
+    for n, p_ in reg.named_parameters():
+        out["reg_grad/" + n] = p_.grad.numpy().copy()
+    for n, b in reg.named_buffers():
+        if n.endswith("running_mean") or n.endswith("running_var"):
+            out["reg_buf/" + n] = b.numpy().copy()
+    save("train_grad_small.npz", **out)
