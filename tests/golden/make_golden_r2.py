@@ -1,6 +1,6 @@
 """Round-2 golden vectors, produced by RUNNING THE UNMODIFIED REFERENCE on CPU (authoring container only).
 
-    PYTHONPATH=/root/reference python tests/golden/make_golden_r2.py [idx] [tanks] [render_full] [geo] [loss] [train_grad]
+    PYTHONPATH=/root/reference python tests/golden/make_golden_r2.py [idx] [tanks] [render_full] [geo] [loss] [train_grad] [mask]
 
   idx          depth_index of the three stages of mvs_small.npz, computed with the reference's own op sequence
                (models/casmvsnet.py:111-121: softmax -> depth_regression with arange -> .long() -> clamp)
@@ -12,6 +12,7 @@
   train_grad   the reference's FeatureNet and CostRegNet (stage 1, 32 input channels) in train() mode on CPU: outputs, the
                gradients of every parameter and of the input for fixed random cotangents, BatchNorm running statistics
                after the step — what pins the torch checker of the GPU gradient tests (tests/test_gpu_r2.py) to the reference
+  mask         losses/aug_loss.py random_image_mask under fixed np.random seeds (host RNG call order of the training step)
   tanks_sensitivity  (prints only) the reference re-run on ~1-ulp-perturbed images: its own conditioning at cfg 5
 
 Inputs always come from rcmvs.synth with the seeds written next to each case, so the GPU tests regenerate them.
@@ -269,3 +270,21 @@ if "train_grad" in what:
         if n.endswith("running_mean") or n.endswith("running_var"):
             out["reg_buf/" + n] = b.numpy().copy()
     save("train_grad_small.npz", **out)
+
+
+# ---- mask ----------------------------------------------------------------------------------------------------------
+if "mask" in what:
+    from losses.aug_loss import random_image_mask  # reference
+    rng = np.random.default_rng(3)
+    img = t(rng.standard_normal((2, 3, 48, 60), dtype=np.float32))
+    out = {"img": img.numpy(), "filter_size": np.array([16, 20])}
+    for seed in (0, 5, 11):
+        np.random.seed(seed)
+        a, m = random_image_mask(img, (16, 20))
+        b, m2 = random_image_mask(img, (16, 20))           # second draw from the same stream
+        out["masked_%d" % seed], out["mask_%d" % seed] = a.numpy(), m.numpy().astype(np.uint8)
+        out["mask2_%d" % seed] = m2.numpy().astype(np.uint8)
+    np.random.seed(1)
+    a, m = random_image_mask(img, (48, 60))                # filter = whole image: (img, None)
+    out["full_is_none"] = np.array([m is None and a is img])
+    save("aug_mask_small.npz", **out)
